@@ -1,0 +1,106 @@
+// Shared helpers for libdgtd_ops.so (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dgtd_ops.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libdgtd_ops targets sm_100a only"
+#endif
+
+namespace dgtd {
+
+// ---- error plumbing (thread local, never throws across the ABI) ---------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define DGTD_CHECK_ARG(cond, ...)        \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::dgtd::set_error(__VA_ARGS__);    \
+      return -1;                         \
+    }                                    \
+  } while (0)
+
+// Checks the launch (not the execution: no sync) and counts it.
+#define DGTD_LAUNCH_CHECK(name)                                                  \
+  do {                                                                           \
+    cudaError_t e__ = cudaGetLastError();                                        \
+    if (e__ != cudaSuccess) {                                                    \
+      ::dgtd::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+      return -2;                                                                 \
+    }                                                                            \
+    ::dgtd::count_launch();                                                      \
+  } while (0)
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- device helpers -----------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <int ACT>
+__device__ __forceinline__ float apply_act(float x) {
+  if (ACT == DGTD_ACT_GELU) return gelu_erf(x);
+  if (ACT == DGTD_ACT_RELU) return fmaxf(x, 0.0f);
+  return x;
+}
+
+__device__ __forceinline__ float to_float(float v) { return v; }
+__device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__device__ __forceinline__ T from_float(float v);
+template <>
+__device__ __forceinline__ float from_float<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+
+// store 4 consecutive values
+__device__ __forceinline__ void store4(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* p, float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&lo);
+  u.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+__device__ __forceinline__ float4 load4(const float* p) {
+  return *reinterpret_cast<const float4*>(p);
+}
+__device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 lo = *reinterpret_cast<__nv_bfloat162*>(&u.x);
+  __nv_bfloat162 hi = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+  float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// Bilinear source coordinate, align_corners=False (ATen area_pixel_compute_source_index).
+__device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, int& i0, int& i1,
+                                             float& l1) {
+  float s = (dst + 0.5f) * scale - 0.5f;
+  s = s < 0.f ? 0.f : s;
+  i0 = (int)s;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = s - (float)i0;
+}
+
+}  // namespace dgtd

@@ -1,0 +1,509 @@
+"""`nn.Module` mirror of the texture diffuser, ``twig/model/cod.py:1025-1323`` in the reference.
+
+Same class names, constructor / forward signatures, attribute names (hence identical
+``state_dict`` keys and YAML ``custom_keys`` prefixes, config/cod.yml:88-101) and the same
+parameter initialisation order, so a reference checkpoint loads unchanged and
+``torch.manual_seed(s)`` + construction gives bit-identical parameters.  Every ``forward`` runs on
+the sm_100a kernels of ``libdgtd_ops.so``; there is no ATen compute path and no CPU fallback.
+
+Precision: fp32 (exact CUDA-core path) by default; bf16 operands on tcgen05 tensor cores with
+fp32 accumulation / fp32 residual stream when ``set_precision(module, "bf16")`` was called or the
+forward runs under ``torch.autocast``.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from ..ops.capi import ACT_GELU, ACT_NONE, ACT_RELU, BF16, F32
+from ..ops.functions import texture_diffusion_func as OP
+
+__all__ = [
+    "LayerNorm", "ShapePropWeightRegressor", "convnext_Block", "ShapePropEncoder", "MessagePassing",
+    "ShapePropDecoder", "prompt_encoder", "prompt_decoder", "DropPath", "init_weights_", "set_precision",
+    "build_texture_diffuser", "pvt_token_grids", "texture_prompts", "PVT_EMBED_DIMS", "PVT_DEPTHS",
+]
+
+PVT_EMBED_DIMS = (64, 128, 320, 512)  # pvt_v2_b2, cod.py:1785
+PVT_DEPTHS = (3, 4, 6, 3)             # cod.py:1786
+
+
+# ------------------------------------------------------------------------------------------------
+def _mode(module: nn.Module) -> int:
+    p = getattr(module, "_dgtd_precision", None)
+    if p is None:
+        p = "bf16" if torch.is_autocast_enabled() else "fp32"
+    return BF16 if p == "bf16" else F32
+
+
+def set_precision(module: nn.Module, precision: Optional[str]) -> nn.Module:
+    """precision in {"fp32", "bf16", None}; None = follow torch.autocast."""
+    assert precision in ("fp32", "bf16", None)
+    for m in module.modules():
+        m._dgtd_precision = precision
+    return module
+
+
+class _Packed:
+    """Cache of re-laid-out / down-cast parameters, refreshed when the source changes
+    (``load_state_dict`` and optimizer steps bump ``Tensor._version``)."""
+
+    def __init__(self):
+        self._store: Dict[str, Tuple[tuple, torch.Tensor]] = {}
+
+    def get(self, key: str, srcs: Sequence[torch.Tensor], fn):
+        sig = tuple((t.data_ptr(), t._version, t.device) for t in srcs)
+        hit = self._store.get(key)
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        with torch.no_grad():
+            val = fn()
+        self._store[key] = (sig, val)
+        return val
+
+
+def _packed(module: nn.Module) -> _Packed:
+    pk = module.__dict__.get("_dgtd_packed")
+    if pk is None:
+        pk = module.__dict__["_dgtd_packed"] = _Packed()
+    return pk
+
+
+def _as(t: torch.Tensor, mode: int) -> torch.Tensor:
+    return t.detach().to(torch.bfloat16).contiguous() if mode == BF16 else t.detach().float().contiguous()
+
+
+def _no_grad_only(module: nn.Module, what: str) -> None:
+    if torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()):
+        raise NotImplementedError(
+            f"{what}: the fused forward has no autograd graph in this build; call it under "
+            "torch.no_grad() (inference) -- training kernels are tracked in DESIGN.md")
+
+
+# ------------------------------------------------------------------------------------------------
+class DropPath(nn.Module):
+    """timm ``DropPath`` (per-sample stochastic depth, scale by 1/keep_prob); cod.py:816,1102."""
+
+    def __init__(self, drop_prob: float = 0.0, scale_by_keep: bool = True):
+        super().__init__()
+        self.drop_prob = drop_prob
+        self.scale_by_keep = scale_by_keep
+
+    def keep_scale(self, batch: int, device, dtype=torch.float32) -> Optional[torch.Tensor]:
+        if self.drop_prob == 0.0 or not self.training:
+            return None
+        keep = 1.0 - self.drop_prob
+        mask = torch.empty(batch, device=device, dtype=dtype).bernoulli_(keep)
+        if keep > 0.0 and self.scale_by_keep:
+            mask.div_(keep)
+        return mask
+
+    def forward(self, x):
+        ks = self.keep_scale(x.shape[0], x.device, x.dtype)
+        return x if ks is None else x * ks.view((-1,) + (1,) * (x.dim() - 1))
+
+
+class LayerNorm(nn.Module):
+    """cod.py:1025-1049 (channels_last -> F.layer_norm semantics; channels_first -> over dim 1)."""
+
+    def __init__(self, normalized_shape, eps=1e-6, data_format="channels_last"):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(normalized_shape))
+        self.bias = nn.Parameter(torch.zeros(normalized_shape))
+        self.eps = eps
+        self.data_format = data_format
+        if self.data_format not in ["channels_last", "channels_first"]:
+            raise NotImplementedError
+        self.normalized_shape = (normalized_shape,)
+
+    def forward(self, x):
+        return OP.layer_norm(x.contiguous().float(), self.weight.detach(), self.bias.detach(), self.eps,
+                             self.data_format == "channels_first")
+
+
+class ShapePropWeightRegressor(nn.Module):
+    """cod.py:1051-1060."""
+
+    def __init__(self, in_channels, latent_dim):
+        super(ShapePropWeightRegressor, self).__init__()
+        self.latent_dim = latent_dim
+        self.reg = nn.Conv2d(in_channels, self.latent_dim * 49, kernel_size=1)
+
+    def forward(self, x):
+        w = self.reg.weight.detach().reshape(self.reg.out_channels, -1).contiguous()
+        return OP.conv1x1_nchw(x.contiguous().float(), w, self.reg.bias.detach(), sigmoid=True)
+
+
+class convnext_Block(nn.Module):
+    """cod.py:1082-1117."""
+
+    def __init__(self, dim, drop_path=0., layer_scale_init_value=1e-6):
+        super().__init__()
+        self.dwconv = nn.Conv2d(dim, dim, kernel_size=7, padding=3, groups=dim)
+        self.norm = LayerNorm(dim, eps=1e-6)
+        self.pwconv1 = nn.Linear(dim, 4 * dim)
+        self.act = nn.GELU()
+        self.pwconv2 = nn.Linear(4 * dim, dim)
+        self.gamma = nn.Parameter(layer_scale_init_value * torch.ones((dim)),
+                                  requires_grad=True) if layer_scale_init_value > 0 else None
+        self.drop_path = DropPath(drop_path) if drop_path > 0. else nn.Identity()
+
+    # x: NHWC fp32 residual stream, updated in place.
+    def _forward_nhwc(self, x: torch.Tensor, mode: int) -> torch.Tensor:
+        pk = _packed(self)
+        B, h, w, C = x.shape
+        dw_w = pk.get("dw", [self.dwconv.weight], lambda: self.dwconv.weight.detach().reshape(C, 49).float().contiguous())
+        w1 = pk.get(f"w1.{mode}", [self.pwconv1.weight], lambda: _as(self.pwconv1.weight, mode))
+        w2 = pk.get(f"w2.{mode}", [self.pwconv2.weight], lambda: _as(self.pwconv2.weight, mode))
+        a = OP.dwconv7_ln(x, dw_w, self.dwconv.bias.detach(), self.norm.weight.detach(),
+                          self.norm.bias.detach(), mode, self.norm.eps)
+        hid = OP.linear(a.view(-1, C), w1, self.pwconv1.bias.detach(), act=ACT_GELU)
+        keep = self.drop_path.keep_scale(B, x.device) if isinstance(self.drop_path, DropPath) else None
+        gamma = self.gamma.detach() if self.gamma is not None else None
+        OP.linear_residual_(hid, w2, self.pwconv2.bias.detach(), gamma, keep, h * w, x)
+        return x
+
+    def forward(self, x):
+        _no_grad_only(self, "convnext_Block")
+        y = OP.nchw_to_nhwc(x.contiguous().float())
+        y = self._forward_nhwc(y, _mode(self))
+        return y.permute(0, 3, 1, 2)  # (N,C,H,W) view with channels-last strides
+
+
+class ShapePropEncoder(nn.Module):
+    """cod.py:1119-1177: ConvNeXt-B sized trunk + 4-level fusion head."""
+
+    def __init__(self, in_channels, out_dim):
+        super(ShapePropEncoder, self).__init__()
+        self.downsample_layers = nn.ModuleList()
+        dims = [128, 256, 512, 1024]
+        stem = nn.Sequential(
+            nn.Conv2d(3, dims[0], kernel_size=4, stride=4),
+            LayerNorm(dims[0], eps=1e-6, data_format="channels_first")
+        )
+        self.downsample_layers.append(stem)
+        for i in range(3):
+            downsample_layer = nn.Sequential(
+                LayerNorm(dims[i], eps=1e-6, data_format="channels_first"),
+                nn.Conv2d(dims[i], dims[i + 1], kernel_size=2, stride=2),
+            )
+            self.downsample_layers.append(downsample_layer)
+
+        self.stages = nn.ModuleList()
+        drop_path_rate = 0.4
+        depths = [3, 3, 27, 3]
+        layer_scale_init_value = 1.0
+        dp_rates = [x.item() for x in torch.linspace(0, drop_path_rate, sum(depths))]
+        cur = 0
+        for i in range(4):
+            stage = nn.Sequential(
+                *[convnext_Block(dim=dims[i], drop_path=dp_rates[cur + j],
+                                 layer_scale_init_value=layer_scale_init_value) for j in range(depths[i])]
+            )
+            self.stages.append(stage)
+            cur += depths[i]
+
+        self.convs = nn.ModuleList()
+        for i in range(4):
+            self.convs.append(nn.Conv2d(dims[i], out_dim, 1))
+        self.fusion_conv = nn.Conv2d(out_dim * 4, out_dim, 1)
+        self.dims = dims
+        self.out_dim = out_dim
+
+    def _pyramid(self, image: torch.Tensor, grid: Optional[torch.Tensor], mode: int) -> List[torch.Tensor]:
+        """Stem + stages on NHWC fp32; returns the four stage outputs (cod.py:1165-1169)."""
+        pk = _packed(self)
+        st_conv, st_ln = self.downsample_layers[0][0], self.downsample_layers[0][1]
+        w0 = pk.get("stem", [st_conv.weight], lambda: st_conv.weight.detach().reshape(self.dims[0], 48).float().contiguous())
+        x = OP.stem(image, grid, w0, st_conv.bias.detach(), st_ln.weight.detach(), st_ln.bias.detach(), st_ln.eps)
+        outs = []
+        for i in range(4):
+            if i > 0:
+                ln, conv = self.downsample_layers[i][0], self.downsample_layers[i][1]
+                B, h, w, C = x.shape
+                wd = pk.get(f"ds{i}.{mode}", [conv.weight],
+                            lambda conv=conv, C=C: _as(conv.weight.detach().permute(0, 2, 3, 1).reshape(2 * C, 4 * C), mode))
+                a = OP.ln_patchify(x, ln.weight.detach(), ln.bias.detach(), mode, ln.eps)
+                x = OP.linear(a, wd, conv.bias.detach(), out_dtype=F32).view(B, h // 2, w // 2, 2 * C)
+            for blk in self.stages[i]:
+                x = blk._forward_nhwc(x, mode)
+            outs.append(x)
+        return outs
+
+    def _head(self, outs: List[torch.Tensor], want_nchw: bool, pad_to: int = 0):
+        """cod.py:1171-1176 -> embedding3 as (nhwc fp32, nchw fp32 | None, padded bf16 | None)."""
+        pk = _packed(self)
+        B = outs[0].shape[0]
+        levels, hw = [], []
+        for i, o in enumerate(outs):
+            conv = self.convs[i]
+            wl = pk.get(f"head{i}", [conv.weight], lambda conv=conv: conv.weight.detach().reshape(self.out_dim, -1).float().contiguous())
+            levels.append(OP.linear(o.view(-1, o.shape[-1]), wl, conv.bias.detach()))   # fp32 exact (0.15 GFLOP/img)
+            hw.append((o.shape[1], o.shape[2]))
+        wf = pk.get("fusion", [self.fusion_conv.weight],
+                    lambda: self.fusion_conv.weight.detach().reshape(self.out_dim, 4 * self.out_dim).float().contiguous())
+        return OP.fusion_head(levels, hw, wf, self.fusion_conv.bias.detach(), B, want_nhwc=True,
+                              want_nchw=want_nchw, pad_to=pad_to)
+
+    def forward(self, x):
+        _no_grad_only(self, "ShapePropEncoder")
+        outs = self._pyramid(x.contiguous().float(), None, _mode(self))
+        _, nchw, _ = self._head(outs, want_nchw=True)
+        return nchw
+
+
+class MessagePassing(nn.Module):
+    """cod.py:1180-1208.  ``img_size`` keeps the reference attribute; the fused encoder path
+    up-samples to the actual image size instead of the hard-coded 384."""
+
+    def __init__(self, latent_dim, img_size=384, k=7, max_step=4, sym_norm=False):
+        super(MessagePassing, self).__init__()
+        if k != 7:
+            raise NotImplementedError("MessagePassing kernels are built for k=7 (cod.py:1181)")
+        if sym_norm:
+            raise NotImplementedError("sym_norm branch is dead code in the reference (cod.py:1194-1198)")
+        self.k = k
+        self.size = k * k
+        self.max_step = max_step
+        self.sym_norm = sym_norm
+        self.img_size = img_size
+        self.conv = nn.Conv2d(latent_dim, 3, 1)
+
+    def forward(self, input, weight):
+        n, c, h, w = input.size()
+        steps = max(h, w) if self.max_step < 0 else self.max_step
+        x = OP.message_passing_core(input, weight, steps, 1e-5)
+        cw = self.conv.weight.detach().reshape(3, c).contiguous()
+        x = OP.conv1x1_nchw(x.detach(), cw, self.conv.bias.detach())
+        size = self.img_size if isinstance(self.img_size, (tuple, list)) else (self.img_size, self.img_size)
+        return OP.resize_nchw(x, size, bilinear=True)
+
+
+def _pack_conv3(wt: torch.Tensor) -> torch.Tensor:
+    """(Cout,Cin,3,3) OIHW -> (Cout, 9*Cin) tap-major (dy,dx,c)."""
+    return wt.detach().permute(0, 2, 3, 1).reshape(wt.shape[0], -1).float().contiguous()
+
+
+def _fold_conv3_bilinear(wt: torch.Tensor) -> torch.Tensor:
+    """3x3 conv followed by the 2-tap (0.5/0.5 per axis) bilinear down-sample == 4x4 conv:
+    W4[dy,dx] = 1/4 sum_{a,b in {0,1}} W3[dy-a, dx-b]    -> (Cout, 16*Cin)."""
+    w3 = wt.detach().float()
+    co, ci = w3.shape[0], w3.shape[1]
+    w4 = torch.zeros(co, ci, 4, 4, device=w3.device, dtype=torch.float32)
+    for a in (0, 1):
+        for b in (0, 1):
+            w4[:, :, a:a + 3, b:b + 3] += w3
+    w4 *= 0.25
+    return w4.permute(0, 2, 3, 1).reshape(co, -1).contiguous()
+
+
+class ShapePropDecoder(nn.Module):
+    """cod.py:1210-1226."""
+
+    def __init__(self, out_dim, latent_dim):
+        super(ShapePropDecoder, self).__init__()
+        dilation = 1
+        self.decoder = nn.Sequential(
+            nn.Conv2d(latent_dim, latent_dim, kernel_size=3, stride=1, padding=dilation, dilation=dilation),
+            nn.ReLU(True),
+            nn.Conv2d(latent_dim, latent_dim, kernel_size=3, stride=1, padding=dilation, dilation=dilation),
+            nn.ReLU(True),
+            nn.Conv2d(latent_dim, out_dim, kernel_size=3, stride=1, padding=dilation, dilation=dilation),
+        )
+
+    def forward(self, embedding):
+        return _decode_full([self], OP.nchw_to_nhwc(embedding.contiguous().float()))[0]
+
+
+def _decoder_front(decoders: Sequence[ShapePropDecoder], emb: torch.Tensor) -> torch.Tensor:
+    """conv1+ReLU of all decoders as ONE conv (they share the input), then conv2+ReLU per decoder
+    on its 24-channel slice.  emb NHWC (B,h,w,24) fp32 -> (B,h,w,24*D) fp32."""
+    B, h, w, L = emb.shape
+    D = len(decoders)
+    host = decoders[0]
+    pk = _packed(host)
+    ws = [d.decoder[0].weight for d in decoders]
+    key = "c1." + ".".join(str(id(d)) for d in decoders)
+    w1 = pk.get(key + ".w", ws, lambda: torch.cat([_pack_conv3(t) for t in ws], 0).contiguous())
+    b1 = pk.get(key + ".b", [d.decoder[0].bias for d in decoders],
+                lambda: torch.cat([d.decoder[0].bias.detach().float() for d in decoders]).contiguous())
+    h1 = OP.conv_nhwc(emb, w1, b1, L, (h, w), 3, 1, -1, act=ACT_RELU)
+    h2 = torch.empty_like(h1)
+    for i, d in enumerate(decoders):
+        w2 = _packed(d).get("c2", [d.decoder[2].weight], lambda d=d: _pack_conv3(d.decoder[2].weight))
+        OP.conv_nhwc(h1[..., i * L:(i + 1) * L], w2, d.decoder[2].bias.detach(), L, (h, w), 3, 1, -1,
+                     act=ACT_RELU, out=h2[..., i * L:(i + 1) * L], Cout=L)
+    return h2
+
+
+def _decode_full(decoders: Sequence[ShapePropDecoder], emb: torch.Tensor) -> List[torch.Tensor]:
+    """Reference-shaped outputs: list of (B,E,h,w) tensors (channels-last strides)."""
+    B, h, w, L = emb.shape
+    h2 = _decoder_front(decoders, emb)
+    outs = []
+    for i, d in enumerate(decoders):
+        w3 = _packed(d).get("c3", [d.decoder[4].weight], lambda d=d: _pack_conv3(d.decoder[4].weight))
+        y = OP.conv_nhwc(h2[..., i * L:(i + 1) * L], w3, d.decoder[4].bias.detach(), L, (h, w), 3, 1, -1)
+        outs.append(y.permute(0, 3, 1, 2))
+    return outs
+
+
+def _fold_params(src_hw: Tuple[int, int], dst_hw: Tuple[int, int]) -> Optional[Tuple[int, int]]:
+    """(stride, offset) of the folded 4x4 conv when the bilinear resize src->dst is the exact
+    2-tap average (integer ratio r in {2,4,8,...} on both axes); None otherwise."""
+    (h, w), (oh, ow) = src_hw, dst_hw
+    if oh <= 0 or ow <= 0 or h % oh or w % ow or h // oh != w // ow:
+        return None
+    r = h // oh
+    if r < 2 or r % 2:
+        return None
+    return r, r // 2 - 2  # first averaged row is r*Y + r/2 - 1; the 3x3 conv reaches one row above
+
+
+def _decode_tokens(decoders: Sequence[ShapePropDecoder], emb: torch.Tensor, grid: Tuple[int, int],
+                   h2: Optional[torch.Tensor] = None, index0: int = 0) -> List[torch.Tensor]:
+    """Prompts of one PVT stage directly in token layout (B, H_s*W_s, E_s): last conv folded with
+    the bilinear down-sample (cod.py:1471) when the ratio allows, else conv + NHWC resize."""
+    B, h, w, L = emb.shape
+    if h2 is None:
+        h2 = _decoder_front(decoders, emb)
+        index0 = 0
+    outs = []
+    fold = _fold_params((h, w), grid)
+    for i, d in enumerate(decoders):
+        src = h2[..., (index0 + i) * L:(index0 + i + 1) * L]
+        conv = d.decoder[4]
+        if (h, w) == tuple(grid):
+            w3 = _packed(d).get("c3", [conv.weight], lambda conv=conv: _pack_conv3(conv.weight))
+            y = OP.conv_nhwc(src, w3, conv.bias.detach(), L, grid, 3, 1, -1)
+        elif fold is not None:
+            w4 = _packed(d).get("c3fold", [conv.weight], lambda conv=conv: _fold_conv3_bilinear(conv.weight))
+            y = OP.conv_nhwc(src, w4, conv.bias.detach(), L, grid, 4, fold[0], fold[1])
+        else:
+            w3 = _packed(d).get("c3", [conv.weight], lambda conv=conv: _pack_conv3(conv.weight))
+            y = OP.resize_nhwc(OP.conv_nhwc(src, w3, conv.bias.detach(), L, (h, w), 3, 1, -1), grid)
+        outs.append(y.view(B, grid[0] * grid[1], -1))
+    return outs
+
+
+class prompt_encoder(nn.Module):
+    """cod.py:1228-1306."""
+
+    def __init__(self, latent_dim, embed_dim, depth, fusion=False):
+        super(prompt_encoder, self).__init__()
+        self.embed_dim = embed_dim
+        self.depth = depth
+        self.propagation_weight_regressor = ShapePropWeightRegressor(3, latent_dim)
+        self.encoder1 = nn.Conv2d(1, latent_dim, 1)
+        self.encoder2 = ShapePropEncoder(3, 24)
+        self.adaptor = nn.Conv2d(6, 3, 1)   # unused by forward, kept for the checkpoint layout (cod.py:1251)
+        self.message_passing = MessagePassing(latent_dim, img_size=384, sym_norm=False)
+        self.freq_nums = 0.3
+        self.latent_dim = latent_dim
+
+    def fft(self, x, rate):
+        """cod.py:1256-1271."""
+        return OP.fft_highpass(x.contiguous().float(), rate)
+
+    def _forward_fused(self, image: torch.Tensor, cues: torch.Tensor, mode: int, want_nchw: bool = True,
+                       pad_to: int = 0):
+        H = 12                                                                    # cod.py:1283
+        image = image.contiguous().float()
+        cues = cues.contiguous().float()
+        x = self.fft(image, self.freq_nums)                                       # :1288
+        reg = self.propagation_weight_regressor.reg
+        mp = self.message_passing
+        pk = _packed(self)
+        reg_w = pk.get("reg", [reg.weight], lambda: reg.weight.detach().reshape(reg.out_channels, 3).float().contiguous())
+        enc_w = pk.get("enc1", [self.encoder1.weight], lambda: self.encoder1.weight.detach().reshape(-1).float().contiguous())
+        mp_w = pk.get("mpc", [mp.conv.weight], lambda: mp.conv.weight.detach().reshape(3, -1).float().contiguous())
+        steps = H if mp.max_step < 0 else mp.max_step
+        grid3, _, _ = OP.diffusion_front(x, cues, reg_w, reg.bias.detach(), enc_w, self.encoder1.bias.detach(),
+                                         mp_w, mp.conv.bias.detach(), grid=H, steps=steps)   # :1295-1298
+        outs = self.encoder2._pyramid(image, grid3, mode)                         # :1302 (+image fused in the stem)
+        nhwc, nchw, pad = self.encoder2._head(outs, want_nchw=want_nchw, pad_to=pad_to)
+        return x, nhwc, nchw, pad
+
+    def forward(self, image, cues, cross=False):
+        _no_grad_only(self, "prompt_encoder")
+        x, _, emb3, _ = self._forward_fused(image, cues, _mode(self), want_nchw=True)
+        return x, emb3
+
+
+class prompt_decoder(nn.Module):
+    """cod.py:1308-1323."""
+
+    def __init__(self, latent_dim, embed_dim, depth, fusion=False):
+        super(prompt_decoder, self).__init__()
+        self.depth = depth
+        self.decoder = nn.Sequential(*[ShapePropDecoder(embed_dim, 24) for i in range(depth)])
+
+    def forward(self, embedding, cross=False):
+        _no_grad_only(self, "prompt_decoder")
+        emb = OP.nchw_to_nhwc(embedding.contiguous().float())
+        return _decode_full(list(self.decoder), emb)
+
+
+# ------------------------------------------------------------------------------------------------
+def init_weights_(module: nn.Module) -> None:
+    """``PyramidVisionTransformerImpr._init_weights`` (cod.py:1401-1414), applied per sub-module."""
+    if isinstance(module, nn.Linear):
+        nn.init.trunc_normal_(module.weight, std=.02)
+        if module.bias is not None:
+            nn.init.constant_(module.bias, 0)
+    elif isinstance(module, nn.LayerNorm):
+        nn.init.constant_(module.bias, 0)
+        nn.init.constant_(module.weight, 1.0)
+    elif isinstance(module, nn.Conv2d):
+        fan_out = module.kernel_size[0] * module.kernel_size[1] * module.out_channels
+        fan_out //= module.groups
+        module.weight.data.normal_(0, math.sqrt(2.0 / fan_out))
+        if module.bias is not None:
+            module.bias.data.zero_()
+
+
+def build_texture_diffuser(seed: Optional[int] = None, embed_dims=PVT_EMBED_DIMS, depths=PVT_DEPTHS,
+                           latent_dim: int = 24):
+    """The two members ``PyramidVisionTransformerImpr.__init__`` creates for the texture diffuser
+    (cod.py:1394-1396), initialised the way ``self.apply(self._init_weights)`` does (:1399)."""
+    if seed is not None:
+        torch.manual_seed(seed)
+    enc = prompt_encoder(latent_dim, list(embed_dims), list(depths), True)
+    dec = nn.Sequential(*[prompt_decoder(latent_dim, embed_dims[i], depths[i], True) for i in range(len(depths))])
+    enc.apply(init_weights_)
+    dec.apply(init_weights_)
+    return enc, dec
+
+
+def pvt_token_grids(img_hw: Sequence[int]) -> List[Tuple[int, int]]:
+    """Token grids of the four PVT-v2 stages (OverlapPatchEmbed 7/4/3 then 3/2/1 x3, cod.py:1350-1357)."""
+    h, w = int(img_hw[0]), int(img_hw[1])
+    h, w = (h + 6 - 7) // 4 + 1, (w + 6 - 7) // 4 + 1
+    out = [(h, w)]
+    for _ in range(3):
+        h, w = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+        out.append((h, w))
+    return out
+
+
+@torch.no_grad()
+def texture_prompts(enc: prompt_encoder, dec: nn.Sequential, image: torch.Tensor, depth: torch.Tensor,
+                    precision: Optional[str] = None, want_embedding3: bool = True):
+    """The hot path as ``forward_features`` drives it (cod.py:1467-1505) minus the PVT blocks:
+    returns ``(embedding1, embedding3, tokens)`` with ``tokens[s][i]`` the (B, H_s*W_s, E_s)
+    tensor the reference adds to the stage-s token stream before block i
+    (``x = blk(x + prompt[i], H, W)``)."""
+    mode = _mode(enc) if precision is None else (BF16 if precision == "bf16" else F32)
+    emb1, nhwc, nchw, _ = enc._forward_fused(image, depth, mode, want_nchw=want_embedding3)
+    grids = pvt_token_grids(image.shape[-2:])
+    all_dec = [d for s in range(len(dec)) for d in dec[s].decoder]
+    h2 = _decoder_front(all_dec, nhwc)
+    tokens, idx = [], 0
+    for s in range(len(dec)):
+        ds = list(dec[s].decoder)
+        tokens.append(_decode_tokens(ds, nhwc, grids[s], h2=h2, index0=idx))
+        idx += len(ds)
+    return emb1, nchw, tokens

@@ -1,0 +1,120 @@
+"""ctypes binding of ``libdgtd_ops.so`` (declared in ``include/dgtd_ops.h``).
+
+There is deliberately no fallback: if the shared object is missing or a call fails, a
+``RuntimeError`` is raised (the reference's extension raises the same way through
+``AT_ERROR`` -> ``RuntimeError``, twig/ops/src/ms_deform_attn.h:35-38).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdgtd_ops.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+
+_P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
+
+# name -> argument types (return type is always int unless listed in _RESTYPES)
+SIGNATURES = {
+    "dgtd_version": [],
+    "dgtd_last_error": [],
+    "dgtd_launch_count": [],
+    "dgtd_surface_normals_fwd": [_P, _P, _I, _I, _I, _P],
+    "dgtd_lowpass_projector": [_P, _P, _I, _I, _P],
+    "dgtd_fft_highpass_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "dgtd_diffusion_front_fwd": [_P] * 11 + [_I] * 6 + [_P],
+    "dgtd_message_passing_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
+    "dgtd_message_passing_tiled_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P],
+    "dgtd_message_passing_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
+    "dgtd_conv1x1_nchw_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "dgtd_resize_nchw_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "dgtd_layer_norm_fwd": [_P, _P, _P, _P, _L, _I, _L, _F, _P],
+    "dgtd_stem_fwd": [_P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "dgtd_ln_patchify_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "dgtd_dwconv7_ln_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "dgtd_linear_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "dgtd_linear_residual_fwd": [_P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P],
+    "dgtd_fusion_head_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "dgtd_conv_nhwc_fwd": [_P, _P, _P, _P] + [_I] * 15 + [_P],
+    "dgtd_resize_nhwc_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "dgtd_cast_fwd": [_P, _P, _L, _I, _I, _P],
+    "dgtd_nhwc_to_nchw_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "dgtd_nchw_to_nhwc_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+}
+_RESTYPES = {"dgtd_last_error": c_char_p, "dgtd_launch_count": c_int64}
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def load() -> ctypes.CDLL:
+    """Load (once) and type the library.  Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m dgtd_b200.twig.ops.build` "
+            "(there is no CPU or PyTorch fallback for the texture-diffusion kernels)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so lost a symbol
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, c_int)
+    if lib.dgtd_version() != 100:
+        raise RuntimeError(f"libdgtd_ops.so version {lib.dgtd_version()} != 100 (stale build?)")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    msg = load().dgtd_last_error()
+    return msg.decode() if msg else ""
+
+
+def launch_count() -> int:
+    return int(load().dgtd_launch_count())
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return F32
+    if dt == torch.bfloat16:
+        return BF16
+    raise TypeError(f"dgtd ops support float32 / bfloat16 only, got {dt}")
+
+
+def call(name: str, *args) -> None:
+    """Invoke an entry point; raise RuntimeError(dgtd_last_error()) on a non-zero return."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {last_error()}")
+
+
+def check_cuda(*tensors: Optional[torch.Tensor]) -> None:
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("dgtd ops run on CUDA tensors only (no CPU fallback); got a "
+                               f"{t.device} tensor")
+        if not t.is_contiguous():
+            raise RuntimeError("dgtd ops need contiguous tensors")

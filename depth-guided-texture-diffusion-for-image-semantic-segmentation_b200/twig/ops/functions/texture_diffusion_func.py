@@ -1,0 +1,317 @@
+"""Operator functions of the texture-diffusion hot path.
+
+Same role as ``twig/ops/functions/ms_deform_attn_func.py`` in the reference: the Python side
+of the native extension.  Every function allocates its outputs with torch (so the caching
+allocator and autograd own the memory), passes raw device pointers + the current stream to
+``libdgtd_ops.so`` through ctypes and raises ``RuntimeError`` on failure.  Nothing here computes
+on the CPU or through ATen kernels.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from .. import capi
+from ..capi import ACT_GELU, ACT_NONE, ACT_RELU, BF16, F32, call, check_cuda, ptr, stream
+
+__all__ = [
+    "surface_normals", "HighpassPlan", "fft_highpass", "diffusion_front", "MessagePassingFunction",
+    "message_passing_core", "message_passing_tiled", "conv1x1_nchw", "resize_nchw", "layer_norm",
+    "stem", "ln_patchify", "dwconv7_ln", "linear", "linear_residual_", "fusion_head", "conv_nhwc",
+    "resize_nhwc", "cast", "nhwc_to_nchw", "nchw_to_nhwc",
+]
+
+
+def _tdtype(code: int) -> torch.dtype:
+    return torch.float32 if code == F32 else torch.bfloat16
+
+
+# ------------------------------------------------------------------------------------------ a1
+def surface_normals(depth: torch.Tensor) -> torch.Tensor:
+    """cod.py:96-109. depth (B,1,H,W) fp32 -> (B,3,H,W)."""
+    check_cuda(depth)
+    B, _, H, W = depth.shape
+    out = torch.empty(B, 3, H, W, device=depth.device, dtype=torch.float32)
+    call("dgtd_surface_normals_fwd", ptr(depth), ptr(out), B, H, W, stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------ a2
+class HighpassPlan:
+    """Per-(H,W) constants of the projector form of ``prompt_encoder.fft`` (cod.py:1256-1271)."""
+
+    _cache = {}
+
+    def __init__(self, H: int, W: int, rate: float, device: torch.device):
+        line = int((W * H * rate) ** 0.5 // 2)  # cod.py:1261
+        self.H, self.W, self.line = H, W, line
+        self.Ph = torch.empty(H, H, device=device, dtype=torch.float32)
+        self.sc_h = torch.empty(2 * H, device=device, dtype=torch.float32)
+        call("dgtd_lowpass_projector", ptr(self.Ph), ptr(self.sc_h), H, line, stream())
+        if W == H:
+            self.Pw, self.sc_w = self.Ph, self.sc_h
+        else:
+            self.Pw = torch.empty(W, W, device=device, dtype=torch.float32)
+            self.sc_w = torch.empty(2 * W, device=device, dtype=torch.float32)
+            call("dgtd_lowpass_projector", ptr(self.Pw), ptr(self.sc_w), W, line, stream())
+
+    @classmethod
+    def get(cls, H: int, W: int, rate: float, device: torch.device) -> "HighpassPlan":
+        key = (H, W, float(rate), device.index)
+        plan = cls._cache.get(key)
+        if plan is None:
+            plan = cls._cache[key] = cls(H, W, rate, device)
+        return plan
+
+
+def fft_highpass(x: torch.Tensor, rate: float = 0.3) -> torch.Tensor:
+    """|x - lowpass(x)| per plane, the operator of cod.py:1256-1271.  No gradient."""
+    check_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 4
+    B, C, H, W = x.shape
+    plan = HighpassPlan.get(H, W, rate, x.device)
+    tmp = torch.empty_like(x)
+    coef = torch.empty(B * C * 4, device=x.device, dtype=torch.float32)
+    out = torch.empty_like(x)
+    call("dgtd_fft_highpass_fwd", ptr(x), ptr(plan.Ph), ptr(plan.Pw), ptr(plan.sc_h), ptr(plan.sc_w),
+         ptr(tmp), ptr(coef), ptr(out), B * C, H, W, stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------ a3..a6
+def diffusion_front(emb1: torch.Tensor, depth: torch.Tensor, reg_w, reg_b, enc_w, enc_b, conv_w, conv_b,
+                    grid: int = 12, steps: int = 4, save_wn: bool = False):
+    """Fused cod.py:1295-1298 + :1201-1206 -> (B,3,G,G); also returns the saved states
+    (B,T+1,C,G,G) and, on request, the normalised weights (B,C,49,G*G)."""
+    check_cuda(emb1, depth, reg_w, reg_b, enc_w, enc_b, conv_w, conv_b)
+    B, _, H, W = emb1.shape
+    C = enc_w.shape[0]
+    out = torch.empty(B, 3, grid, grid, device=emb1.device, dtype=torch.float32)
+    states = torch.empty(B, steps + 1, C, grid, grid, device=emb1.device, dtype=torch.float32)
+    wn = torch.empty(B, C, 49, grid * grid, device=emb1.device, dtype=torch.float32) if save_wn else None
+    call("dgtd_diffusion_front_fwd", ptr(emb1), ptr(depth), ptr(reg_w), ptr(reg_b), ptr(enc_w), ptr(enc_b),
+         ptr(conv_w), ptr(conv_b), ptr(out), ptr(states), ptr(wn), B, H, W, grid, C, steps, stream())
+    return out, states, wn
+
+
+class MessagePassingFunction(Function):
+    """The diffusion core of ``MessagePassing.forward`` (cod.py:1190-1205) with its backward."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, weight: torch.Tensor, steps: int, eps: float):
+        x = x.contiguous().float()
+        weight = weight.contiguous().float()
+        check_cuda(x, weight)
+        n, c, h, w = x.shape
+        wc = weight.shape[1] // 49
+        out = torch.empty_like(x)
+        need_grad = x.requires_grad or weight.requires_grad
+        states = torch.empty(n, steps + 1, c, h, w, device=x.device, dtype=torch.float32) if need_grad else None
+        call("dgtd_message_passing_fwd", ptr(x), ptr(weight), ptr(out), ptr(states), n, c, h, w, wc, steps,
+             float(eps), stream())
+        if need_grad:
+            ctx.save_for_backward(weight, states)
+        ctx.cfg = (n, c, h, w, wc, steps, float(eps))
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        weight, states = ctx.saved_tensors
+        n, c, h, w, wc, steps, eps = ctx.cfg
+        grad_out = grad_out.contiguous().float()
+        gx = torch.empty(n, c, h, w, device=grad_out.device, dtype=torch.float32)
+        gw = torch.empty_like(weight)
+        call("dgtd_message_passing_bwd", ptr(grad_out), ptr(weight), ptr(states), ptr(gx), ptr(gw), n, c, h,
+             w, wc, steps, eps, stream())
+        return gx, gw, None, None
+
+
+def message_passing_core(x: torch.Tensor, weight: torch.Tensor, steps: int = 4, eps: float = 1e-5):
+    return MessagePassingFunction.apply(x, weight, steps, eps)
+
+
+def message_passing_tiled(x: torch.Tensor, weight: torch.Tensor, steps: int, eps: float = 1e-5):
+    """Large-map variant: x (n,h,w,c) channels-last storage (fp32|bf16), weight (n,49,h,w) fp32."""
+    check_cuda(x, weight)
+    n, h, w, c = x.shape
+    out = torch.empty_like(x)
+    tmp = torch.empty_like(x) if steps > 1 else None
+    call("dgtd_message_passing_tiled_fwd", ptr(x), ptr(weight), ptr(out), ptr(tmp), n, h, w, c, steps,
+         float(eps), capi.dtype_code(x.dtype), stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------ helpers
+def conv1x1_nchw(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], sigmoid: bool = False):
+    check_cuda(x, w, b)
+    B, Cin = x.shape[0], x.shape[1]
+    HW = x.numel() // (B * Cin)
+    Cout = w.shape[0]
+    out = torch.empty((B, Cout) + tuple(x.shape[2:]), device=x.device, dtype=torch.float32)
+    call("dgtd_conv1x1_nchw_fwd", ptr(x), ptr(w), ptr(b), ptr(out), B, Cin, Cout, HW, int(sigmoid), stream())
+    return out
+
+
+def resize_nchw(x: torch.Tensor, size: Sequence[int], bilinear: bool = True) -> torch.Tensor:
+    check_cuda(x)
+    B, C, h, w = x.shape
+    oh, ow = int(size[0]), int(size[1])
+    out = torch.empty(B, C, oh, ow, device=x.device, dtype=torch.float32)
+    call("dgtd_resize_nchw_fwd", ptr(x), ptr(out), B * C, h, w, oh, ow, int(bilinear), stream())
+    return out
+
+
+def layer_norm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, channels_first: bool):
+    check_cuda(x, w, b)
+    out = torch.empty_like(x)
+    if channels_first:
+        outer, C = x.shape[0], x.shape[1]
+        inner = x.numel() // (outer * C)
+    else:
+        C = x.shape[-1]
+        outer, inner = x.numel() // C, 1
+    call("dgtd_layer_norm_fwd", ptr(x), ptr(w), ptr(b), ptr(out), outer, C, inner, float(eps), stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------ a7/a8
+def stem(image: torch.Tensor, grid: Optional[torch.Tensor], w, b, ln_w, ln_b, eps: float = 1e-6):
+    """(up(grid)+image) -> conv4x4/4 -> LN : returns NHWC (B,H/4,W/4,Cout) fp32."""
+    check_cuda(image, grid, w, b, ln_w, ln_b)
+    B, _, H, W = image.shape
+    Cout = w.shape[0]
+    out = torch.empty(B, H // 4, W // 4, Cout, device=image.device, dtype=torch.float32)
+    G = grid.shape[-1] if grid is not None else 0
+    call("dgtd_stem_fwd", ptr(image), ptr(grid), G, ptr(w), ptr(b), ptr(ln_w), ptr(ln_b), ptr(out), B, H, W,
+         Cout, float(eps), stream())
+    return out
+
+
+def ln_patchify(x: torch.Tensor, ln_w, ln_b, out_dtype: int, eps: float = 1e-6) -> torch.Tensor:
+    """x NHWC (B,h,w,C) fp32 -> (B*(h//2)*(w//2), 4C) rows ordered (dy,dx,c)."""
+    check_cuda(x, ln_w, ln_b)
+    B, h, w, C = x.shape
+    out = torch.empty(B * (h // 2) * (w // 2), 4 * C, device=x.device, dtype=_tdtype(out_dtype))
+    call("dgtd_ln_patchify_fwd", ptr(x), ptr(ln_w), ptr(ln_b), ptr(out), out_dtype, B, h, w, C, float(eps),
+         stream())
+    return out
+
+
+def dwconv7_ln(x: torch.Tensor, dw_w, dw_b, ln_w, ln_b, out_dtype: int, eps: float = 1e-6) -> torch.Tensor:
+    check_cuda(x, dw_w, dw_b, ln_w, ln_b)
+    B, h, w, C = x.shape
+    out = torch.empty(B, h, w, C, device=x.device, dtype=_tdtype(out_dtype))
+    call("dgtd_dwconv7_ln_fwd", ptr(x), ptr(dw_w), ptr(dw_b), ptr(ln_w), ptr(ln_b), ptr(out), out_dtype, B, h,
+         w, C, float(eps), stream())
+    return out
+
+
+def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int = ACT_NONE,
+           out_dtype: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias).  a and w share a dtype (fp32 exact / bf16 tcgen05)."""
+    check_cuda(a, w, bias)
+    K = a.shape[-1]
+    M = a.numel() // K
+    N = w.shape[0]
+    assert w.shape[1] == K and a.dtype == w.dtype
+    din = capi.dtype_code(a.dtype)
+    dout = din if out_dtype is None else out_dtype
+    if out is None:
+        out = torch.empty(tuple(a.shape[:-1]) + (N,), device=a.device, dtype=_tdtype(dout))
+    ldo = out.shape[-1]
+    call("dgtd_linear_fwd", ptr(a), ptr(w), ptr(bias), ptr(out), M, N, K, ldo, din, dout, act, stream())
+    return out
+
+
+def linear_residual_(a: torch.Tensor, w: torch.Tensor, bias, gamma, keep: Optional[torch.Tensor],
+                     rows_per_sample: int, residual: torch.Tensor, out: Optional[torch.Tensor] = None):
+    """out = residual + keep[m//rows] * gamma * (a @ w^T + bias); in place on `residual` when
+    `out` is None (each element is read and written by the same thread)."""
+    check_cuda(a, w, bias, gamma, keep, residual)
+    K = a.shape[-1]
+    M = a.numel() // K
+    N = w.shape[0]
+    assert residual.dtype == torch.float32 and residual.numel() == M * N
+    out = residual if out is None else out
+    call("dgtd_linear_residual_fwd", ptr(a), ptr(w), ptr(bias), ptr(gamma), ptr(keep), rows_per_sample,
+         ptr(residual), ptr(out), M, N, K, capi.dtype_code(a.dtype), stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------ a9
+def fusion_head(levels: List[torch.Tensor], hw: List[Tuple[int, int]], wf, bf, B: int, want_nhwc=True,
+                want_nchw=False, pad_to: int = 0):
+    """levels[i]: (B*h_i*w_i, C) fp32 projections.  Returns (nhwc, nchw, padded-bf16) tensors."""
+    check_cuda(*levels, wf, bf)
+    C = wf.shape[0]
+    dev = levels[0].device
+    h0, w0 = hw[0]
+    nhwc = torch.empty(B, h0, w0, C, device=dev, dtype=torch.float32) if want_nhwc else None
+    nchw = torch.empty(B, C, h0, w0, device=dev, dtype=torch.float32) if want_nchw else None
+    pad = torch.empty(B, h0, w0, pad_to, device=dev, dtype=torch.bfloat16) if pad_to else None
+    hw_arr = (capi.c_int * 8)(*[v for pair in hw for v in pair])
+    call("dgtd_fusion_head_fwd", ptr(levels[0]), ptr(levels[1]), ptr(levels[2]), ptr(levels[3]), hw_arr,
+         ptr(wf), ptr(bf), ptr(nhwc), ptr(nchw), ptr(pad), pad_to, B, C, stream())
+    return nhwc, nchw, pad
+
+
+# ------------------------------------------------------------------------------------------ a10/a11
+def conv_nhwc(x: torch.Tensor, w: torch.Tensor, bias, Cin: int, out_hw: Tuple[int, int], ks: int,
+              stride: int, off: int, act: int = ACT_NONE, out: Optional[torch.Tensor] = None,
+              out_dtype: Optional[int] = None, Cout: Optional[int] = None) -> torch.Tensor:
+    """KxK conv over NHWC as implicit GEMM.  `x` may be a channel slice of a wider tensor
+    (last-dim stride 1, pixel stride = ldx); `w` is packed (Cout, ks*ks*Cin) tap-major."""
+    B, h, wd = x.shape[0], x.shape[1], x.shape[2]
+    ldx = x.stride(2)
+    assert x.stride(3) == 1 and x.stride(1) == wd * ldx and x.stride(0) == h * wd * ldx
+    Cout = w.shape[0] if Cout is None else Cout
+    oh, ow = out_hw
+    din = capi.dtype_code(x.dtype)
+    dout = din if out_dtype is None else out_dtype
+    if out is None:
+        out = torch.empty(B, oh, ow, Cout, device=x.device, dtype=_tdtype(dout))
+    ldo = out.stride(2)
+    call("dgtd_conv_nhwc_fwd", x.data_ptr(), ptr(w), ptr(bias), out.data_ptr(), B, h, wd, Cin, ldx, oh, ow,
+         Cout, ldo, ks, stride, off, act, din, dout, stream())
+    return out
+
+
+def resize_nhwc(x: torch.Tensor, size: Tuple[int, int], out_dtype: Optional[int] = None) -> torch.Tensor:
+    check_cuda(x)
+    B, h, w, C = x.shape
+    din = capi.dtype_code(x.dtype)
+    dout = din if out_dtype is None else out_dtype
+    out = torch.empty(B, size[0], size[1], C, device=x.device, dtype=_tdtype(dout))
+    call("dgtd_resize_nhwc_fwd", ptr(x), ptr(out), B, h, w, C, size[0], size[1], din, dout, stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------ plumbing
+def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    check_cuda(x)
+    out = torch.empty(x.shape, device=x.device, dtype=dtype)
+    call("dgtd_cast_fwd", ptr(x), ptr(out), x.numel(), capi.dtype_code(x.dtype), capi.dtype_code(dtype),
+         stream())
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor, C: Optional[int] = None) -> torch.Tensor:
+    check_cuda(x)
+    B, h, w, ld = x.shape
+    C = ld if C is None else C
+    out = torch.empty(B, C, h, w, device=x.device, dtype=torch.float32)
+    call("dgtd_nhwc_to_nchw_fwd", ptr(x), ptr(out), B, h, w, C, ld, capi.dtype_code(x.dtype), stream())
+    return out
+
+
+def nchw_to_nhwc(x: torch.Tensor, dtype: torch.dtype = torch.float32, ld: Optional[int] = None):
+    check_cuda(x)
+    B, C, h, w = x.shape
+    ld = C if ld is None else ld
+    out = torch.empty(B, h, w, ld, device=x.device, dtype=dtype)
+    call("dgtd_nchw_to_nhwc_fwd", ptr(x), ptr(out), B, h, w, C, ld, capi.dtype_code(dtype), stream())
+    return out

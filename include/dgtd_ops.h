@@ -1,0 +1,172 @@
+/*
+ * dgtd_ops.h -- C ABI of libdgtd_ops.so: hand-written sm_100a kernels for the depth-guided
+ * texture-diffusion hot path (reference: twig/model/cod.py:1025-1323, call sites :1467-1505).
+ *
+ * This is the drop-in boundary.  The reference's operator convention for native code is
+ * twig/ops: autograd.Function -> pybind -> CUDA (twig/ops/functions/ms_deform_attn_func.py:19-46,
+ * twig/ops/src/vision.cpp:13-16, twig/ops/src/cuda/ms_deform_attn_cuda.cu:20-80).  The hot path
+ * itself is pure ATen calls today, so each entry point below names the reference lines it
+ * replaces.  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - plain C types only; every pointer is a DEVICE pointer owned by the caller (PyTorch's
+ *    caching allocator); the library allocates nothing and keeps no reference after return;
+ *  - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*);
+ *    no hidden synchronisation; the current CUDA device is the caller's;
+ *  - return value 0 = success, negative = error (message via dgtd_last_error(), thread local);
+ *    nothing throws or aborts across the ABI;
+ *  - "NHWC" = pixel-major (B,H,W,C) contiguous, "NCHW" = PyTorch default contiguous;
+ *  - dtype codes: DGTD_F32 / DGTD_BF16.  fp32 mode is the exact path (CUDA-core FMA,
+ *    <=1e-4 of the reference); bf16 mode feeds tcgen05 tensor cores with fp32 accumulation.
+ */
+#ifndef DGTD_OPS_H_
+#define DGTD_OPS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGTD_VERSION 100
+#define DGTD_F32 0
+#define DGTD_BF16 1
+
+#define DGTD_ACT_NONE 0
+#define DGTD_ACT_GELU 1 /* exact erf GELU, cod.py:1098 */
+#define DGTD_ACT_RELU 2 /* cod.py:1218 */
+
+typedef void* dgtd_stream_t; /* cudaStream_t */
+
+/* ---- library ---------------------------------------------------------------------------- */
+int dgtd_version(void);
+const char* dgtd_last_error(void);
+/* number of kernel launches this library has enqueued since load (bench.py `gpu_launches`) */
+int64_t dgtd_launch_count(void);
+
+/* ---- a1: cod.compute_surface_normals, cod.py:96-109 -------------------------------------- */
+/* depth (B,1,H,W) -> normals (B,3,H,W), NCHW fp32 */
+int dgtd_surface_normals_fwd(const float* depth, float* normals, int B, int H, int W,
+                             dgtd_stream_t stream);
+
+/* ---- a2: prompt_encoder.fft, cod.py:1256-1271 -------------------------------------------- */
+/* Real part of the low-pass projector for an axis of length n (removed band [-line, line-1]),
+ * P (n*n fp32, symmetric circulant), plus sc (2*n fp32): sin and cos of 2*pi*line*a/n, which
+ * carry the rank-2 imaginary part.  Built once per image size and cached by the caller. */
+int dgtd_lowpass_projector(float* P, float* sc, int n, int line, dgtd_stream_t stream);
+/* out = | x - Re(P_h x P_w^T) | per (H,W) plane.  x,out: (planes,H,W) fp32.
+ * tmp: planes*H*W floats, coef: planes*4 floats (both scratch). */
+int dgtd_fft_highpass_fwd(const float* x, const float* Ph, const float* Pw, const float* sc_h,
+                          const float* sc_w, float* tmp, float* coef, float* out, int planes,
+                          int H, int W, dgtd_stream_t stream);
+
+/* ---- a3..a6 fused: cod.py:1295-1298 + MessagePassing.forward :1189-1206 ------------------- */
+/* nearest GxG sample of emb1 -> regressor 1x1 conv (3 -> C*49) + sigmoid -> random-walk
+ * normalisation; depth -> (encoder1 1x1 conv o bilinear down) -> C x G x G state; T stencil
+ * iterations on chip; 1x1 conv C -> 3.  out_grid: (B,3,G,G).  Optional saves for backward:
+ * save_states (B,T+1,C,G,G) and save_wn (B,C,49,G*G).  k is fixed at 7 (cod.py:1181). */
+int dgtd_diffusion_front_fwd(const float* emb1, const float* depth, const float* reg_w,
+                             const float* reg_b, const float* enc_w, const float* enc_b,
+                             const float* conv_w, const float* conv_b, float* out_grid,
+                             float* save_states, float* save_wn, int B, int H, int W, int G, int C,
+                             int T, dgtd_stream_t stream);
+
+/* ---- a6: MessagePassing core as a stand-alone operator, cod.py:1190-1205 ------------------ */
+/* x,out (n,c,h,w), weight (n,wc*49,h,w), wc in {1,c}, NCHW fp32; whole plane kept on chip
+ * for all T iterations (h*w <= 1024).  save_states nullable: (n,T+1,c,h,w). */
+int dgtd_message_passing_fwd(const float* x, const float* weight, float* out, float* save_states,
+                             int n, int c, int h, int w, int wc, int T, float eps,
+                             dgtd_stream_t stream);
+/* Halo-tiled variant for large maps (the 1024^2 x 256 microbench): x,out NHWC (n,h,w,c),
+ * dtype fp32 or bf16 storage (fp32 accumulate); weight (n,49,h,w) fp32 shared by all channels
+ * (wc == 1).  One launch per iteration; `tmp` (same size as x) is the ping-pong buffer when
+ * T > 1.  c must be a multiple of 64. */
+int dgtd_message_passing_tiled_fwd(const void* x, const float* weight, void* out, void* tmp,
+                                   int n, int h, int w, int c, int T, float eps, int dtype,
+                                   dgtd_stream_t stream);
+/* backward of the stand-alone operator: grad_out (n,c,h,w) -> grad_x (n,c,h,w) and
+ * grad_weight (n,wc*49,h,w) (through the normalisation), from the saved states. */
+int dgtd_message_passing_bwd(const float* grad_out, const float* weight, const float* states,
+                             float* grad_x, float* grad_weight, int n, int c, int h, int w, int wc,
+                             int T, float eps, dgtd_stream_t stream);
+
+/* ---- small NCHW helpers so every nn.Module of the path is callable on its own ------------- */
+/* 1x1 conv (+ optional sigmoid) in NCHW: ShapePropWeightRegressor (cod.py:1056-1060),
+ * encoder1 (:1249), message_passing.conv (:1188). */
+int dgtd_conv1x1_nchw_fwd(const float* x, const float* w, const float* b, float* out, int B,
+                          int Cin, int Cout, int HW, int sigmoid, dgtd_stream_t stream);
+/* F.interpolate(mode='bilinear', align_corners=False) on NCHW fp32 (cod.py:1207,1298) and
+ * nearest (cod.py:1295). */
+int dgtd_resize_nchw_fwd(const float* x, float* out, int planes, int h, int w, int oh, int ow,
+                         int bilinear, dgtd_stream_t stream);
+/* custom LayerNorm, cod.py:1041-1049: x viewed as (outer, C, inner); channels_last: inner=1 */
+int dgtd_layer_norm_fwd(const float* x, const float* w, const float* b, float* out, int64_t outer,
+                        int C, int64_t inner, float eps, dgtd_stream_t stream);
+
+/* ---- a7: `embedding2 + image` (cod.py:1302) + ConvNeXt stem / downsample (:1126-1136) ------ */
+/* bilinear up-sample of grid (B,3,G,G) to (H,W) + image (B,3,H,W NCHW) -> conv 4x4/4 ->
+ * LayerNorm(channels_first) -> out NHWC (B,H/4,W/4,Cout) fp32.  grid may be NULL. */
+int dgtd_stem_fwd(const float* image, const float* grid, int G, const float* w, const float* b,
+                  const float* ln_w, const float* ln_b, float* out, int B, int H, int W, int Cout,
+                  float eps, dgtd_stream_t stream);
+/* per-pixel LayerNorm then 2x2/2 patch gather: x NHWC (B,h,w,C) fp32 -> rows (B*(h/2)*(w/2))
+ * of 4C values ordered (dy,dx,c); the following linear with the repacked conv weight is the
+ * 2x2 stride-2 conv of cod.py:1134. */
+int dgtd_ln_patchify_fwd(const float* x, const float* ln_w, const float* ln_b, void* out,
+                         int out_dtype, int B, int h, int w, int C, float eps,
+                         dgtd_stream_t stream);
+
+/* ---- a8: convnext_Block, cod.py:1104-1117 ------------------------------------------------- */
+/* depthwise 7x7 (pad 3) + channels-last LayerNorm: x NHWC fp32 -> out NHWC (fp32|bf16) */
+int dgtd_dwconv7_ln_fwd(const float* x, const float* dw_w, const float* dw_b, const float* ln_w,
+                        const float* ln_b, void* out, int out_dtype, int B, int h, int w, int C,
+                        float eps, dgtd_stream_t stream);
+/* out[M,N] = act(a[M,K] . w[N,K]^T + bias): pwconv1+GELU (:1109-1110), downsample conv
+ * (:1134), head 1x1 convs (:1160,1174).  a/w dtype = dtype_in (fp32: CUDA-core exact path,
+ * bf16: tcgen05), out dtype = dtype_out, ldo = row stride of out in elements. */
+int dgtd_linear_fwd(const void* a, const void* w, const float* bias, void* out, int M, int N,
+                    int K, int ldo, int dtype_in, int dtype_out, int act, dgtd_stream_t stream);
+/* out = residual + keep[m / rows_per_sample] * gamma * (a . w^T + bias)   (cod.py:1111-1116;
+ * keep = DropPath mask/keep_prob per sample, NULL in eval); residual/out fp32 [M,N]. */
+int dgtd_linear_residual_fwd(const void* a, const void* w, const float* bias, const float* gamma,
+                             const float* keep, int rows_per_sample, const float* residual,
+                             float* out, int M, int N, int K, int dtype_in, dgtd_stream_t stream);
+
+/* ---- a9: ShapePropEncoder head, cod.py:1171-1176 ------------------------------------------ */
+/* lv[i]: level-i projection (B*h_i*w_i, C) fp32 (output of the per-level 1x1 conv);
+ * bilinear up to (h_0,w_0), concat, 1x1 conv (wf: C x 4C, bf: C).  Writes any of:
+ * out_nhwc (B,h0,w0,C) fp32, out_nchw (B,C,h0,w0) fp32, out_pad (B,h0,w0,Cpad) bf16 zero
+ * padded to Cpad channels (operand of the tensor-core decoders).  hw = {h0,w0,...,h3,w3}. */
+int dgtd_fusion_head_fwd(const float* lv0, const float* lv1, const float* lv2, const float* lv3,
+                         const int* hw, const float* wf, const float* bf, float* out_nhwc,
+                         float* out_nchw, void* out_pad, int Cpad, int B, int C,
+                         dgtd_stream_t stream);
+
+/* ---- a10/a11: ShapePropDecoder convs (cod.py:1216-1222) + prompt injection (:1471) -------- */
+/* KxK conv as implicit GEMM on NHWC: x (B,h,w,ldx) -> out (B,oh,ow,ldo);
+ * input pixel = o*stride + off + tap, zero outside; w packed (Cout, ks*ks*Cin) tap-major;
+ * ks=3,stride=1,off=-1 is the reference conv; ks=4,stride s,off o is the last conv folded
+ * with the bilinear down-sample to the PVT token grid (exact), whose
+ * NHWC output *is* the (B, H_s*W_s, E_s) token layout of cod.py:1471. */
+int dgtd_conv_nhwc_fwd(const void* x, const void* w, const float* bias, void* out, int B, int h,
+                       int wd, int Cin, int ldx, int oh, int ow, int Cout, int ldo, int ks,
+                       int stride, int off, int act, int dtype_in, int dtype_out,
+                       dgtd_stream_t stream);
+/* generic bilinear resize NHWC (B,h,w,C) -> (B,oh,ow,C) == tokens (B,oh*ow,C) */
+int dgtd_resize_nhwc_fwd(const void* x, void* out, int B, int h, int w, int C, int oh, int ow,
+                         int dtype_in, int dtype_out, dgtd_stream_t stream);
+
+/* ---- dtype / layout plumbing -------------------------------------------------------------- */
+int dgtd_cast_fwd(const void* src, void* dst, int64_t n, int dtype_src, int dtype_dst,
+                  dgtd_stream_t stream);
+/* NHWC (B,h,w,ldx>=C) any dtype -> NCHW (B,C,h,w) fp32 */
+int dgtd_nhwc_to_nchw_fwd(const void* x, float* out, int B, int h, int w, int C, int ldx,
+                          int dtype_in, dgtd_stream_t stream);
+int dgtd_nchw_to_nhwc_fwd(const float* x, void* out, int B, int h, int w, int C, int ldo,
+                          int dtype_out, dgtd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGTD_OPS_H_ */

@@ -1,0 +1,94 @@
+"""Seeded inputs / parameter recipes shared by the tests, the golden generator and bench.py."""
+from __future__ import annotations
+
+import json
+import os
+import sys
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+PVT_EMBED_DIMS = (64, 128, 320, 512)
+PVT_DEPTHS = (3, 4, 6, 3)
+
+
+def synthetic_inputs(B: int, S: int, seed: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """ImageNet-normalised image ~ N(0,1), depth ~ U[0,1) ('L' PNG via ToTensor)."""
+    g = torch.Generator("cpu").manual_seed(seed)
+    image = torch.randn(B, 3, S, S, generator=g)
+    depth = torch.rand(B, 1, S, S, generator=g)
+    return image, depth
+
+
+def perturb_regressor_(pe) -> None:
+    """Non-trivial diffusion weights: at random init the regressor logits are ~0 (sigma ~ 0.5
+    everywhere) and a box-filter bug would pass; scale x20 and randomise the bias."""
+    g = torch.Generator("cpu").manual_seed(1)
+    reg = pe.propagation_weight_regressor.reg
+    with torch.no_grad():
+        reg.weight.mul_(20.0)
+        reg.bias.copy_(torch.randn(reg.bias.shape, generator=g))
+
+
+def pvt_token_grids(img_hw: Sequence[int]) -> List[Tuple[int, int]]:
+    h, w = int(img_hw[0]), int(img_hw[1])
+    h, w = (h + 6 - 7) // 4 + 1, (w + 6 - 7) // 4 + 1
+    out = [(h, w)]
+    for _ in range(3):
+        h, w = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+        out.append((h, w))
+    return out
+
+
+def flatten_outputs(e1, e3, toks) -> Dict[str, torch.Tensor]:
+    out = {"embedding1": e1, "embedding3": e3}
+    for s, lst in enumerate(toks):
+        for i, t in enumerate(lst):
+            out[f"tokens.{s}.{i}"] = t
+    return out
+
+
+def subsample(key: str, t: torch.Tensor) -> torch.Tensor:
+    """Deterministic sub-sample small enough to commit (a few thousand values per tensor)."""
+    if key == "embedding1":
+        return t[:, :, ::8, ::8]
+    if key == "embedding3":
+        return t[:, :, ::4, ::4]
+    n = t.shape[1]                      # tokens (B, HW, E)
+    step = max(1, n // 64)
+    return t[:, ::step, ::4]
+
+
+def moments(t: torch.Tensor) -> np.ndarray:
+    t = t.detach().double()
+    return np.array([float(t.mean()), float(t.abs().mean()), float((t * t).mean())])
+
+
+def load_params_fixture() -> dict:
+    with open(os.path.join(GOLDEN, "params_seed0.json")) as f:
+        return json.load(f)
+
+
+def package():
+    import dgtd_b200  # noqa: F401  (root-level alias module)
+    from dgtd_b200.twig.model import texture_diffuser
+    return texture_diffuser
+
+
+def oracle_params(enc, dec) -> Tuple[dict, dict]:
+    """state_dicts of the product modules as float64 CPU dicts for the oracle."""
+    e = {k: v.detach().double().cpu() for k, v in enc.state_dict().items()}
+    d = {k: v.detach().double().cpu() for k, v in dec.state_dict().items()}
+    return e, d
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    """max|a-b| / max|b| (the parity metric of SURVEY.md 8c)."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))

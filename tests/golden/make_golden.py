@@ -177,9 +177,20 @@ def full_path(m, S, w20):
             rec["ref_f32_relerr"] = np.array(
                 [float((outs[k].double() - master[k]).abs().max() / master[k].abs().max()) for k in sorted(outs)])
             rec["ref_f32_keys"] = np.array(sorted(outs))
+    # the reference under bf16 autocast (what `AmpOptimWrapper` training / a bf16 deployment of the
+    # stock model computes): its distance to the fp64 master sets the bf16 tolerance of the kernels
+    pe_, pd_ = pe.to(torch.float32).eval(), pd.to(torch.float32).eval()
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        e1, e3 = pe_(image, depth)
+        toks = [[F.interpolate(p, size=grids[s], mode="bilinear").flatten(2).permute(0, 2, 1)
+                 for p in pd_[s](e3)] for s in range(4)]
+    outs = common.flatten_outputs(e1, e3, toks)
+    rec["ref_bf16_relerr"] = np.array(
+        [float((outs[k].double() - master[k]).abs().max() / master[k].abs().max()) for k in sorted(outs)])
     name = f"path_{S}{'_w20' if w20 else ''}.npz"
     np.savez_compressed(os.path.join(OUT, name), **rec)
-    print(name, "max ref fp32 relerr", rec["ref_f32_relerr"].max())
+    print(name, "max ref fp32 relerr", rec["ref_f32_relerr"].max(), "ref bf16-autocast relerr",
+          rec["ref_bf16_relerr"].min(), rec["ref_bf16_relerr"].max())
 
 
 def main():

@@ -1,0 +1,77 @@
+"""tcgen05 / TMEM / TMA GEMM (bf16 operands, fp32 accumulation) through `dgtd_linear_fwd`.
+Reference = float64 product of the SAME bf16-rounded operands, so only accumulation order and
+the output rounding differ: fp32 outputs must agree to 1e-4, bf16 outputs to one bf16 ulp."""
+import pytest
+import torch
+
+import common
+from oracle import texture_diffuser_ref as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def OP():
+    common.package()
+    from dgtd_b200.twig.ops.functions import texture_diffusion_func
+    return texture_diffusion_func
+
+
+def operands(M, N, K, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16)
+    b = torch.randn(N, generator=g)
+    return a, w, b
+
+
+def rel(got, ref):
+    return float((got.double().cpu() - ref).abs().max() / ref.abs().max())
+
+
+# (M, N, K): single tile, M/N/K tails, every BN variant (32/64/128/256), multi-wave persistent
+SHAPES = [(128, 128, 64), (128, 128, 512), (200, 128, 128), (144, 24, 128), (384, 64, 192),
+          (1000, 320, 288), (4096, 512, 128), (36992, 512, 128), (20000, 2048, 512), (9216, 256, 2048)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_linear_bf16_fp32_out(OP, M, N, K):
+    from dgtd_b200.twig.ops.capi import F32
+    a, w, b = operands(M, N, K)
+    ref = a.double() @ w.double().t() + b.double()
+    got = OP.linear(a.cuda(), w.cuda(), b.cuda(), out_dtype=F32)
+    assert rel(got, ref) <= 1e-4
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 512, 128), (5000, 2048, 512)])
+def test_linear_bf16_gelu_bf16_out(OP, M, N, K):
+    a, w, b = operands(M, N, K, seed=1)
+    ref = O.gelu_erf(a.double() @ w.double().t() + b.double())
+    got = OP.linear(a.cuda(), w.cuda(), b.cuda(), act=1)
+    assert got.dtype == torch.bfloat16
+    # bf16 rounding (2^-9 relative) + 2.8e-5 absolute of the polynomial GELU
+    err = (got.double().cpu() - ref).abs()
+    assert float((err - ref.abs() * 2 ** -8).max()) <= 1e-3
+
+
+def test_linear_residual_bf16(OP):
+    g = torch.Generator().manual_seed(2)
+    B, rows, N, K = 4, 600, 128, 512
+    M = B * rows
+    a, w, b = operands(M, N, K, seed=2)
+    gam = torch.randn(N, generator=g)
+    keep = torch.tensor([1.0, 0.0, 1.6, 1.6])
+    res = torch.randn(M, N, generator=g)
+    ref = res.double() + keep.double().repeat_interleave(rows)[:, None] * (gam.double() * (a.double() @ w.double().t() + b.double()))
+    r = res.clone().cuda()
+    OP.linear_residual_(a.cuda(), w.cuda(), b.cuda(), gam.cuda(), keep.cuda(), rows, r)
+    assert rel(r, ref) <= 1e-4
+
+
+def test_repeated_launches_are_deterministic(OP):
+    from dgtd_b200.twig.ops.capi import F32
+    a, w, b = operands(3000, 512, 256, seed=3)
+    a, w, b = a.cuda(), w.cuda(), b.cuda()
+    y0 = OP.linear(a, w, b, out_dtype=F32)
+    for _ in range(5):
+        assert torch.equal(OP.linear(a, w, b, out_dtype=F32), y0)

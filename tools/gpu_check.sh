@@ -1,0 +1,13 @@
+#!/usr/bin/env bash
+# Run the GPU test files in separate processes (a trapped kernel must not poison the others).
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
+rc=0
+for f in "$@"; do
+  name=$(basename "$f" .py)
+  timeout 600 python -m pytest "$f" -m gpu -q -x --no-header -p no:cacheprovider > "gpurun_out/$name.log" 2>&1
+  r=$?
+  echo "== $name exit $r"; tail -n 25 "gpurun_out/$name.log"
+  [ $r -ne 0 ] && rc=$r
+done
+exit $rc

@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""Benchmark of the depth-guided texture-diffusion hot path (BASELINE.json metric: RGB-D images/s
+at 384^2).
+
+    python bench.py [--gpus N --steps K --warmup W]            # our arm (N>1: under torchrun)
+    python bench.py --impl reference [...]                      # CPU arm (oracle port of the reference)
+
+One "step" = one pass of the hot path (prompt_encoder + 16 ShapePropDecoders + injection layout,
+cod.py:1467-1505 minus the PVT blocks) over one batch of synthetic RGB-D input.  Workload =
+BASELINE.json configs[1]: COD inference, batch 64 per GPU, 384x384, bf16.  The path shards by
+image, so N GPUs run N independent replicas on different images (weak scaling, no collective).
+Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "rgbd_images_per_sec_384"
+UNIT = "images/s"
+# algorithmic FLOPs (2*MAC) of the tensor-core GEMMs per 384^2 image: 36 ConvNeXt blocks x 2
+# pointwise GEMMs + 3 down-sample convs, as executed (DESIGN.md "Work per unit")
+GEMM_FLOP_PER_IMAGE = 36 * 2 * 2 * 9216 * 128 * 512 + 2 * (2304 * 512 * 256 + 576 * 1024 * 512 + 144 * 2048 * 1024)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--size", type=int, default=384)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-sample", type=int, default=2, help="images per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.stop, self.th = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active")
+                                                          for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def cpu_reference_rate(size: int, images: int, steps: int, warmup: int):
+    """The reference algorithm on the host cores (oracle port, fp32, all threads): images/s."""
+    import common
+    from oracle import texture_diffuser_ref as O
+    TD = common.package()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    enc, dec = TD.build_texture_diffuser(seed=0)
+    pe = {k: v.detach().float() for k, v in enc.state_dict().items()}
+    pd = {k: v.detach().float() for k, v in dec.state_dict().items()}
+    image, depth = common.synthetic_inputs(images, size)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.texture_prompts(image, depth, pe, pd)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return images / dt, dt, cores
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 3))
+    rate, dt, cores = cpu_reference_rate(args.size, args.cpu_sample, steps, warmup)
+    sample = f"{args.cpu_sample} images of the batch-{args.batch} workload per step, fp32, torch CPU, {cpu_model()}"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"COD inference hot path, batch {args.batch}/GPU, {args.size}x{args.size} RGB-D "
+                               "(BASELINE configs[1]); CPU arm = oracle port of the reference modules"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import common
+    TD = common.package()
+    from dgtd_b200.twig.ops import capi
+    from dgtd_b200.twig.ops.functions import texture_diffusion_func as OP
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback on the product path)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    B, S = args.batch, args.size
+
+    enc, dec = TD.build_texture_diffuser(seed=0)
+    common.perturb_regressor_(enc)
+    enc, dec = enc.to(dev).eval(), dec.to(dev).eval()
+    # every rank gets different images (seed = rank): the path shards by image
+    image_h, depth_h = common.synthetic_inputs(B, S, seed=rank)
+    image_h, depth_h = image_h.pin_memory(), depth_h.pin_memory()
+    image, depth = image_h.to(dev), depth_h.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step(img, dep):
+        return TD.texture_prompts(enc, dec, img, dep, precision=args.precision, want_embedding3=False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(image, depth)
+    barrier()
+
+    # ---- timed region: inputs resident in HBM --------------------------------------------------
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    n0 = capi.launch_count()
+    with ClockSampler(local) as clocks:
+        for a, b in ev:
+            flush.zero_()                       # L2 flush between timed iterations (not timed)
+            a.record()
+            step(image, depth)
+            b.record()
+        barrier()
+    launches = capi.launch_count() - n0
+    t_dev = sum(a.elapsed_time(b) for a, b in ev) / 1e3
+    tt = torch.tensor([t_dev], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_max = float(tt.item())
+    value = world * B * args.steps / t_max
+
+    # ---- end to end: pinned host inputs -> H2D -> path -> D2H of the result ---------------------
+    res_h = torch.empty(B, 144, 512, dtype=torch.float32).pin_memory()   # last-stage prompt tokens
+    e2e_steps = max(3, args.steps // 2)
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(e2e_steps):
+        img = image_h.to(dev, non_blocking=True)
+        dep = depth_h.to(dev, non_blocking=True)
+        _, _, toks = step(img, dep)
+        res_h.copy_(toks[3][2].float(), non_blocking=True)
+    t1.record()
+    barrier()
+    te = torch.tensor([t0.elapsed_time(t1) / 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = world * B * e2e_steps / float(te.item())
+    h2d = image_h.numel() * 4 + depth_h.numel() * 4
+    d2h = res_h.numel() * 4
+
+    # ---- roofline of the dominant kernel family (tcgen05 GEMM), measured live with CUDA events ---
+    roof = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        prof = OP.enable_gemm_profile(True) if hasattr(OP, "enable_gemm_profile") else None
+        if prof is not None and args.precision == "bf16":
+            for _ in range(2):
+                step(image, depth)
+            torch.cuda.synchronize()
+            flops, ms, n = OP.collect_gemm_profile()
+            OP.enable_gemm_profile(False)
+            peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+            ach = flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+            roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "traffic": None, "kernel": "tc_gemm_kernel (tcgen05, all pointwise/down-sample GEMMs)",
+                    "launches_timed": n, "avg_launch_ms": ms / max(n, 1),
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        rate, dt, cores = cpu_reference_rate(S, args.cpu_sample, 3, 1)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_sample} images of the same workload per step, 3 steps, fp32 torch CPU, {cpu_model()}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"COD inference hot path (prompt_encoder + 16 ShapePropDecoders + token layout), "
+                                   f"batch {B}/GPU, {S}x{S} RGB-D, random-init weights (BASELINE configs[1])",
+                       "l2": "256 MiB buffer written between timed iterations", "sharding": "by image, no collective"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "result": "stage-4 prompt tokens of the last block (B,144,512) fp32"},
+            "gpu_launches": int(launches), "clocks": clocks.summary(),
+            "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -21,8 +21,42 @@ __all__ = [
     "surface_normals", "HighpassPlan", "fft_highpass", "diffusion_front", "MessagePassingFunction",
     "message_passing_core", "message_passing_tiled", "conv1x1_nchw", "resize_nchw", "layer_norm",
     "stem", "ln_patchify", "dwconv7_ln", "linear", "linear_residual_", "fusion_head", "conv_nhwc",
-    "resize_nhwc", "cast", "nhwc_to_nchw", "nchw_to_nhwc",
+    "resize_nhwc", "cast", "nhwc_to_nchw", "nchw_to_nhwc", "enable_gemm_profile", "collect_gemm_profile",
 ]
+
+
+# ---- optional per-launch timing of the tensor-core GEMMs (bench.py roofline) --------------------
+_PROFILE = {"on": False, "events": []}
+
+
+def enable_gemm_profile(on: bool = True):
+    _PROFILE["on"] = bool(on)
+    _PROFILE["events"] = []
+    return _PROFILE
+
+
+def collect_gemm_profile():
+    """(total algorithmic FLOPs, total milliseconds, launches) of the profiled tcgen05 GEMMs."""
+    torch.cuda.synchronize()
+    flops = sum(f for f, _, _ in _PROFILE["events"])
+    ms = sum(a.elapsed_time(b) for _, a, b in _PROFILE["events"])
+    return flops, ms, len(_PROFILE["events"])
+
+
+class _timed:
+    def __init__(self, flops: float, active: bool):
+        self.flops, self.active = flops, active and _PROFILE["on"]
+
+    def __enter__(self):
+        if self.active:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if self.active:
+            self.b.record()
+            _PROFILE["events"].append((self.flops, self.a, self.b))
 
 
 def _tdtype(code: int) -> torch.dtype:
@@ -223,7 +257,8 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: 
     if out is None:
         out = torch.empty(tuple(a.shape[:-1]) + (N,), device=a.device, dtype=_tdtype(dout))
     ldo = out.shape[-1]
-    call("dgtd_linear_fwd", ptr(a), ptr(w), ptr(bias), ptr(out), M, N, K, ldo, din, dout, act, stream())
+    with _timed(2.0 * M * N * K, din == BF16):
+        call("dgtd_linear_fwd", ptr(a), ptr(w), ptr(bias), ptr(out), M, N, K, ldo, din, dout, act, stream())
     return out
 
 
@@ -237,8 +272,9 @@ def linear_residual_(a: torch.Tensor, w: torch.Tensor, bias, gamma, keep: Option
     N = w.shape[0]
     assert residual.dtype == torch.float32 and residual.numel() == M * N
     out = residual if out is None else out
-    call("dgtd_linear_residual_fwd", ptr(a), ptr(w), ptr(bias), ptr(gamma), ptr(keep), rows_per_sample,
-         ptr(residual), ptr(out), M, N, K, capi.dtype_code(a.dtype), stream())
+    with _timed(2.0 * M * N * K, a.dtype == torch.bfloat16):
+        call("dgtd_linear_residual_fwd", ptr(a), ptr(w), ptr(bias), ptr(gamma), ptr(keep), rows_per_sample,
+             ptr(residual), ptr(out), M, N, K, capi.dtype_code(a.dtype), stream())
     return out
 
 

@@ -18,7 +18,8 @@ def run(S, w20, precision, B=1):
     if w20:
         common.perturb_regressor_(enc)
     enc, dec = enc.cuda().eval(), dec.cuda().eval()
-    image, depth = common.synthetic_inputs(B, S)
+    pairs = [common.synthetic_inputs(1, S, seed=i) for i in range(B)]   # image i depends on seed i only
+    image, depth = torch.cat([p[0] for p in pairs]), torch.cat([p[1] for p in pairs])
     e1, e3, toks = TD.texture_prompts(enc, dec, image.cuda(), depth.cuda(), precision=precision)
     torch.cuda.synchronize()
     return common.flatten_outputs(e1, e3, toks)

@@ -5,47 +5,64 @@
 #include "simt_gemm.cuh"
 
 namespace dgtd {
-int tc_conv_nhwc(const void* x, const void* w, const float* bias, void* out, int B, int h, int wd,
-                 int Cin, int ldx, int oh, int ow, int Cout, int ldo, int ks, int stride, int off,
-                 int act, int dtype_out, cudaStream_t s);
+int tc_conv_nhwc(const void* x, const void* w, const float* bias, void* out, int B, int h, int wd, int Cin,
+                 int ldx, int oh, int ow, int Cout, int ldo, int ks, int stride, int off, int act,
+                 int dtype_out, int groups, int w_group_rows, int64_t out_group_stride, cudaStream_t s);
 }
 using namespace dgtd;
 
-extern "C" int dgtd_conv_nhwc_fwd(const void* x, const void* w, const float* bias, void* out, int B,
-                                  int h, int wd, int Cin, int ldx, int oh, int ow, int Cout, int ldo,
-                                  int ks, int stride, int off, int act, int dtype_in, int dtype_out,
-                                  dgtd_stream_t stream) {
+extern "C" {
+
+int dgtd_conv_nhwc_grouped_fwd(const void* x, const void* w, const float* bias, void* out, int B, int h,
+                               int wd, int Cin, int ldx, int oh, int ow, int Cout, int ldo, int ks,
+                               int stride, int off, int act, int dtype_in, int dtype_out, int groups,
+                               int x_group_stride, int w_group_rows, int64_t out_group_stride,
+                               dgtd_stream_t stream) {
   DGTD_CHECK_ARG(x && w && out, "conv_nhwc: null pointer");
-  DGTD_CHECK_ARG(B > 0 && h > 0 && wd > 0 && oh > 0 && ow > 0 && Cin > 0 && Cout > 0 && ks > 0 && stride > 0,
+  DGTD_CHECK_ARG(B > 0 && h > 0 && wd > 0 && oh > 0 && ow > 0 && Cin > 0 && Cout > 0 && ks > 0 && stride > 0 &&
+                     groups > 0,
                  "conv_nhwc: bad shape");
   DGTD_CHECK_ARG(ldx >= Cin && ldo >= Cout, "conv_nhwc: leading dims too small");
-  DGTD_CHECK_ARG(act >= 0 && act <= 2, "conv_nhwc: bad activation");
+  DGTD_CHECK_ARG(act == DGTD_ACT_NONE || act == DGTD_ACT_RELU, "conv_nhwc: activation must be none or relu");
+  DGTD_CHECK_ARG(groups == 1 || w_group_rows >= Cout, "conv_nhwc: w_group_rows < Cout");
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype_in == DGTD_BF16) {
-    int rc = tc_conv_nhwc(x, w, bias, out, B, h, wd, Cin, ldx, oh, ow, Cout, ldo, ks, stride, off, act,
-                          dtype_out, s);
+    DGTD_CHECK_ARG(groups == 1 || x_group_stride == 32, "conv_nhwc(bf16): x_group_stride must be 32");
+    int rc = tc_conv_nhwc(x, w, bias, out, B, h, wd, Cin, ldx, oh, ow, Cout, ldo, ks, stride, off, act, dtype_out,
+                          groups, groups == 1 ? Cout : w_group_rows, out_group_stride, s);
     if (rc) return rc;
     DGTD_LAUNCH_CHECK("conv_nhwc(tcgen05)");
     return 0;
   }
   DGTD_CHECK_ARG(dtype_in == DGTD_F32 && dtype_out == DGTD_F32, "conv_nhwc(fp32): fp32 in/out only");
-  DGTD_CHECK_ARG(Cin % 4 == 0 && ldx % 4 == 0 && Cout % 4 == 0 && ldo % 4 == 0,
-                 "conv_nhwc(fp32): channel counts must be multiples of 4");
+  DGTD_CHECK_ARG(Cin % 4 == 0 && ldx % 4 == 0 && Cout % 4 == 0 && ldo % 4 == 0 && x_group_stride % 4 == 0 &&
+                     out_group_stride % 4 == 0,
+                 "conv_nhwc(fp32): channel counts / strides must be multiples of 4");
   const int64_t M64 = (int64_t)B * oh * ow;
   DGTD_CHECK_ARG(M64 < (1ll << 31), "conv_nhwc: too many output pixels");
   const int M = (int)M64, K = ks * ks * Cin;
-  Im2colLoader al{(const float*)x, h, wd, ldx, Cin, oh, ow, ks, stride, off, M, K};
-  RowMajorLoader bl{(const float*)w, K, 0, Cout, K};
-  if (act == DGTD_ACT_RELU) {
-    EpiBiasAct<float, DGTD_ACT_RELU> ep{(float*)out, bias, ldo};
-    launch_simt_gemm<true, true>(al, bl, ep, M, Cout, K, 1, s);
-  } else if (act == DGTD_ACT_GELU) {
-    EpiBiasAct<float, DGTD_ACT_GELU> ep{(float*)out, bias, ldo};
-    launch_simt_gemm<true, true>(al, bl, ep, M, Cout, K, 1, s);
-  } else {
-    EpiBiasAct<float, DGTD_ACT_NONE> ep{(float*)out, bias, ldo};
-    launch_simt_gemm<true, true>(al, bl, ep, M, Cout, K, 1, s);
+  for (int g = 0; g < groups; ++g) {
+    Im2colLoader al{(const float*)x + (int64_t)g * x_group_stride, h, wd, ldx, Cin, oh, ow, ks, stride, off, M, K};
+    RowMajorLoader bl{(const float*)w + (int64_t)g * w_group_rows * K, K, 0, Cout, K};
+    const float* bg = bias ? bias + (int64_t)g * w_group_rows : nullptr;
+    float* og = (float*)out + g * out_group_stride;
+    if (act == DGTD_ACT_RELU) {
+      EpiBiasAct<float, DGTD_ACT_RELU> ep{og, bg, ldo};
+      launch_simt_gemm<true, true>(al, bl, ep, M, Cout, K, 1, s);
+    } else {
+      EpiBiasAct<float, DGTD_ACT_NONE> ep{og, bg, ldo};
+      launch_simt_gemm<true, true>(al, bl, ep, M, Cout, K, 1, s);
+    }
+    DGTD_LAUNCH_CHECK("conv_nhwc(fp32)");
   }
-  DGTD_LAUNCH_CHECK("conv_nhwc(fp32)");
   return 0;
 }
+
+int dgtd_conv_nhwc_fwd(const void* x, const void* w, const float* bias, void* out, int B, int h, int wd,
+                       int Cin, int ldx, int oh, int ow, int Cout, int ldo, int ks, int stride, int off,
+                       int act, int dtype_in, int dtype_out, dgtd_stream_t stream) {
+  return dgtd_conv_nhwc_grouped_fwd(x, w, bias, out, B, h, wd, Cin, ldx, oh, ow, Cout, ldo, ks, stride, off,
+                                    act, dtype_in, dtype_out, 1, 0, Cout, 0, stream);
+}
+
+}  // extern "C"

@@ -1,10 +1,289 @@
-// tcgen05 implicit-GEMM convolution over NHWC bf16 (decoder convs).  Placeholder entry until the
-// TMA-im2col producer lands: fails loudly rather than falling back.
+// tcgen05 implicit-GEMM convolution over NHWC bf16 for the ShapePropDecoder stack
+// (cod.py:1216-1222) and the injection-folded last conv (cod.py:1471).
+//
+// GEMM view: M = output pixels, N = Cout, K = taps x 32 (input channels padded to 32).
+// Nothing is materialised: per tap the TMA producer loads the (TH x TW) pixel tile shifted by
+// the tap offset straight from the NHWC tensor (4-D tensor map, element strides = conv stride,
+// out-of-bounds = zero padding) into a 64B-swizzled K-major smem tile that tcgen05.mma consumes.
+// Groups (the 16 decoders of the path) are a grid dimension: group g reads channel slice
+// [32g, 32g+32) of x, weight rows [g*w_group_rows, ...) and writes out + g*out_group_stride.
+#include "blackwell.cuh"
 #include "common.cuh"
+
 namespace dgtd {
-int tc_conv_nhwc(const void*, const void*, const float*, void*, int, int, int, int, int, int, int, int,
-                 int, int, int, int, int, int, cudaStream_t) {
-  set_error("conv_nhwc(bf16): tcgen05 implicit-GEMM convolution is not built in this version");
-  return -4;
+
+int sm_count();
+
+struct ConvParams {
+  int B, oh, ow, Cout, ldo;
+  int ks, stride, off;
+  int TW, TH, tiles_x, tiles_y, tiles_n, groups;
+  int w_group_rows;
+  int64_t out_group_stride;
+  const float* bias;  // [groups * w_group_rows] nullable
+  void* out;
+};
+
+template <int BN>
+struct ConvCfg {
+  static constexpr int BM = 128, CP = 32;                 // channels per tap (padded)
+  static constexpr int A_BYTES = BM * CP * 2, B_BYTES = BN * CP * 2;
+  static constexpr int STAGES = 8;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 + 1024;
+};
+
+template <int BN, int ACT, typename OT>
+__global__ void __launch_bounds__(256, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+               const ConvParams p) {
+  using Cfg = ConvCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES));
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int taps = p.ks * p.ks;
+  const int tiles_img = p.tiles_x * p.tiles_y;
+  const int num_tiles = p.groups * p.B * tiles_img * p.tiles_n;
+  const uint32_t a_bytes = (uint32_t)(p.TW * p.TH) * Cfg::CP * 2;
+
+  auto decode = [&](int tile, int& g, int& b, int& ty, int& tx, int& nb) {
+    nb = tile % p.tiles_n; tile /= p.tiles_n;
+    tx = tile % p.tiles_x; tile /= p.tiles_x;
+    ty = tile % p.tiles_y; tile /= p.tiles_y;
+    b = tile % p.B;
+    g = tile / p.B;
+  };
+
+  if (warp == 0 && lane == 0) {
+    bw::prefetch_tmap(&tmX);
+    bw::prefetch_tmap(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      bw::mbar_init(&full[i], 1);
+      bw::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      bw::mbar_init(&tfull[i], 1);
+      bw::mbar_init(&tempty[i], 128);
+    }
+    bw::fence_mbar_init();
+  }
+  if (warp == 2) bw::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  bw::tc_fence_before();
+  __syncthreads();
+  bw::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int g, b, ty, tx, nb;
+        decode(tile, g, b, ty, tx, nb);
+        const int ix0 = tx * p.TW * p.stride + p.off, iy0 = ty * p.TH * p.stride + p.off;
+        for (int t = 0; t < taps; ++t) {
+          const int dy = t / p.ks, dx = t - dy * p.ks;
+          bw::mbar_wait(&empty[stage], phase ^ 1);
+          bw::mbar_arrive_expect_tx(&full[stage], a_bytes + Cfg::B_BYTES);
+          bw::tma_load_4d(&tmX, &full[stage], sA + stage * Cfg::A_BYTES, g * Cfg::CP, ix0 + dx, iy0 + dy, b);
+          bw::tma_load_2d(&tmW, &full[stage], sB + stage * Cfg::B_BYTES, t * Cfg::CP,
+                          g * p.w_group_rows + nb * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = bw::umma_idesc_bf16(128, BN);
+      int stage = 0, iter = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+        const int as = iter & 1;
+        const uint32_t aphase = (iter >> 1) & 1;
+        bw::mbar_wait(&tempty[as], aphase ^ 1);
+        bw::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int t = 0; t < taps; ++t) {
+          bw::mbar_wait(&full[stage], phase);
+          bw::tc_fence_after();
+          const uint64_t da = bw::umma_smem_desc_kmajor(bw::smem_u32(sA + stage * Cfg::A_BYTES), 64);
+          const uint64_t db = bw::umma_smem_desc_kmajor(bw::smem_u32(sB + stage * Cfg::B_BYTES), 64);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) bw::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (t | k) != 0);
+          bw::umma_commit(&empty[stage]);
+          if (t == taps - 1) bw::umma_commit(&tfull[as]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+      int g, b, ty, tx, nb;
+      decode(tile, g, b, ty, tx, nb);
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1;
+      bw::mbar_wait(&tfull[as], aphase);
+      bw::tc_fence_after();
+      const int r = ew * 32 + lane;                 // row of the tile = (j, i) pixel
+      const int j = r / p.TW, i = r - j * p.TW;
+      const int oy = ty * p.TH + j, ox = tx * p.TW + i;
+      const bool row_ok = (j < p.TH) && oy < p.oh && ox < p.ow;
+      OT* orow = reinterpret_cast<OT*>(p.out) + (int64_t)g * p.out_group_stride +
+                 (((int64_t)b * p.oh + oy) * p.ow + ox) * p.ldo;
+      const float* bias = p.bias ? p.bias + g * p.w_group_rows : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        bw::tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN + c0, v);
+        bw::tmem_ld_wait();
+        const int col0 = nb * BN + c0;
+        if (row_ok && col0 < p.Cout) {
+#pragma unroll
+          for (int q = 0; q < 32; q += 8) {
+            if (col0 + q >= p.Cout) break;
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q + e]);
+            if (bias) {
+              float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + q));
+              float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + q + 4));
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            if (ACT == DGTD_ACT_RELU) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+            }
+            store4(orow + col0 + q, f[0], f[1], f[2], f[3]);
+            store4(orow + col0 + q + 4, f[4], f[5], f[6], f[7]);
+          }
+        }
+      }
+      bw::tc_fence_before();
+      bw::mbar_arrive(&tempty[as]);
+    }
+  }
+
+  bw::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    bw::tc_fence_after();
+    bw::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
 }
+
+static void pick_tile(int ow, int oh, int stride, int& TW, int& TH) {
+  int lim = 256 / stride;
+  if (lim > 32) lim = 32;
+  TW = ow < lim ? ow : lim;
+  for (int d = TW; d >= 8; --d)
+    if (ow % d == 0) { TW = d; break; }
+  TH = 128 / TW;
+  if (TH > oh) TH = oh;
+  if (TH * stride > 256) TH = 256 / stride;
+}
+
+template <int BN, int ACT, typename OT>
+static int conv_launch(const CUtensorMap& tmX, const __nv_bfloat16* w, int Ktot, int Wrows, ConvParams p,
+                       cudaStream_t s) {
+  using Cfg = ConvCfg<BN>;
+  auto kern = tc_conv_kernel<BN, ACT, OT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("tc_conv: cannot opt in to %d B of shared memory: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return -2;
+    }
+    configured = true;
+  }
+  CUtensorMap tmW;
+  uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)Wrows}, str[1] = {(uint64_t)Ktot * 2};
+  uint32_t box[2] = {32, (uint32_t)BN};
+  int rc = make_tmap(&tmW, w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc) return rc;
+  p.tiles_n = cdiv(p.Cout, BN);
+  int64_t tiles = (int64_t)p.groups * p.B * p.tiles_x * p.tiles_y * p.tiles_n;
+  int grid = tiles < sm_count() ? (int)tiles : sm_count();
+  kern<<<grid, 256, Cfg::SMEM_BYTES, s>>>(tmX, tmW, p);
+  return 0;
+}
+
+template <int ACT, typename OT>
+static int conv_dispatch_bn(const CUtensorMap& tmX, const __nv_bfloat16* w, int Ktot, int Wrows,
+                            const ConvParams& p, cudaStream_t s) {
+  if (p.Cout <= 32) return conv_launch<32, ACT, OT>(tmX, w, Ktot, Wrows, p, s);
+  if (p.Cout <= 64) return conv_launch<64, ACT, OT>(tmX, w, Ktot, Wrows, p, s);
+  return conv_launch<128, ACT, OT>(tmX, w, Ktot, Wrows, p, s);
+}
+
+// x: NHWC bf16, 32-channel slices per group (ldx >= 32*groups... or the caller's channel offset)
+int tc_conv_nhwc(const void* x, const void* w, const float* bias, void* out, int B, int h, int wd, int Cin,
+                 int ldx, int oh, int ow, int Cout, int ldo, int ks, int stride, int off, int act,
+                 int dtype_out, int groups, int w_group_rows, int64_t out_group_stride, cudaStream_t s) {
+  if (Cin != 32) {
+    set_error("conv_nhwc(bf16): Cin must be padded to 32 channels per group (got %d)", Cin);
+    return -1;
+  }
+  if (ldx % 8 || ldo % 8 || Cout % 8 || (reinterpret_cast<uintptr_t>(x) & 15)) {
+    set_error("conv_nhwc(bf16): ldx, ldo, Cout must be multiples of 8 and x 16-byte aligned");
+    return -1;
+  }
+  if (stride > 8 || ks > 4) {
+    set_error("conv_nhwc(bf16): stride <= 8 and ks <= 4 only");
+    return -1;
+  }
+  ConvParams p{};
+  p.B = B; p.oh = oh; p.ow = ow; p.Cout = Cout; p.ldo = ldo; p.ks = ks; p.stride = stride; p.off = off;
+  p.groups = groups; p.w_group_rows = w_group_rows; p.out_group_stride = out_group_stride;
+  p.bias = bias; p.out = out;
+  pick_tile(ow, oh, stride, p.TW, p.TH);
+  p.tiles_x = cdiv(ow, p.TW);
+  p.tiles_y = cdiv(oh, p.TH);
+  CUtensorMap tmX;
+  {
+    // dims innermost first: channels (all groups), W, H, B
+    uint64_t dims[4] = {(uint64_t)ldx, (uint64_t)wd, (uint64_t)h, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)ldx * 2, (uint64_t)wd * ldx * 2, (uint64_t)h * wd * ldx * 2};
+    uint32_t box[4] = {32, (uint32_t)(p.TW * stride), (uint32_t)(p.TH * stride), 1};
+    PFN_tmapEncodeTiled enc = get_tmap_encoder();
+    if (!enc) return -3;
+    cuuint64_t gd[4], gs[3];
+    cuuint32_t bx[4], es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    for (int i = 0; i < 4; ++i) { gd[i] = dims[i]; bx[i] = box[i]; }
+    for (int i = 0; i < 3; ++i) gs[i] = str[i];
+    CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gd, gs, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("conv_nhwc(bf16): cuTensorMapEncodeTiled(x) failed (%d): dims=[%d,%d,%d,%d] box=[32,%d,%d,1] stride %d",
+                (int)r, ldx, wd, h, B, p.TW * stride, p.TH * stride, stride);
+      return -3;
+    }
+  }
+  const int Ktot = ks * ks * 32;
+  const int Wrows = groups * w_group_rows;
+  const __nv_bfloat16* wp = (const __nv_bfloat16*)w;
+  if (dtype_out == DGTD_BF16) {
+    if (act == DGTD_ACT_RELU) return conv_dispatch_bn<DGTD_ACT_RELU, __nv_bfloat16>(tmX, wp, Ktot, Wrows, p, s);
+    return conv_dispatch_bn<DGTD_ACT_NONE, __nv_bfloat16>(tmX, wp, Ktot, Wrows, p, s);
+  }
+  if (act == DGTD_ACT_RELU) return conv_dispatch_bn<DGTD_ACT_RELU, float>(tmX, wp, Ktot, Wrows, p, s);
+  return conv_dispatch_bn<DGTD_ACT_NONE, float>(tmX, wp, Ktot, Wrows, p, s);
+}
+
 }  // namespace dgtd

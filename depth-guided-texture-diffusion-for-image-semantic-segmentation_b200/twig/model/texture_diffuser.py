@@ -300,6 +300,22 @@ def _fold_conv3_bilinear(wt: torch.Tensor) -> torch.Tensor:
     return w4.permute(0, 2, 3, 1).reshape(co, -1).contiguous()
 
 
+def _pad_taps_bf16(packed: torch.Tensor, cin: int, rows_to: Optional[int] = None) -> torch.Tensor:
+    """(Cout, taps*cin) fp32 tap-major -> (rows_to or Cout, taps*32) bf16 with zero channel / row padding
+    (operand layout of the tcgen05 implicit-GEMM conv: 32 channels = one 64-byte swizzled row)."""
+    co = packed.shape[0]
+    taps = packed.shape[1] // cin
+    out = torch.zeros(rows_to or co, taps, 32, device=packed.device, dtype=torch.float32)
+    out[:co, :, :cin] = packed.reshape(co, taps, cin)
+    return out.reshape(out.shape[0], taps * 32).to(torch.bfloat16).contiguous()
+
+
+def _pad_rows(v: torch.Tensor, rows_to: int) -> torch.Tensor:
+    out = torch.zeros(rows_to, device=v.device, dtype=torch.float32)
+    out[:v.shape[0]] = v.detach().float()
+    return out
+
+
 class ShapePropDecoder(nn.Module):
     """cod.py:1210-1226."""
 
@@ -337,6 +353,58 @@ def _decoder_front(decoders: Sequence[ShapePropDecoder], emb: torch.Tensor) -> t
         OP.conv_nhwc(h1[..., i * L:(i + 1) * L], w2, d.decoder[2].bias.detach(), L, (h, w), 3, 1, -1,
                      act=ACT_RELU, out=h2[..., i * L:(i + 1) * L], Cout=L)
     return h2
+
+
+def _decoder_front_bf16(decoders: Sequence[ShapePropDecoder], emb_pad: torch.Tensor) -> torch.Tensor:
+    """tcgen05 path: emb_pad NHWC (B,h,w,32) bf16 (24 latent channels + zero pad) ->
+    (B,h,w,32*D) bf16; decoder d owns channels [32d, 32d+24), the pad channels stay zero."""
+    B, h, w, _ = emb_pad.shape
+    D = len(decoders)
+    L = decoders[0].decoder[0].in_channels
+    pk = _packed(decoders[0])
+    key = "bf16." + ".".join(str(id(d)) for d in decoders)
+    w1 = pk.get(key + ".w1", [d.decoder[0].weight for d in decoders],
+                lambda: torch.cat([_pad_taps_bf16(_pack_conv3(d.decoder[0].weight), L, 32) for d in decoders], 0).contiguous())
+    b1 = pk.get(key + ".b1", [d.decoder[0].bias for d in decoders],
+                lambda: torch.cat([_pad_rows(d.decoder[0].bias, 32) for d in decoders]).contiguous())
+    w2 = pk.get(key + ".w2", [d.decoder[2].weight for d in decoders],
+                lambda: torch.cat([_pad_taps_bf16(_pack_conv3(d.decoder[2].weight), L, 32) for d in decoders], 0).contiguous())
+    b2 = pk.get(key + ".b2", [d.decoder[2].bias for d in decoders],
+                lambda: torch.cat([_pad_rows(d.decoder[2].bias, 32) for d in decoders]).contiguous())
+    h1 = torch.empty(B, h, w, 32 * D, device=emb_pad.device, dtype=torch.bfloat16)
+    OP.conv_nhwc_grouped(emb_pad, w1, b1, 32, (h, w), 3, 1, -1, ACT_RELU, h1, 32 * D, 32 * D, 1, 0, 32 * D, 0)
+    h2 = torch.empty_like(h1)
+    OP.conv_nhwc_grouped(h1, w2, b2, 32, (h, w), 3, 1, -1, ACT_RELU, h2, 32, 32 * D, D, 32, 32, 32)
+    return h2
+
+
+def _decode_tokens_bf16(decoders: Sequence[ShapePropDecoder], h2: torch.Tensor, index0: int,
+                        src_hw: Tuple[int, int], grid: Tuple[int, int]) -> List[torch.Tensor]:
+    """All decoders of one PVT stage in ONE grouped tcgen05 launch, output (D_s, B, H_s*W_s, E_s) bf16."""
+    B = h2.shape[0]
+    D = len(decoders)
+    E = decoders[0].decoder[4].out_channels
+    L = decoders[0].decoder[4].in_channels
+    h, w = src_hw
+    fold = _fold_params((h, w), grid)
+    pk = _packed(decoders[0])
+    key = f"bf16.c3.{grid}." + ".".join(str(id(d)) for d in decoders)
+    ws = [d.decoder[4].weight for d in decoders]
+    if (h, w) == tuple(grid):
+        ks, stride, off = 3, 1, -1
+        w3 = pk.get(key, ws, lambda: torch.cat([_pad_taps_bf16(_pack_conv3(t), L) for t in ws], 0).contiguous())
+    elif fold is not None:
+        ks, stride, off = 4, fold[0], fold[1]
+        w3 = pk.get(key, ws, lambda: torch.cat([_pad_taps_bf16(_fold_conv3_bilinear(t), L) for t in ws], 0).contiguous())
+    else:
+        raise NotImplementedError(f"bf16 prompt injection needs an integer power-of-two ratio, got {(h, w)} -> {grid}")
+    b3 = pk.get(key + ".b", [d.decoder[4].bias for d in decoders],
+                lambda: torch.cat([d.decoder[4].bias.detach().float() for d in decoders]).contiguous())
+    out = torch.empty(D, B, grid[0] * grid[1], E, device=h2.device, dtype=torch.bfloat16)
+    src = h2[..., index0 * 32:]
+    OP.conv_nhwc_grouped(src, w3, b3, 32, grid, ks, stride, off, ACT_NONE, out, E, E, D, 32, E,
+                         B * grid[0] * grid[1] * E)
+    return [out[i] for i in range(D)]
 
 
 def _decode_full(decoders: Sequence[ShapePropDecoder], emb: torch.Tensor) -> List[torch.Tensor]:
@@ -497,11 +565,21 @@ def texture_prompts(enc: prompt_encoder, dec: nn.Sequential, image: torch.Tensor
     tensor the reference adds to the stage-s token stream before block i
     (``x = blk(x + prompt[i], H, W)``)."""
     mode = _mode(enc) if precision is None else (BF16 if precision == "bf16" else F32)
-    emb1, nhwc, nchw, _ = enc._forward_fused(image, depth, mode, want_nchw=want_embedding3)
     grids = pvt_token_grids(image.shape[-2:])
     all_dec = [d for s in range(len(dec)) for d in dec[s].decoder]
-    h2 = _decoder_front(all_dec, nhwc)
+    src_hw = (image.shape[-2] // 4, image.shape[-1] // 4)
+    tc_ok = mode == BF16 and all(tuple(g) == src_hw or _fold_params(src_hw, g) is not None for g in grids)
+    emb1, nhwc, nchw, pad = enc._forward_fused(image, depth, mode, want_nchw=want_embedding3,
+                                               pad_to=32 if tc_ok else 0)
     tokens, idx = [], 0
+    if tc_ok:     # decoders on tcgen05 (bf16 operands, fp32 accumulate), 6 launches for all 16 decoders
+        h2 = _decoder_front_bf16(all_dec, pad)
+        for s in range(len(dec)):
+            ds = list(dec[s].decoder)
+            tokens.append(_decode_tokens_bf16(ds, h2, idx, src_hw, grids[s]))
+            idx += len(ds)
+        return emb1, nchw, tokens
+    h2 = _decoder_front(all_dec, nhwc)
     for s in range(len(dec)):
         ds = list(dec[s].decoder)
         tokens.append(_decode_tokens(ds, nhwc, grids[s], h2=h2, index0=idx))

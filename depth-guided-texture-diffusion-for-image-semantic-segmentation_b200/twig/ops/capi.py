@@ -43,6 +43,7 @@ SIGNATURES = {
     "dgtd_linear_residual_fwd": [_P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P],
     "dgtd_fusion_head_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "dgtd_conv_nhwc_fwd": [_P, _P, _P, _P] + [_I] * 15 + [_P],
+    "dgtd_conv_nhwc_grouped_fwd": [_P, _P, _P, _P] + [_I] * 18 + [_L, _P],
     "dgtd_resize_nhwc_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "dgtd_cast_fwd": [_P, _P, _L, _I, _I, _P],
     "dgtd_nhwc_to_nchw_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _P],

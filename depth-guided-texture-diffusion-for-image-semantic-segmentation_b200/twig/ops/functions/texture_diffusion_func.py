@@ -20,7 +20,7 @@ from ..capi import ACT_GELU, ACT_NONE, ACT_RELU, BF16, F32, call, check_cuda, pt
 __all__ = [
     "surface_normals", "HighpassPlan", "fft_highpass", "diffusion_front", "MessagePassingFunction",
     "message_passing_core", "message_passing_tiled", "conv1x1_nchw", "resize_nchw", "layer_norm",
-    "stem", "ln_patchify", "dwconv7_ln", "linear", "linear_residual_", "fusion_head", "conv_nhwc",
+    "stem", "ln_patchify", "dwconv7_ln", "linear", "linear_residual_", "fusion_head", "conv_nhwc", "conv_nhwc_grouped",
     "resize_nhwc", "cast", "nhwc_to_nchw", "nchw_to_nhwc", "enable_gemm_profile", "collect_gemm_profile",
 ]
 
@@ -313,6 +313,20 @@ def conv_nhwc(x: torch.Tensor, w: torch.Tensor, bias, Cin: int, out_hw: Tuple[in
     ldo = out.stride(2)
     call("dgtd_conv_nhwc_fwd", x.data_ptr(), ptr(w), ptr(bias), out.data_ptr(), B, h, wd, Cin, ldx, oh, ow,
          Cout, ldo, ks, stride, off, act, din, dout, stream())
+    return out
+
+
+def conv_nhwc_grouped(x: torch.Tensor, w: torch.Tensor, bias, Cin: int, out_hw: Tuple[int, int], ks: int,
+                      stride: int, off: int, act: int, out: torch.Tensor, Cout: int, ldo: int, groups: int,
+                      x_group_stride: int, w_group_rows: int, out_group_stride: int) -> torch.Tensor:
+    """Grouped implicit-GEMM conv (all decoders of a stage in one launch); see dgtd_ops.h."""
+    B, h, wd = x.shape[0], x.shape[1], x.shape[2]
+    ldx = x.stride(2)
+    assert x.stride(3) == 1 and x.stride(1) == wd * ldx and x.stride(0) == h * wd * ldx
+    oh, ow = out_hw
+    call("dgtd_conv_nhwc_grouped_fwd", x.data_ptr(), ptr(w), ptr(bias), out.data_ptr(), B, h, wd, Cin, ldx,
+         oh, ow, Cout, ldo, ks, stride, off, act, capi.dtype_code(x.dtype), capi.dtype_code(out.dtype), groups,
+         x_group_stride, w_group_rows, out_group_stride, stream())
     return out
 
 

@@ -75,3 +75,43 @@ def test_repeated_launches_are_deterministic(OP):
     y0 = OP.linear(a, w, b, out_dtype=F32)
     for _ in range(5):
         assert torch.equal(OP.linear(a, w, b, out_dtype=F32), y0)
+
+
+# ---- implicit-GEMM convolution (TMA im2col producer, 64B swizzle, grouped) ----------------------
+CONV_CASES = [  # (B, h, w, groups, Cout, ks, stride, off, relu)
+    (2, 16, 16, 3, 32, 3, 1, -1, True),      # decoder conv2 shape class (N=32 tile)
+    (1, 96, 96, 1, 512, 3, 1, -1, True),     # conv1 of all 16 decoders (N=512)
+    (2, 96, 96, 2, 64, 3, 1, -1, False),     # stage-1 prompts, no resize
+    (2, 96, 96, 2, 128, 4, 2, -1, False),    # folded, ratio 2
+    (1, 96, 96, 3, 320, 4, 4, 0, False),     # folded, ratio 4
+    (3, 96, 96, 2, 512, 4, 8, 2, False),     # folded, ratio 8
+    (1, 88, 88, 2, 64, 4, 2, -1, False),     # 352^2 input: 88 -> 44
+    (1, 20, 28, 1, 40, 3, 1, -1, False),     # odd tile shapes / N tail
+]
+
+
+@pytest.mark.parametrize("B,h,w,G,Cout,ks,stride,off,relu", CONV_CASES)
+def test_conv_nhwc_grouped_bf16(OP, B, h, w, G, Cout, ks, stride, off, relu):
+    import torch.nn.functional as F
+    from dgtd_b200.twig.ops.capi import ACT_NONE, ACT_RELU
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(B, h, w, 32 * G, generator=g).to(torch.bfloat16)
+    x[..., 24::32] = 0                                   # a few zero pad channels like the real layout
+    wt = (torch.randn(G, Cout, ks, ks, 32, generator=g) / (ks * 6.0)).to(torch.bfloat16)
+    bias = torch.randn(G, Cout, generator=g)
+    oh = (h - 1) // stride + 1 if ks == 3 else h // stride
+    ow = (w - 1) // stride + 1 if ks == 3 else w // stride
+    out = torch.empty(G, B, oh, ow, Cout, dtype=torch.float32).cuda()
+    OP.conv_nhwc_grouped(x.cuda(), wt.reshape(G * Cout, ks * ks * 32).cuda().contiguous(), bias.reshape(-1).cuda(),
+                         32, (oh, ow), ks, stride, off, ACT_RELU if relu else ACT_NONE, out, Cout, Cout, G, 32,
+                         Cout, B * oh * ow * Cout)
+    torch.cuda.synchronize()
+    for gi in range(G):
+        xi = x[..., 32 * gi:32 * gi + 32].double().permute(0, 3, 1, 2)
+        wi = wt[gi].double().permute(0, 3, 1, 2)          # (Cout, 32, ks, ks)
+        pad = 4 * stride + ks
+        xp = F.pad(xi, (pad, pad, pad, pad))
+        ref = F.conv2d(xp[:, :, pad + off:, pad + off:], wi, bias[gi].double(), stride=stride)[:, :, :oh, :ow]
+        ref = ref.clamp_min(0) if relu else ref
+        got = out[gi].permute(0, 3, 1, 2).double().cpu()
+        assert rel(got, ref) <= 1e-4, (gi, rel(got, ref))

@@ -7,8 +7,9 @@
 //   warp 0 (one lane)  TMA producer: 128xBK A tile + BNxBK B tile per stage, 128B swizzle
 //   warp 1 (one lane)  tcgen05.mma issuer: 128 x BN x 16 UMMAs, accumulator in TMEM
 //   warp 2             TMEM allocation / release
-//   warps 4-7          epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> registers ->
-//                      bias / GELU / gamma / DropPath scale / residual -> global
+//   warps 4-11         epilogue: tcgen05.ld (32 lanes x 32 columns, double buffered; two warps per
+//                      TMEM lane quadrant split the columns) -> registers -> bias / GELU (packed
+//                      fp32x2) / gamma / DropPath scale / residual -> 16-byte global stores
 // Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
 #include <mutex>
 
@@ -87,6 +88,62 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return x * phi;
 }
 
+// Packed fp32x2 arithmetic (Blackwell FFMA2/FMUL2/FADD2): halves the issue slots of the epilogue.
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void up2(uint64_t r, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// gelu_fast on two values at once (same polynomial, 8 issue slots per element)
+__device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
+  const float c0 = fminf(fmaxf(x0, -4.5f), 4.5f), c1 = fminf(fmaxf(x1, -4.5f), 4.5f);
+  const uint64_t xc = pk2(c0, c1);
+  const uint64_t t = mul2(xc, xc);
+  uint64_t q = pk2(-1.400070736e-12f, -1.400070736e-12f);
+  q = fma2(q, t, pk2(1.697307069e-10f, 1.697307069e-10f));
+  q = fma2(q, t, pk2(-9.193762573e-09f, -9.193762573e-09f));
+  q = fma2(q, t, pk2(2.958901695e-07f, 2.958901695e-07f));
+  q = fma2(q, t, pk2(-6.365260363e-06f, -6.365260363e-06f));
+  q = fma2(q, t, pk2(9.787139965e-05f, 9.787139965e-05f));
+  q = fma2(q, t, pk2(-1.122678685e-03f, -1.122678685e-03f));
+  q = fma2(q, t, pk2(9.833185488e-03f, 9.833185488e-03f));
+  q = fma2(q, t, pk2(-6.633705714e-02f, -6.633705714e-02f));
+  q = fma2(q, t, pk2(3.988837948e-01f, 3.988837948e-01f));
+  const uint64_t phi = fma2(xc, q, pk2(0.5f, 0.5f));   // within 3e-5 of [0,1]: no clamp needed
+  up2(mul2(pk2(x0, x1), phi), x0, x1);
+}
+
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(f[4], f[5]), d = __floats2bfloat162_rn(f[6], f[7]);
+  uint4 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+  u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void store8(float* p, const float (&f)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+
 template <int ACT>
 __device__ __forceinline__ float tc_act(float x) {
   if (ACT == DGTD_ACT_GELU) return gelu_fast(x);
@@ -117,7 +174,7 @@ struct TcCfg {
 };
 
 template <int BN, int ACT, typename OT, bool RESIDUAL>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcParams p) {
   using Cfg = TcCfg<BN>;
@@ -148,7 +205,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       bw::mbar_init(&tfull[i], 1);
-      bw::mbar_init(&tempty[i], 128);
+      bw::mbar_init(&tempty[i], 256);
     }
     bw::fence_mbar_init();
   }
@@ -202,8 +259,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int ew = warp - 4;  // == warp % 4: the TMEM lane quadrant this warp may read
+    // ===================== epilogue (8 warps) =====================
+    // warp w may read TMEM lanes [32*(w%4), +32); the two warps of a quadrant split the columns.
+    const int quad = warp & 3, half = (warp - 4) >> 2;
+    constexpr int HALF_COLS = BN >= 64 ? BN / 2 : BN;          // columns per warp
+    constexpr int NCH = HALF_COLS / 32;                         // 32-column chunks per warp
+    const bool has_work = (BN >= 64) || half == 0;
     OT* out = reinterpret_cast<OT*>(p.out);
     int iter = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
@@ -212,23 +273,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t aphase = (iter >> 1) & 1;
       bw::mbar_wait(&tfull[as], aphase);
       bw::tc_fence_after();
-      const int row = m_blk * BM + ew * 32 + lane;
+      const int row = m_blk * BM + quad * 32 + lane;
       const bool row_ok = row < p.M;
       float ks = 1.f;
       if (RESIDUAL && p.keep && row_ok) ks = p.keep[row / p.rows_per_sample];
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        bw::tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN + c0, v);
-        bw::tmem_ld_wait();
-        const int col0 = n_blk * BN + c0;
-        if (row_ok && col0 < p.N) {
+      const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN + half * HALF_COLS;
+      uint32_t v[2][32];
+      if (has_work) bw::tmem_ld_32x32(t0, v[0]);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        if (has_work) {
+          bw::tmem_ld_wait();
+          if (c + 1 < NCH) bw::tmem_ld_32x32(t0 + (c + 1) * 32, v[(c + 1) & 1]);
+        }
+        if (c == NCH - 1) {   // every TMEM read of this tile has landed: release the accumulator
+          bw::tc_fence_before();
+          bw::mbar_arrive(&tempty[as]);
+        }
+        const int col0 = n_blk * BN + half * HALF_COLS + c * 32;
+        if (has_work && row_ok && col0 < p.N) {
+          const uint32_t(&vv)[32] = v[c & 1];
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             if (col0 + j >= p.N) break;  // N is a multiple of 8
             float f[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]);
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(vv[j + e]);
             if (p.bias) {
               float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
               float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j + 4));
@@ -249,18 +319,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               float r[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = r[e] + ks * (g[e] * f[e]);
+            } else if (ACT == DGTD_ACT_GELU) {
+#pragma unroll
+              for (int e = 0; e < 8; e += 2) gelu_fast2(f[e], f[e + 1]);
             } else {
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = tc_act<ACT>(f[e]);
             }
-            OT* op = out + (int64_t)row * p.ldo + col0 + j;
-            store4(op, f[0], f[1], f[2], f[3]);
-            store4(op + 4, f[4], f[5], f[6], f[7]);
+            store8(out + (int64_t)row * p.ldo + col0 + j, f);
           }
         }
       }
-      bw::tc_fence_before();
-      bw::mbar_arrive(&tempty[as]);
     }
   }
 
@@ -303,7 +372,7 @@ static int tc_launch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B
   p.tiles_n = cdiv(p.N, BN);
   int tiles = p.tiles_m * p.tiles_n;
   int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, 256, Cfg::SMEM_BYTES, s>>>(tmA, tmB, p);
+  kern<<<grid, 384, Cfg::SMEM_BYTES, s>>>(tmA, tmB, p);
   return 0;
 }
 

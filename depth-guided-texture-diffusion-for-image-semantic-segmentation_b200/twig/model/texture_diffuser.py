@@ -233,15 +233,19 @@ class ShapePropEncoder(nn.Module):
             outs.append(x)
         return outs
 
-    def _head(self, outs: List[torch.Tensor], want_nchw: bool, pad_to: int = 0):
+    def _head(self, outs: List[torch.Tensor], want_nchw: bool, pad_to: int = 0, mode: int = F32):
         """cod.py:1171-1176 -> embedding3 as (nhwc fp32, nchw fp32 | None, padded bf16 | None)."""
         pk = _packed(self)
         B = outs[0].shape[0]
         levels, hw = [], []
         for i, o in enumerate(outs):
             conv = self.convs[i]
-            wl = pk.get(f"head{i}", [conv.weight], lambda conv=conv: conv.weight.detach().reshape(self.out_dim, -1).float().contiguous())
-            levels.append(OP.linear(o.view(-1, o.shape[-1]), wl, conv.bias.detach()))   # fp32 exact (0.15 GFLOP/img)
+            wl = pk.get(f"head{i}.{mode}", [conv.weight],
+                        lambda conv=conv: _as(conv.weight.detach().reshape(self.out_dim, -1), mode))
+            a = o.view(-1, o.shape[-1])
+            if mode == BF16:       # tcgen05 projection (N=24): cast the fp32 stage output once
+                a = OP.cast(a, torch.bfloat16)
+            levels.append(OP.linear(a, wl, conv.bias.detach(), out_dtype=F32))
             hw.append((o.shape[1], o.shape[2]))
         wf = pk.get("fusion", [self.fusion_conv.weight],
                     lambda: self.fusion_conv.weight.detach().reshape(self.out_dim, 4 * self.out_dim).float().contiguous())
@@ -251,7 +255,7 @@ class ShapePropEncoder(nn.Module):
     def forward(self, x):
         _no_grad_only(self, "ShapePropEncoder")
         outs = self._pyramid(x.contiguous().float(), None, _mode(self))
-        _, nchw, _ = self._head(outs, want_nchw=True)
+        _, nchw, _ = self._head(outs, want_nchw=True, mode=_mode(self))
         return nchw
 
 
@@ -492,7 +496,7 @@ class prompt_encoder(nn.Module):
         grid3, _, _ = OP.diffusion_front(x, cues, reg_w, reg.bias.detach(), enc_w, self.encoder1.bias.detach(),
                                          mp_w, mp.conv.bias.detach(), grid=H, steps=steps)   # :1295-1298
         outs = self.encoder2._pyramid(image, grid3, mode)                         # :1302 (+image fused in the stem)
-        nhwc, nchw, pad = self.encoder2._head(outs, want_nchw=want_nchw, pad_to=pad_to)
+        nhwc, nchw, pad = self.encoder2._head(outs, want_nchw=want_nchw, pad_to=pad_to, mode=mode)
         return x, nhwc, nchw, pad
 
     def forward(self, image, cues, cross=False):

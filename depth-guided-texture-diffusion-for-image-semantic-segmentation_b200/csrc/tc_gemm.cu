@@ -13,8 +13,8 @@
 // Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
 #include <mutex>
 
-#include "blackwell.cuh"
 #include "simt_gemm.cuh"
+#include "tc_common.cuh"
 
 namespace dgtd {
 
@@ -67,101 +67,6 @@ int sm_count() {
   }
   return n;
 }
-
-// ---------------------------------------------------------------- fast GELU for the bf16 path
-// Phi(x) = 0.5 + x Q(x^2) on |x| <= 4.5 (odd minimax-style fit of the erf form, clamped to
-// [0,1]); max |gelu_fast - gelu_erf| = 2.8e-5 over the reals, i.e. ~1/100 of a bf16 ulp at 1.
-__device__ __forceinline__ float gelu_fast(float x) {
-  float xc = fminf(fmaxf(x, -4.5f), 4.5f);
-  float t = xc * xc;
-  float q = -1.400070736e-12f;
-  q = fmaf(q, t, 1.697307069e-10f);
-  q = fmaf(q, t, -9.193762573e-09f);
-  q = fmaf(q, t, 2.958901695e-07f);
-  q = fmaf(q, t, -6.365260363e-06f);
-  q = fmaf(q, t, 9.787139965e-05f);
-  q = fmaf(q, t, -1.122678685e-03f);
-  q = fmaf(q, t, 9.833185488e-03f);
-  q = fmaf(q, t, -6.633705714e-02f);
-  q = fmaf(q, t, 3.988837948e-01f);
-  float phi = fminf(fmaxf(fmaf(xc, q, 0.5f), 0.f), 1.f);
-  return x * phi;
-}
-
-// Packed fp32x2 arithmetic (Blackwell FFMA2/FMUL2/FADD2): halves the issue slots of the epilogue.
-__device__ __forceinline__ uint64_t pk2(float a, float b) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void up2(uint64_t r, float& a, float& b) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r));
-}
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-// gelu_fast on two values at once (same polynomial, 8 issue slots per element)
-__device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
-  const float c0 = fminf(fmaxf(x0, -4.5f), 4.5f), c1 = fminf(fmaxf(x1, -4.5f), 4.5f);
-  const uint64_t xc = pk2(c0, c1);
-  const uint64_t t = mul2(xc, xc);
-  uint64_t q = pk2(-1.400070736e-12f, -1.400070736e-12f);
-  q = fma2(q, t, pk2(1.697307069e-10f, 1.697307069e-10f));
-  q = fma2(q, t, pk2(-9.193762573e-09f, -9.193762573e-09f));
-  q = fma2(q, t, pk2(2.958901695e-07f, 2.958901695e-07f));
-  q = fma2(q, t, pk2(-6.365260363e-06f, -6.365260363e-06f));
-  q = fma2(q, t, pk2(9.787139965e-05f, 9.787139965e-05f));
-  q = fma2(q, t, pk2(-1.122678685e-03f, -1.122678685e-03f));
-  q = fma2(q, t, pk2(9.833185488e-03f, 9.833185488e-03f));
-  q = fma2(q, t, pk2(-6.633705714e-02f, -6.633705714e-02f));
-  q = fma2(q, t, pk2(3.988837948e-01f, 3.988837948e-01f));
-  const uint64_t phi = fma2(xc, q, pk2(0.5f, 0.5f));   // within 3e-5 of [0,1]: no clamp needed
-  up2(mul2(pk2(x0, x1), phi), x0, x1);
-}
-
-__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
-  __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
-  __nv_bfloat162 c = __floats2bfloat162_rn(f[4], f[5]), d = __floats2bfloat162_rn(f[6], f[7]);
-  uint4 u;
-  u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
-  u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
-  *reinterpret_cast<uint4*>(p) = u;
-}
-__device__ __forceinline__ void store8(float* p, const float (&f)[8]) {
-  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
-  *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
-}
-
-template <int ACT>
-__device__ __forceinline__ float tc_act(float x) {
-  if (ACT == DGTD_ACT_GELU) return gelu_fast(x);
-  if (ACT == DGTD_ACT_RELU) return fmaxf(x, 0.f);
-  return x;
-}
-
-struct TcParams {
-  int M, N, K;
-  int tiles_m, tiles_n;
-  const float* bias;      // [N] nullable
-  const float* gamma;     // [N] nullable          (RESIDUAL)
-  const float* keep;      // [M / rows_per_sample]  nullable (RESIDUAL)
-  const float* residual;  // [M, ldo] fp32          (RESIDUAL)
-  int rows_per_sample;
-  void* out;
-  int64_t ldo;
-};
 
 template <int BN>
 struct TcCfg {
@@ -262,10 +167,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== epilogue (8 warps) =====================
     // warp w may read TMEM lanes [32*(w%4), +32); the two warps of a quadrant split the columns.
     const int quad = warp & 3, half = (warp - 4) >> 2;
-    constexpr int HALF_COLS = BN >= 64 ? BN / 2 : BN;          // columns per warp
-    constexpr int NCH = HALF_COLS / 32;                         // 32-column chunks per warp
-    const bool has_work = (BN >= 64) || half == 0;
-    OT* out = reinterpret_cast<OT*>(p.out);
     int iter = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
       const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
@@ -273,63 +174,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t aphase = (iter >> 1) & 1;
       bw::mbar_wait(&tfull[as], aphase);
       bw::tc_fence_after();
-      const int row = m_blk * BM + quad * 32 + lane;
-      const bool row_ok = row < p.M;
-      float ks = 1.f;
-      if (RESIDUAL && p.keep && row_ok) ks = p.keep[row / p.rows_per_sample];
-      const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN + half * HALF_COLS;
-      uint32_t v[2][32];
-      if (has_work) bw::tmem_ld_32x32(t0, v[0]);
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        if (has_work) {
-          bw::tmem_ld_wait();
-          if (c + 1 < NCH) bw::tmem_ld_32x32(t0 + (c + 1) * 32, v[(c + 1) & 1]);
-        }
-        if (c == NCH - 1) {   // every TMEM read of this tile has landed: release the accumulator
-          bw::tc_fence_before();
-          bw::mbar_arrive(&tempty[as]);
-        }
-        const int col0 = n_blk * BN + half * HALF_COLS + c * 32;
-        if (has_work && row_ok && col0 < p.N) {
-          const uint32_t(&vv)[32] = v[c & 1];
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (col0 + j >= p.N) break;  // N is a multiple of 8
-            float f[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(vv[j + e]);
-            if (p.bias) {
-              float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-              float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j + 4));
-              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-            }
-            if (RESIDUAL) {
-              float g[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
-              if (p.gamma) {
-                float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + col0 + j));
-                float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + col0 + j + 4));
-                g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w;
-                g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
-              }
-              const float* rp = p.residual + (int64_t)row * p.ldo + col0 + j;
-              float4 r0 = *reinterpret_cast<const float4*>(rp);
-              float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
-              float r[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = r[e] + ks * (g[e] * f[e]);
-            } else if (ACT == DGTD_ACT_GELU) {
-#pragma unroll
-              for (int e = 0; e < 8; e += 2) gelu_fast2(f[e], f[e + 1]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = tc_act<ACT>(f[e]);
-            }
-            store8(out + (int64_t)row * p.ldo + col0 + j, f);
-          }
-        }
-      }
+      uint64_t* rel = &tempty[as];
+      tc_epilogue_tile<BN, ACT, OT, RESIDUAL>(p, tmem_base + as * BN, quad, half, lane,
+                                              m_blk * BM + quad * 32 + lane, n_blk,
+                                              [rel] { bw::mbar_arrive(rel); });
     }
   }
 
@@ -408,6 +256,10 @@ int tc_linear_residual(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16*
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.gamma = gamma; p.keep = keep;
   p.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : 1;
   p.residual = residual; p.out = out; p.ldo = N;
+  {
+    int rc2 = tc_gemm2_launch(A, lda, B, ldb, p, DGTD_ACT_NONE, DGTD_F32, true, s);
+    if (rc2 <= 0) return rc2;
+  }
   return tc_dispatch_bn<DGTD_ACT_NONE, float, true>(A, lda, B, ldb, p, s);
 }
 

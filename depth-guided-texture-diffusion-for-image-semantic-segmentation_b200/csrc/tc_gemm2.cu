@@ -1,0 +1,261 @@
+// 2-CTA (cta_group::2) tcgen05 GEMM: a CTA pair on one TPC computes a 256 x BN tile.
+//
+// Why: a single-CTA 128x256 tile needs 96 B/clk/SM of operand traffic at full MMA rate, more
+// than the L2->SM fabric delivers (~43 B/clk/SM measured: profiles/r1_launches_b64_v2.md shows
+// the K=2048 GEMM stuck at 36% tensor-pipe).  In a pair each CTA stages its own 128 rows of A
+// and only HALF of the B tile; tcgen05.mma.cta_group::2 reads both halves through the pair's
+// shared memory, so the per-SM feed drops to 64 B/clk.
+//
+// Protocol (rank 0 = leader):
+//   * both CTAs run a TMA producer (own A rows + own half of B); the transaction bytes of both
+//     land on the LEADER's `full` barrier (cp.async.bulk.tensor ... .cta_group::2);
+//   * the leader's MMA thread issues M=256 UMMAs; tcgen05.commit multicasts to the `empty` /
+//     `tmem_full` barriers of both CTAs;
+//   * each CTA's 8 epilogue warps drain their own 128 TMEM lanes and arrive (remotely for
+//     rank 1) on the leader's `tmem_empty` barrier.
+#include "tc_common.cuh"
+
+namespace dgtd {
+
+namespace bw2 {
+__device__ __forceinline__ uint32_t cta_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p`'s counterpart in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_rank(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(bw::smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* m, uint32_t leader_bar, void* dst, int c0,
+                                                int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(bw::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bw::smem_u32(dst_smem)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the same-offset barrier of both CTAs of the pair when the issued MMAs retire
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bw::smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+}  // namespace bw2
+
+template <int BN>
+struct Tc2Cfg {
+  static constexpr int BM = 128, BK = 64;                          // per CTA; the pair covers 256 rows
+  static constexpr int A_BYTES = BM * BK * 2, B_BYTES = (BN / 2) * BK * 2;   // B: this CTA's half
+  static constexpr int STAGES = 6;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 + 1024;
+};
+
+template <int BN, int ACT, typename OT, bool RESIDUAL>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const TcParams p) {
+  using Cfg = Tc2Cfg<BN>;
+  constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // identical carve-up in both CTAs (the hardware addresses the peer's operands by offset)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES));
+  uint64_t* full = bars;                     // used on the leader only
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 2;  // used on the leader only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = bw2::cta_rank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_tiles = p.tiles_m * p.tiles_n;   // tiles_m counts 256-row pair tiles
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  bw2::cluster_sync();  // both CTAs resident before the pair-wide TMEM allocation
+  if (warp == 0 && lane == 0) {
+    bw::prefetch_tmap(&tmA);
+    bw::prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      bw::mbar_init(&full[i], 2);     // one arrival per CTA's producer
+      bw::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      bw::mbar_init(&tfull[i], 1);
+      bw::mbar_init(&tempty[i], 512);  // 8 epilogue warps x 2 CTAs
+    }
+    bw::fence_mbar_init();
+  }
+  if (warp == 2) bw2::tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+  bw::tc_fence_before();
+  bw2::cluster_sync();
+  bw::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer (both CTAs) =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
+        const int m0 = m_blk * 256 + (int)rank * BM;
+        const int n0 = n_blk * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          bw::mbar_wait(&empty[stage], phase ^ 1);
+          const uint32_t lbar = bw2::map_to_rank(&full[stage], 0);
+          bw2::tma_load_2d_2sm(&tmA, lbar, sA + stage * Cfg::A_BYTES, kb * BK, m0);
+          bw2::tma_load_2d_2sm(&tmB, lbar, sB + stage * Cfg::B_BYTES, kb * BK, n0);
+          if (leader) bw::mbar_arrive_expect_tx(&full[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
+          else bw2::mbar_arrive_cluster(lbar);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      // ===================== MMA issuer (leader CTA only) =====================
+      constexpr uint32_t idesc = bw::umma_idesc_bf16(256, BN);
+      int stage = 0, iter = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++iter) {
+        const int as = iter & 1;
+        const uint32_t aphase = (iter >> 1) & 1;
+        bw::mbar_wait(&tempty[as], aphase ^ 1);
+        bw::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          bw::mbar_wait(&full[stage], phase);
+          bw::tc_fence_after();
+          const uint64_t da = bw::umma_smem_desc_kmajor(bw::smem_u32(sA + stage * Cfg::A_BYTES), 128);
+          const uint64_t db = bw::umma_smem_desc_kmajor(bw::smem_u32(sB + stage * Cfg::B_BYTES), 128);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            bw2::umma_bf16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          bw2::umma_commit_2sm(&empty[stage]);
+          if (kb == num_kb - 1) bw2::umma_commit_2sm(&tfull[as]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own 128 TMEM lanes) =====================
+    const int quad = warp & 3, half = (warp - 4) >> 2;
+    int iter = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++iter) {
+      const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1;
+      bw::mbar_wait(&tfull[as], aphase);
+      bw::tc_fence_after();
+      const uint32_t rel = bw2::map_to_rank(&tempty[as], 0);
+      tc_epilogue_tile<BN, ACT, OT, RESIDUAL>(p, tmem_base + as * BN, quad, half, lane,
+                                              m_blk * 256 + (int)rank * BM + quad * 32 + lane, n_blk,
+                                              [rel] { bw2::mbar_arrive_cluster(rel); });
+    }
+  }
+
+  // nobody leaves (or frees TMEM) while the peer may still signal our barriers / read our smem
+  bw::tc_fence_before();
+  bw2::cluster_sync();
+  if (warp == 2) {
+    bw::tc_fence_after();
+    bw2::tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN, int ACT, typename OT, bool RESIDUAL>
+static int tc2_launch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B, int64_t ldb, TcParams p,
+                      cudaStream_t s) {
+  using Cfg = Tc2Cfg<BN>;
+  auto kern = tc_gemm2_kernel<BN, ACT, OT, RESIDUAL>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("tc_gemm2: cannot opt in to %d B of shared memory: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return -2;
+    }
+    configured = true;
+  }
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.M}, str[1] = {(uint64_t)lda * 2};
+    uint32_t box[2] = {64, 128};
+    int rc = make_tmap(&tmA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N}, str[1] = {(uint64_t)ldb * 2};
+    uint32_t box[2] = {64, (uint32_t)(BN / 2)};
+    int rc = make_tmap(&tmB, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  p.tiles_m = cdiv(p.M, 256);
+  p.tiles_n = cdiv(p.N, BN);
+  int tiles = p.tiles_m * p.tiles_n;
+  int pairs = sm_count() / 2;
+  int clusters = tiles < pairs ? tiles : pairs;
+  kern<<<2 * clusters, 384, Cfg::SMEM_BYTES, s>>>(tmA, tmB, p);
+  return 0;
+}
+
+template <int BN>
+static int tc2_dispatch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B, int64_t ldb,
+                        const TcParams& p, int act, int dtype_out, bool residual, cudaStream_t s) {
+  if (residual) return tc2_launch<BN, DGTD_ACT_NONE, float, true>(A, lda, B, ldb, p, s);
+  if (dtype_out == DGTD_BF16) {
+    if (act == DGTD_ACT_GELU) return tc2_launch<BN, DGTD_ACT_GELU, __nv_bfloat16, false>(A, lda, B, ldb, p, s);
+    if (act == DGTD_ACT_RELU) return tc2_launch<BN, DGTD_ACT_RELU, __nv_bfloat16, false>(A, lda, B, ldb, p, s);
+    return tc2_launch<BN, DGTD_ACT_NONE, __nv_bfloat16, false>(A, lda, B, ldb, p, s);
+  }
+  if (act == DGTD_ACT_GELU) return tc2_launch<BN, DGTD_ACT_GELU, float, false>(A, lda, B, ldb, p, s);
+  if (act == DGTD_ACT_RELU) return tc2_launch<BN, DGTD_ACT_RELU, float, false>(A, lda, B, ldb, p, s);
+  return tc2_launch<BN, DGTD_ACT_NONE, float, false>(A, lda, B, ldb, p, s);
+}
+
+// Returns 0 launched, <0 error, 1 = shape not handled here (caller uses the 1-CTA kernel).
+int tc_gemm2_launch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B, int64_t ldb, TcParams p,
+                    int act, int dtype_out, bool residual, cudaStream_t s) {
+  if (p.N < 128 || p.M < 256) return 1;
+  const int64_t pair_tiles_256 = (int64_t)cdiv(p.M, 256) * cdiv(p.N, 256);
+  if (p.N % 256 == 0 && pair_tiles_256 >= sm_count() / 2)
+    return tc2_dispatch<256>(A, lda, B, ldb, p, act, dtype_out, residual, s);
+  return tc2_dispatch<128>(A, lda, B, ldb, p, act, dtype_out, residual, s);
+}
+
+}  // namespace dgtd

@@ -169,6 +169,123 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
   }
 }
 
+// Same epilogue with TMA-staged global I/O (used by the 2-CTA kernel, BN in {128, 256}).
+// Each warp owns two 4 KB staging tiles (32 rows x 128 B, 128B-swizzled) used alternately
+// (`sbuf` = running use count, persists across tiles).  Residual rows come in by TMA (the next
+// chunk is requested right after the current store is committed), results leave by TMA store:
+// full 128-byte lines instead of 32 scattered 16-byte accesses per instruction.
+// Invariant: before a staging tile is overwritten (by a TMA load or by the lanes) the store that
+// last read it -- two commits ago -- has finished reading: cp.async.bulk.wait_group.read 1.
+template <int BN, int ACT, typename OT, bool RESIDUAL, class Release>
+__device__ __forceinline__ void tc_epilogue_tile_tma(const TcParams& p, const CUtensorMap* tmOut,
+                                                     const CUtensorMap* tmRes, uint32_t tmem_tile, int quad,
+                                                     int half, int lane, int row0, int n_blk, uint8_t* stg,
+                                                     uint64_t* rbar, uint32_t& sbuf, Release release) {
+  constexpr int HALF_COLS = BN / 2;
+  constexpr int NCH = HALF_COLS / 32;
+  constexpr bool BF16_OUT = sizeof(OT) == 2;
+  static_assert(!(RESIDUAL && BF16_OUT), "residual epilogue writes fp32");
+  const int row = row0 + lane;
+  float ks = 1.f;
+  if (RESIDUAL && p.keep && row < p.M) ks = p.keep[row / p.rows_per_sample];
+  const uint32_t t0 = tmem_tile + ((uint32_t)(quad * 32) << 16) + half * HALF_COLS;
+  const int colbase = n_blk * BN + half * HALF_COLS;
+  const uint32_t swz = (uint32_t)(lane & 7);
+  uint32_t v[2][32];
+  bw::tmem_ld_32x32(t0, v[0]);
+  if (RESIDUAL && lane == 0) {
+    bw::tma_store_wait_read<1>();
+    bw::mbar_arrive_expect_tx(&rbar[sbuf & 1], 4096);
+    bw::tma_load_2d(tmRes, &rbar[sbuf & 1], stg + (sbuf & 1) * 4096, colbase, row0);
+  }
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const uint32_t b = sbuf & 1;
+    uint8_t* tile = stg + b * 4096;
+    const bool first_of_tile = !BF16_OUT || (c & 1) == 0;
+    const bool last_of_tile = !BF16_OUT || (c & 1) == 1;
+    bw::tmem_ld_wait();
+    if (c + 1 < NCH) bw::tmem_ld_32x32(t0 + (c + 1) * 32, v[(c + 1) & 1]);
+    if (c == NCH - 1) {
+      bw::tc_fence_before();
+      release();
+    }
+    if (RESIDUAL) {
+      bw::mbar_wait(&rbar[b], (sbuf >> 1) & 1);
+    } else if (first_of_tile) {
+      if (lane == 0) bw::tma_store_wait_read<1>();
+      __syncwarp();
+    }
+    const uint32_t(&vv)[32] = v[c & 1];
+    const int col0 = colbase + c * 32;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(vv[j + e]);
+      if (p.bias && col0 + j < p.N) {
+        float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+        float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j + 4));
+        f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+        f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+      }
+      // 16-byte chunk q of row `lane` lives at chunk (q ^ (lane & 7)) of the 128-byte row
+      if (RESIDUAL) {
+        float g[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+        if (p.gamma && col0 + j < p.N) {
+          float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + col0 + j));
+          float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + col0 + j + 4));
+          g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w;
+          g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+        }
+        float4* s0 = reinterpret_cast<float4*>(tile + lane * 128 + ((((uint32_t)(j >> 2)) ^ swz) << 4));
+        float4* s1 = reinterpret_cast<float4*>(tile + lane * 128 + ((((uint32_t)(j >> 2) + 1) ^ swz) << 4));
+        float4 r0 = *s0, r1 = *s1;
+        *s0 = make_float4(r0.x + ks * (g[0] * f[0]), r0.y + ks * (g[1] * f[1]), r0.z + ks * (g[2] * f[2]),
+                          r0.w + ks * (g[3] * f[3]));
+        *s1 = make_float4(r1.x + ks * (g[4] * f[4]), r1.y + ks * (g[5] * f[5]), r1.z + ks * (g[6] * f[6]),
+                          r1.w + ks * (g[7] * f[7]));
+      } else {
+        if (ACT == DGTD_ACT_GELU) {
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) gelu_fast2(f[e], f[e + 1]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = tc_act<ACT>(f[e]);
+        }
+        if (BF16_OUT) {   // 8 bf16 = one 16-byte chunk of the 64-column row
+          const uint32_t q = (uint32_t)((c & 1) * 4 + (j >> 3));
+          __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), bq = __floats2bfloat162_rn(f[2], f[3]);
+          __nv_bfloat162 cq = __floats2bfloat162_rn(f[4], f[5]), d = __floats2bfloat162_rn(f[6], f[7]);
+          uint4 u;
+          u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&bq);
+          u.z = *reinterpret_cast<uint32_t*>(&cq); u.w = *reinterpret_cast<uint32_t*>(&d);
+          *reinterpret_cast<uint4*>(tile + lane * 128 + ((q ^ swz) << 4)) = u;
+        } else {
+          *reinterpret_cast<float4*>(tile + lane * 128 + ((((uint32_t)(j >> 2)) ^ swz) << 4)) =
+              make_float4(f[0], f[1], f[2], f[3]);
+          *reinterpret_cast<float4*>(tile + lane * 128 + ((((uint32_t)(j >> 2) + 1) ^ swz) << 4)) =
+              make_float4(f[4], f[5], f[6], f[7]);
+        }
+      }
+    }
+    if (last_of_tile) {   // staging tile complete: hand it to the TMA store
+      bw::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        bw::tma_store_2d(tmOut, tile, BF16_OUT ? col0 - 32 : col0, row0);
+        bw::tma_store_commit();
+      }
+      ++sbuf;
+      if (RESIDUAL && c + 1 < NCH && lane == 0) {   // request the next residual chunk
+        bw::tma_store_wait_read<1>();
+        bw::mbar_arrive_expect_tx(&rbar[sbuf & 1], 4096);
+        bw::tma_load_2d(tmRes, &rbar[sbuf & 1], stg + (sbuf & 1) * 4096, colbase + (c + 1) * 32, row0);
+      }
+    }
+  }
+}
+
 int sm_count();
 // 2-CTA (cta_group::2) variant, tc_gemm2.cu; returns 1 when the shape is not handled there.
 int tc_gemm2_launch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B, int64_t ldb, TcParams p,

@@ -74,14 +74,16 @@ template <int BN>
 struct Tc2Cfg {
   static constexpr int BM = 128, BK = 64;                          // per CTA; the pair covers 256 rows
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = (BN / 2) * BK * 2;   // B: this CTA's half
-  static constexpr int STAGES = 6;
+  static constexpr int STAGES = BN >= 256 ? 5 : 6;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 + 1024;
+  static constexpr int STG_BYTES = 8 * 2 * 4096;   // 8 epilogue warps x 2 staging tiles of 4 KB
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + STG_BYTES + 512 + 1024;
 };
 
 template <int BN, int ACT, typename OT, bool RESIDUAL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                 const TcParams p) {
   using Cfg = Tc2Cfg<BN>;
   constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
@@ -90,7 +92,9 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES));
+  uint8_t* sStg = smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES);   // epilogue staging, 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + Cfg::STG_BYTES);
+  uint64_t* rbars = bars + 2 * STAGES + 6;   // [8 warps][2] residual-tile barriers
   uint64_t* full = bars;                     // used on the leader only
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
@@ -118,6 +122,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       bw::mbar_init(&tfull[i], 1);
       bw::mbar_init(&tempty[i], 512);  // 8 epilogue warps x 2 CTAs
     }
+    for (int i = 0; i < 16; ++i) bw::mbar_init(&rbars[i], 1);
     bw::fence_mbar_init();
   }
   if (warp == 2) bw2::tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
@@ -175,6 +180,9 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs, own 128 TMEM lanes) =====================
     const int quad = warp & 3, half = (warp - 4) >> 2;
+    uint8_t* stg = sStg + (warp - 4) * 8192;
+    uint64_t* rbar = rbars + (warp - 4) * 2;
+    uint32_t sbuf = 0;
     int iter = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++iter) {
       const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
@@ -183,10 +191,11 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       bw::mbar_wait(&tfull[as], aphase);
       bw::tc_fence_after();
       const uint32_t rel = bw2::map_to_rank(&tempty[as], 0);
-      tc_epilogue_tile<BN, ACT, OT, RESIDUAL>(p, tmem_base + as * BN, quad, half, lane,
-                                              m_blk * 256 + (int)rank * BM + quad * 32 + lane, n_blk,
-                                              [rel] { bw2::mbar_arrive_cluster(rel); });
+      tc_epilogue_tile_tma<BN, ACT, OT, RESIDUAL>(p, &tmOut, &tmRes, tmem_base + as * BN, quad, half, lane,
+                                                  m_blk * 256 + (int)rank * BM + quad * 32, n_blk, stg, rbar,
+                                                  sbuf, [rel] { bw2::mbar_arrive_cluster(rel); });
     }
+    if (lane == 0) bw::tma_store_wait_all<0>();   // all results are in global memory before exit
   }
 
   // nobody leaves (or frees TMEM) while the peer may still signal our barriers / read our smem
@@ -225,12 +234,27 @@ static int tc2_launch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* 
     int rc = make_tmap(&tmB, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
+  CUtensorMap tmOut, tmRes;
+  {
+    constexpr bool BF = sizeof(OT) == 2;
+    uint64_t dims[2] = {(uint64_t)p.N, (uint64_t)p.M}, str[1] = {(uint64_t)p.ldo * sizeof(OT)};
+    uint32_t box[2] = {BF ? 64u : 32u, 32u};
+    int rc = make_tmap(&tmOut, p.out, BF ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                       dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    tmRes = tmOut;
+    if (RESIDUAL) {
+      rc = make_tmap(&tmRes, p.residual, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, str, box,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
+  }
   p.tiles_m = cdiv(p.M, 256);
   p.tiles_n = cdiv(p.N, BN);
   int tiles = p.tiles_m * p.tiles_n;
   int pairs = sm_count() / 2;
   int clusters = tiles < pairs ? tiles : pairs;
-  kern<<<2 * clusters, 384, Cfg::SMEM_BYTES, s>>>(tmA, tmB, p);
+  kern<<<2 * clusters, 384, Cfg::SMEM_BYTES, s>>>(tmA, tmB, tmOut, tmRes, p);
   return 0;
 }
 
@@ -252,6 +276,10 @@ static int tc2_dispatch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16
 int tc_gemm2_launch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B, int64_t ldb, TcParams p,
                     int act, int dtype_out, bool residual, cudaStream_t s) {
   if (p.N < 128 || p.M < 256) return 1;
+  const size_t esz = dtype_out == DGTD_BF16 ? 2 : 4;
+  if ((p.ldo * esz) % 16 || (reinterpret_cast<uintptr_t>(p.out) & 15) ||
+      (residual && (reinterpret_cast<uintptr_t>(p.residual) & 15)))
+    return 1;   // TMA store needs 16-byte aligned rows
   const int64_t pair_tiles_256 = (int64_t)cdiv(p.M, 256) * cdiv(p.N, 256);
   if (p.N % 256 == 0 && pair_tiles_256 >= sm_count() / 2)
     return tc2_dispatch<256>(A, lda, B, ldb, p, act, dtype_out, residual, s);

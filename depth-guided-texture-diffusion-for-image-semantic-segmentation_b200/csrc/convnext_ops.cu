@@ -292,6 +292,10 @@ __global__ void resize_nhwc_kernel(const IT* __restrict__ x, OT* __restrict__ ou
 
 }  // namespace dgtd
 
+namespace dgtd {
+int dwconv7_ln_tma(const float* x, const float* wT, const float* dw_b, const float* ln_w, const float* ln_b,
+                   float* ws, void* out, int out_dtype, int B, int h, int w, int C, float eps, cudaStream_t s);
+}
 using namespace dgtd;
 
 extern "C" {
@@ -380,6 +384,22 @@ int dgtd_dwconv7_ln_fwd(const float* x, const float* dw_w, const float* dw_b, co
                : dwconv_launch(x, dw_w, dw_b, ln_w, ln_b, (float*)out, B, h, w, C, eps, (cudaStream_t)stream);
   if (rc) return rc;
   DGTD_LAUNCH_CHECK("dwconv7_ln");
+  return 0;
+}
+
+int dgtd_dwconv7_ln_tma_fwd(const float* x, const float* dw_wT, const float* dw_b, const float* ln_w,
+                            const float* ln_b, float* ws, void* out, int out_dtype, int B, int h, int w,
+                            int C, float eps, dgtd_stream_t stream) {
+  DGTD_CHECK_ARG(x && dw_wT && dw_b && ln_w && ln_b && ws && out, "dwconv7_ln_tma: null pointer");
+  DGTD_CHECK_ARG(B > 0 && h > 0 && w > 0 && C >= 128 && C % 128 == 0 && C <= 1024,
+                 "dwconv7_ln_tma: bad shape B=%d h=%d w=%d C=%d (C must be a multiple of 128)", B, h, w, C);
+  int rc = dwconv7_ln_tma(x, dw_wT, dw_b, ln_w, ln_b, ws, out, out_dtype, B, h, w, C, eps, (cudaStream_t)stream);
+  if (rc > 0) {
+    set_error("dwconv7_ln_tma: shape not supported by the TMA variant");
+    return -1;
+  }
+  if (rc) return rc;
+  DGTD_LAUNCH_CHECK("dwconv7_ln_tma.ln");
   return 0;
 }
 

@@ -1,0 +1,213 @@
+// a8 (cod.py:1106-1108), large-batch path: depthwise 7x7 on NHWC fp32 with TMA-staged halo
+// tiles, followed by a row LayerNorm kernel.
+//
+// K1 dwconv7_tma_kernel: CTA = (4*SY x 8*SX) output pixels x 128 channels.  The (TH+6)x(TW+6)
+//    halo tile of one 32-channel chunk (128 B per pixel) is fetched by ONE 4-D TMA box load
+//    (zero fill outside the image == conv padding), double buffered across the 4 chunks.
+//    warp = one 4x8 pixel sub-tile, lane = channel: 49 taps + 32 accumulators in registers, every
+//    input row is read once from shared memory (conflict-free 128 B per warp) and feeds up to
+//    4 output rows x 7 taps (LDS : FMA = 1 : 11).  Writes y (pre-norm) fp32, coalesced.
+// K2 ln_rows_kernel: one warp per pixel, two-pass statistics in registers, writes bf16 / fp32.
+//    y is consumed straight out of L2 for the 24x24 and 12x12 stages (75 MB / 19 MB at B=64).
+#include "blackwell.cuh"
+#include "common.cuh"
+
+namespace dgtd {
+
+template <int SY, int SX>
+__global__ void __launch_bounds__(SY * SX * 32, 2)
+dwconv7_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ wT,
+                   const float* __restrict__ bias, float* __restrict__ y, int h, int w, int C,
+                   int tiles_x, int tiles_y) {
+  constexpr int TH = 4 * SY, TW = 8 * SX, PH = TH + 6, PW = TW + 6, NCH = 4;
+  constexpr int TILE_FLOATS = PH * PW * 32;
+  constexpr uint32_t TILE_BYTES = TILE_FLOATS * 4;
+  extern __shared__ uint8_t smem_raw[];
+  float* xs = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  __shared__ uint64_t bar[2];
+
+  int bid = blockIdx.x;
+  const int cgs = C >> 7;
+  const int cg = bid % cgs; bid /= cgs;
+  const int tx = bid % tiles_x; bid /= tiles_x;
+  const int ty = bid % tiles_y;
+  const int b = bid / tiles_y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sy = warp / SX, sx = warp - sy * SX;
+  const int x0 = tx * TW, y0 = ty * TH;
+
+  if (threadIdx.x == 0) {
+    bw::prefetch_tmap(&tmX);
+    bw::mbar_init(&bar[0], 1);
+    bw::mbar_init(&bar[1], 1);
+    bw::fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    bw::mbar_arrive_expect_tx(&bar[0], TILE_BYTES);
+    bw::tma_load_4d(&tmX, &bar[0], xs, cg * 128, x0 - 3, y0 - 3, b);
+  }
+
+#pragma unroll 1
+  for (int i = 0; i < NCH; ++i) {
+    const int c = cg * 128 + i * 32 + lane;
+    if (threadIdx.x == 0 && i + 1 < NCH) {   // buffer (i+1)&1 was released by the barrier below
+      bw::fence_proxy_async_smem();
+      bw::mbar_arrive_expect_tx(&bar[(i + 1) & 1], TILE_BYTES);
+      bw::tma_load_4d(&tmX, &bar[(i + 1) & 1], xs + ((i + 1) & 1) * TILE_FLOATS, cg * 128 + (i + 1) * 32, x0 - 3,
+                      y0 - 3, b);
+    }
+    float wr[49];
+#pragma unroll
+    for (int k = 0; k < 49; ++k) wr[k] = __ldg(wT + (int64_t)k * C + c);
+    const float bc = __ldg(bias + c);
+    float acc[4][8];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[a][j] = bc;
+
+    bw::mbar_wait(&bar[i & 1], (i >> 1) & 1);
+    const float* base = xs + (i & 1) * TILE_FLOATS + ((4 * sy) * PW + 8 * sx) * 32 + lane;
+#pragma unroll
+    for (int iy = 0; iy < 10; ++iy) {
+      float in[14];
+#pragma unroll
+      for (int j = 0; j < 14; ++j) in[j] = base[(iy * PW + j) * 32];
+#pragma unroll
+      for (int oy = 0; oy < 4; ++oy) {
+        const int ky = iy - oy;
+        if (ky < 0 || ky >= 7) continue;
+#pragma unroll
+        for (int ox = 0; ox < 8; ++ox)
+#pragma unroll
+          for (int kx = 0; kx < 7; ++kx) acc[oy][ox] = fmaf(wr[ky * 7 + kx], in[ox + kx], acc[oy][ox]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int oy = y0 + 4 * sy + a;
+      if (oy >= h) continue;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int ox = x0 + 8 * sx + j;
+        if (ox < w) y[(((int64_t)b * h + oy) * w + ox) * C + c] = acc[a][j];
+      }
+    }
+    __syncthreads();   // every warp is done with buffer i&1 before it is refilled
+  }
+}
+
+template <typename OT, int VPL>
+__global__ void __launch_bounds__(256)
+ln_rows_kernel(const float* __restrict__ y, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+               OT* __restrict__ out, int64_t rows, int C, float eps) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* p = y + row * C;
+  float4 v[VPL];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    v[j] = *reinterpret_cast<const float4*>(p + (j * 32 + lane) * 4);
+    s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / C + eps);
+  OT* o = out + row * C;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int c0 = (j * 32 + lane) * 4;
+    float4 g = *reinterpret_cast<const float4*>(ln_w + c0), be = *reinterpret_cast<const float4*>(ln_b + c0);
+    store4(o + c0, (v[j].x - mean) * rstd * g.x + be.x, (v[j].y - mean) * rstd * g.y + be.y,
+           (v[j].z - mean) * rstd * g.z + be.z, (v[j].w - mean) * rstd * g.w + be.w);
+  }
+}
+
+template <int SY, int SX>
+static int dw_launch(const CUtensorMap& tm, const float* wT, const float* bias, float* y, int B, int h, int w,
+                     int C, cudaStream_t s) {
+  constexpr int PH = 4 * SY + 6, PW = 8 * SX + 6;
+  constexpr int SMEM = 2 * PH * PW * 128 + 128;
+  auto kern = dwconv7_tma_kernel<SY, SX>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) {
+      set_error("dwconv7_tma: cannot opt in to %d B smem: %s", SMEM, cudaGetErrorString(e));
+      return -2;
+    }
+    configured = true;
+  }
+  const int tiles_x = cdiv(w, 8 * SX), tiles_y = cdiv(h, 4 * SY);
+  const int64_t blocks = (int64_t)B * tiles_x * tiles_y * (C / 128);
+  kern<<<(unsigned)blocks, SY * SX * 32, SMEM, s>>>(tm, wT, bias, y, h, w, C, tiles_x, tiles_y);
+  return 0;
+}
+
+template <typename OT>
+static int ln_rows_launch(const float* y, const float* ln_w, const float* ln_b, OT* out, int64_t rows, int C,
+                          float eps, cudaStream_t s) {
+  const int blocks = cdiv(rows, 8);
+  switch (C / 128) {
+    case 1: ln_rows_kernel<OT, 1><<<blocks, 256, 0, s>>>(y, ln_w, ln_b, out, rows, C, eps); break;
+    case 2: ln_rows_kernel<OT, 2><<<blocks, 256, 0, s>>>(y, ln_w, ln_b, out, rows, C, eps); break;
+    case 4: ln_rows_kernel<OT, 4><<<blocks, 256, 0, s>>>(y, ln_w, ln_b, out, rows, C, eps); break;
+    case 8: ln_rows_kernel<OT, 8><<<blocks, 256, 0, s>>>(y, ln_w, ln_b, out, rows, C, eps); break;
+    default:
+      set_error("dwconv7_ln(tma): C=%d must be 128*{1,2,4,8}", C);
+      return -1;
+  }
+  return 0;
+}
+
+// Two launches: TMA depthwise conv into `ws` (B*h*w*C fp32), then LayerNorm rows -> out.
+// wT: depthwise taps transposed to (49, C).  Returns 1 when the shape is not handled here.
+int dwconv7_ln_tma(const float* x, const float* wT, const float* dw_b, const float* ln_w, const float* ln_b,
+                   float* ws, void* out, int out_dtype, int B, int h, int w, int C, float eps, cudaStream_t s) {
+  if (C % 128 || C > 1024 || (reinterpret_cast<uintptr_t>(x) & 15)) return 1;
+  const int SX = (w % 24 == 0 && w % 16 != 0) ? 3 : 2;                 // 24-wide maps: 8x24 tiles
+  const int SY = (h % 8 == 0 || h > 12) ? 2 : 3;                       // 12-high maps: 12x16 tiles
+  CUtensorMap tm;
+  {
+    PFN_tmapEncodeTiled enc = get_tmap_encoder();
+    if (!enc) return -3;
+    cuuint64_t gd[4] = {(cuuint64_t)C, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
+    cuuint64_t gs[3] = {(cuuint64_t)C * 4, (cuuint64_t)w * C * 4, (cuuint64_t)h * w * C * 4};
+    cuuint32_t bx[4] = {32, (cuuint32_t)(8 * SX + 6), (cuuint32_t)(4 * SY + 6), 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), gd, gs, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("dwconv7_ln(tma): cuTensorMapEncodeTiled failed (%d) for x (%d,%d,%d,%d)", (int)r, B, h, w, C);
+      return -3;
+    }
+  }
+  int rc;
+  if (SY == 2 && SX == 2) rc = dw_launch<2, 2>(tm, wT, dw_b, ws, B, h, w, C, s);
+  else if (SY == 2 && SX == 3) rc = dw_launch<2, 3>(tm, wT, dw_b, ws, B, h, w, C, s);
+  else if (SY == 3 && SX == 2) rc = dw_launch<3, 2>(tm, wT, dw_b, ws, B, h, w, C, s);
+  else rc = dw_launch<3, 3>(tm, wT, dw_b, ws, B, h, w, C, s);
+  if (rc) return rc;
+  {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_error("dwconv7_tma: launch failed: %s", cudaGetErrorString(e));
+      return -2;
+    }
+    count_launch();
+  }
+  const int64_t rows = (int64_t)B * h * w;
+  return out_dtype == DGTD_BF16 ? ln_rows_launch(ws, ln_w, ln_b, (__nv_bfloat16*)out, rows, C, eps, s)
+                                : ln_rows_launch(ws, ln_w, ln_b, (float*)out, rows, C, eps, s);
+}
+
+}  // namespace dgtd

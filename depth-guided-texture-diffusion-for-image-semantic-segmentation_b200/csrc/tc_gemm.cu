@@ -239,6 +239,10 @@ int tc_linear(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B, int64
               void* out, int M, int N, int K, int64_t ldo, int dtype_out, int act, cudaStream_t s) {
   TcParams p{};
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.ldo = ldo; p.rows_per_sample = 1;
+  {
+    int rc2 = tc_gemm2_launch(A, lda, B, ldb, p, act, dtype_out, false, s);
+    if (rc2 <= 0) return rc2;
+  }
   if (dtype_out == DGTD_BF16) {
     if (act == DGTD_ACT_GELU) return tc_dispatch_bn<DGTD_ACT_GELU, __nv_bfloat16, false>(A, lda, B, ldb, p, s);
     if (act == DGTD_ACT_RELU) return tc_dispatch_bn<DGTD_ACT_RELU, __nv_bfloat16, false>(A, lda, B, ldb, p, s);

@@ -72,6 +72,18 @@ def _packed(module: nn.Module) -> _Packed:
     return pk
 
 
+_SCRATCH: Dict[torch.device, torch.Tensor] = {}
+
+
+def _scratch(device: torch.device, numel: int) -> torch.Tensor:
+    """Per-device fp32 scratch reused by every block (stream-ordered: producer and consumer of the
+    scratch are consecutive launches of the same call)."""
+    buf = _SCRATCH.get(device)
+    if buf is None or buf.numel() < numel:
+        buf = _SCRATCH[device] = torch.empty(numel, device=device, dtype=torch.float32)
+    return buf
+
+
 def _as(t: torch.Tensor, mode: int) -> torch.Tensor:
     return t.detach().to(torch.bfloat16).contiguous() if mode == BF16 else t.detach().float().contiguous()
 
@@ -158,8 +170,15 @@ class convnext_Block(nn.Module):
         dw_w = pk.get("dw", [self.dwconv.weight], lambda: self.dwconv.weight.detach().reshape(C, 49).float().contiguous())
         w1 = pk.get(f"w1.{mode}", [self.pwconv1.weight], lambda: _as(self.pwconv1.weight, mode))
         w2 = pk.get(f"w2.{mode}", [self.pwconv2.weight], lambda: _as(self.pwconv2.weight, mode))
-        a = OP.dwconv7_ln(x, dw_w, self.dwconv.bias.detach(), self.norm.weight.detach(),
-                          self.norm.bias.detach(), mode, self.norm.eps)
+        if C % 128 == 0 and B * h * w >= 2048:   # TMA-staged conv + row LayerNorm (large maps)
+            dw_wT = pk.get("dwT", [self.dwconv.weight],
+                           lambda: self.dwconv.weight.detach().reshape(C, 49).t().float().contiguous())
+            ws = _scratch(x.device, x.numel())
+            a = OP.dwconv7_ln_tma(x, dw_wT, self.dwconv.bias.detach(), self.norm.weight.detach(),
+                                  self.norm.bias.detach(), mode, ws, self.norm.eps)
+        else:
+            a = OP.dwconv7_ln(x, dw_w, self.dwconv.bias.detach(), self.norm.weight.detach(),
+                              self.norm.bias.detach(), mode, self.norm.eps)
         hid = OP.linear(a.view(-1, C), w1, self.pwconv1.bias.detach(), act=ACT_GELU)
         keep = self.drop_path.keep_scale(B, x.device) if isinstance(self.drop_path, DropPath) else None
         gamma = self.gamma.detach() if self.gamma is not None else None

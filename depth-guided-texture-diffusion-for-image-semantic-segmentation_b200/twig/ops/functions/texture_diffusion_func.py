@@ -20,7 +20,7 @@ from ..capi import ACT_GELU, ACT_NONE, ACT_RELU, BF16, F32, call, check_cuda, pt
 __all__ = [
     "surface_normals", "HighpassPlan", "fft_highpass", "diffusion_front", "MessagePassingFunction",
     "message_passing_core", "message_passing_tiled", "conv1x1_nchw", "resize_nchw", "layer_norm",
-    "stem", "ln_patchify", "dwconv7_ln", "linear", "linear_residual_", "fusion_head", "conv_nhwc", "conv_nhwc_grouped",
+    "stem", "ln_patchify", "dwconv7_ln", "dwconv7_ln_tma", "linear", "linear_residual_", "fusion_head", "conv_nhwc", "conv_nhwc_grouped",
     "resize_nhwc", "cast", "nhwc_to_nchw", "nchw_to_nhwc", "enable_gemm_profile", "collect_gemm_profile",
 ]
 
@@ -241,6 +241,18 @@ def dwconv7_ln(x: torch.Tensor, dw_w, dw_b, ln_w, ln_b, out_dtype: int, eps: flo
     out = torch.empty(B, h, w, C, device=x.device, dtype=_tdtype(out_dtype))
     call("dgtd_dwconv7_ln_fwd", ptr(x), ptr(dw_w), ptr(dw_b), ptr(ln_w), ptr(ln_b), ptr(out), out_dtype, B, h,
          w, C, float(eps), stream())
+    return out
+
+
+def dwconv7_ln_tma(x: torch.Tensor, dw_wT, dw_b, ln_w, ln_b, out_dtype: int, ws: torch.Tensor,
+                   eps: float = 1e-6) -> torch.Tensor:
+    """TMA-staged variant for large maps: dw_wT is (49, C); ws is a (B,h,w,C) fp32 scratch."""
+    check_cuda(x, dw_wT, dw_b, ln_w, ln_b, ws)
+    B, h, w, C = x.shape
+    assert ws.numel() >= x.numel() and ws.dtype == torch.float32
+    out = torch.empty(B, h, w, C, device=x.device, dtype=_tdtype(out_dtype))
+    call("dgtd_dwconv7_ln_tma_fwd", ptr(x), ptr(dw_wT), ptr(dw_b), ptr(ln_w), ptr(ln_b), ptr(ws), ptr(out),
+         out_dtype, B, h, w, C, float(eps), stream())
     return out
 
 

@@ -122,6 +122,12 @@ int dgtd_ln_patchify_fwd(const float* x, const float* ln_w, const float* ln_b, v
 int dgtd_dwconv7_ln_fwd(const float* x, const float* dw_w, const float* dw_b, const float* ln_w,
                         const float* ln_b, void* out, int out_dtype, int B, int h, int w, int C,
                         float eps, dgtd_stream_t stream);
+/* Same operator, large-batch variant: TMA-staged halo tiles (4-D box loads, zero fill = padding)
+ * + a row LayerNorm pass.  dw_wT = taps transposed to (49, C); ws = B*h*w*C fp32 scratch for the
+ * pre-norm conv output.  C must be a multiple of 128. */
+int dgtd_dwconv7_ln_tma_fwd(const float* x, const float* dw_wT, const float* dw_b, const float* ln_w,
+                            const float* ln_b, float* ws, void* out, int out_dtype, int B, int h, int w,
+                            int C, float eps, dgtd_stream_t stream);
 /* out[M,N] = act(a[M,K] . w[N,K]^T + bias): pwconv1+GELU (:1109-1110), downsample conv
  * (:1134), head 1x1 convs (:1160,1174).  a/w dtype = dtype_in (fp32: CUDA-core exact path,
  * bf16: tcgen05), out dtype = dtype_out, ldo = row stride of out in elements. */

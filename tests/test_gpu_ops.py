@@ -184,6 +184,22 @@ def test_dwconv7_ln(OP, C, h, w):
     check(got, ref, 1e-5)
 
 
+@pytest.mark.parametrize("C,h,w,B", [(128, 96, 96, 1), (128, 20, 28, 2), (256, 48, 48, 1), (512, 24, 24, 2),
+                                     (512, 22, 22, 1), (1024, 12, 12, 3), (1024, 11, 11, 2)])
+def test_dwconv7_ln_tma_variant(OP, C, h, w, B):
+    from dgtd_b200.twig.ops.capi import F32
+    g = torch.Generator().manual_seed(18)
+    x = torch.randn(B, C, h, w, generator=g)
+    dw, db = torch.randn(C, 1, 7, 7, generator=g) * 0.2, torch.randn(C, generator=g) * 0.1
+    lw, lb = 1 + 0.2 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    y = F.conv2d(x.double(), dw.double(), db.double(), padding=3, groups=C).permute(0, 2, 3, 1)
+    ref = O.layer_norm_channels_last(y, lw.double(), lb.double())
+    xn = x.permute(0, 2, 3, 1).contiguous().cuda()
+    ws = torch.empty(xn.numel(), device="cuda")
+    got = OP.dwconv7_ln_tma(xn, dw.reshape(C, 49).t().contiguous().cuda(), db.cuda(), lw.cuda(), lb.cuda(), F32, ws)
+    check(got, ref, 1e-5)
+
+
 @pytest.mark.parametrize("M,N,K,act", [(300, 128, 64, 0), (257, 24, 128, 1), (128, 320, 216, 2), (1000, 512, 2048, 1)])
 def test_linear_fp32_exact_path(OP, M, N, K, act):
     g = torch.Generator().manual_seed(9)

@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample", type=int, default=2, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-diffusion", action="store_true")
     return ap.parse_args()
 
 
@@ -85,6 +86,39 @@ class ClockSampler:
                                                           for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
+
+
+def diffusion_microbench(OP, dev, peaks, C=256, S=1024, steps=(1, 2, 4, 8)):
+    """MessagePassing core (cod.py:1190-1205), shared weights, fp32 NHWC; one kernel per step.
+    Algorithmic bytes are T-independent when steps are fused; this kernel runs one pass per step,
+    so both the per-step GB/s (what the kernel achieves) and the T-step roofline fraction are given."""
+    g = torch.Generator("cpu").manual_seed(0)
+    x = torch.randn(1, S, S, C, generator=g).to(dev)
+    wgt = torch.rand(1, 49, S, S, generator=g).to(dev)
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    fma_roof = 148 * 128 * 2 * 1.965e9
+    step_bytes = (2 * C + 49) * S * S * 4
+    out = {"shape": [1, C, S, S], "k": 7, "dtype": "f32", "layout": "NHWC", "weights": "shared (wc=1)",
+           "alg_bytes_per_step": step_bytes, "hbm_peak_gbs": hbm, "sweep": []}
+    for T in steps:
+        for _ in range(2):
+            OP.message_passing_tiled(x, wgt, T)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        reps = 3
+        a.record()
+        for _ in range(reps):
+            OP.message_passing_tiled(x, wgt, T)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        flops = 2.0 * 49 * C * S * S * T
+        bound_ms = max(step_bytes / (hbm * 1e9), flops / fma_roof) * 1e3     # fused-T roofline (SURVEY 8d)
+        out["sweep"].append({"T": T, "ms": ms, "gbs_per_step": step_bytes * T / (ms * 1e-3) / 1e9,
+                             "tflops": flops / (ms * 1e-3) / 1e12, "roofline_ms": bound_ms,
+                             "frac_of_roofline": bound_ms / ms})
+    out["hbm_frac_T1"] = out["sweep"][0]["gbs_per_step"] / hbm
+    return out
 
 
 def cpu_model() -> str:
@@ -240,6 +274,11 @@ def run_ours(args):
                     "launches_timed": n, "avg_launch_ms": ms / max(n, 1),
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"}
 
+    # ---- diffusion microbench (BASELINE configs[3]): MessagePassing core, 1024^2 x 256, shared weights
+    diff = None
+    if rank == 0 and not args.no_diffusion:
+        diff = diffusion_microbench(OP, dev, peaks if rank == 0 else {})
+
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         rate, dt, cores = cpu_reference_rate(S, args.cpu_sample, 3, 1)
@@ -257,7 +296,7 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "result": "stage-4 prompt tokens of the last block (B,144,512) fp32"},
             "gpu_launches": int(launches), "clocks": clocks.summary(),
-            "roofline": roof, "cpu_baseline": cpu,
+            "roofline": roof, "cpu_baseline": cpu, "diffusion_microbench": diff,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

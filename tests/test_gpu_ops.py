@@ -91,6 +91,17 @@ def test_message_passing_is_linear_and_mass_conserving(OP):
     assert float((ones[:, :, 9:-9, 9:-9] - 1.0).abs().max()) < 1e-4
 
 
+@pytest.mark.parametrize("n,h,w,c,T", [(1, 40, 70, 64, 1), (2, 17, 33, 32, 3), (1, 64, 64, 256, 2)])
+def test_message_passing_tiled_large_map_variant(OP, n, h, w, c, T):
+    """Halo-tiled TMA kernel (shared weights, NHWC) == the reference operator semantics."""
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(n, c, h, w, generator=g)
+    wgt = torch.rand(n, 49, h, w, generator=g)
+    ref = O.message_passing_core(x.double(), wgt.double(), 7, T)
+    got = OP.message_passing_tiled(x.permute(0, 2, 3, 1).contiguous().cuda(), wgt.cuda(), T)
+    check(got.permute(0, 3, 1, 2), ref, 1e-5)
+
+
 def test_message_passing_module_bilinear_upsample(OP, golden_ops):
     tag = "mp24"
     core = OP.message_passing_core(dev(golden_ops[f"{tag}_x"]), dev(golden_ops[f"{tag}_w"]), 4)

@@ -224,11 +224,9 @@ def run_ours(args):
             b.record()
         barrier()
     launches = capi.launch_count() - n0
+    from dgtd_b200.twig import sharding
     t_dev = sum(a.elapsed_time(b) for a, b in ev) / 1e3
-    tt = torch.tensor([t_dev], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_max = float(tt.item())
+    t_max = sharding.max_over_ranks(t_dev, dev)                     # device time, max over ranks
     value = world * B * args.steps / t_max
 
     # ---- end to end: pinned host inputs -> H2D -> path -> D2H of the result ---------------------
@@ -245,10 +243,7 @@ def run_ours(args):
         res_h.copy_(toks[3][2].float(), non_blocking=True)
     t1.record()
     barrier()
-    te = torch.tensor([t0.elapsed_time(t1) / 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e = world * B * e2e_steps / float(te.item())
+    e2e = world * B * e2e_steps / sharding.max_over_ranks(t0.elapsed_time(t1) / 1e3, dev)
     h2d = image_h.numel() * 4 + depth_h.numel() * 4
     d2h = res_h.numel() * 4
 

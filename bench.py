@@ -187,6 +187,7 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback on the product path)"
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     B, S = args.batch, args.size

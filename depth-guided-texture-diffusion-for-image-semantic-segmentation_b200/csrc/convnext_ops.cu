@@ -10,75 +10,84 @@ namespace dgtd {
 // CTA = 16 consecutive output pixels of one output row; thread = output channel.
 constexpr int STEM_PX = 16;
 
+constexpr int STEM_TILES_PER_CTA = 12;
+
 __global__ void __launch_bounds__(256)
 stem_kernel(const float* __restrict__ image, const float* __restrict__ grid, int G,
             const float* __restrict__ w, const float* __restrict__ bias,
             const float* __restrict__ ln_w, const float* __restrict__ ln_b, float* __restrict__ out,
-            int H, int W, int oh, int ow, int Cout, float eps) {
+            int H, int W, int oh, int ow, int Cout, float eps, int total_tiles) {
   extern __shared__ float sm[];
   float* in = sm;                    // [STEM_PX][48]
   float* ys = sm + STEM_PX * 48;     // [STEM_PX][Cout]
   const int tiles_x = (ow + STEM_PX - 1) / STEM_PX;
-  const int tx = blockIdx.x % tiles_x, oy = blockIdx.x / tiles_x, b = blockIdx.y;
-  const int ox0 = tx * STEM_PX;
   const int c = threadIdx.x;
-
-  // gather the 4 x (4*STEM_PX) x 3 input patch, adding the up-sampled diffusion result
-  for (int e = threadIdx.x; e < 3 * 4 * 4 * STEM_PX; e += blockDim.x) {
-    int ci = e / (16 * STEM_PX), r = e - ci * 16 * STEM_PX;
-    int ky = r / (4 * STEM_PX), j = r - ky * 4 * STEM_PX;
-    int px = j >> 2, kx = j & 3;
-    int iy = oy * 4 + ky, ix = ox0 * 4 + j;
-    float v = 0.f;
-    if (ox0 + px < ow) {
-      v = image[(((int64_t)b * 3 + ci) * H + iy) * W + ix];
-      if (grid) {
-        int y0, y1, x0, x1;
-        float ly, lx;
-        bilinear_src(iy, (float)G / H, G, y0, y1, ly);
-        bilinear_src(ix, (float)G / W, G, x0, x1, lx);
-        const float* g = grid + ((int64_t)b * 3 + ci) * G * G;
-        v += (1.f - ly) * ((1.f - lx) * g[y0 * G + x0] + lx * g[y0 * G + x1]) +
-             ly * ((1.f - lx) * g[y1 * G + x0] + lx * g[y1 * G + x1]);
-      }
-    }
-    in[px * 48 + ci * 16 + ky * 4 + kx] = v;
-  }
   float wr[48];
 #pragma unroll
   for (int k = 0; k < 48; ++k) wr[k] = w[(int64_t)c * 48 + k];
   const float bc = bias[c];
-  __syncthreads();
-#pragma unroll 4
-  for (int px = 0; px < STEM_PX; ++px) {
-    float acc = bc;
-#pragma unroll
-    for (int k4 = 0; k4 < 12; ++k4) {
-      float4 v = *reinterpret_cast<const float4*>(&in[px * 48 + k4 * 4]);
-      acc = fmaf(wr[k4 * 4 + 0], v.x, acc);
-      acc = fmaf(wr[k4 * 4 + 1], v.y, acc);
-      acc = fmaf(wr[k4 * 4 + 2], v.z, acc);
-      acc = fmaf(wr[k4 * 4 + 3], v.w, acc);
-    }
-    ys[px * Cout + c] = acc;
-  }
-  __syncthreads();
-  // LayerNorm(channels_first) == per-pixel LN over channels (cod.py:1045-1048)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int px = wid; px < STEM_PX; px += nw) {
-    if (ox0 + px >= ow) continue;
-    float s = 0.f;
-    for (int cc = lane; cc < Cout; cc += 32) s += ys[px * Cout + cc];
-    float mean = warp_sum(s) / Cout;
-    float q = 0.f;
-    for (int cc = lane; cc < Cout; cc += 32) {
-      float d = ys[px * Cout + cc] - mean;
-      q = fmaf(d, d, q);
+
+  for (int it = 0; it < STEM_TILES_PER_CTA; ++it) {
+    int tile = blockIdx.x * STEM_TILES_PER_CTA + it;
+    if (tile >= total_tiles) break;               // block-uniform
+    const int tx = tile % tiles_x;
+    tile /= tiles_x;
+    const int oy = tile % oh, b = tile / oh;
+    const int ox0 = tx * STEM_PX;
+    // gather the 4 x (4*STEM_PX) x 3 input patch, adding the up-sampled diffusion result
+    for (int e = threadIdx.x; e < 3 * 4 * 4 * STEM_PX; e += blockDim.x) {
+      int ci = e / (16 * STEM_PX), r = e - ci * 16 * STEM_PX;
+      int ky = r / (4 * STEM_PX), j = r - ky * 4 * STEM_PX;
+      int px = j >> 2, kx = j & 3;
+      int iy = oy * 4 + ky, ix = ox0 * 4 + j;
+      float v = 0.f;
+      if (ox0 + px < ow) {
+        v = image[(((int64_t)b * 3 + ci) * H + iy) * W + ix];
+        if (grid) {
+          int y0, y1, x0, x1;
+          float ly, lx;
+          bilinear_src(iy, (float)G / H, G, y0, y1, ly);
+          bilinear_src(ix, (float)G / W, G, x0, x1, lx);
+          const float* g = grid + ((int64_t)b * 3 + ci) * G * G;
+          v += (1.f - ly) * ((1.f - lx) * g[y0 * G + x0] + lx * g[y0 * G + x1]) +
+               ly * ((1.f - lx) * g[y1 * G + x0] + lx * g[y1 * G + x1]);
+        }
+      }
+      in[px * 48 + ci * 16 + ky * 4 + kx] = v;
     }
-    float rstd = 1.0f / sqrtf(warp_sum(q) / Cout + eps);
-    float* o = out + (((int64_t)b * oh + oy) * ow + ox0 + px) * Cout;
-    for (int cc = lane; cc < Cout; cc += 32)
-      o[cc] = (ys[px * Cout + cc] - mean) * rstd * ln_w[cc] + ln_b[cc];
+    __syncthreads();
+#pragma unroll 4
+    for (int px = 0; px < STEM_PX; ++px) {
+      float acc = bc;
+#pragma unroll
+      for (int k4 = 0; k4 < 12; ++k4) {
+        float4 v = *reinterpret_cast<const float4*>(&in[px * 48 + k4 * 4]);
+        acc = fmaf(wr[k4 * 4 + 0], v.x, acc);
+        acc = fmaf(wr[k4 * 4 + 1], v.y, acc);
+        acc = fmaf(wr[k4 * 4 + 2], v.z, acc);
+        acc = fmaf(wr[k4 * 4 + 3], v.w, acc);
+      }
+      ys[px * Cout + c] = acc;
+    }
+    __syncthreads();
+    // LayerNorm(channels_first) == per-pixel LN over channels (cod.py:1045-1048)
+    for (int px = wid; px < STEM_PX; px += nw) {
+      if (ox0 + px >= ow) continue;
+      float s = 0.f;
+      for (int cc = lane; cc < Cout; cc += 32) s += ys[px * Cout + cc];
+      float mean = warp_sum(s) / Cout;
+      float q = 0.f;
+      for (int cc = lane; cc < Cout; cc += 32) {
+        float d = ys[px * Cout + cc] - mean;
+        q = fmaf(d, d, q);
+      }
+      float rstd = 1.0f / sqrtf(warp_sum(q) / Cout + eps);
+      float* o = out + (((int64_t)b * oh + oy) * ow + ox0 + px) * Cout;
+      for (int cc = lane; cc < Cout; cc += 32)
+        o[cc] = (ys[px * Cout + cc] - mean) * rstd * ln_w[cc] + ln_b[cc];
+    }
+    __syncthreads();   // ys / in are rewritten by the next tile
   }
 }
 
@@ -206,62 +215,60 @@ dwconv7_ln_kernel(const float* __restrict__ x, const float* __restrict__ dw_w,
 // per output pixel: bilinear gather of the 4 projected levels (C ch each) -> 4C vector ->
 // 1x1 conv (C x 4C) + bias.  CTA = 32 pixels, 128 threads.
 template <int C>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 fusion_tail_kernel(const float* __restrict__ l0, const float* __restrict__ l1,
                    const float* __restrict__ l2, const float* __restrict__ l3, int h0, int w0, int h1,
                    int w1, int h2, int w2, int h3, int w3, const float* __restrict__ wf,
                    const float* __restrict__ bf, float* __restrict__ out_nhwc,
                    float* __restrict__ out_nchw, __nv_bfloat16* __restrict__ out_pad, int Cpad,
                    int64_t total_px) {
-  constexpr int PX = 32, K = 4 * C;
-  __shared__ float cat[PX][K + 1];
-  __shared__ float wsm[C][K + 1];
-  for (int i = threadIdx.x; i < C * K; i += 128) wsm[i / K][i % K] = wf[i];
-  const int64_t p0 = (int64_t)blockIdx.x * PX;
-  for (int e = threadIdx.x; e < PX * K; e += 128) {
-    int px = e / K, k = e - px * K;
-    int lv = k / C, c = k - lv * C;
-    int64_t p = p0 + px;
-    float v = 0.f;
-    if (p < total_px) {
-      int ox = (int)(p % w0);
-      int64_t t = p / w0;
-      int oy = (int)(t % h0), b = (int)(t / h0);
-      const float* src = lv == 0 ? l0 : lv == 1 ? l1 : lv == 2 ? l2 : l3;
-      int hh = lv == 0 ? h0 : lv == 1 ? h1 : lv == 2 ? h2 : h3;
-      int ww = lv == 0 ? w0 : lv == 1 ? w1 : lv == 2 ? w2 : w3;
-      int y0, y1, x0, x1;
-      float ly, lx;
-      bilinear_src(oy, (float)hh / h0, hh, y0, y1, ly);
-      bilinear_src(ox, (float)ww / w0, ww, x0, x1, lx);
-      const float* sb = src + (int64_t)b * hh * ww * C + c;
-      v = (1.f - ly) * ((1.f - lx) * sb[((int64_t)y0 * ww + x0) * C] + lx * sb[((int64_t)y0 * ww + x1) * C]) +
-          ly * ((1.f - lx) * sb[((int64_t)y1 * ww + x0) * C] + lx * sb[((int64_t)y1 * ww + x1) * C]);
-    }
-    cat[px][k] = v;
+  // one warp per output pixel; lane = channel (C <= 32).  wT[k][co] keeps the 1x1 conv weights
+  // transposed so that lanes read consecutive banks.
+  constexpr int K = 4 * C;
+  __shared__ float wT[K][32];
+  __shared__ float cat[8][K];
+  for (int i = threadIdx.x; i < K * 32; i += 256) {
+    int k = i >> 5, co = i & 31;
+    wT[k][co] = co < C ? wf[co * K + k] : 0.f;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < PX * C; e += 128) {
-    int px = e / C, co = e - px * C;
-    int64_t p = p0 + px;
-    if (p >= total_px) continue;
-    float acc = bf[co];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const float bias = lane < C ? bf[lane] : 0.f;
+  const int64_t hw = (int64_t)h0 * w0;
+  for (int64_t p = (int64_t)blockIdx.x * 8 + wid; p < total_px; p += (int64_t)gridDim.x * 8) {
+    const int ox = (int)(p % w0);
+    const int64_t t = p / w0;
+    const int oy = (int)(t % h0), b = (int)(t / h0);
+#pragma unroll
+    for (int lv = 0; lv < 4; ++lv) {
+      const float* src = lv == 0 ? l0 : lv == 1 ? l1 : lv == 2 ? l2 : l3;
+      const int hh = lv == 0 ? h0 : lv == 1 ? h1 : lv == 2 ? h2 : h3;
+      const int ww = lv == 0 ? w0 : lv == 1 ? w1 : lv == 2 ? w2 : w3;
+      float v = 0.f;
+      if (lane < C) {
+        int y0, y1, x0, x1;
+        float ly, lx;
+        bilinear_src(oy, (float)hh / h0, hh, y0, y1, ly);
+        bilinear_src(ox, (float)ww / w0, ww, x0, x1, lx);
+        const float* sb = src + (int64_t)b * hh * ww * C + lane;
+        v = (1.f - ly) * ((1.f - lx) * sb[((int64_t)y0 * ww + x0) * C] + lx * sb[((int64_t)y0 * ww + x1) * C]) +
+            ly * ((1.f - lx) * sb[((int64_t)y1 * ww + x0) * C] + lx * sb[((int64_t)y1 * ww + x1) * C]);
+        cat[wid][lv * C + lane] = v;
+      }
+    }
+    __syncwarp();
+    float acc = bias;
 #pragma unroll 8
-    for (int k = 0; k < K; ++k) acc = fmaf(wsm[co][k], cat[px][k], acc);
-    if (out_nhwc) out_nhwc[p * C + co] = acc;
-    if (out_pad) out_pad[p * Cpad + co] = __float2bfloat16_rn(acc);
-    if (out_nchw) {
-      int64_t hw = (int64_t)h0 * w0;
-      int64_t b = p / hw, r = p - b * hw;
-      out_nchw[(b * C + co) * hw + r] = acc;
+    for (int k = 0; k < K; ++k) acc = fmaf(wT[k][lane], cat[wid][k], acc);
+    __syncwarp();
+    if (lane < C) {
+      if (out_nhwc) out_nhwc[p * C + lane] = acc;
+      if (out_nchw) {
+        const int64_t bb = p / hw, r = p - bb * hw;
+        out_nchw[(bb * C + lane) * hw + r] = acc;
+      }
     }
-  }
-  if (out_pad && Cpad > C) {
-    for (int e = threadIdx.x; e < PX * (Cpad - C); e += 128) {
-      int px = e / (Cpad - C), co = C + e % (Cpad - C);
-      int64_t p = p0 + px;
-      if (p < total_px) out_pad[p * Cpad + co] = __float2bfloat16_rn(0.f);
-    }
+    if (out_pad && lane < Cpad) out_pad[p * Cpad + lane] = __float2bfloat16_rn(lane < C ? acc : 0.f);
   }
 }
 
@@ -309,9 +316,9 @@ int dgtd_stem_fwd(const float* image, const float* grid, int G, const float* w, 
   DGTD_CHECK_ARG(!grid || G > 0, "stem: bad grid size");
   const int oh = H / 4, ow = W / 4;
   size_t smem = (size_t)(STEM_PX * 48 + STEM_PX * Cout) * sizeof(float);
-  dim3 g(cdiv(ow, STEM_PX) * oh, B);
-  stem_kernel<<<g, Cout, smem, (cudaStream_t)stream>>>(image, grid, G, w, b, ln_w, ln_b, out, H, W, oh,
-                                                       ow, Cout, eps);
+  const int total_tiles = cdiv(ow, STEM_PX) * oh * B;
+  stem_kernel<<<cdiv(total_tiles, STEM_TILES_PER_CTA), Cout, smem, (cudaStream_t)stream>>>(
+      image, grid, G, w, b, ln_w, ln_b, out, H, W, oh, ow, Cout, eps, total_tiles);
   DGTD_LAUNCH_CHECK("stem");
   return 0;
 }
@@ -412,7 +419,10 @@ int dgtd_fusion_head_fwd(const float* lv0, const float* lv1, const float* lv2, c
   DGTD_CHECK_ARG(out_nhwc || out_nchw || out_pad, "fusion_head: no output requested");
   DGTD_CHECK_ARG(!out_pad || Cpad >= C, "fusion_head: Cpad < C");
   int64_t total = (int64_t)B * hw[0] * hw[1];
-  fusion_tail_kernel<24><<<cdiv(total, 32), 128, 0, (cudaStream_t)stream>>>(
+  DGTD_CHECK_ARG(!out_pad || Cpad <= 32, "fusion_head: Cpad must be <= 32");
+  int blocks = cdiv(total, 8);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  fusion_tail_kernel<24><<<blocks, 256, 0, (cudaStream_t)stream>>>(
       lv0, lv1, lv2, lv3, hw[0], hw[1], hw[2], hw[3], hw[4], hw[5], hw[6], hw[7], wf, bf, out_nhwc,
       out_nchw, (__nv_bfloat16*)out_pad, Cpad, total);
   DGTD_LAUNCH_CHECK("fusion_head");

@@ -103,10 +103,36 @@ def dtype_code(dt: torch.dtype) -> int:
     raise TypeError(f"dgtd ops support float32 / bfloat16 only, got {dt}")
 
 
+_PROF = {"on": False, "events": []}
+
+
+def enable_profile(on: bool = True) -> None:
+    """Per-entry-point CUDA-event timing (tools/op_profile.py); off by default."""
+    _PROF["on"] = bool(on)
+    _PROF["events"] = []
+
+
+def profile_summary() -> dict:
+    torch.cuda.synchronize()
+    out = {}
+    for name, a, b in _PROF["events"]:
+        e = out.setdefault(name, [0, 0.0])
+        e[0] += 1
+        e[1] += a.elapsed_time(b)
+    return out
+
+
 def call(name: str, *args) -> None:
     """Invoke an entry point; raise RuntimeError(dgtd_last_error()) on a non-zero return."""
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if _PROF["on"]:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = getattr(lib, name)(*args)
+        b.record()
+        _PROF["events"].append((name, a, b))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {last_error()}")
 

@@ -118,6 +118,22 @@ def diffusion_microbench(OP, dev, peaks, C=256, S=1024, steps=(1, 2, 4, 8)):
                              "tflops": flops / (ms * 1e-3) / 1e12, "roofline_ms": bound_ms,
                              "frac_of_roofline": bound_ms / ms})
     out["hbm_frac_T1"] = out["sweep"][0]["gbs_per_step"] / hbm
+    # bf16 storage / fp32 accumulate (configs[3] second dtype), T = 1
+    xb = x.to(torch.bfloat16)
+    del x
+    for _ in range(2):
+        OP.message_passing_tiled(xb, wgt, 1)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(3):
+        OP.message_passing_tiled(xb, wgt, 1)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 3
+    bb = (2 * C * 2 + 49 * 4) * S * S
+    out["bf16_storage_T1"] = {"ms": ms, "alg_bytes": bb, "gbs": bb / (ms * 1e-3) / 1e9, "hbm_frac": bb / (ms * 1e-3) / 1e9 / hbm,
+                              "tflops": 2.0 * 49 * C * S * S / (ms * 1e-3) / 1e12}
     return out
 
 

@@ -277,6 +277,96 @@ diffuse_plane_bwd_kernel(const float* __restrict__ grad_out, const float* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------ small backward ops
+// 1x1 conv NCHW backward.  y_out non-null => the forward applied a sigmoid: g <- g * y (1 - y).
+// dx: thread per (b, ci, p);  dw/db: one CTA per output channel, fixed-order tree reduction.
+__global__ void conv1x1_nchw_bwd_dx_kernel(const float* __restrict__ g, const float* __restrict__ y_out,
+                                           const float* __restrict__ w, float* __restrict__ dx, int Cin,
+                                           int Cout, int HW) {
+  int b = blockIdx.z, ci = blockIdx.y;
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const float* gp = g + (int64_t)b * Cout * HW + p;
+  const float* yp = y_out ? y_out + (int64_t)b * Cout * HW + p : nullptr;
+  float acc = 0.f;
+  for (int co = 0; co < Cout; ++co) {
+    float gv = gp[(int64_t)co * HW];
+    if (yp) {
+      float yv = yp[(int64_t)co * HW];
+      gv *= yv * (1.f - yv);
+    }
+    acc = fmaf(w[(int64_t)co * Cin + ci], gv, acc);
+  }
+  dx[((int64_t)b * Cin + ci) * HW + p] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+conv1x1_nchw_bwd_dw_kernel(const float* __restrict__ g, const float* __restrict__ y_out,
+                           const float* __restrict__ x, float* __restrict__ dw, float* __restrict__ db, int B,
+                           int Cin, int Cout, int HW) {
+  __shared__ float red[256];
+  const int co = blockIdx.x;
+  for (int ci = -1; ci < Cin; ++ci) {   // ci == -1: bias gradient
+    float acc = 0.f;
+    for (int64_t i = threadIdx.x; i < (int64_t)B * HW; i += 256) {
+      int b = (int)(i / HW);
+      int p = (int)(i - (int64_t)b * HW);
+      float gv = g[((int64_t)b * Cout + co) * HW + p];
+      if (y_out) {
+        float yv = y_out[((int64_t)b * Cout + co) * HW + p];
+        gv *= yv * (1.f - yv);
+      }
+      acc += ci < 0 ? gv : gv * x[((int64_t)b * Cin + ci) * HW + p];
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      if (ci < 0) { if (db) db[co] = red[0]; }
+      else dw[(int64_t)co * Cin + ci] = red[0];
+    }
+    __syncthreads();
+  }
+}
+
+// adjoint of the bilinear resize (gather form, deterministic): one thread per INPUT pixel walks
+// the output window that can reference it.
+__global__ void resize_bilinear_nchw_bwd_kernel(const float* __restrict__ g, float* __restrict__ dx, int h,
+                                                int w, int oh, int ow) {
+  int plane = blockIdx.z;
+  int ix = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y * blockDim.y + threadIdx.y;
+  if (ix >= w || iy >= h) return;
+  const float sy = (float)h / oh, sx = (float)w / ow;
+  int oy_lo = (int)floorf((iy - 1 + 0.5f) / sy - 0.5f) - 1, oy_hi = (int)ceilf((iy + 1 + 0.5f) / sy - 0.5f) + 1;
+  int ox_lo = (int)floorf((ix - 1 + 0.5f) / sx - 0.5f) - 1, ox_hi = (int)ceilf((ix + 1 + 0.5f) / sx - 0.5f) + 1;
+  if (iy == 0) oy_lo = 0;             // clamped source coordinates pile up on the border pixels
+  if (ix == 0) ox_lo = 0;
+  if (iy == h - 1) oy_hi = oh - 1;
+  if (ix == w - 1) ox_hi = ow - 1;
+  oy_lo = max(oy_lo, 0); ox_lo = max(ox_lo, 0);
+  oy_hi = min(oy_hi, oh - 1); ox_hi = min(ox_hi, ow - 1);
+  const float* gp = g + (int64_t)plane * oh * ow;
+  float acc = 0.f;
+  for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+    int y0, y1;
+    float ly;
+    bilinear_src(oy, sy, h, y0, y1, ly);
+    float wy = (y0 == iy ? 1.f - ly : 0.f) + (y1 == iy ? ly : 0.f);
+    if (wy == 0.f) continue;
+    for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+      int x0, x1;
+      float lx;
+      bilinear_src(ox, sx, w, x0, x1, lx);
+      float wx = (x0 == ix ? 1.f - lx : 0.f) + (x1 == ix ? lx : 0.f);
+      if (wx != 0.f) acc = fmaf(wy * wx, gp[(int64_t)oy * ow + ox], acc);
+    }
+  }
+  dx[((int64_t)plane * h + iy) * w + ix] = acc;
+}
+
 }  // namespace dgtd
 
 using namespace dgtd;
@@ -391,6 +481,33 @@ int dgtd_conv1x1_nchw_fwd(const float* x, const float* w, const float* b, float*
   else
     conv1x1_nchw_kernel<false><<<grid, 128, 0, s>>>(x, w, b, out, Cin, Cout, HW, (int64_t)Cin * HW);
   DGTD_LAUNCH_CHECK("conv1x1_nchw");
+  return 0;
+}
+
+int dgtd_conv1x1_nchw_bwd(const float* grad_out, const float* y_out, const float* x, const float* w,
+                          float* grad_x, float* grad_w, float* grad_b, int B, int Cin, int Cout, int HW,
+                          dgtd_stream_t stream) {
+  DGTD_CHECK_ARG(grad_out && x && w && B > 0 && Cin > 0 && Cout > 0 && HW > 0, "conv1x1_nchw_bwd: bad args");
+  DGTD_CHECK_ARG(Cin <= 65535 && B <= 65535 && Cout <= 65535, "conv1x1_nchw_bwd: grid too large");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (grad_x) {
+    conv1x1_nchw_bwd_dx_kernel<<<dim3(cdiv(HW, 128), Cin, B), 128, 0, s>>>(grad_out, y_out, w, grad_x, Cin, Cout, HW);
+    DGTD_LAUNCH_CHECK("conv1x1_nchw_bwd.dx");
+  }
+  if (grad_w) {
+    conv1x1_nchw_bwd_dw_kernel<<<Cout, 256, 0, s>>>(grad_out, y_out, x, grad_w, grad_b, B, Cin, Cout, HW);
+    DGTD_LAUNCH_CHECK("conv1x1_nchw_bwd.dw");
+  }
+  return 0;
+}
+
+int dgtd_resize_bilinear_nchw_bwd(const float* grad_out, float* grad_x, int planes, int h, int w, int oh,
+                                  int ow, dgtd_stream_t stream) {
+  DGTD_CHECK_ARG(grad_out && grad_x && planes > 0 && h > 0 && w > 0 && oh > 0 && ow > 0, "resize_bwd: bad args");
+  DGTD_CHECK_ARG(planes <= 65535, "resize_bwd: too many planes");
+  dim3 block(16, 8), grid(cdiv(w, 16), cdiv(h, 8), planes);
+  resize_bilinear_nchw_bwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(grad_out, grad_x, h, w, oh, ow);
+  DGTD_LAUNCH_CHECK("resize_bilinear_nchw_bwd");
   return 0;
 }
 

@@ -145,8 +145,7 @@ class ShapePropWeightRegressor(nn.Module):
         self.reg = nn.Conv2d(in_channels, self.latent_dim * 49, kernel_size=1)
 
     def forward(self, x):
-        w = self.reg.weight.detach().reshape(self.reg.out_channels, -1).contiguous()
-        return OP.conv1x1_nchw(x.contiguous().float(), w, self.reg.bias.detach(), sigmoid=True)
+        return OP.conv1x1_nchw_autograd(x, self.reg.weight, self.reg.bias, True)   # differentiable
 
 
 class convnext_Block(nn.Module):
@@ -298,11 +297,12 @@ class MessagePassing(nn.Module):
     def forward(self, input, weight):
         n, c, h, w = input.size()
         steps = max(h, w) if self.max_step < 0 else self.max_step
+        # every step is an autograd.Function backed by the CUDA kernels: differentiable w.r.t.
+        # input, weight and self.conv (backward obligations of row a6)
         x = OP.message_passing_core(input, weight, steps, 1e-5)
-        cw = self.conv.weight.detach().reshape(3, c).contiguous()
-        x = OP.conv1x1_nchw(x.detach(), cw, self.conv.bias.detach())
+        x = OP.conv1x1_nchw_autograd(x, self.conv.weight, self.conv.bias, False)
         size = self.img_size if isinstance(self.img_size, (tuple, list)) else (self.img_size, self.img_size)
-        return OP.resize_nchw(x, size, bilinear=True)
+        return OP.resize_bilinear_nchw_autograd(x, size)
 
 
 def _pack_conv3(wt: torch.Tensor) -> torch.Tensor:

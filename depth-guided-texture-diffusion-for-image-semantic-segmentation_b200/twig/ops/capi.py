@@ -34,6 +34,8 @@ SIGNATURES = {
     "dgtd_message_passing_tiled_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P],
     "dgtd_message_passing_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     "dgtd_conv1x1_nchw_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "dgtd_conv1x1_nchw_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "dgtd_resize_bilinear_nchw_bwd": [_P, _P, _I, _I, _I, _I, _I, _P],
     "dgtd_resize_nchw_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "dgtd_layer_norm_fwd": [_P, _P, _P, _P, _L, _I, _L, _F, _P],
     "dgtd_stem_fwd": [_P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],

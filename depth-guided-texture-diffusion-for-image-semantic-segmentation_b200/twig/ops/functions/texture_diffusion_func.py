@@ -19,7 +19,7 @@ from ..capi import ACT_GELU, ACT_NONE, ACT_RELU, BF16, F32, call, check_cuda, pt
 
 __all__ = [
     "surface_normals", "HighpassPlan", "fft_highpass", "diffusion_front", "MessagePassingFunction",
-    "message_passing_core", "message_passing_tiled", "conv1x1_nchw", "resize_nchw", "layer_norm",
+    "message_passing_core", "message_passing_tiled", "conv1x1_nchw_autograd", "resize_bilinear_nchw_autograd", "conv1x1_nchw", "resize_nchw", "layer_norm",
     "stem", "ln_patchify", "dwconv7_ln", "dwconv7_ln_tma", "linear", "linear_residual_", "fusion_head", "conv_nhwc", "conv_nhwc_grouped",
     "resize_nhwc", "cast", "nhwc_to_nchw", "nchw_to_nhwc", "enable_gemm_profile", "collect_gemm_profile",
 ]
@@ -166,6 +166,67 @@ class MessagePassingFunction(Function):
 
 def message_passing_core(x: torch.Tensor, weight: torch.Tensor, steps: int = 4, eps: float = 1e-5):
     return MessagePassingFunction.apply(x, weight, steps, eps)
+
+
+class Conv1x1NCHWFunction(Function):
+    """1x1 conv (+ optional sigmoid) on NCHW maps with gradients for x, weight and bias:
+    ShapePropWeightRegressor (cod.py:1058-1060), encoder1 (:1297), message_passing.conv (:1206)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, sigmoid: bool):
+        x = x.contiguous().float()
+        w2 = weight.reshape(weight.shape[0], -1).contiguous().float()
+        out = conv1x1_nchw(x, w2, None if bias is None else bias.contiguous().float(), sigmoid)
+        ctx.sigmoid = bool(sigmoid)
+        ctx.wshape = tuple(weight.shape)
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, w2, out if sigmoid else None)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, w2, y = ctx.saved_tensors
+        g = g.contiguous().float()
+        B, Cin = x.shape[0], x.shape[1]
+        HW = x.numel() // (B * Cin)
+        Cout = w2.shape[0]
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gw = torch.empty_like(w2) if (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) else None
+        gb = torch.empty(Cout, device=x.device, dtype=torch.float32) if gw is not None else None
+        call("dgtd_conv1x1_nchw_bwd", ptr(g), ptr(y), ptr(x), ptr(w2), ptr(gx), ptr(gw), ptr(gb), B, Cin, Cout, HW,
+             stream())
+        return (gx, gw.reshape(ctx.wshape) if gw is not None and ctx.needs_input_grad[1] else None,
+                gb if ctx.has_bias and ctx.needs_input_grad[2] else None, None)
+
+
+class ResizeBilinearNCHWFunction(Function):
+    """F.interpolate(mode='bilinear', align_corners=False) with its exact adjoint (cod.py:1207,1298)."""
+
+    @staticmethod
+    def forward(ctx, x, size):
+        x = x.contiguous().float()
+        ctx.in_hw = (x.shape[2], x.shape[3])
+        ctx.out_hw = (int(size[0]), int(size[1]))
+        return resize_nchw(x, ctx.out_hw, bilinear=True)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        g = g.contiguous().float()
+        B, C = g.shape[0], g.shape[1]
+        gx = torch.empty(B, C, ctx.in_hw[0], ctx.in_hw[1], device=g.device, dtype=torch.float32)
+        call("dgtd_resize_bilinear_nchw_bwd", ptr(g), ptr(gx), B * C, ctx.in_hw[0], ctx.in_hw[1], ctx.out_hw[0],
+             ctx.out_hw[1], stream())
+        return gx, None
+
+
+def conv1x1_nchw_autograd(x, weight, bias, sigmoid: bool = False):
+    return Conv1x1NCHWFunction.apply(x, weight, bias, sigmoid)
+
+
+def resize_bilinear_nchw_autograd(x, size):
+    return ResizeBilinearNCHWFunction.apply(x, size)
 
 
 def message_passing_tiled(x: torch.Tensor, weight: torch.Tensor, steps: int, eps: float = 1e-5):

@@ -81,7 +81,7 @@ int dgtd_message_passing_fwd(const float* x, const float* weight, float* out, fl
 /* Halo-tiled variant for large maps (the 1024^2 x 256 microbench): x,out NHWC (n,h,w,c),
  * dtype fp32 or bf16 storage (fp32 accumulate); weight (n,49,h,w) fp32 shared by all channels
  * (wc == 1).  One launch per iteration; `tmp` (same size as x) is the ping-pong buffer when
- * T > 1.  c must be a multiple of 64. */
+ * T > 1.  c must be a multiple of 64 (fp32) / 128 (bf16). */
 int dgtd_message_passing_tiled_fwd(const void* x, const float* weight, void* out, void* tmp,
                                    int n, int h, int w, int c, int T, float eps, int dtype,
                                    dgtd_stream_t stream);
@@ -96,6 +96,14 @@ int dgtd_message_passing_bwd(const float* grad_out, const float* weight, const f
  * encoder1 (:1249), message_passing.conv (:1188). */
 int dgtd_conv1x1_nchw_fwd(const float* x, const float* w, const float* b, float* out, int B,
                           int Cin, int Cout, int HW, int sigmoid, dgtd_stream_t stream);
+/* backward of the 1x1 conv: y_out non-NULL = the forward applied the sigmoid (its output is passed
+ * back); grad_x / grad_w (+grad_b) are optional outputs.  Deterministic reductions. */
+int dgtd_conv1x1_nchw_bwd(const float* grad_out, const float* y_out, const float* x, const float* w,
+                          float* grad_x, float* grad_w, float* grad_b, int B, int Cin, int Cout, int HW,
+                          dgtd_stream_t stream);
+/* adjoint of the bilinear resize (h,w) -> (oh,ow): grad_out (planes,oh,ow) -> grad_x (planes,h,w) */
+int dgtd_resize_bilinear_nchw_bwd(const float* grad_out, float* grad_x, int planes, int h, int w, int oh,
+                                  int ow, dgtd_stream_t stream);
 /* F.interpolate(mode='bilinear', align_corners=False) on NCHW fp32 (cod.py:1207,1298) and
  * nearest (cod.py:1295). */
 int dgtd_resize_nchw_fwd(const float* x, float* out, int planes, int h, int w, int oh, int ow,

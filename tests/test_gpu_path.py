@@ -79,3 +79,49 @@ def test_bf16_path_within_stated_tolerance(name, S, w20):
         return max(2.0 * ref_err, 2e-2) if k != "embedding1" else 1e-4   # embedding1 stays fp32
     rep = compare(outs, name, tol)
     print("bf16 max rel err", max(rep.values()))
+
+
+def oracle_outputs(S, B):
+    from oracle import texture_diffuser_ref as O
+    TD = common.package()
+    enc, dec = TD.build_texture_diffuser(seed=0)
+    common.perturb_regressor_(enc)
+    pe, pd = common.oracle_params(enc, dec)
+    pairs = [common.synthetic_inputs(1, S, seed=i) for i in range(B)]
+    image, depth = torch.cat([p[0] for p in pairs]), torch.cat([p[1] for p in pairs])
+    with torch.no_grad():
+        e1, e3, toks = O.texture_prompts(image.double(), depth.double(), pe, pd)
+    return common.flatten_outputs(e1, e3, toks)
+
+
+def test_high_res_768_fp32_and_bf16_against_oracle():
+    """BASELINE configs[4] geometry (768x768: FFT line 210, nearest stride 64, trunk 192/96/48/24,
+    token grids 192/96/48/24) checked against the CPU oracle computed on the spot (float64)."""
+    ref = oracle_outputs(768, 1)
+    got = run(768, True, "fp32", B=1)
+    assert got["tokens.0.0"].shape == (1, 192 * 192, 64) and got["tokens.3.2"].shape == (1, 24 * 24, 512)
+    for k in ref:
+        assert common.rel_err(got[k], ref[k]) <= 1e-4, (k, common.rel_err(got[k], ref[k]))
+    got = run(768, True, "bf16", B=1)
+    for k in ref:
+        tol = 1e-4 if k == "embedding1" else 3e-2
+        assert common.rel_err(got[k], ref[k]) <= tol, (k, common.rel_err(got[k], ref[k]))
+
+
+def test_large_batch_matches_single_image_bf16():
+    """configs[1] batch (B=64, bf16, 2-CTA tcgen05 tiles + TMA conv paths): image 5 of the batch equals
+    the B=1 run of the same image up to bf16-level noise (different tile shapes, same math)."""
+    TD = common.package()
+    enc, dec = TD.build_texture_diffuser(seed=0)
+    common.perturb_regressor_(enc)
+    enc, dec = enc.cuda().eval(), dec.cuda().eval()
+    pairs = [common.synthetic_inputs(1, 384, seed=i) for i in range(64)]
+    image, depth = torch.cat([p[0] for p in pairs]).cuda(), torch.cat([p[1] for p in pairs]).cuda()
+    e1, e3, toks = TD.texture_prompts(enc, dec, image, depth, precision="bf16")
+    big = common.flatten_outputs(e1, e3, toks)
+    e1, e3, toks = TD.texture_prompts(enc, dec, image[5:6].contiguous(), depth[5:6].contiguous(), precision="bf16")
+    one = common.flatten_outputs(e1, e3, toks)
+    for k in one:
+        a, b = big[k][5:6].float(), one[k].float()
+        assert torch.isfinite(big[k].float()).all(), k
+        assert float((a - b).abs().max()) <= 2e-2 * float(b.abs().max()), k

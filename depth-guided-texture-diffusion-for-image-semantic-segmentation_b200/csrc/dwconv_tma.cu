@@ -22,8 +22,7 @@ dwconv7_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restr
   constexpr int TH = 4 * SY, TW = 8 * SX, PH = TH + 6, PW = TW + 6, NCH = 4;
   constexpr int TILE_FLOATS = PH * PW * 32;
   constexpr uint32_t TILE_BYTES = TILE_FLOATS * 4;
-  extern __shared__ uint8_t smem_raw[];
-  float* xs = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  extern __shared__ __align__(128) float xs[];   // TMA destination; keeps ld.shared addressing
   __shared__ uint64_t bar[2];
 
   int bid = blockIdx.x;
@@ -57,15 +56,20 @@ dwconv7_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restr
       bw::tma_load_4d(&tmX, &bar[(i + 1) & 1], xs + ((i + 1) & 1) * TILE_FLOATS, cg * 128 + (i + 1) * 32, x0 - 3,
                       y0 - 3, b);
     }
-    float wr[49];
+    // taps duplicated into both halves of a 64-bit register: fma.rn.f32x2 then updates two
+    // horizontally adjacent output pixels per instruction (half the FMA issue slots)
+    uint64_t w2[49];
 #pragma unroll
-    for (int k = 0; k < 49; ++k) wr[k] = __ldg(wT + (int64_t)k * C + c);
+    for (int k = 0; k < 49; ++k) {
+      const float t = __ldg(wT + (int64_t)k * C + c);
+      w2[k] = pk2(t, t);
+    }
     const float bc = __ldg(bias + c);
-    float acc[4][8];
+    uint64_t acc[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[a][j] = bc;
+      for (int j = 0; j < 4; ++j) acc[a][j] = pk2(bc, bc);
 
     bw::mbar_wait(&bar[i & 1], (i >> 1) & 1);
     const float* base = xs + (i & 1) * TILE_FLOATS + ((4 * sy) * PW + 8 * sx) * 32 + lane;
@@ -74,14 +78,20 @@ dwconv7_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restr
       float in[14];
 #pragma unroll
       for (int j = 0; j < 14; ++j) in[j] = base[(iy * PW + j) * 32];
+      uint64_t pe[7], po[6];   // (in[2m], in[2m+1]) and (in[2m+1], in[2m+2])
+#pragma unroll
+      for (int m = 0; m < 7; ++m) pe[m] = pk2(in[2 * m], in[2 * m + 1]);
+#pragma unroll
+      for (int m = 0; m < 6; ++m) po[m] = pk2(in[2 * m + 1], in[2 * m + 2]);
 #pragma unroll
       for (int oy = 0; oy < 4; ++oy) {
         const int ky = iy - oy;
         if (ky < 0 || ky >= 7) continue;
 #pragma unroll
-        for (int ox = 0; ox < 8; ++ox)
+        for (int kx = 0; kx < 7; ++kx)
 #pragma unroll
-          for (int kx = 0; kx < 7; ++kx) acc[oy][ox] = fmaf(wr[ky * 7 + kx], in[ox + kx], acc[oy][ox]);
+          for (int pp = 0; pp < 4; ++pp)
+            acc[oy][pp] = fma2(w2[ky * 7 + kx], (kx & 1) ? po[pp + (kx >> 1)] : pe[pp + (kx >> 1)], acc[oy][pp]);
       }
     }
 #pragma unroll
@@ -89,9 +99,13 @@ dwconv7_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restr
       const int oy = y0 + 4 * sy + a;
       if (oy >= h) continue;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int ox = x0 + 8 * sx + j;
-        if (ox < w) y[(((int64_t)b * h + oy) * w + ox) * C + c] = acc[a][j];
+      for (int pp = 0; pp < 4; ++pp) {
+        float v0, v1;
+        up2(acc[a][pp], v0, v1);
+        const int ox = x0 + 8 * sx + 2 * pp;
+        float* dst = y + (((int64_t)b * h + oy) * w + ox) * C + c;
+        if (ox < w) dst[0] = v0;
+        if (ox + 1 < w) dst[C] = v1;
       }
     }
     __syncthreads();   // every warp is done with buffer i&1 before it is refilled

@@ -56,8 +56,7 @@ __global__ void __launch_bounds__(256, 1)
 mp_tiled_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ weight,
                 typename MpVec<RC>::T* __restrict__ out, int h, int w, int C, float eps) {
   using V = MpVec<RC>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* xs = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  extern __shared__ __align__(128) uint8_t xs[];   // TMA destination; keeps ld.shared addressing
   float* wn = reinterpret_cast<float*>(xs + 2 * MP_TILE_BYTES);
   __shared__ uint64_t bar[2];
 

@@ -25,30 +25,6 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return x * phi;
 }
 
-// Packed fp32x2 arithmetic (Blackwell FFMA2/FMUL2/FADD2): halves the issue slots of the epilogue.
-__device__ __forceinline__ uint64_t pk2(float a, float b) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void up2(uint64_t r, float& a, float& b) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r));
-}
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
 // gelu_fast on two values at once (same polynomial, 8 issue slots per element)
 __device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
   const float c0 = fminf(fmaxf(x0, -4.5f), 4.5f), c1 = fminf(fmaxf(x1, -4.5f), 4.5f);

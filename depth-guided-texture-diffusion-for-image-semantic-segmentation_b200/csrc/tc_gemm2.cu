@@ -87,9 +87,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const TcParams p) {
   using Cfg = Tc2Cfg<BN>;
   constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
   // identical carve-up in both CTAs (the hardware addresses the peer's operands by offset)
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
   uint8_t* sStg = smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES);   // epilogue staging, 1024-aligned

@@ -22,11 +22,42 @@ struct RowMajorLoader {   // element (r, c) at p[z*bs + r*ld + c], 4 consecutive
   }
 };
 
+// Split-K view for weight gradients: batch z covers rows [z*zrows, (z+1)*zrows) of an R-row matrix.
+// Optional per-row / per-column scaling folds `keep[m / rows_per_sample] * gamma[c]` into the load
+// (the DropPath / layer-scale factors of cod.py:1112-1116).
+struct SplitRowLoader {
+  const float* p;
+  int64_t ld;
+  int R, Ccols, zrows;
+  const float* keep;    // nullable
+  const float* gamma;   // nullable
+  int rows_per_sample;
+  __device__ __forceinline__ float4 load(int r, int c, int z) const {
+    const int gr = z * zrows + r;
+    if (r >= zrows || gr >= R || c >= Ccols) return make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v = load4(p + (int64_t)gr * ld + c);
+    if (keep) {
+      const float k = keep[gr / rows_per_sample];
+      v.x *= k; v.y *= k; v.z *= k; v.w *= k;
+    }
+    if (gamma) {
+      const float4 g = load4(gamma + c);
+      v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
+    }
+    return v;
+  }
+};
+
 // NHWC convolution gather: row m = (b, oy, ox), col k = (tap, c), tap-major.
 struct Im2colLoader {
   const float* x;
   int h, w, ldx, Cin, oh, ow, ks, stride, off, M, K;
-  __device__ __forceinline__ float4 load(int m, int k, int) const {
+  int zrows = 0;   // > 0: split-K view, batch z covers rows [z*zrows, (z+1)*zrows)
+  __device__ __forceinline__ float4 load(int m, int k, int z) const {
+    if (zrows > 0) {
+      if (m >= zrows) return make_float4(0.f, 0.f, 0.f, 0.f);
+      m += z * zrows;
+    }
     if (m >= M || k >= K) return make_float4(0.f, 0.f, 0.f, 0.f);
     int tap = k / Cin, c = k - tap * Cin;
     int ty = tap / ks, tx = tap - ty * ks;

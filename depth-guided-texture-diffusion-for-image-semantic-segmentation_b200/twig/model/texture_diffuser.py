@@ -20,11 +20,13 @@ import torch.nn as nn
 
 from ..ops.capi import ACT_GELU, ACT_NONE, ACT_RELU, BF16, F32
 from ..ops.functions import texture_diffusion_func as OP
+from ..ops.functions import train_func as TF
 
 __all__ = [
     "LayerNorm", "ShapePropWeightRegressor", "convnext_Block", "ShapePropEncoder", "MessagePassing",
     "ShapePropDecoder", "prompt_encoder", "prompt_decoder", "DropPath", "init_weights_", "set_precision",
-    "build_texture_diffuser", "pvt_token_grids", "texture_prompts", "PVT_EMBED_DIMS", "PVT_DEPTHS",
+    "build_texture_diffuser", "pvt_token_grids", "texture_prompts", "texture_prompts_train", "PVT_EMBED_DIMS",
+    "PVT_DEPTHS",
 ]
 
 PVT_EMBED_DIMS = (64, 128, 320, 512)  # pvt_v2_b2, cod.py:1785
@@ -88,11 +90,13 @@ def _as(t: torch.Tensor, mode: int) -> torch.Tensor:
     return t.detach().to(torch.bfloat16).contiguous() if mode == BF16 else t.detach().float().contiguous()
 
 
-def _no_grad_only(module: nn.Module, what: str) -> None:
-    if torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()):
-        raise NotImplementedError(
-            f"{what}: the fused forward has no autograd graph in this build; call it under "
-            "torch.no_grad() (inference) -- training kernels are tracked in DESIGN.md")
+def _wants_grad(module: nn.Module, *inputs) -> bool:
+    """True when the forward has to build an autograd graph (training path: exact fp32
+    autograd Functions, ops/functions/train_func.py); False = fused inference kernels."""
+    if not torch.is_grad_enabled():
+        return False
+    return any(p.requires_grad for p in module.parameters()) or any(
+        isinstance(t, torch.Tensor) and t.requires_grad for t in inputs)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -184,8 +188,16 @@ class convnext_Block(nn.Module):
         OP.linear_residual_(hid, w2, self.pwconv2.bias.detach(), gamma, keep, h * w, x)
         return x
 
+    def _forward_train(self, x: torch.Tensor) -> torch.Tensor:
+        """NHWC fp32 in/out with an autograd graph (DropPath mask drawn like timm's, cod.py:1102)."""
+        keep = self.drop_path.keep_scale(x.shape[0], x.device) if isinstance(self.drop_path, DropPath) else None
+        return TF.ConvNextBlockFn.apply(x, self.dwconv.weight, self.dwconv.bias, self.norm.weight, self.norm.bias,
+                                        self.pwconv1.weight, self.pwconv1.bias, self.pwconv2.weight,
+                                        self.pwconv2.bias, self.gamma, keep, self.norm.eps)
+
     def forward(self, x):
-        _no_grad_only(self, "convnext_Block")
+        if _wants_grad(self, x):
+            return TF.LayoutFn.apply(self._forward_train(TF.LayoutFn.apply(x, True)), False)
         y = OP.nchw_to_nhwc(x.contiguous().float())
         y = self._forward_nhwc(y, _mode(self))
         return y.permute(0, 3, 1, 2)  # (N,C,H,W) view with channels-last strides
@@ -270,8 +282,24 @@ class ShapePropEncoder(nn.Module):
         return OP.fusion_head(levels, hw, wf, self.fusion_conv.bias.detach(), B, want_nhwc=True,
                               want_nchw=want_nchw, pad_to=pad_to)
 
+    def _forward_train(self, image: torch.Tensor, grid: Optional[torch.Tensor]) -> torch.Tensor:
+        """Autograd-building path (exact fp32): returns embedding3 as NHWC (B,h0,w0,out_dim)."""
+        st_conv, st_ln = self.downsample_layers[0][0], self.downsample_layers[0][1]
+        x = TF.StemFn.apply(image, grid, st_conv.weight, st_conv.bias, st_ln.weight, st_ln.bias, st_ln.eps)
+        levels = []
+        for i in range(4):
+            if i > 0:
+                ln, conv = self.downsample_layers[i][0], self.downsample_layers[i][1]
+                x = TF.DownsampleFn.apply(x, ln.weight, ln.bias, conv.weight, conv.bias, ln.eps)
+            for blk in self.stages[i]:
+                x = blk._forward_train(x)
+            levels.append(TF.LinearFn.apply(x, self.convs[i].weight, self.convs[i].bias))
+        return TF.FusionFn.apply(levels[0], levels[1], levels[2], levels[3], self.fusion_conv.weight,
+                                 self.fusion_conv.bias)
+
     def forward(self, x):
-        _no_grad_only(self, "ShapePropEncoder")
+        if _wants_grad(self, x):
+            return TF.LayoutFn.apply(self._forward_train(x, None), False)
         outs = self._pyramid(x.contiguous().float(), None, _mode(self))
         _, nchw, _ = self._head(outs, want_nchw=True, mode=_mode(self))
         return nchw
@@ -353,7 +381,15 @@ class ShapePropDecoder(nn.Module):
             nn.Conv2d(latent_dim, out_dim, kernel_size=3, stride=1, padding=dilation, dilation=dilation),
         )
 
+    def _forward_train(self, emb_nhwc: torch.Tensor) -> torch.Tensor:
+        d = self.decoder
+        y = TF.Conv3x3Fn.apply(emb_nhwc, d[0].weight, d[0].bias, True)
+        y = TF.Conv3x3Fn.apply(y, d[2].weight, d[2].bias, True)
+        return TF.Conv3x3Fn.apply(y, d[4].weight, d[4].bias, False)
+
     def forward(self, embedding):
+        if _wants_grad(self, embedding):
+            return self._forward_train(TF.LayoutFn.apply(embedding, True)).permute(0, 3, 1, 2)
         return _decode_full([self], OP.nchw_to_nhwc(embedding.contiguous().float()))[0]
 
 
@@ -518,8 +554,26 @@ class prompt_encoder(nn.Module):
         nhwc, nchw, pad = self.encoder2._head(outs, want_nchw=want_nchw, pad_to=pad_to, mode=mode)
         return x, nhwc, nchw, pad
 
+    def _forward_train(self, image: torch.Tensor, cues: torch.Tensor):
+        """Training path (cod.py:1288-1302 op by op, each an autograd Function on the CUDA kernels):
+        returns (embedding1, embedding3 NHWC)."""
+        H = 12
+        image = image.contiguous().float()
+        x = self.fft(image, self.freq_nums)                                            # no parameter upstream
+        xx = OP.resize_nchw(x, (H, H), bilinear=False)                                 # nearest, :1295
+        weights = self.propagation_weight_regressor(xx)                                # :1296
+        e1 = OP.conv1x1_nchw_autograd(cues.contiguous().float(), self.encoder1.weight, self.encoder1.bias, False)
+        d12 = OP.resize_bilinear_nchw_autograd(e1, (H, H))                             # :1298
+        mp = self.message_passing
+        steps = H if mp.max_step < 0 else mp.max_step
+        core = OP.message_passing_core(d12, weights, steps, 1e-5)
+        grid3 = OP.conv1x1_nchw_autograd(core, mp.conv.weight, mp.conv.bias, False)     # :1206 (up-sample fused in the stem)
+        return x, self.encoder2._forward_train(image, grid3)                           # :1302
+
     def forward(self, image, cues, cross=False):
-        _no_grad_only(self, "prompt_encoder")
+        if _wants_grad(self, cues):
+            x, emb3 = self._forward_train(image, cues)
+            return x, TF.LayoutFn.apply(emb3, False)
         x, _, emb3, _ = self._forward_fused(image, cues, _mode(self), want_nchw=True)
         return x, emb3
 
@@ -533,7 +587,9 @@ class prompt_decoder(nn.Module):
         self.decoder = nn.Sequential(*[ShapePropDecoder(embed_dim, 24) for i in range(depth)])
 
     def forward(self, embedding, cross=False):
-        _no_grad_only(self, "prompt_decoder")
+        if _wants_grad(self, embedding):
+            emb = TF.LayoutFn.apply(embedding, True)
+            return [d._forward_train(emb).permute(0, 3, 1, 2) for d in self.decoder]
         emb = OP.nchw_to_nhwc(embedding.contiguous().float())
         return _decode_full(list(self.decoder), emb)
 
@@ -580,9 +636,33 @@ def pvt_token_grids(img_hw: Sequence[int]) -> List[Tuple[int, int]]:
     return out
 
 
+def texture_prompts_train(enc: "prompt_encoder", dec: nn.Sequential, image: torch.Tensor, depth: torch.Tensor):
+    """Same contract as `texture_prompts`, building an autograd graph (exact fp32 training path)."""
+    emb1, emb3 = enc._forward_train(image, depth)                  # emb3: NHWC
+    grids = pvt_token_grids(image.shape[-2:])
+    B = image.shape[0]
+    tokens = []
+    for s in range(len(dec)):
+        row = []
+        for d in dec[s].decoder:
+            y = d._forward_train(emb3)                             # (B,h,w,E)
+            if tuple(y.shape[1:3]) != tuple(grids[s]):
+                y = TF.ResizeNHWCFn.apply(y, grids[s])
+            row.append(y.reshape(B, grids[s][0] * grids[s][1], -1))
+        tokens.append(row)
+    return emb1, TF.LayoutFn.apply(emb3, False), tokens
+
+
 @torch.no_grad()
-def texture_prompts(enc: prompt_encoder, dec: nn.Sequential, image: torch.Tensor, depth: torch.Tensor,
+def texture_prompts(enc: "prompt_encoder", dec: nn.Sequential, image: torch.Tensor, depth: torch.Tensor,
                     precision: Optional[str] = None, want_embedding3: bool = True):
+    """Inference entry (fused kernels, no autograd graph).  Training uses `texture_prompts_train`
+    or the module forwards, which switch to the autograd Functions when a graph is requested."""
+    return _texture_prompts_infer(enc, dec, image, depth, precision, want_embedding3)
+
+
+def _texture_prompts_infer(enc: "prompt_encoder", dec: nn.Sequential, image: torch.Tensor, depth: torch.Tensor,
+                           precision: Optional[str] = None, want_embedding3: bool = True):
     """The hot path as ``forward_features`` drives it (cod.py:1467-1505) minus the PVT blocks:
     returns ``(embedding1, embedding3, tokens)`` with ``tokens[s][i]`` the (B, H_s*W_s, E_s)
     tensor the reference adds to the stage-s token stream before block i

@@ -48,6 +48,22 @@ SIGNATURES = {
     "dgtd_conv_nhwc_fwd": [_P, _P, _P, _P] + [_I] * 15 + [_P],
     "dgtd_conv_nhwc_grouped_fwd": [_P, _P, _P, _P] + [_I] * 18 + [_L, _P],
     "dgtd_resize_nhwc_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "dgtd_linear_dgrad": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "dgtd_linear_wgrad": [_P, _P, _P, _P, _P] + [_I] * 13 + [_P],
+    "dgtd_linear_wgrad_ws_floats": [_I, _I, _I],
+    "dgtd_colsum": [_P, _P, _I, _P, _P, _I, _I, _P],
+    "dgtd_layer_scale_finalize": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "dgtd_gelu_fwd": [_P, _P, _L, _P],
+    "dgtd_relu_bwd": [_P, _P, _P, _L, _P],
+    "dgtd_ln_rows_bwd": [_P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
+    "dgtd_ln_rows_bwd_ws_floats": [_L, _I],
+    "dgtd_dwconv7_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "dgtd_dwconv7_wgrad": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "dgtd_stem_patchify": [_P, _P, _I, _P, _I, _I, _I, _P],
+    "dgtd_stem_unpatchify": [_P, _P, _I, _I, _I, _P],
+    "dgtd_patchify2": [_P, _P, _I, _I, _I, _I, _P],
+    "dgtd_unpatchify2": [_P, _P, _I, _I, _I, _I, _P],
+    "dgtd_resize_nhwc_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "dgtd_cast_fwd": [_P, _P, _L, _I, _I, _P],
     "dgtd_nhwc_to_nchw_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "dgtd_nchw_to_nhwc_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _P],

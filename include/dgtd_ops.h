@@ -180,6 +180,49 @@ int dgtd_conv_nhwc_grouped_fwd(const void* x, const void* w, const float* bias, 
 int dgtd_resize_nhwc_fwd(const void* x, void* out, int B, int h, int w, int C, int oh, int ow,
                          int dtype_in, int dtype_out, dgtd_stream_t stream);
 
+/* ---- training path (config/sod.yml): backward of the trunk / decoders, exact fp32 --------------
+ * Gradient GEMMs reuse the CUDA-core GEMM with transposed operand loaders; every reduction is
+ * fixed-order (bit-stable gradients).  keep/gamma (nullable) fold the DropPath and layer-scale
+ * factors of cod.py:1112-1116 into the operand load. */
+/* dx[M,K] (+)= (keep.gamma.g)[M,N] . W[N,K]   (. gelu'(pre[M,K]) when pre != NULL) */
+int dgtd_linear_dgrad(const float* g, const float* w, float* dx, const float* pre, const float* keep,
+                      const float* gamma, int rows_per_sample, int M, int N, int K, int accumulate,
+                      dgtd_stream_t stream);
+/* dw[N,K] = (keep.g)^T . a   (split over rows + reduce; ws: dgtd_linear_wgrad_ws_floats floats).
+ * ks > 0: `a` is an NHWC tensor read through the im2col view of dgtd_conv_nhwc_fwd (conv wgrad). */
+int dgtd_linear_wgrad(const float* g, const float* a, float* dw, float* ws, const float* keep, int rows_per_sample,
+                      int M, int N, int K, int ks, int h, int wd, int Cin, int ldx, int oh, int ow, int stride,
+                      int off, dgtd_stream_t stream);
+int dgtd_linear_wgrad_ws_floats(int M, int N, int K);
+/* out[N] = sum_m keep[m/rows] x[m,n]   (ws: cdiv(M,1024)*N floats) */
+int dgtd_colsum(const float* x, const float* keep, int rows_per_sample, float* ws, float* out, int M, int N,
+                dgtd_stream_t stream);
+/* dW2 = gamma.G, db2 = gamma.s, dgamma_n = sum_k W2_nk G_nk + b2_n s_n  (G = (keep.g)^T.h, s = colsum) */
+int dgtd_layer_scale_finalize(const float* G, const float* s, const float* W2, const float* b2, const float* gamma,
+                              float* dW2, float* db2, float* dgamma, int N, int K, dgtd_stream_t stream);
+int dgtd_gelu_fwd(const float* x, float* out, int64_t n, dgtd_stream_t stream);
+int dgtd_relu_bwd(const float* g, const float* out, float* dx, int64_t n, dgtd_stream_t stream);
+/* LayerNorm over rows of C (cod.py:1042-1049) backward: y = pre-norm input, g = dL/d(out) */
+int dgtd_ln_rows_bwd(const float* g, const float* y, const float* w, float* dy, float* ws, float* dw, float* db,
+                     int64_t rows, int C, float eps, dgtd_stream_t stream);
+int dgtd_ln_rows_bwd_ws_floats(int64_t rows, int C);
+/* depthwise 7x7 without the LayerNorm: y = conv(x; wT (49,C), bias) (+ add); flip = rotated taps (dgrad) */
+int dgtd_dwconv7_fwd(const float* x, const float* wT, const float* bias, const float* add, float* y, int B, int h,
+                     int w, int C, int flip, dgtd_stream_t stream);
+/* dwT (49,C), db (C) from x and dy;  ws: (B*cdiv(h,8) + 1) * 50 * C floats */
+int dgtd_dwconv7_wgrad(const float* x, const float* dy, float* ws, float* dwT, float* db, int B, int h, int w, int C,
+                       dgtd_stream_t stream);
+/* stem input gather: patches[(b,oy,ox)][ci*16+ky*4+kx] = image + up(grid); and its adjoint */
+int dgtd_stem_patchify(const float* image, const float* grid, int G, float* patches, int B, int H, int W,
+                       dgtd_stream_t stream);
+int dgtd_stem_unpatchify(const float* dpatches, float* dimg, int B, int H, int W, dgtd_stream_t stream);
+/* 2x2/2 patch gather of an NHWC tensor (rows of 4C, order (dy,dx,c)) and its adjoint */
+int dgtd_patchify2(const float* x, float* out, int B, int h, int w, int C, dgtd_stream_t stream);
+int dgtd_unpatchify2(const float* dp, float* dx, int B, int h, int w, int C, dgtd_stream_t stream);
+/* adjoint of dgtd_resize_nhwc_fwd (fp32): g (B,oh,ow,C) -> dx (B,h,w,C) */
+int dgtd_resize_nhwc_bwd(const float* g, float* dx, int B, int h, int w, int C, int oh, int ow, int accumulate,
+                         dgtd_stream_t stream);
+
 /* ---- dtype / layout plumbing -------------------------------------------------------------- */
 int dgtd_cast_fwd(const void* src, void* dst, int64_t n, int dtype_src, int dtype_dst,
                   dgtd_stream_t stream);

@@ -1,0 +1,100 @@
+"""Training path (config/sod.yml semantics): gradients of every parameter of the hot path through
+the CUDA autograd Functions vs float64 autograd of the CPU oracle on the same seeded inputs.
+Small image (96x96 -> trunk 24/12/6/3) so the oracle backward finishes in seconds."""
+import pytest
+import torch
+
+import common
+from oracle import texture_diffuser_ref as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_grads(enc, dec, image, depth, gout_e3, gout_tok):
+    pe = {k: v.detach().double().clone().requires_grad_(True) for k, v in enc.state_dict().items()}
+    pd = {k: v.detach().double().clone().requires_grad_(True) for k, v in dec.state_dict().items()}
+    e1, e3, toks = O.texture_prompts(image.double(), depth.double(), pe, pd)
+    loss = (e3 * gout_e3.double()).sum()
+    for s in range(4):
+        for i, t in enumerate(toks[s]):
+            loss = loss + (t * gout_tok[s][i].double()).sum()
+    names = [k for k in pe if not k.startswith("adaptor")]
+    ge = torch.autograd.grad(loss, [pe[k] for k in names] + list(pd.values()), allow_unused=True)
+    out = {"enc." + k: g for k, g in zip(names, ge[:len(names)])}
+    out.update({"dec." + k: g for k, g in zip(pd, ge[len(names):])})
+    return (e1, e3, toks), out
+
+
+def test_full_path_gradients_match_oracle():
+    TD = common.package()
+    S, B = 96, 2
+    enc, dec = TD.build_texture_diffuser(seed=0)
+    common.perturb_regressor_(enc)
+    image, depth = common.synthetic_inputs(B, S, seed=3)
+    grids = common.pvt_token_grids((S, S))
+    g = torch.Generator().manual_seed(7)
+    gout_e3 = torch.randn(B, 24, S // 4, S // 4, generator=g) * 1e-2
+    gout_tok = [[torch.randn(B, grids[s][0] * grids[s][1], e, generator=g) * 1e-2 for _ in range(n)]
+                for s, (e, n) in enumerate(zip(common.PVT_EMBED_DIMS, common.PVT_DEPTHS))]
+    (r1, r3, rtoks), ref = _oracle_grads(enc, dec, image, depth, gout_e3, gout_tok)
+
+    enc, dec = enc.cuda().eval(), dec.cuda().eval()      # eval: DropPath off (masks are tested separately)
+    e1, e3, toks = TD.texture_prompts_train(enc, dec, image.cuda(), depth.cuda())
+    assert common.rel_err(e3, r3) <= 1e-4 and common.rel_err(e1, r1) <= 1e-4
+    loss = (e3 * gout_e3.cuda()).sum()
+    for s in range(4):
+        for i, t in enumerate(toks[s]):
+            assert common.rel_err(t, rtoks[s][i]) <= 1e-4
+            loss = loss + (t * gout_tok[s][i].cuda()).sum()
+    loss.backward()
+    worst = ("", 0.0)
+    n_checked = 0
+    for prefix, mod in (("enc.", enc), ("dec.", dec)):
+        for k, p in mod.named_parameters():
+            r = ref.get(prefix + k)
+            if r is None:                                   # adaptor.* never receives a gradient (cod.py:1251)
+                assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+                continue
+            assert p.grad is not None, k
+            err = common.rel_err(p.grad, r)
+            n_checked += 1
+            if err > worst[1]:
+                worst = (prefix + k, err)
+    print("checked", n_checked, "gradients; worst", worst)
+    assert n_checked == 358 - 2 + 96
+    assert worst[1] <= 2e-3, worst     # fp32 accumulation through 36 blocks vs float64
+
+
+def test_module_forwards_build_graphs_like_the_reference_modules():
+    """prompt_encoder(image, cues) / prompt_decoder[s](embedding3) called the reference's way."""
+    TD = common.package()
+    enc, dec = TD.build_texture_diffuser(seed=0)
+    enc, dec = enc.cuda().train(), dec.cuda().train()
+    image, depth = common.synthetic_inputs(1, 96, seed=4)
+    x, emb3 = enc(image.cuda(), depth.cuda())
+    assert emb3.requires_grad and emb3.shape == (1, 24, 24, 24) and not x.requires_grad
+    prompts = dec[1](emb3)
+    assert len(prompts) == 4 and prompts[0].shape == (1, 128, 24, 24)
+    sum(p.sum() for p in prompts).backward()
+    assert enc.encoder2.stages[2][5].pwconv1.weight.grad is not None
+    assert enc.encoder1.weight.grad is not None and enc.propagation_weight_regressor.reg.weight.grad is not None
+    assert dec[1].decoder[3].decoder[4].weight.grad is not None
+    assert dec[0].decoder[0].decoder[0].weight.grad is None and enc.adaptor.weight.grad is None
+
+
+def test_drop_path_mask_scales_the_branch():
+    """Stochastic depth (cod.py:1102,1116): with keep = 0 the block is the identity, with keep = s
+    the branch is scaled by s (timm semantics: mask / keep_prob per sample)."""
+    TD = common.package()
+    from dgtd_b200.twig.ops.functions import train_func as TF
+    blk = TD.convnext_Block(128, drop_path=0.5, layer_scale_init_value=1.0).cuda()
+    x = torch.randn(3, 6, 5, 128, device="cuda")
+    args = (blk.dwconv.weight, blk.dwconv.bias, blk.norm.weight, blk.norm.bias, blk.pwconv1.weight,
+            blk.pwconv1.bias, blk.pwconv2.weight, blk.pwconv2.bias, blk.gamma)
+    with torch.no_grad():
+        full = TF.ConvNextBlockFn.apply(x, *args, None, 1e-6)
+        keep = torch.tensor([0.0, 2.0, 1.0], device="cuda")
+        y = TF.ConvNextBlockFn.apply(x, *args, keep, 1e-6)
+    assert torch.equal(y[0], x[0])
+    assert float((y[1] - (x[1] + 2.0 * (full[1] - x[1]))).abs().max()) < 1e-4
+    assert float((y[2] - full[2]).abs().max()) < 1e-5

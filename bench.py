@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=2, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-diffusion", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--train-batch", type=int, default=16, help="images per GPU per training step (configs[2])")
     return ap.parse_args()
 
 
@@ -135,6 +137,58 @@ def diffusion_microbench(OP, dev, peaks, C=256, S=1024, steps=(1, 2, 4, 8)):
     out["bf16_storage_T1"] = {"ms": ms, "alg_bytes": bb, "gbs": bb / (ms * 1e-3) / 1e9, "hbm_frac": bb / (ms * 1e-3) / 1e9 / hbm,
                               "tflops": 2.0 * 49 * C * S * S / (ms * 1e-3) / 1e12}
     return out
+
+
+def train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding, steps=3, warmup=1):
+    """Forward + backward of the hot path (exact fp32 autograd Functions) on `train-batch` images per
+    GPU; with N > 1 the parameter gradients are all-reduced by DistributedDataParallel (bucketed NCCL
+    all-reduce overlapped with backward -- the reference's own mechanism, cod.py:8,238)."""
+    import torch.distributed as dist
+    import torch.nn as nn
+
+    class HotPath(nn.Module):
+        def __init__(self, enc, dec):
+            super().__init__()
+            self.prompt_encoder, self.prompt_decoder = enc, dec
+
+        def forward(self, image, depth):
+            _, e3, toks = TD.texture_prompts_train(self.prompt_encoder, self.prompt_decoder, image, depth)
+            # scalar stand-in for the downstream loss: every prompt tensor contributes
+            return sum(t.float().mean() for row in toks for t in row) + e3.mean()
+
+    B, S = args.train_batch, args.size
+    model = HotPath(enc, dec).train()
+    if world > 1:
+        model = nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
+    image, depth = common.synthetic_inputs(B, S, seed=100 + rank)
+    image, depth = image.to(dev), depth.to(dev)
+    for p in model.parameters():
+        p.grad = None
+
+    def one():
+        loss = model(image, depth)
+        loss.backward()
+        for p in model.parameters():
+            p.grad = None
+
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        one()
+    b.record()
+    torch.cuda.synchronize()
+    t = sharding.max_over_ranks(a.elapsed_time(b) / 1e3, dev)
+    n_grad = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    enc.eval(); dec.eval()
+    return {"value": world * B * steps / t, "unit": UNIT, "batch_per_gpu": B, "steps": steps, "ms_per_step": t / steps * 1e3,
+            "precision": "fp32 (exact CUDA-core path; tensor-core backward is future work)",
+            "grad_allreduce": "DistributedDataParallel bucketed NCCL all-reduce, %d fp32 grads" % n_grad if world > 1
+            else "none (1 GPU)"}
 
 
 def cpu_model() -> str:
@@ -286,6 +340,11 @@ def run_ours(args):
                     "launches_timed": n, "avg_launch_ms": ms / max(n, 1),
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"}
 
+    # ---- fwd+bwd (BASELINE configs[2]: SOD training, batch 16/GPU, 384^2, data parallel) ----------
+    train = None
+    if not args.no_train:
+        train = train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding)
+
     # ---- diffusion microbench (BASELINE configs[3]): MessagePassing core, 1024^2 x 256, shared weights
     diff = None
     if rank == 0 and not args.no_diffusion:
@@ -308,7 +367,7 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "result": "stage-4 prompt tokens of the last block (B,144,512) fp32"},
             "gpu_launches": int(launches), "clocks": clocks.summary(),
-            "roofline": roof, "cpu_baseline": cpu, "diffusion_microbench": diff,
+            "roofline": roof, "cpu_baseline": cpu, "train_fwd_bwd": train, "diffusion_microbench": diff,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

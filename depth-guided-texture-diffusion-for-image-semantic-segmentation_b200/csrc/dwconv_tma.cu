@@ -17,8 +17,8 @@ namespace dgtd {
 template <int SY, int SX>
 __global__ void __launch_bounds__(SY * SX * 32, 2)
 dwconv7_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ wT,
-                   const float* __restrict__ bias, float* __restrict__ y, int h, int w, int C,
-                   int tiles_x, int tiles_y) {
+                   const float* __restrict__ bias, const float* __restrict__ add, float* __restrict__ y, int h,
+                   int w, int C, int tiles_x, int tiles_y) {
   constexpr int TH = 4 * SY, TW = 8 * SX, PH = TH + 6, PW = TW + 6, NCH = 4;
   constexpr int TILE_FLOATS = PH * PW * 32;
   constexpr uint32_t TILE_BYTES = TILE_FLOATS * 4;
@@ -64,7 +64,7 @@ dwconv7_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restr
       const float t = __ldg(wT + (int64_t)k * C + c);
       w2[k] = pk2(t, t);
     }
-    const float bc = __ldg(bias + c);
+    const float bc = bias ? __ldg(bias + c) : 0.f;
     uint64_t acc[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -103,9 +103,9 @@ dwconv7_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restr
         float v0, v1;
         up2(acc[a][pp], v0, v1);
         const int ox = x0 + 8 * sx + 2 * pp;
-        float* dst = y + (((int64_t)b * h + oy) * w + ox) * C + c;
-        if (ox < w) dst[0] = v0;
-        if (ox + 1 < w) dst[C] = v1;
+        const int64_t o = (((int64_t)b * h + oy) * w + ox) * C + c;
+        if (ox < w) y[o] = add ? v0 + add[o] : v0;
+        if (ox + 1 < w) y[o + C] = add ? v1 + add[o + C] : v1;
       }
     }
     __syncthreads();   // every warp is done with buffer i&1 before it is refilled
@@ -146,8 +146,8 @@ ln_rows_kernel(const float* __restrict__ y, const float* __restrict__ ln_w, cons
 }
 
 template <int SY, int SX>
-static int dw_launch(const CUtensorMap& tm, const float* wT, const float* bias, float* y, int B, int h, int w,
-                     int C, cudaStream_t s) {
+static int dw_launch(const CUtensorMap& tm, const float* wT, const float* bias, const float* add, float* y, int B,
+                     int h, int w, int C, cudaStream_t s) {
   constexpr int PH = 4 * SY + 6, PW = 8 * SX + 6;
   constexpr int SMEM = 2 * PH * PW * 128 + 128;
   auto kern = dwconv7_tma_kernel<SY, SX>;
@@ -162,7 +162,7 @@ static int dw_launch(const CUtensorMap& tm, const float* wT, const float* bias, 
   }
   const int tiles_x = cdiv(w, 8 * SX), tiles_y = cdiv(h, 4 * SY);
   const int64_t blocks = (int64_t)B * tiles_x * tiles_y * (C / 128);
-  kern<<<(unsigned)blocks, SY * SX * 32, SMEM, s>>>(tm, wT, bias, y, h, w, C, tiles_x, tiles_y);
+  kern<<<(unsigned)blocks, SY * SX * 32, SMEM, s>>>(tm, wT, bias, add, y, h, w, C, tiles_x, tiles_y);
   return 0;
 }
 
@@ -182,10 +182,10 @@ static int ln_rows_launch(const float* y, const float* ln_w, const float* ln_b, 
   return 0;
 }
 
-// Two launches: TMA depthwise conv into `ws` (B*h*w*C fp32), then LayerNorm rows -> out.
-// wT: depthwise taps transposed to (49, C).  Returns 1 when the shape is not handled here.
-int dwconv7_ln_tma(const float* x, const float* wT, const float* dw_b, const float* ln_w, const float* ln_b,
-                   float* ws, void* out, int out_dtype, int B, int h, int w, int C, float eps, cudaStream_t s) {
+// TMA depthwise conv only: y = conv(x; wT (49,C), bias) (+ add).  Returns 1 when the shape is not
+// handled here (C not a multiple of 128 / misaligned x).
+int dwconv7_tma(const float* x, const float* wT, const float* dw_b, const float* add, float* y, int B, int h, int w,
+                int C, cudaStream_t s) {
   if (C % 128 || C > 1024 || (reinterpret_cast<uintptr_t>(x) & 15)) return 1;
   const int SX = (w % 24 == 0 && w % 16 != 0) ? 3 : 2;                 // 24-wide maps: 8x24 tiles
   const int SY = (h % 8 == 0 || h > 12) ? 2 : 3;                       // 12-high maps: 12x16 tiles
@@ -201,27 +201,40 @@ int dwconv7_ln_tma(const float* x, const float* wT, const float* dw_b, const flo
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-      set_error("dwconv7_ln(tma): cuTensorMapEncodeTiled failed (%d) for x (%d,%d,%d,%d)", (int)r, B, h, w, C);
+      set_error("dwconv7(tma): cuTensorMapEncodeTiled failed (%d) for x (%d,%d,%d,%d)", (int)r, B, h, w, C);
       return -3;
     }
   }
   int rc;
-  if (SY == 2 && SX == 2) rc = dw_launch<2, 2>(tm, wT, dw_b, ws, B, h, w, C, s);
-  else if (SY == 2 && SX == 3) rc = dw_launch<2, 3>(tm, wT, dw_b, ws, B, h, w, C, s);
-  else if (SY == 3 && SX == 2) rc = dw_launch<3, 2>(tm, wT, dw_b, ws, B, h, w, C, s);
-  else rc = dw_launch<3, 3>(tm, wT, dw_b, ws, B, h, w, C, s);
+  if (SY == 2 && SX == 2) rc = dw_launch<2, 2>(tm, wT, dw_b, add, y, B, h, w, C, s);
+  else if (SY == 2 && SX == 3) rc = dw_launch<2, 3>(tm, wT, dw_b, add, y, B, h, w, C, s);
+  else if (SY == 3 && SX == 2) rc = dw_launch<3, 2>(tm, wT, dw_b, add, y, B, h, w, C, s);
+  else rc = dw_launch<3, 3>(tm, wT, dw_b, add, y, B, h, w, C, s);
   if (rc) return rc;
-  {
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) {
-      set_error("dwconv7_tma: launch failed: %s", cudaGetErrorString(e));
-      return -2;
-    }
-    count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("dwconv7_tma: launch failed: %s", cudaGetErrorString(e));
+    return -2;
   }
+  count_launch();
+  return 0;
+}
+
+// Two launches: TMA depthwise conv into `ws` (B*h*w*C fp32), then LayerNorm rows -> out.
+int dwconv7_ln_tma(const float* x, const float* wT, const float* dw_b, const float* ln_w, const float* ln_b,
+                   float* ws, void* out, int out_dtype, int B, int h, int w, int C, float eps, cudaStream_t s) {
+  int rc = dwconv7_tma(x, wT, dw_b, nullptr, ws, B, h, w, C, s);
+  if (rc) return rc;
   const int64_t rows = (int64_t)B * h * w;
   return out_dtype == DGTD_BF16 ? ln_rows_launch(ws, ln_w, ln_b, (__nv_bfloat16*)out, rows, C, eps, s)
                                 : ln_rows_launch(ws, ln_w, ln_b, (float*)out, rows, C, eps, s);
+}
+
+// LayerNorm rows only (fp32 in, fp32|bf16 out); C multiple of 128
+int ln_rows_any(const float* y, const float* ln_w, const float* ln_b, void* out, int out_dtype, int64_t rows, int C,
+                float eps, cudaStream_t s) {
+  return out_dtype == DGTD_BF16 ? ln_rows_launch(y, ln_w, ln_b, (__nv_bfloat16*)out, rows, C, eps, s)
+                                : ln_rows_launch(y, ln_w, ln_b, (float*)out, rows, C, eps, s);
 }
 
 }  // namespace dgtd

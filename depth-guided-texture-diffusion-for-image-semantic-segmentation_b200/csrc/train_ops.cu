@@ -6,6 +6,9 @@
 
 namespace dgtd {
 
+int dwconv7_tma(const float* x, const float* wT, const float* dw_b, const float* add, float* y, int B, int h, int w,
+                int C, cudaStream_t s);
+
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   // d/dx [0.5 x (1 + erf(x/sqrt2))] = Phi(x) + x phi(x)
   const float phi = 0.3989422804014327f * expf(-0.5f * x * x);
@@ -457,6 +460,10 @@ int dgtd_ln_rows_bwd_ws_floats(int64_t rows, int C) {
 int dgtd_dwconv7_fwd(const float* x, const float* wT, const float* bias, const float* add, float* y, int B, int h,
                      int w, int C, int flip, dgtd_stream_t stream) {
   DGTD_CHECK_ARG(x && wT && y && B > 0 && h > 0 && w > 0 && C % 128 == 0, "dwconv7: bad args (C multiple of 128)");
+  if (!flip && (int64_t)B * h * w >= 2048) {   // TMA-staged kernel (the caller passes rotated taps for dgrad)
+    int rc = dwconv7_tma(x, wT, bias, add, y, B, h, w, C, (cudaStream_t)stream);
+    if (rc <= 0) return rc;
+  }
   dwconv7_plain_kernel<<<dim3(C / 128, cdiv(h, 8), B), 128, 0, (cudaStream_t)stream>>>(x, wT, bias, add, y, h, w, C, flip);
   DGTD_LAUNCH_CHECK("dwconv7");
   return 0;

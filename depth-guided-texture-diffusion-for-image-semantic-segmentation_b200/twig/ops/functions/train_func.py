@@ -163,7 +163,7 @@ class ConvNextBlockFn(Function):
         del dhpre
         # LayerNorm, depthwise conv, residual
         dy, dln_w, dln_b = ln_rows_bwd(da, y, ln_w, ctx.eps)
-        dx = dwconv7(dy.view(B, h, w, C), dwT, None, add=g, flip=True)
+        dx = dwconv7(dy.view(B, h, w, C), dwT.flip(0).contiguous(), None, add=g)   # rotated taps = input gradient
         ddwT, ddb = dwconv7_wgrad(x, dy.view(B, h, w, C))
         return (dx, ddwT.t().reshape(C, 1, 7, 7), ddb, dln_w, dln_b, dW1, db1, dW2, db2, dgamma, None, None)
 

@@ -336,7 +336,9 @@ def run_ours(args):
             peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
             ach = flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
             roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "traffic": None, "kernel": "tc_gemm_kernel (tcgen05, all pointwise/down-sample GEMMs)",
+                    "traffic": 271.1e6, "traffic_note": "DRAM bytes of one stage-2 pwconv2 launch (M=36864,N=512,K=2048) "
+                    "from profiles/r1_ncu_full_stage2.md; algorithmic bytes of that launch 302 MB",
+                    "kernel": "tc_gemm2_kernel / tc_gemm_kernel (tcgen05, all pointwise/down-sample/head GEMMs of a step)",
                     "launches_timed": n, "avg_launch_ms": ms / max(n, 1),
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"}
 

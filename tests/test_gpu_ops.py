@@ -362,7 +362,68 @@ def test_bilinear_resize_adjoint_identity():
         x = torch.randn(2, 3, h, w, generator=g).cuda().requires_grad_(True)
         y = torch.randn(2, 3, oh, ow, generator=g).cuda()
         r = OPS.resize_bilinear_nchw_autograd(x, (oh, ow))
-        lhs = float((r.double() * y.double()).sum())
+        lhs = float((r.detach().double() * y.double()).sum())
         r.backward(y)
         rhs = float((x.detach().double() * x.grad.double()).sum())
         assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs)), (h, w, oh, ow, lhs, rhs)
+
+
+# ---- randomized shape sweeps (hypothesis), oracle = float64 torch on the same inputs ---------------
+from hypothesis import given, settings, strategies as st, HealthCheck
+
+_sweep = settings(max_examples=12, deadline=None, derandomize=True,
+                  suppress_health_check=[HealthCheck.function_scoped_fixture])
+
+
+@_sweep
+@given(n=st.integers(1, 3), c=st.integers(1, 5), h=st.integers(1, 20), w=st.integers(1, 20),
+       shared=st.booleans(), T=st.integers(0, 5))
+def test_sweep_message_passing_core(OP, n, c, h, w, shared, T):
+    g = torch.Generator().manual_seed(1000 * n + 100 * c + 10 * h + w)
+    x = torch.randn(n, c, h, w, generator=g)
+    wgt = torch.rand(n, (1 if shared else c) * 49, h, w, generator=g)
+    ref = O.message_passing_core(x.double(), wgt.double(), 7, T)
+    check(OP.message_passing_core(x.cuda(), wgt.cuda(), T), ref, 1e-5)
+
+
+@_sweep
+@given(M=st.integers(1, 700), N4=st.integers(1, 40), K4=st.integers(1, 40), act=st.sampled_from([0, 1, 2]))
+def test_sweep_linear_fp32(OP, M, N4, K4, act):
+    N, K = 4 * N4, 4 * K4
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    a, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    ref = a.double() @ w.double().t() + b.double()
+    ref = O.gelu_erf(ref) if act == 1 else (ref.clamp_min(0) if act == 2 else ref)
+    check(OP.linear(a.cuda(), w.cuda(), b.cuda(), act=act), ref, 1e-5)
+
+
+@_sweep
+@given(planes=st.integers(1, 4), h=st.integers(1, 30), w=st.integers(1, 30), oh=st.integers(1, 40), ow=st.integers(1, 40))
+def test_sweep_bilinear_resize(OP, planes, h, w, oh, ow):
+    x = torch.randn(1, planes, h, w, generator=torch.Generator().manual_seed(h * 31 + w))
+    check(OP.resize_nchw(x.cuda(), (oh, ow), True), O.bilinear_resize(x.double(), (oh, ow)), 2e-5)
+
+
+@_sweep
+@given(B=st.integers(1, 2), h4=st.integers(3, 12), w4=st.integers(3, 12))
+def test_sweep_fft_highpass_sizes(OP, B, h4, w4):
+    """H, W multiples of 4 (the only constraint of the projector form); non-square, tiny, line = 0 .. n/2."""
+    H, W = 4 * h4, 4 * w4
+    x = torch.randn(B, 3, H, W, generator=torch.Generator().manual_seed(H * 100 + W))
+    check(OP.fft_highpass(x.cuda()), O.fft_highpass(x.double()), 2e-5)
+
+
+def test_fft_highpass_properties_at_full_size(OP):
+    """Size-independent properties at 384^2, B=8: output >= 0; the operator |x - P x| kills what P keeps
+    (a pure low-frequency image maps to ~0) and leaves a pure high-frequency image unchanged in magnitude."""
+    S = 384
+    yy, xx = torch.meshgrid(torch.arange(S, dtype=torch.float64), torch.arange(S, dtype=torch.float64), indexing="ij")
+    low = torch.cos(2 * torch.pi * 5 * yy / S) * torch.cos(2 * torch.pi * 40 * xx / S)       # |k| < 105: removed band
+    high = torch.cos(2 * torch.pi * 150 * yy / S) * torch.cos(2 * torch.pi * 120 * xx / S)   # outside the band
+    mixed = torch.cos(2 * torch.pi * 5 * yy / S) * torch.cos(2 * torch.pi * 150 * xx / S)    # one axis outside: kept
+    x = torch.stack([low, high, mixed]).float()[None].repeat(8, 1, 1, 1).cuda()
+    y = OP.fft_highpass(x)
+    assert float(y.min()) >= 0.0
+    assert float(y[:, 0].abs().max()) < 1e-4
+    assert float((y[:, 1] - x[:, 1].abs()).abs().max()) < 1e-4
+    assert float((y[:, 2] - x[:, 2].abs()).abs().max()) < 1e-4

@@ -300,6 +300,8 @@ __global__ void resize_nhwc_kernel(const IT* __restrict__ x, OT* __restrict__ ou
 }  // namespace dgtd
 
 namespace dgtd {
+int ln_rows_any(const float* y, const float* ln_w, const float* ln_b, void* out, int out_dtype, int64_t rows, int C,
+                float eps, cudaStream_t s);
 int dwconv7_ln_tma(const float* x, const float* wT, const float* dw_b, const float* ln_w, const float* ln_b,
                    float* ws, void* out, int out_dtype, int B, int h, int w, int C, float eps, cudaStream_t s);
 }
@@ -407,6 +409,15 @@ int dgtd_dwconv7_ln_tma_fwd(const float* x, const float* dw_wT, const float* dw_
   }
   if (rc) return rc;
   DGTD_LAUNCH_CHECK("dwconv7_ln_tma.ln");
+  return 0;
+}
+
+int dgtd_ln_rows_fwd(const float* y, const float* ln_w, const float* ln_b, void* out, int out_dtype, int64_t rows,
+                     int C, float eps, dgtd_stream_t stream) {
+  DGTD_CHECK_ARG(y && ln_w && ln_b && out && rows > 0 && C % 128 == 0 && C <= 1024, "ln_rows: bad args");
+  int rc = ln_rows_any(y, ln_w, ln_b, out, out_dtype, rows, C, eps, (cudaStream_t)stream);
+  if (rc) return rc;
+  DGTD_LAUNCH_CHECK("ln_rows");
   return 0;
 }
 

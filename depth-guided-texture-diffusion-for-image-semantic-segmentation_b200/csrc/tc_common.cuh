@@ -74,6 +74,8 @@ struct TcParams {
   int rows_per_sample;
   void* out;
   int64_t ldo;
+  int splits = 1;         // split-K (weight gradients): split z handles k-blocks [z*kb_per_split, ...)
+  int kb_per_split = 0;   // and writes rows [z*M, (z+1)*M) of a (splits*M) x N partial buffer
 };
 
 

@@ -104,8 +104,10 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t rank = bw2::cta_rank();
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-  const int num_tiles = p.tiles_m * p.tiles_n;   // tiles_m counts 256-row pair tiles
+  const int tiles_mn = p.tiles_m * p.tiles_n;    // tiles_m counts 256-row pair tiles
+  const int num_tiles = tiles_mn * p.splits;
   const int num_kb = (p.K + BK - 1) / BK;
+  const int kbs = p.splits > 1 ? p.kb_per_split : num_kb;
 
   bw2::cluster_sync();  // both CTAs resident before the pair-wide TMEM allocation
   if (warp == 0 && lane == 0) {
@@ -136,10 +138,12 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
+        const int z = tile / tiles_mn, t2 = tile - z * tiles_mn;
+        const int m_blk = t2 / p.tiles_n, n_blk = t2 - m_blk * p.tiles_n;
         const int m0 = m_blk * 256 + (int)rank * BM;
         const int n0 = n_blk * BN + (int)rank * (BN / 2);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = z * kbs, kb1 = min(num_kb, kb0 + kbs);
+        for (int kb = kb0; kb < kb1; ++kb) {
           bw::mbar_wait(&empty[stage], phase ^ 1);
           const uint32_t lbar = bw2::map_to_rank(&full[stage], 0);
           bw2::tma_load_2d_2sm(&tmA, lbar, sA + stage * Cfg::A_BYTES, kb * BK, m0);
@@ -162,16 +166,18 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         bw::mbar_wait(&tempty[as], aphase ^ 1);
         bw::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int z = tile / tiles_mn;
+        const int kb0 = z * kbs, kb1 = min(num_kb, kb0 + kbs);
+        for (int kb = kb0; kb < kb1; ++kb) {
           bw::mbar_wait(&full[stage], phase);
           bw::tc_fence_after();
           const uint64_t da = bw::umma_smem_desc_kmajor(bw::smem_u32(sA + stage * Cfg::A_BYTES), 128);
           const uint64_t db = bw::umma_smem_desc_kmajor(bw::smem_u32(sB + stage * Cfg::B_BYTES), 128);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            bw2::umma_bf16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            bw2::umma_bf16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, ((kb - kb0) | k) != 0);
           bw2::umma_commit_2sm(&empty[stage]);
-          if (kb == num_kb - 1) bw2::umma_commit_2sm(&tfull[as]);
+          if (kb == kb1 - 1) bw2::umma_commit_2sm(&tfull[as]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -184,14 +190,15 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t sbuf = 0;
     int iter = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++iter) {
-      const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
+      const int z = tile / tiles_mn, t2 = tile - z * tiles_mn;
+      const int m_blk = t2 / p.tiles_n, n_blk = t2 - m_blk * p.tiles_n;
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
       bw::mbar_wait(&tfull[as], aphase);
       bw::tc_fence_after();
       const uint32_t rel = bw2::map_to_rank(&tempty[as], 0);
       tc_epilogue_tile_tma<BN, ACT, OT, RESIDUAL>(p, &tmOut, &tmRes, tmem_base + as * BN, quad, half, lane,
-                                                  m_blk * 256 + (int)rank * BM + quad * 32, n_blk, stg, rbar,
+                                                  z * p.M + m_blk * 256 + (int)rank * BM + quad * 32, n_blk, stg, rbar,
                                                   sbuf, [rel] { bw2::mbar_arrive_cluster(rel); });
     }
     if (lane == 0) bw::tma_store_wait_all<0>();   // all results are in global memory before exit
@@ -236,7 +243,7 @@ static int tc2_launch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* 
   CUtensorMap tmOut, tmRes;
   {
     constexpr bool BF = sizeof(OT) == 2;
-    uint64_t dims[2] = {(uint64_t)p.N, (uint64_t)p.M}, str[1] = {(uint64_t)p.ldo * sizeof(OT)};
+    uint64_t dims[2] = {(uint64_t)p.N, (uint64_t)p.M * (uint64_t)p.splits}, str[1] = {(uint64_t)p.ldo * sizeof(OT)};
     uint32_t box[2] = {BF ? 64u : 32u, 32u};
     int rc = make_tmap(&tmOut, p.out, BF ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                        dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -250,7 +257,7 @@ static int tc2_launch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* 
   }
   p.tiles_m = cdiv(p.M, 256);
   p.tiles_n = cdiv(p.N, BN);
-  int tiles = p.tiles_m * p.tiles_n;
+  int tiles = p.tiles_m * p.tiles_n * p.splits;
   int pairs = sm_count() / 2;
   int clusters = tiles < pairs ? tiles : pairs;
   kern<<<2 * clusters, 384, Cfg::SMEM_BYTES, s>>>(tmA, tmB, tmOut, tmRes, p);
@@ -283,6 +290,25 @@ int tc_gemm2_launch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B,
   if (p.N % 256 == 0 && pair_tiles_256 >= sm_count() / 2)
     return tc2_dispatch<256>(A, lda, B, ldb, p, act, dtype_out, residual, s);
   return tc2_dispatch<128>(A, lda, B, ldb, p, act, dtype_out, residual, s);
+}
+
+// Split-K partial products for weight gradients: partial[z] (M x N fp32) = A[:, Kz] . B[:, Kz]^T
+int tc_gemm2_splitk(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B, int64_t ldb, float* partial, int M,
+                    int N, int K, int splits, cudaStream_t s) {
+  TcParams p{};
+  p.M = M; p.N = N; p.K = K; p.out = partial; p.ldo = N; p.rows_per_sample = 1;
+  p.splits = splits;
+  const int num_kb = cdiv(K, 64);
+  p.kb_per_split = cdiv(num_kb, splits);
+  if ((int64_t)(splits - 1) * p.kb_per_split >= num_kb) {   // every split must own at least one k-block
+    p.splits = cdiv(num_kb, p.kb_per_split);
+  }
+  if (p.splits != splits) {
+    set_error("tc_gemm2_splitk: %d splits leave an empty split for K=%d", splits, K);
+    return -1;
+  }
+  if (N % 256 == 0) return tc2_launch<256, DGTD_ACT_NONE, float, false>(A, lda, B, ldb, p, s);
+  return tc2_launch<128, DGTD_ACT_NONE, float, false>(A, lda, B, ldb, p, s);
 }
 
 }  // namespace dgtd

@@ -1,0 +1,160 @@
+// bf16 / tensor-core training path of the trunk: operand preparation for the tcgen05 gradient GEMMs.
+//   dgrad  dX[M,K] = dY[M,N] . W[N,K]      -> tc_gemm2 with A = dY (bf16), B = W^T (cached)
+//   wgrad  dW^T[K,N] = X^T[K,M] . dY^T[N,M] -> tc_gemm2 with both operands transposed (K-major over
+//                                             the M rows) and split-K over M + fixed-order reduce
+// The transposes are fused with the element-wise work that is needed anyway (DropPath / layer-scale
+// factors, GELU and its derivative, bf16 down-cast), one pass over each tensor.
+#include "tc_common.cuh"
+
+namespace dgtd {
+
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float phi = 0.3989422804014327f * expf(-0.5f * x * x);
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * phi;
+}
+
+// MODE 0: v = keep[m] * src[m,n]            (dst additionally * gamma[n])
+// MODE 1: v = gelu(src[m,n])
+// MODE 2: v = src[m,n] * gelu'(aux[m,n])    (src = dH, aux = pre-activation)
+// dst  (M x N, bf16, nullable) = v (* gamma);  dstT (N x M, bf16, nullable) = v
+template <typename ST, int MODE>
+__global__ void __launch_bounds__(256)
+transpose_op_kernel(const ST* __restrict__ src, const __nv_bfloat16* __restrict__ aux,
+                    __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dstT,
+                    const float* __restrict__ keep, const float* __restrict__ gamma, int rows_per_sample, int M,
+                    int N) {
+  __shared__ float t[32][33];
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int m = m0 + i, n = n0 + threadIdx.x;
+    float v = 0.f;
+    if (m < M && n < N) {
+      v = to_float(src[(int64_t)m * N + n]);
+      if (MODE == 0 && keep) v *= keep[m / rows_per_sample];
+      if (MODE == 1) v = gelu_erf(v);
+      if (MODE == 2) v *= gelu_grad_f(__bfloat162float(aux[(int64_t)m * N + n]));
+      // MODE 3: plain bf16 transpose / copy
+      if (dst) dst[(int64_t)m * N + n] = __float2bfloat16_rn(MODE == 0 && gamma ? v * gamma[n] : v);
+    }
+    t[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (dstT)
+    for (int i = threadIdx.y; i < 32; i += 8) {
+      const int n = n0 + i, m = m0 + threadIdx.x;
+      if (n < N && m < M) dstT[(int64_t)n * M + m] = __float2bfloat16_rn(t[threadIdx.x][i]);
+    }
+}
+
+// column sums of a bf16 matrix: part[blk][n], then sum over blocks
+__global__ void __launch_bounds__(256)
+colsum_bf16_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ part, int M, int N,
+                           int rows_per_block) {
+  __shared__ float red[8][32];
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float s = 0.f;
+  if (n < N)
+    for (int r = r0 + (threadIdx.x >> 5); r < r1; r += 8) s += __bfloat162float(x[(int64_t)r * N + n]);
+  red[threadIdx.x >> 5][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (threadIdx.x < 32 && n < N) {
+    float tt = 0.f;
+    for (int i = 0; i < 8; ++i) tt += red[i][threadIdx.x];
+    part[(int64_t)blockIdx.y * N + n] = tt;
+  }
+}
+__global__ void sum_parts_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int S,
+                                 int transpose_rows, int transpose_cols) {
+  // out[i] = sum_z part[z][i];  with transpose_rows > 0 the (rows x cols) result is written transposed
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int z = 0; z < S; ++z) s += part[(int64_t)z * n + i];
+  if (transpose_rows > 0) {
+    const int64_t r = i / transpose_cols, c = i - r * transpose_cols;
+    out[c * transpose_rows + r] = s;
+  } else {
+    out[i] = s;
+  }
+}
+
+int tc_gemm2_splitk(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B, int64_t ldb, float* partial, int M,
+                    int N, int K, int splits, cudaStream_t s);
+
+}  // namespace dgtd
+
+using namespace dgtd;
+
+extern "C" {
+
+// mode 0: scale/cast (src fp32), 1: gelu (src bf16), 2: gelu backward (src = dH bf16, aux = pre bf16), 3: copy
+int dgtd_transpose_op(const void* src, const void* aux, void* dst, void* dstT, const float* keep, const float* gamma,
+                      int rows_per_sample, int M, int N, int mode, dgtd_stream_t stream) {
+  DGTD_CHECK_ARG(src && (dst || dstT) && M > 0 && N > 0 && mode >= 0 && mode <= 3, "transpose_op: bad args");
+  DGTD_CHECK_ARG(mode != 2 || aux, "transpose_op: gelu backward needs the pre-activation");
+  dim3 grid(cdiv(N, 32), cdiv(M, 32)), block(32, 8);
+  DGTD_CHECK_ARG(grid.y <= 65535, "transpose_op: too many rows for one launch");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int rps = rows_per_sample > 0 ? rows_per_sample : 1;
+  if (mode == 0)
+    transpose_op_kernel<float, 0><<<grid, block, 0, s>>>((const float*)src, nullptr, (__nv_bfloat16*)dst,
+                                                          (__nv_bfloat16*)dstT, keep, gamma, rps, M, N);
+  else if (mode == 1)
+    transpose_op_kernel<__nv_bfloat16, 1><<<grid, block, 0, s>>>((const __nv_bfloat16*)src, nullptr,
+                                                                  (__nv_bfloat16*)dst, (__nv_bfloat16*)dstT, nullptr,
+                                                                  nullptr, 1, M, N);
+  else if (mode == 2)
+    transpose_op_kernel<__nv_bfloat16, 2><<<grid, block, 0, s>>>((const __nv_bfloat16*)src, (const __nv_bfloat16*)aux,
+                                                                  (__nv_bfloat16*)dst, (__nv_bfloat16*)dstT, nullptr,
+                                                                  nullptr, 1, M, N);
+  else
+    transpose_op_kernel<__nv_bfloat16, 3><<<grid, block, 0, s>>>((const __nv_bfloat16*)src, nullptr,
+                                                                  (__nv_bfloat16*)dst, (__nv_bfloat16*)dstT, nullptr,
+                                                                  nullptr, 1, M, N);
+  DGTD_LAUNCH_CHECK("transpose_op");
+  return 0;
+}
+
+int dgtd_colsum_bf16(const void* x, float* ws, float* out, int M, int N, dgtd_stream_t stream) {
+  DGTD_CHECK_ARG(x && ws && out && M > 0 && N > 0, "colsum_bf16: bad args");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nb = cdiv(M, 1024);
+  colsum_bf16_partial_kernel<<<dim3(cdiv(N, 32), nb), 256, 0, s>>>((const __nv_bfloat16*)x, ws, M, N, 1024);
+  DGTD_LAUNCH_CHECK("colsum_bf16");
+  sum_parts_kernel<<<cdiv(N, 256), 256, 0, s>>>(ws, out, N, nb, 0, 0);
+  DGTD_LAUNCH_CHECK("colsum_bf16.reduce");
+  return 0;
+}
+
+// out = aT[Mo, Kr] . bT[No, Kr]^T  (fp32), reduction over the long Kr axis split across CTA pairs.
+// transpose_out != 0 writes out as (No x Mo).  ws: splits*Mo*No floats (dgtd_wgrad_tc_ws_floats).
+static int wgrad_splits(int Mo, int No, int Kr) {
+  const int tiles = cdiv(Mo, 256) * cdiv(No, No % 256 == 0 ? 256 : 128);
+  int s = cdiv(148, tiles);
+  const int kb = cdiv(Kr, 64);
+  if (s > kb / 4) s = kb / 4;
+  if (s < 1) s = 1;
+  if (s > 64) s = 64;
+  const int kbps = cdiv(kb, s);
+  return cdiv(kb, kbps);   // no empty split
+}
+int dgtd_wgrad_tc_ws_floats(int Mo, int No, int Kr) { return wgrad_splits(Mo, No, Kr) * Mo * No; }
+
+int dgtd_wgrad_tc(const void* aT, const void* bT, float* out, float* ws, int Mo, int No, int Kr, int transpose_out,
+                  dgtd_stream_t stream) {
+  DGTD_CHECK_ARG(aT && bT && out && ws, "wgrad_tc: null pointer");
+  DGTD_CHECK_ARG(Mo >= 256 && Mo % 256 == 0 && No >= 128 && No % 8 == 0 && Kr >= 64 && Kr % 8 == 0,
+                 "wgrad_tc: need Mo %% 256 == 0, No >= 128, Kr %% 8 == 0 (got %d, %d, %d)", Mo, No, Kr);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int S = wgrad_splits(Mo, No, Kr);
+  int rc = tc_gemm2_splitk((const __nv_bfloat16*)aT, Kr, (const __nv_bfloat16*)bT, Kr, ws, Mo, No, Kr, S, s);
+  if (rc) return rc;
+  DGTD_LAUNCH_CHECK("wgrad_tc");
+  const int64_t n = (int64_t)Mo * No;
+  sum_parts_kernel<<<cdiv(n, 256), 256, 0, s>>>(ws, out, n, S, transpose_out ? Mo : 0, No);
+  DGTD_LAUNCH_CHECK("wgrad_tc.reduce");
+  return 0;
+}
+
+}  // extern "C"

@@ -188,16 +188,19 @@ class convnext_Block(nn.Module):
         OP.linear_residual_(hid, w2, self.pwconv2.bias.detach(), gamma, keep, h * w, x)
         return x
 
-    def _forward_train(self, x: torch.Tensor) -> torch.Tensor:
-        """NHWC fp32 in/out with an autograd graph (DropPath mask drawn like timm's, cod.py:1102)."""
+    def _forward_train(self, x: torch.Tensor, mode: int = F32) -> torch.Tensor:
+        """NHWC fp32 in/out with an autograd graph (DropPath mask drawn like timm's, cod.py:1102).
+        mode BF16: pointwise GEMMs and their gradients on tcgen05 (bf16 operands, fp32 accumulate)."""
         keep = self.drop_path.keep_scale(x.shape[0], x.device) if isinstance(self.drop_path, DropPath) else None
-        return TF.ConvNextBlockFn.apply(x, self.dwconv.weight, self.dwconv.bias, self.norm.weight, self.norm.bias,
+        M = x.shape[0] * x.shape[1] * x.shape[2]
+        fn = TF.ConvNextBlockBf16Fn if (mode == BF16 and TF.tc_rows_ok(M) and x.shape[-1] % 128 == 0) else TF.ConvNextBlockFn
+        return fn.apply(x, self.dwconv.weight, self.dwconv.bias, self.norm.weight, self.norm.bias,
                                         self.pwconv1.weight, self.pwconv1.bias, self.pwconv2.weight,
                                         self.pwconv2.bias, self.gamma, keep, self.norm.eps)
 
     def forward(self, x):
         if _wants_grad(self, x):
-            return TF.LayoutFn.apply(self._forward_train(TF.LayoutFn.apply(x, True)), False)
+            return TF.LayoutFn.apply(self._forward_train(TF.LayoutFn.apply(x, True), _mode(self)), False)
         y = OP.nchw_to_nhwc(x.contiguous().float())
         y = self._forward_nhwc(y, _mode(self))
         return y.permute(0, 3, 1, 2)  # (N,C,H,W) view with channels-last strides
@@ -282,24 +285,27 @@ class ShapePropEncoder(nn.Module):
         return OP.fusion_head(levels, hw, wf, self.fusion_conv.bias.detach(), B, want_nhwc=True,
                               want_nchw=want_nchw, pad_to=pad_to)
 
-    def _forward_train(self, image: torch.Tensor, grid: Optional[torch.Tensor]) -> torch.Tensor:
-        """Autograd-building path (exact fp32): returns embedding3 as NHWC (B,h0,w0,out_dim)."""
+    def _forward_train(self, image: torch.Tensor, grid: Optional[torch.Tensor], mode: int = F32) -> torch.Tensor:
+        """Autograd-building path: returns embedding3 as NHWC (B,h0,w0,out_dim).  mode F32 = exact
+        CUDA-core path; BF16 = trunk GEMMs (forward, dgrad, wgrad) on tcgen05."""
         st_conv, st_ln = self.downsample_layers[0][0], self.downsample_layers[0][1]
         x = TF.StemFn.apply(image, grid, st_conv.weight, st_conv.bias, st_ln.weight, st_ln.bias, st_ln.eps)
         levels = []
         for i in range(4):
             if i > 0:
                 ln, conv = self.downsample_layers[i][0], self.downsample_layers[i][1]
-                x = TF.DownsampleFn.apply(x, ln.weight, ln.bias, conv.weight, conv.bias, ln.eps)
+                Mo = x.shape[0] * (x.shape[1] // 2) * (x.shape[2] // 2)
+                ds = TF.DownsampleBf16Fn if (mode == BF16 and TF.tc_rows_ok(Mo)) else TF.DownsampleFn
+                x = ds.apply(x, ln.weight, ln.bias, conv.weight, conv.bias, ln.eps)
             for blk in self.stages[i]:
-                x = blk._forward_train(x)
+                x = blk._forward_train(x, mode)
             levels.append(TF.LinearFn.apply(x, self.convs[i].weight, self.convs[i].bias))
         return TF.FusionFn.apply(levels[0], levels[1], levels[2], levels[3], self.fusion_conv.weight,
                                  self.fusion_conv.bias)
 
     def forward(self, x):
         if _wants_grad(self, x):
-            return TF.LayoutFn.apply(self._forward_train(x, None), False)
+            return TF.LayoutFn.apply(self._forward_train(x, None, _mode(self)), False)
         outs = self._pyramid(x.contiguous().float(), None, _mode(self))
         _, nchw, _ = self._head(outs, want_nchw=True, mode=_mode(self))
         return nchw
@@ -554,9 +560,10 @@ class prompt_encoder(nn.Module):
         nhwc, nchw, pad = self.encoder2._head(outs, want_nchw=want_nchw, pad_to=pad_to, mode=mode)
         return x, nhwc, nchw, pad
 
-    def _forward_train(self, image: torch.Tensor, cues: torch.Tensor):
+    def _forward_train(self, image: torch.Tensor, cues: torch.Tensor, mode: Optional[int] = None):
         """Training path (cod.py:1288-1302 op by op, each an autograd Function on the CUDA kernels):
         returns (embedding1, embedding3 NHWC)."""
+        mode = _mode(self) if mode is None else mode
         H = 12
         image = image.contiguous().float()
         x = self.fft(image, self.freq_nums)                                            # no parameter upstream
@@ -568,7 +575,7 @@ class prompt_encoder(nn.Module):
         steps = H if mp.max_step < 0 else mp.max_step
         core = OP.message_passing_core(d12, weights, steps, 1e-5)
         grid3 = OP.conv1x1_nchw_autograd(core, mp.conv.weight, mp.conv.bias, False)     # :1206 (up-sample fused in the stem)
-        return x, self.encoder2._forward_train(image, grid3)                           # :1302
+        return x, self.encoder2._forward_train(image, grid3, mode)                     # :1302
 
     def forward(self, image, cues, cross=False):
         if _wants_grad(self, cues):
@@ -636,9 +643,12 @@ def pvt_token_grids(img_hw: Sequence[int]) -> List[Tuple[int, int]]:
     return out
 
 
-def texture_prompts_train(enc: "prompt_encoder", dec: nn.Sequential, image: torch.Tensor, depth: torch.Tensor):
-    """Same contract as `texture_prompts`, building an autograd graph (exact fp32 training path)."""
-    emb1, emb3 = enc._forward_train(image, depth)                  # emb3: NHWC
+def texture_prompts_train(enc: "prompt_encoder", dec: nn.Sequential, image: torch.Tensor, depth: torch.Tensor,
+                          precision: Optional[str] = None):
+    """Same contract as `texture_prompts`, building an autograd graph.  precision "fp32" = exact path,
+    "bf16" = trunk GEMMs on tcgen05 (None: follow set_precision / torch.autocast)."""
+    mode = _mode(enc) if precision is None else (BF16 if precision == "bf16" else F32)
+    emb1, emb3 = enc._forward_train(image, depth, mode)            # emb3: NHWC
     grids = pvt_token_grids(image.shape[-2:])
     B = image.shape[0]
     tokens = []

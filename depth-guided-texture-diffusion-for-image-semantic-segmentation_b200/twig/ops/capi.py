@@ -64,6 +64,11 @@ SIGNATURES = {
     "dgtd_patchify2": [_P, _P, _I, _I, _I, _I, _P],
     "dgtd_unpatchify2": [_P, _P, _I, _I, _I, _I, _P],
     "dgtd_resize_nhwc_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "dgtd_transpose_op": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "dgtd_colsum_bf16": [_P, _P, _P, _I, _I, _P],
+    "dgtd_wgrad_tc": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "dgtd_wgrad_tc_ws_floats": [_I, _I, _I],
+    "dgtd_ln_rows_fwd": [_P, _P, _P, _P, _I, _L, _I, _F, _P],
     "dgtd_cast_fwd": [_P, _P, _L, _I, _I, _P],
     "dgtd_nhwc_to_nchw_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "dgtd_nchw_to_nhwc_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _P],

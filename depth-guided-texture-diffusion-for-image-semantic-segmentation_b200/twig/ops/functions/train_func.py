@@ -15,7 +15,7 @@ from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
 from .. import capi
-from ..capi import ACT_NONE, ACT_RELU, F32, call, check_cuda, ptr, stream
+from ..capi import ACT_NONE, ACT_RELU, BF16, F32, call, check_cuda, ptr, stream
 from . import texture_diffusion_func as OP
 
 
@@ -93,7 +93,137 @@ def dwconv7_wgrad(x, dy):
     return dwT, db
 
 
+# ---- bf16 / tensor-core helpers (operands of the tcgen05 gradient GEMMs) ------------------------------
+def transpose_op(src, mode, aux=None, want_dst=False, want_T=True, keep=None, gamma=None, rows_per_sample=1):
+    """One pass over a 2-D tensor producing bf16 `dst` (same layout) and / or `dstT` (transposed):
+    mode 0 scale+cast (fp32 src), 1 gelu, 2 src*gelu'(aux), 3 copy (bf16 src).  See dgtd_ops.h."""
+    M, N = src.shape
+    dst = torch.empty(M, N, device=src.device, dtype=torch.bfloat16) if want_dst else None
+    dstT = torch.empty(N, M, device=src.device, dtype=torch.bfloat16) if want_T else None
+    call("dgtd_transpose_op", ptr(src), ptr(aux), ptr(dst), ptr(dstT), ptr(keep), ptr(gamma), rows_per_sample, M, N,
+         mode, stream())
+    return dst, dstT
+
+
+def wgrad_tc(aT, bT, transpose_out=False):
+    """(Mo x No) = aT[Mo,Kr] @ bT[No,Kr]^T on tcgen05 (split-K over Kr); fp32 result (optionally transposed)."""
+    Mo, Kr = aT.shape
+    No = bT.shape[0]
+    out = _empty((No, Mo) if transpose_out else (Mo, No), aT)
+    ws = _empty((capi.load().dgtd_wgrad_tc_ws_floats(Mo, No, Kr),), aT)
+    call("dgtd_wgrad_tc", ptr(aT), ptr(bT), ptr(out), ptr(ws), Mo, No, Kr, int(transpose_out), stream())
+    return out
+
+
+def colsum_bf16(x):
+    M, N = x.shape
+    ws = _empty(((M + 1023) // 1024 * N,), x)
+    out = _empty((N,), x)
+    call("dgtd_colsum_bf16", ptr(x), ptr(ws), ptr(out), M, N, stream())
+    return out
+
+
+def ln_rows_any(y, w, b, eps, out_dtype):
+    C = y.shape[-1]
+    out = torch.empty(y.shape, device=y.device, dtype=torch.bfloat16 if out_dtype == BF16 else torch.float32)
+    call("dgtd_ln_rows_fwd", ptr(y), ptr(w), ptr(b), ptr(out), out_dtype, y.numel() // C, C, float(eps), stream())
+    return out
+
+
+def tc_rows_ok(M: int) -> bool:
+    """The tcgen05 gradient GEMMs reduce over the M rows: TMA needs 16-byte row pitch, and tiny maps
+    are not worth a split-K launch."""
+    return M % 8 == 0 and M >= 256
+
+
 # ---- Functions ---------------------------------------------------------------------------------------
+class ConvNextBlockBf16Fn(Function):
+    """convnext_Block with bf16 tensor-core GEMMs in forward AND backward (fp32 residual stream,
+    fp32 accumulation, fp32 LayerNorm / depthwise conv); same signature as ConvNextBlockFn."""
+
+    @staticmethod
+    def forward(ctx, x, dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, gamma, keep, eps):
+        x = _f32(x)
+        B, h, w, C = x.shape
+        dwT = _f32(dw_w).reshape(C, 49).t().contiguous()
+        dw_b, ln_w, ln_b, w1, b1, w2, b2 = map(_f32, (dw_b, ln_w, ln_b, w1, b1, w2, b2))
+        gamma, keep = _f32(gamma), _f32(keep)
+        w1b, w2b = w1.to(torch.bfloat16), w2.to(torch.bfloat16)
+        y = dwconv7(x, dwT, dw_b)
+        a = ln_rows_any(y, ln_w, ln_b, eps, BF16).view(-1, C)
+        hpre = OP.linear(a, w1b, b1)                                   # bf16 (M, 4C), pre-activation kept
+        hid, _ = transpose_op(hpre, 1, want_dst=True, want_T=False)    # GELU
+        out = torch.empty_like(x)
+        OP.linear_residual_(hid, w2b, b2, gamma, keep, h * w, x, out=out)
+        ctx.eps = eps
+        ctx.save_for_backward(x, y, a, hpre, dwT, ln_w, w1b, w2, w2b, b2, gamma, keep)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, y, a, hpre, dwT, ln_w, w1b, w2, w2b, b2, gamma, keep = ctx.saved_tensors
+        g = _f32(g)
+        B, h, w, C = x.shape
+        rows, C4, M = h * w, 4 * C, B * h * w
+        g2 = g.view(M, C)
+        s = colsum(g2, C, keep, rows)
+        gs, gT = transpose_op(g2, 0, want_dst=True, want_T=True, keep=keep, gamma=gamma, rows_per_sample=rows)
+        _, hidT = transpose_op(hpre, 1)                                # gelu(hpre)^T  (4C, M)
+        G = wgrad_tc(hidT, gT, transpose_out=True)                     # (C, 4C) = (keep g)^T hid
+        del hidT, gT
+        dW2, db2 = torch.empty_like(w2), _empty((C,), g)
+        dgamma = _empty((C,), g) if gamma is not None else None
+        call("dgtd_layer_scale_finalize", ptr(G), ptr(s), ptr(w2), ptr(b2), ptr(gamma), ptr(dW2), ptr(db2),
+             ptr(dgamma), C, C4, stream())
+        dh = OP.linear(gs, w2b.t().contiguous(), None)                 # bf16 (M, 4C) = (keep gamma g) @ W2
+        dhpre, dhpreT = transpose_op(dh, 2, aux=hpre, want_dst=True, want_T=True)
+        del dh, gs
+        _, aT = transpose_op(a, 3)
+        dW1 = wgrad_tc(dhpreT, aT)                                     # (4C, C)
+        db1 = colsum_bf16(dhpre)
+        da = OP.linear(dhpre, w1b.t().contiguous(), None, out_dtype=F32)   # fp32 (M, C)
+        del dhpre, dhpreT, aT
+        dy, dln_w, dln_b = ln_rows_bwd(da, y, ln_w, ctx.eps)
+        dx = dwconv7(dy.view(B, h, w, C), dwT.flip(0).contiguous(), None, add=g)
+        ddwT, ddb = dwconv7_wgrad(x, dy.view(B, h, w, C))
+        return (dx, ddwT.t().reshape(C, 1, 7, 7), ddb, dln_w, dln_b, dW1, db1, dW2, db2, dgamma, None, None)
+
+
+class DownsampleBf16Fn(Function):
+    """LayerNorm + 2x2/2 conv with the conv (and its gradients) on tcgen05."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, w, b, eps):
+        x = _f32(x)
+        B, h, wd, C = x.shape
+        ln_w, ln_b, b = _f32(ln_w), _f32(ln_b), _f32(b)
+        wpb = _f32(w).permute(0, 2, 3, 1).reshape(2 * C, 4 * C).to(torch.bfloat16).contiguous()
+        p = OP.ln_patchify(x, ln_w, ln_b, BF16, eps)                   # (M', 4C) bf16
+        out = OP.linear(p, wpb, b, out_dtype=F32).view(B, h // 2, wd // 2, 2 * C)
+        ctx.eps = eps
+        ctx.save_for_backward(x, p, wpb, ln_w)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, p, wpb, ln_w = ctx.saved_tensors
+        B, h, wd, C = x.shape
+        g = _f32(g)
+        g2 = g.view(-1, 2 * C)
+        gs, gT = transpose_op(g2, 0, want_dst=True, want_T=True)
+        _, pT = transpose_op(p, 3)
+        dWp = wgrad_tc(gT, pT)                                         # (2C, 4C)
+        dW = dWp.view(2 * C, 2, 2, C).permute(0, 3, 1, 2).contiguous()
+        db = colsum(g2, 2 * C)
+        dp = OP.linear(gs, wpb.t().contiguous(), None, out_dtype=F32)  # (M', 4C) fp32
+        da = torch.empty_like(x)
+        call("dgtd_unpatchify2", ptr(dp), ptr(da), B, h, wd, C, stream())
+        dx, dln_w, dln_b = ln_rows_bwd(da, x, ln_w, ctx.eps)
+        return dx, dln_w, dln_b, dW, db, None
+
+
 class LinearFn(Function):
     """out = a @ w^T + b on (..., K) fp32 rows (head 1x1 convs, cod.py:1160,1174)."""
 

@@ -223,6 +223,22 @@ int dgtd_unpatchify2(const float* dp, float* dx, int B, int h, int w, int C, dgt
 int dgtd_resize_nhwc_bwd(const float* g, float* dx, int B, int h, int w, int C, int oh, int ow, int accumulate,
                          dgtd_stream_t stream);
 
+/* ---- bf16 / tensor-core training path of the trunk ------------------------------------------------
+ * One-pass operand preparation for the tcgen05 gradient GEMMs.  mode 0: src fp32, v = keep*src
+ * (dst also *gamma); mode 1: src bf16, v = gelu(src); mode 2: src = dH bf16, aux = pre-activation
+ * bf16, v = src*gelu'(aux).  dst (M x N) and/or dstT (N x M) in bf16. */
+int dgtd_transpose_op(const void* src, const void* aux, void* dst, void* dstT, const float* keep, const float* gamma,
+                      int rows_per_sample, int M, int N, int mode, dgtd_stream_t stream);
+int dgtd_colsum_bf16(const void* x, float* ws, float* out, int M, int N, dgtd_stream_t stream);
+/* out (Mo x No fp32, or its transpose) = aT[Mo,Kr] . bT[No,Kr]^T: weight gradient on tcgen05 with
+ * split-K over the long row axis Kr + fixed-order reduction.  ws: dgtd_wgrad_tc_ws_floats floats. */
+int dgtd_wgrad_tc(const void* aT, const void* bT, float* out, float* ws, int Mo, int No, int Kr, int transpose_out,
+                  dgtd_stream_t stream);
+int dgtd_wgrad_tc_ws_floats(int Mo, int No, int Kr);
+/* LayerNorm over rows of C (fp32 in, fp32|bf16 out), C a multiple of 128 */
+int dgtd_ln_rows_fwd(const float* y, const float* ln_w, const float* ln_b, void* out, int out_dtype, int64_t rows,
+                     int C, float eps, dgtd_stream_t stream);
+
 /* ---- dtype / layout plumbing -------------------------------------------------------------- */
 int dgtd_cast_fwd(const void* src, void* dst, int64_t n, int dtype_src, int dtype_dst,
                   dgtd_stream_t stream);

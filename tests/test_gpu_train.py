@@ -98,3 +98,41 @@ def test_drop_path_mask_scales_the_branch():
     assert torch.equal(y[0], x[0])
     assert float((y[1] - (x[1] + 2.0 * (full[1] - x[1]))).abs().max()) < 1e-4
     assert float((y[2] - full[2]).abs().max()) < 1e-5
+
+
+def test_bf16_tensor_core_training_gradients():
+    """Trunk GEMMs (forward, dgrad, split-K wgrad) on tcgen05 with bf16 operands: gradients of all
+    parameters vs float64 autograd of the oracle.  Stated tolerance: 6e-2 of max|grad| per tensor
+    (bf16 operand rounding through 36 blocks; the reference under bf16 autocast is itself 1.2e-2 off
+    in the forward, tests/golden/path_384.npz)."""
+    TD = common.package()
+    S, B = 192, 2
+    enc, dec = TD.build_texture_diffuser(seed=0)
+    common.perturb_regressor_(enc)
+    image, depth = common.synthetic_inputs(B, S, seed=5)
+    grids = common.pvt_token_grids((S, S))
+    g = torch.Generator().manual_seed(8)
+    gout_e3 = torch.randn(B, 24, S // 4, S // 4, generator=g) * 1e-2
+    gout_tok = [[torch.randn(B, grids[s][0] * grids[s][1], e, generator=g) * 1e-2 for _ in range(n)]
+                for s, (e, n) in enumerate(zip(common.PVT_EMBED_DIMS, common.PVT_DEPTHS))]
+    (_, r3, rtoks), ref = _oracle_grads(enc, dec, image, depth, gout_e3, gout_tok)
+    enc, dec = enc.cuda().eval(), dec.cuda().eval()
+    e1, e3, toks = TD.texture_prompts_train(enc, dec, image.cuda(), depth.cuda(), precision="bf16")
+    assert common.rel_err(e3, r3) <= 3e-2
+    loss = (e3 * gout_e3.cuda()).sum()
+    for s in range(4):
+        for i, t in enumerate(toks[s]):
+            loss = loss + (t * gout_tok[s][i].cuda()).sum()
+    loss.backward()
+    worst = ("", 0.0)
+    for prefix, mod in (("enc.", enc), ("dec.", dec)):
+        for k, p in mod.named_parameters():
+            r = ref.get(prefix + k)
+            if r is None:
+                continue
+            assert p.grad is not None and torch.isfinite(p.grad).all(), k
+            err = common.rel_err(p.grad, r)
+            if err > worst[1]:
+                worst = (prefix + k, err)
+    print("bf16 training: worst gradient error", worst)
+    assert worst[1] <= 6e-2, worst

@@ -139,8 +139,9 @@ def diffusion_microbench(OP, dev, peaks, C=256, S=1024, steps=(1, 2, 4, 8)):
     return out
 
 
-def train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding, steps=3, warmup=1):
-    """Forward + backward of the hot path (exact fp32 autograd Functions) on `train-batch` images per
+def train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding, steps=3, warmup=1, precision="bf16"):
+    """Forward + backward of the hot path (block-level autograd Functions; `precision` selects the exact
+    fp32 CUDA-core path or the bf16 tcgen05 path of the trunk) on `train-batch` images per
     GPU; with N > 1 the parameter gradients are all-reduced by DistributedDataParallel (bucketed NCCL
     all-reduce overlapped with backward -- the reference's own mechanism, cod.py:8,238)."""
     import torch.distributed as dist
@@ -152,7 +153,8 @@ def train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding, s
             self.prompt_encoder, self.prompt_decoder = enc, dec
 
         def forward(self, image, depth):
-            _, e3, toks = TD.texture_prompts_train(self.prompt_encoder, self.prompt_decoder, image, depth)
+            _, e3, toks = TD.texture_prompts_train(self.prompt_encoder, self.prompt_decoder, image, depth,
+                                                           precision=precision)
             # scalar stand-in for the downstream loss: every prompt tensor contributes
             return sum(t.float().mean() for row in toks for t in row) + e3.mean()
 
@@ -186,7 +188,7 @@ def train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding, s
     n_grad = sum(p.numel() for p in model.parameters() if p.requires_grad)
     enc.eval(); dec.eval()
     return {"value": world * B * steps / t, "unit": UNIT, "batch_per_gpu": B, "steps": steps, "ms_per_step": t / steps * 1e3,
-            "precision": "fp32 (exact CUDA-core path; tensor-core backward is future work)",
+            "precision": precision,
             "grad_allreduce": "DistributedDataParallel bucketed NCCL all-reduce, %d fp32 grads" % n_grad if world > 1
             else "none (1 GPU)"}
 
@@ -345,7 +347,9 @@ def run_ours(args):
     # ---- fwd+bwd (BASELINE configs[2]: SOD training, batch 16/GPU, 384^2, data parallel) ----------
     train = None
     if not args.no_train:
-        train = train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding)
+        train = train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding, precision="bf16")
+        train["fp32_exact"] = train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding, steps=2,
+                                          precision="fp32")
 
     # ---- diffusion microbench (BASELINE configs[3]): MessagePassing core, 1024^2 x 256, shared weights
     diff = None

@@ -112,6 +112,101 @@ dwconv7_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restr
   }
 }
 
+
+// Weight/bias gradient of the depthwise 7x7 (training backward of cod.py:1106):
+//   dW[ky,kx,c] = sum_{b,oy,ox} dy[b,oy,ox,c] * x[b,oy+ky-3,ox+kx-3,c],   db[c] = sum dy
+// CTA = one 32-channel chunk, looping over (image, tile) pairs with stride gridDim.y; x halo tiles
+// arrive by TMA (double buffered, zero fill = padding), dy of the warp's 4x8 sub-tile sits in
+// registers, the 49 + 1 sums stay in registers across all tiles of the CTA.  One partial (50 x 32)
+// per CTA, reduced across warps in shared memory in a fixed order (deterministic).
+template <int SY, int SX>
+__global__ void __launch_bounds__(SY * SX * 32, 2)
+dwconv7_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ dy,
+                         float* __restrict__ part, int h, int w, int C, int tiles_x, int tiles_y, int ntiles) {
+  constexpr int TH = 4 * SY, TW = 8 * SX, PH = TH + 6, PW = TW + 6, NW = SY * SX;
+  constexpr int TILE_FLOATS = PH * PW * 32;
+  constexpr uint32_t TILE_BYTES = TILE_FLOATS * 4;
+  static_assert(NW * 50 * 32 <= 2 * TILE_FLOATS, "reduction scratch must fit in the tile buffers");
+  extern __shared__ __align__(128) float xs[];
+  __shared__ uint64_t bar[2];
+
+  const int chunk = blockIdx.x, P = gridDim.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sy = warp / SX, sx = warp - sy * SX;
+  const int c = chunk * 32 + lane;
+
+  auto issue = [&](int t, int buf) {
+    const int tx = t % tiles_x;
+    const int r = t / tiles_x;
+    const int ty = r % tiles_y, b = r / tiles_y;
+    bw::mbar_arrive_expect_tx(&bar[buf], TILE_BYTES);
+    bw::tma_load_4d(&tmX, &bar[buf], xs + buf * TILE_FLOATS, chunk * 32, tx * TW - 3, ty * TH - 3, b);
+  };
+  if (threadIdx.x == 0) {
+    bw::prefetch_tmap(&tmX);
+    bw::mbar_init(&bar[0], 1);
+    bw::mbar_init(&bar[1], 1);
+    bw::fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) issue(blockIdx.y, 0);
+
+  float acc[50];
+#pragma unroll
+  for (int k = 0; k < 50; ++k) acc[k] = 0.f;
+
+  int it = 0;
+#pragma unroll 1
+  for (int t = blockIdx.y; t < ntiles; t += P, ++it) {
+    if (threadIdx.x == 0 && t + P < ntiles) {   // buffer (it+1)&1 was released by the barrier below
+      bw::fence_proxy_async_smem();
+      issue(t + P, (it + 1) & 1);
+    }
+    const int tx = t % tiles_x;
+    const int r = t / tiles_x;
+    const int ty = r % tiles_y, b = r / tiles_y;
+    const int oy0 = ty * TH + 4 * sy, ox0 = tx * TW + 8 * sx;
+    float g[4][8];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int oy = oy0 + a, ox = ox0 + j;
+        g[a][j] = (oy < h && ox < w) ? __ldg(dy + (((int64_t)b * h + oy) * w + ox) * C + c) : 0.f;
+        acc[49] += g[a][j];
+      }
+    bw::mbar_wait(&bar[it & 1], (it >> 1) & 1);
+    const float* base = xs + (it & 1) * TILE_FLOATS + ((4 * sy) * PW + 8 * sx) * 32 + lane;
+#pragma unroll
+    for (int iy = 0; iy < 10; ++iy) {
+      float in[14];
+#pragma unroll
+      for (int j = 0; j < 14; ++j) in[j] = base[(iy * PW + j) * 32];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int ky = iy - a;
+        if (ky < 0 || ky >= 7) continue;
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[ky * 7 + kx] = fmaf(g[a][j], in[j + kx], acc[ky * 7 + kx]);
+      }
+    }
+    __syncthreads();   // every warp is done with buffer it&1 before it is refilled
+  }
+  // all issued loads were waited on: the tile buffers are free for the cross-warp reduction
+  float* red = xs;
+#pragma unroll
+  for (int k = 0; k < 50; ++k) red[(warp * 50 + k) * 32 + lane] = acc[k];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 50 * 32; i += NW * 32) {
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < NW; ++q) v += red[q * 50 * 32 + i];
+    part[((int64_t)blockIdx.y * 50 + (i >> 5)) * C + chunk * 32 + (i & 31)] = v;
+  }
+}
+
 template <typename OT, int VPL>
 __global__ void __launch_bounds__(256)
 ln_rows_kernel(const float* __restrict__ y, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
@@ -217,6 +312,80 @@ int dwconv7_tma(const float* x, const float* wT, const float* dw_b, const float*
     return -2;
   }
   count_launch();
+  return 0;
+}
+
+
+template <int SY, int SX>
+static int dwg_launch(const CUtensorMap& tm, const float* dy, float* part, int P, int B, int h, int w, int C,
+                      cudaStream_t s) {
+  constexpr int PH = 4 * SY + 6, PW = 8 * SX + 6;
+  constexpr int SMEM = 2 * PH * PW * 128 + 128;
+  auto kern = dwconv7_wgrad_tma_kernel<SY, SX>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) {
+      set_error("dwconv7_wgrad_tma: cannot opt in to %d B smem: %s", SMEM, cudaGetErrorString(e));
+      return -2;
+    }
+    configured = true;
+  }
+  const int tiles_x = cdiv(w, 8 * SX), tiles_y = cdiv(h, 4 * SY);
+  kern<<<dim3(C / 32, P), SY * SX * 32, SMEM, s>>>(tm, dy, part, h, w, C, tiles_x, tiles_y, B * tiles_x * tiles_y);
+  return 0;
+}
+
+static int dw_tile_shape(int h, int w, int* SY, int* SX) {
+  *SX = (w % 24 == 0 && w % 16 != 0) ? 3 : 2;   // 24-wide maps: 8x24 tiles
+  *SY = (h % 8 == 0 || h > 12) ? 2 : 3;         // 12-high maps: 12x16 tiles
+  return 0;
+}
+
+static int dw_make_tmap(CUtensorMap* tm, const float* x, int B, int h, int w, int C, int SY, int SX) {
+  PFN_tmapEncodeTiled enc = get_tmap_encoder();
+  if (!enc) return -3;
+  cuuint64_t gd[4] = {(cuuint64_t)C, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
+  cuuint64_t gs[3] = {(cuuint64_t)C * 4, (cuuint64_t)w * C * 4, (cuuint64_t)h * w * C * 4};
+  cuuint32_t bx[4] = {32, (cuuint32_t)(8 * SX + 6), (cuuint32_t)(4 * SY + 6), 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("dwconv7(tma): cuTensorMapEncodeTiled failed (%d) for x (%d,%d,%d,%d)", (int)r, B, h, w, C);
+    return -3;
+  }
+  return 0;
+}
+
+// Partial weight/bias gradients: part[P][50][C] (49 taps + bias), P <= max_parts returned in *parts.
+// Returns 1 when the shape is not handled here.
+int dwconv7_wgrad_tma(const float* x, const float* dy, float* part, int max_parts, int* parts, int B, int h, int w,
+                      int C, cudaStream_t s) {
+  if (C % 128 || (reinterpret_cast<uintptr_t>(x) & 15) || (int64_t)B * h * w < 2048) return 1;
+  int SY, SX;
+  dw_tile_shape(h, w, &SY, &SX);
+  const int ntiles = B * cdiv(w, 8 * SX) * cdiv(h, 4 * SY);
+  int P = cdiv(2 * 148, C / 32);
+  if (P > ntiles) P = ntiles;
+  if (P > max_parts) P = max_parts;
+  if (P < 1) return 1;
+  CUtensorMap tm;
+  int rc = dw_make_tmap(&tm, x, B, h, w, C, SY, SX);
+  if (rc) return rc;
+  if (SY == 2 && SX == 2) rc = dwg_launch<2, 2>(tm, dy, part, P, B, h, w, C, s);
+  else if (SY == 2 && SX == 3) rc = dwg_launch<2, 3>(tm, dy, part, P, B, h, w, C, s);
+  else if (SY == 3 && SX == 2) rc = dwg_launch<3, 2>(tm, dy, part, P, B, h, w, C, s);
+  else rc = dwg_launch<3, 3>(tm, dy, part, P, B, h, w, C, s);
+  if (rc) return rc;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("dwconv7_wgrad_tma: launch failed: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  count_launch();
+  *parts = P;
   return 0;
 }
 

@@ -279,7 +279,7 @@ diffuse_plane_bwd_kernel(const float* __restrict__ grad_out, const float* __rest
 
 // ------------------------------------------------------------------------------------ small backward ops
 // 1x1 conv NCHW backward.  y_out non-null => the forward applied a sigmoid: g <- g * y (1 - y).
-// dx: thread per (b, ci, p);  dw/db: one CTA per output channel, fixed-order tree reduction.
+// dx: thread per (b, ci, p);  dw/db: one CTA per (input, output) channel pair, fixed-order reduction.
 __global__ void conv1x1_nchw_bwd_dx_kernel(const float* __restrict__ g, const float* __restrict__ y_out,
                                            const float* __restrict__ w, float* __restrict__ dx, int Cin,
                                            int Cout, int HW) {
@@ -304,31 +304,31 @@ __global__ void __launch_bounds__(256)
 conv1x1_nchw_bwd_dw_kernel(const float* __restrict__ g, const float* __restrict__ y_out,
                            const float* __restrict__ x, float* __restrict__ dw, float* __restrict__ db, int B,
                            int Cin, int Cout, int HW) {
-  __shared__ float red[256];
-  const int co = blockIdx.x;
-  for (int ci = -1; ci < Cin; ++ci) {   // ci == -1: bias gradient
-    float acc = 0.f;
-    for (int64_t i = threadIdx.x; i < (int64_t)B * HW; i += 256) {
-      int b = (int)(i / HW);
-      int p = (int)(i - (int64_t)b * HW);
-      float gv = g[((int64_t)b * Cout + co) * HW + p];
-      if (y_out) {
-        float yv = y_out[((int64_t)b * Cout + co) * HW + p];
+  // CTA = one (ci, co) pair (blockIdx.x == 0: bias gradient); fixed-order reduction
+  __shared__ float red[8];
+  const int co = blockIdx.y, ci = (int)blockIdx.x - 1;
+  float acc = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float* gp = g + ((int64_t)b * Cout + co) * HW;
+    const float* yp = y_out ? y_out + ((int64_t)b * Cout + co) * HW : nullptr;
+    const float* xp = ci < 0 ? nullptr : x + ((int64_t)b * Cin + ci) * HW;
+    for (int p = threadIdx.x; p < HW; p += 256) {
+      float gv = gp[p];
+      if (yp) {
+        const float yv = yp[p];
         gv *= yv * (1.f - yv);
       }
-      acc += ci < 0 ? gv : gv * x[((int64_t)b * Cin + ci) * HW + p];
+      acc += xp ? gv * xp[p] : gv;
     }
-    red[threadIdx.x] = acc;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-      if (ci < 0) { if (db) db[co] = red[0]; }
-      else dw[(int64_t)co * Cin + ci] = red[0];
-    }
-    __syncthreads();
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    if (ci < 0) { if (db) db[co] = t; }
+    else dw[(int64_t)co * Cin + ci] = t;
   }
 }
 
@@ -495,7 +495,7 @@ int dgtd_conv1x1_nchw_bwd(const float* grad_out, const float* y_out, const float
     DGTD_LAUNCH_CHECK("conv1x1_nchw_bwd.dx");
   }
   if (grad_w) {
-    conv1x1_nchw_bwd_dw_kernel<<<Cout, 256, 0, s>>>(grad_out, y_out, x, grad_w, grad_b, B, Cin, Cout, HW);
+    conv1x1_nchw_bwd_dw_kernel<<<dim3(Cin + 1, Cout), 256, 0, s>>>(grad_out, y_out, x, grad_w, grad_b, B, Cin, Cout, HW);
     DGTD_LAUNCH_CHECK("conv1x1_nchw_bwd.dw");
   }
   return 0;

@@ -8,6 +8,8 @@ namespace dgtd {
 
 int dwconv7_tma(const float* x, const float* wT, const float* dw_b, const float* add, float* y, int B, int h, int w,
                 int C, cudaStream_t s);
+int dwconv7_wgrad_tma(const float* x, const float* dy, float* part, int max_parts, int* parts, int B, int h, int w,
+                      int C, cudaStream_t s);
 
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   // d/dx [0.5 x (1 + erf(x/sqrt2))] = Phi(x) + x phi(x)
@@ -474,11 +476,17 @@ int dgtd_dwconv7_wgrad(const float* x, const float* dy, float* ws, float* dwT, f
   DGTD_CHECK_ARG(x && dy && ws && dwT && db && C % 128 == 0, "dwconv7_wgrad: bad args");
   cudaStream_t s = (cudaStream_t)stream;
   const int bands = cdiv(h, 8);
-  dwconv7_wgrad_kernel<<<dim3(C / 128, bands, B), 128, 0, s>>>(x, dy, ws, h, w, C);
-  DGTD_LAUNCH_CHECK("dwconv7_wgrad");
   const int64_t n = (int64_t)50 * C;
   float* red = ws + (int64_t)B * bands * n;
-  sum_splits_kernel<<<cdiv(n, 256), 256, 0, s>>>(ws, red, n, B * bands);
+  int parts = 0;
+  const int rc = dwconv7_wgrad_tma(x, dy, ws, B * bands, &parts, B, h, w, C, s);
+  if (rc < 0) return rc;
+  if (rc > 0) {   // small maps: thread-per-channel kernel
+    dwconv7_wgrad_kernel<<<dim3(C / 128, bands, B), 128, 0, s>>>(x, dy, ws, h, w, C);
+    DGTD_LAUNCH_CHECK("dwconv7_wgrad");
+    parts = B * bands;
+  }
+  sum_splits_kernel<<<cdiv(n, 256), 256, 0, s>>>(ws, red, n, parts);
   DGTD_LAUNCH_CHECK("dwconv7_wgrad.reduce");
   cudaMemcpyAsync(dwT, red, (size_t)49 * C * sizeof(float), cudaMemcpyDeviceToDevice, s);
   cudaMemcpyAsync(db, red + (int64_t)49 * C, (size_t)C * sizeof(float), cudaMemcpyDeviceToDevice, s);

@@ -21,6 +21,7 @@ import torch.nn as nn
 from ..ops.capi import ACT_GELU, ACT_NONE, ACT_RELU, BF16, F32
 from ..ops.functions import texture_diffusion_func as OP
 from ..ops.functions import train_func as TF
+from ..ops.functions import decoder_bank as DB
 
 __all__ = [
     "LayerNorm", "ShapePropWeightRegressor", "convnext_Block", "ShapePropEncoder", "MessagePassing",
@@ -339,38 +340,11 @@ class MessagePassing(nn.Module):
         return OP.resize_bilinear_nchw_autograd(x, size)
 
 
-def _pack_conv3(wt: torch.Tensor) -> torch.Tensor:
-    """(Cout,Cin,3,3) OIHW -> (Cout, 9*Cin) tap-major (dy,dx,c)."""
-    return wt.detach().permute(0, 2, 3, 1).reshape(wt.shape[0], -1).float().contiguous()
-
-
-def _fold_conv3_bilinear(wt: torch.Tensor) -> torch.Tensor:
-    """3x3 conv followed by the 2-tap (0.5/0.5 per axis) bilinear down-sample == 4x4 conv:
-    W4[dy,dx] = 1/4 sum_{a,b in {0,1}} W3[dy-a, dx-b]    -> (Cout, 16*Cin)."""
-    w3 = wt.detach().float()
-    co, ci = w3.shape[0], w3.shape[1]
-    w4 = torch.zeros(co, ci, 4, 4, device=w3.device, dtype=torch.float32)
-    for a in (0, 1):
-        for b in (0, 1):
-            w4[:, :, a:a + 3, b:b + 3] += w3
-    w4 *= 0.25
-    return w4.permute(0, 2, 3, 1).reshape(co, -1).contiguous()
-
-
-def _pad_taps_bf16(packed: torch.Tensor, cin: int, rows_to: Optional[int] = None) -> torch.Tensor:
-    """(Cout, taps*cin) fp32 tap-major -> (rows_to or Cout, taps*32) bf16 with zero channel / row padding
-    (operand layout of the tcgen05 implicit-GEMM conv: 32 channels = one 64-byte swizzled row)."""
-    co = packed.shape[0]
-    taps = packed.shape[1] // cin
-    out = torch.zeros(rows_to or co, taps, 32, device=packed.device, dtype=torch.float32)
-    out[:co, :, :cin] = packed.reshape(co, taps, cin)
-    return out.reshape(out.shape[0], taps * 32).to(torch.bfloat16).contiguous()
-
-
-def _pad_rows(v: torch.Tensor, rows_to: int) -> torch.Tensor:
-    out = torch.zeros(rows_to, device=v.device, dtype=torch.float32)
-    out[:v.shape[0]] = v.detach().float()
-    return out
+_pack_conv3 = DB.pack_conv3
+_fold_conv3_bilinear = DB.fold_conv3_bilinear
+_pad_taps_bf16 = DB.pad_taps_bf16
+_pad_rows = DB.pad_rows
+_fold_params = DB.fold_params
 
 
 class ShapePropDecoder(nn.Module):
@@ -482,18 +456,6 @@ def _decode_full(decoders: Sequence[ShapePropDecoder], emb: torch.Tensor) -> Lis
         y = OP.conv_nhwc(h2[..., i * L:(i + 1) * L], w3, d.decoder[4].bias.detach(), L, (h, w), 3, 1, -1)
         outs.append(y.permute(0, 3, 1, 2))
     return outs
-
-
-def _fold_params(src_hw: Tuple[int, int], dst_hw: Tuple[int, int]) -> Optional[Tuple[int, int]]:
-    """(stride, offset) of the folded 4x4 conv when the bilinear resize src->dst is the exact
-    2-tap average (integer ratio r in {2,4,8,...} on both axes); None otherwise."""
-    (h, w), (oh, ow) = src_hw, dst_hw
-    if oh <= 0 or ow <= 0 or h % oh or w % ow or h // oh != w // ow:
-        return None
-    r = h // oh
-    if r < 2 or r % 2:
-        return None
-    return r, r // 2 - 2  # first averaged row is r*Y + r/2 - 1; the 3x3 conv reaches one row above
 
 
 def _decode_tokens(decoders: Sequence[ShapePropDecoder], emb: torch.Tensor, grid: Tuple[int, int],
@@ -651,6 +613,19 @@ def texture_prompts_train(enc: "prompt_encoder", dec: nn.Sequential, image: torc
     emb1, emb3 = enc._forward_train(image, depth, mode)            # emb3: NHWC
     grids = pvt_token_grids(image.shape[-2:])
     B = image.shape[0]
+    if DB.bank_supported(tuple(emb3.shape[1:3]), grids):
+        # all 16 decoders + the folded injection as one Function (tokens bf16 in bf16 mode)
+        cfg = {"stages": [(len(dec[s].decoder), tuple(grids[s])) for s in range(len(dec))], "mode": mode}
+        params = [t for s in range(len(dec)) for d in dec[s].decoder
+                  for t in (d.decoder[0].weight, d.decoder[0].bias, d.decoder[2].weight, d.decoder[2].bias,
+                            d.decoder[4].weight, d.decoder[4].bias)]
+        flat = DB.DecoderBankFn.apply(emb3, cfg, *params)
+        tokens, i = [], 0
+        for s in range(len(dec)):
+            n = len(dec[s].decoder)
+            tokens.append(list(flat[i:i + n]))
+            i += n
+        return emb1, TF.LayoutFn.apply(emb3, False), tokens
     tokens = []
     for s in range(len(dec)):
         row = []

@@ -235,6 +235,20 @@ int dgtd_colsum_bf16(const void* x, float* ws, float* out, int M, int N, dgtd_st
 int dgtd_wgrad_tc(const void* aT, const void* bT, float* out, float* ws, int Mo, int No, int Kr, int transpose_out,
                   dgtd_stream_t stream);
 int dgtd_wgrad_tc_ws_floats(int Mo, int No, int Kr);
+/* Decoder-bank backward, data-movement halves (ShapePropDecoder cod.py:1210-1226 + folded injection :1471).
+ * col2im: out[b,iy,ix,c] (pixel pitch ldo) = mask > 0 ? sum over the conv taps that read input pixel
+ * (iy,ix) of dcol[(b,oy,ox)][(ty*ks+tx)*Ct + c] : 0; mask (nullable, dtype of out, pitch ldm) is the
+ * forward ReLU output.  ks = 1 is a strided masked copy.  dtypes DGTD_F32 | DGTD_BF16. */
+int dgtd_col2im_nhwc(const void* dcol, int dcol_dtype, int ldc, int Ct, const void* mask, int ldm, void* out,
+                     int out_dtype, int ldo, int B, int h, int w, int C, int ks, int stride, int off, int oh, int ow,
+                     dgtd_stream_t stream);
+/* outT[(tap*32 + c)][m] = x[b, oy*stride+off+ty, ox*stride+off+tx, c] (bf16, 32-channel slice at x, pixel
+ * pitch ldx, zero outside the map): transposed im2col, the K-major operand of dgtd_wgrad_tc. */
+int dgtd_im2col_t(const void* x, int ldx, void* outT, int B, int h, int w, int ks, int stride, int off, int oh, int ow,
+                  dgtd_stream_t stream);
+/* out[m][c] (fp32) = sum_g x[m][g*group_stride + c], c < C */
+int dgtd_group_sum(const void* x, int dtype, float* out, int64_t M, int groups, int group_stride, int C,
+                   dgtd_stream_t stream);
 /* LayerNorm over rows of C (fp32 in, fp32|bf16 out), C a multiple of 128 */
 int dgtd_ln_rows_fwd(const float* y, const float* ln_w, const float* ln_b, void* out, int out_dtype, int64_t rows,
                      int C, float eps, dgtd_stream_t stream);

@@ -140,3 +140,77 @@ def test_bf16_tensor_core_training_gradients():
     # reference itself under torch.autocast(bfloat16), same inputs (measured in the authoring container,
     # CPU): median 5.9e-2, p95 9.2e-2, max 1.25e-1.  Bound = about 1.3x those figures.
     assert med <= 8e-2 and p95 <= 1.2e-1 and worst[1] <= 2e-1, (med, p95, worst)
+
+
+# ---- decoder bank: data-movement halves of the conv gradients ---------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("ks,stride,off,h,oh", [(3, 1, -1, 12, 12), (4, 2, -1, 12, 6), (4, 4, 0, 16, 4), (4, 8, 2, 16, 2)])
+def test_col2im_is_the_adjoint_of_the_conv_gather(ks, stride, off, h, oh):
+    """<im2col(x), dcol> == <x, col2im(dcol)> with im2col written as plain torch indexing; bit-level
+    determinism (gather form, no atomics)."""
+    from dgtd_b200.twig.ops.functions import decoder_bank as DB
+    g = torch.Generator().manual_seed(3)
+    B, w, ow, C = 2, h, oh, 24
+    x = torch.randn(B, h, w, C, generator=g, dtype=torch.float64)
+    dcol = torch.randn(B * oh * ow, ks * ks * C, generator=g, dtype=torch.float64)
+    # reference im2col (zero outside the map)
+    xp = torch.zeros(B, h + 16, w + 16, C, dtype=torch.float64)
+    xp[:, 8:8 + h, 8:8 + w] = x
+    cols = []
+    for ty in range(ks):
+        for tx in range(ks):
+            ys = torch.arange(oh) * stride + off + ty + 8
+            xs = torch.arange(ow) * stride + off + tx + 8
+            cols.append(xp[:, ys][:, :, xs])
+    col = torch.stack(cols, 3).reshape(B * oh * ow, ks * ks * C)
+    lhs = (col * dcol).sum()
+    out = torch.empty(B, h, w, C, device="cuda")
+    DB.col2im(dcol.float().cuda(), C, None, out, C, ks, stride, off, (oh, ow))
+    rhs = (x * out.double().cpu()).sum()
+    assert abs(lhs - rhs) <= 1e-5 * (abs(lhs) + 1.0)
+    out2 = torch.empty_like(out)
+    DB.col2im(dcol.float().cuda(), C, None, out2, C, ks, stride, off, (oh, ow))
+    assert torch.equal(out, out2)
+    # ReLU mask: zero where the forward activation was not positive
+    mask = torch.randn(B, h, w, C, generator=g).cuda()
+    out3 = torch.empty_like(out)
+    DB.col2im(dcol.float().cuda(), C, mask, out3, C, ks, stride, off, (oh, ow))
+    assert torch.equal(out3, torch.where(mask > 0, out, torch.zeros_like(out)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ks,stride,off,h,oh", [(3, 1, -1, 12, 12), (4, 2, -1, 12, 6), (4, 8, 2, 16, 2)])
+def test_im2col_t_and_group_sum(ks, stride, off, h, oh):
+    from dgtd_b200.twig.ops.functions import decoder_bank as DB
+    g = torch.Generator().manual_seed(4)
+    B, w, ow, D = 3, h, oh, 3
+    x = torch.randn(B, h, w, 32 * D, generator=g).to(torch.bfloat16)
+    xs_ = x[..., 32:64].float()
+    xp = torch.zeros(B, h + 16, w + 16, 32)
+    xp[:, 8:8 + h, 8:8 + w] = xs_
+    cols = []
+    for ty in range(ks):
+        for tx in range(ks):
+            ys = torch.arange(oh) * stride + off + ty + 8
+            xx = torch.arange(ow) * stride + off + tx + 8
+            cols.append(xp[:, ys][:, :, xx])
+    col = torch.stack(cols, 3).reshape(B * oh * ow, ks * ks * 32)
+    xc = x.cuda()
+    got = DB.im2col_t(xc[..., 32:64], ks, stride, off, (oh, ow))
+    assert torch.equal(got.float().cpu(), col.t())
+    padded = DB.im2col_t(xc[..., 32:64], ks, stride, off, (oh, ow), rows_to=ks * ks * 32 + 64, tag="test")
+    assert torch.equal(padded[:ks * ks * 32].float().cpu(), col.t()) and float(padded[ks * ks * 32:].abs().max()) == 0.0
+    s = DB.group_sum(xc, D, 32, 24)
+    want = x.float().view(-1, D, 32)[:, :, :24].sum(1)
+    assert torch.allclose(s.cpu(), want, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_decoder_bank_falls_back_per_decoder_for_non_power_of_two_grids():
+    """200^2 input: PVT grids 50/25/13/7 are not 2^k folds of the 50x50 decoder map -> per-decoder path;
+    gradients still reach every decoder parameter."""
+    TD = common.package()
+    from dgtd_b200.twig.ops.functions import decoder_bank as DB
+    assert not DB.bank_supported((50, 50), TD.pvt_token_grids((200, 200)))
+    assert DB.bank_supported((96, 96), TD.pvt_token_grids((384, 384)))
+    assert DB.bank_supported((88, 88), TD.pvt_token_grids((352, 352)))

@@ -156,7 +156,18 @@ __device__ __forceinline__ uint64_t umma_smem_desc_kmajor(uint32_t smem_addr, ui
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((8 * row_bytes) >> 4) << 32) |
          (1ull << 46) | (layout << 61);
 }
-// kind::f16 instruction descriptor: fp32 accumulate, bf16 A/B, both K-major, M x N tile.
+// MN-major operand, 128-byte swizzle: the tile is stored as K rows of 64 contiguous MN elements
+// (128 B, exactly what a {64 MN, k rows} SWIZZLE_128B TMA box writes).  Canonical layout (CUTLASS
+// cute/atom/mma_traits_sm100.hpp, "make_umma_desc<Major::MN>", units of 16 B):
+//   ((8,n),(8,k)) : ((1,LBO),(8,SBO))   LBO = pitch between 64-element MN blocks,
+//                                         SBO = pitch between groups of 8 K rows (1024 B when dense)
+__device__ __forceinline__ uint64_t umma_smem_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                                 uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: fp32 accumulate, bf16 A/B, both K-major, M x N tile
+// (bits 15 / 16 set = A / B MN-major).
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }

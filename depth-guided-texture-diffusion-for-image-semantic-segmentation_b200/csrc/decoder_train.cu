@@ -2,7 +2,7 @@
 // cod.py:1471): data-movement halves of the convolution gradients.  The contractions themselves
 // run in the GEMM families (simt_gemm.cuh exact fp32 / tcgen05 bf16):
 //   input gradient   dcol[M_out, ks*ks*Ct] = g[M_out, E] . W[E, ks*ks*Ct]     then col2im (this file)
-//   weight gradient  dW^T[ks*ks*Ct, E]     = im2col(x)^T . g                   im2col^T (this file) + split-K GEMM
+//   weight gradient  dW^T[ks*ks*Ct, E]     = im2col(x)^T . g                   im2col (this file) + split-K GEMM (MN-major)
 #include "common.cuh"
 
 namespace dgtd {
@@ -44,46 +44,28 @@ col2im_kernel(const IT* __restrict__ dcol, int ldc, int Ct, const OT* __restrict
   store1(out + pix * ldo + c, acc);
 }
 
-// outT[(tap*32 + c)][m] = x[b, oy*stride+off+ty, ox*stride+off+tx, c]   (zero outside the map),
-// m = (b*oh + oy)*ow + ox, c < 32: the K-major operand of the tcgen05 weight-gradient GEMM.
-// CTA = 64 pixels x 32 channels of one tap, transposed through shared memory.
+// col[m][tap*32 + c] = x[b, oy*stride+off+ty, ox*stride+off+tx, c]   (zero outside the map),
+// m = (b*oh + oy)*ow + ox, c < 32: the row-major im2col matrix that dgtd_wgrad_tc_mn consumes as an
+// MN-major operand.  Thread = 8 channels (one 16-byte load and store).
 __global__ void __launch_bounds__(256)
-im2col_t_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ outT, int64_t M, int h,
-                int w, int ks, int stride, int off, int oh, int ow) {
-  __shared__ float t[64][33];
-  const int tap = blockIdx.y, ty = tap / ks, tx = tap - ty * ks;
-  const int64_t m0 = (int64_t)blockIdx.x * 64;
-  {
-    const int c = threadIdx.x & 31;
-    for (int mi = threadIdx.x >> 5; mi < 64; mi += 8) {
-      const int64_t m = m0 + mi;
-      float v = 0.f;
-      if (m < M) {
-        const int ox = (int)(m % ow);
-        const int64_t r = m / ow;
-        const int oy = (int)(r % oh);
-        const int b = (int)(r / oh);
-        const int iy = oy * stride + off + ty, ix = ox * stride + off + tx;
-        if ((unsigned)iy < (unsigned)h && (unsigned)ix < (unsigned)w)
-          v = __bfloat162float(x[(((int64_t)b * h + iy) * w + ix) * ldx + c]);
-      }
-      t[mi][c] = v;
-    }
-  }
-  __syncthreads();
-  {
-    const int mp = threadIdx.x & 31;
-    const int64_t m = m0 + 2 * mp;
-    for (int c = threadIdx.x >> 5; c < 32; c += 8) {
-      __nv_bfloat16* o = outT + ((int64_t)tap * 32 + c) * M + m;
-      if (m + 1 < M && (M & 1) == 0)
-        *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(t[2 * mp][c], t[2 * mp + 1][c]);
-      else {
-        if (m < M) o[0] = __float2bfloat16_rn(t[2 * mp][c]);
-        if (m + 1 < M) o[1] = __float2bfloat16_rn(t[2 * mp + 1][c]);
-      }
-    }
-  }
+im2col_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ col, int64_t total, int h,
+              int w, int ks, int stride, int off, int oh, int ow) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int chunk = (int)(i & 3);
+  const int taps = ks * ks;
+  const int tap = (int)((i >> 2) % taps);
+  const int64_t m = (i >> 2) / taps;
+  const int ty = tap / ks, tx = tap - ty * ks;
+  const int ox = (int)(m % ow);
+  const int64_t r = m / ow;
+  const int oy = (int)(r % oh);
+  const int b = (int)(r / oh);
+  const int iy = oy * stride + off + ty, ix = ox * stride + off + tx;
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if ((unsigned)iy < (unsigned)h && (unsigned)ix < (unsigned)w)
+    v = *reinterpret_cast<const uint4*>(x + (((int64_t)b * h + iy) * w + ix) * ldx + chunk * 8);
+  *reinterpret_cast<uint4*>(col + (m * taps + tap) * 32 + chunk * 8) = v;
 }
 
 // out[m][c] = sum_g x[m][g*gs + c], c < C   (input gradients of the decoders' first convs, summed over decoders)
@@ -127,15 +109,18 @@ int dgtd_col2im_nhwc(const void* dcol, int dcol_dtype, int ldc, int Ct, const vo
   return 0;
 }
 
-// x: NHWC bf16, the 32-channel slice starting at the pointer (pixel pitch ldx); outT: (ks*ks*32) rows x M, M = B*oh*ow
-int dgtd_im2col_t(const void* x, int ldx, void* outT, int B, int h, int w, int ks, int stride, int off, int oh, int ow,
-                  dgtd_stream_t stream) {
-  DGTD_CHECK_ARG(x && outT && B > 0 && h > 0 && w > 0 && ks >= 1 && ks <= 8 && stride >= 1 && oh > 0 && ow > 0 && ldx >= 32,
-                 "im2col_t: bad args");
-  const int64_t M = (int64_t)B * oh * ow;
-  im2col_t_kernel<<<dim3((unsigned)cdiv(M, (int64_t)64), ks * ks), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)outT, M, h, w, ks, stride, off, oh, ow);
-  DGTD_LAUNCH_CHECK("im2col_t");
+// x: NHWC bf16, the 32-channel slice starting at the pointer (pixel pitch ldx, multiple of 8, 16-byte
+// aligned); col: (B*oh*ow) rows x (ks*ks*32)
+int dgtd_im2col_nhwc(const void* x, int ldx, void* col, int B, int h, int w, int ks, int stride, int off, int oh,
+                     int ow, dgtd_stream_t stream) {
+  DGTD_CHECK_ARG(x && col && B > 0 && h > 0 && w > 0 && ks >= 1 && ks <= 8 && stride >= 1 && oh > 0 && ow > 0,
+                 "im2col_nhwc: bad args");
+  DGTD_CHECK_ARG(ldx >= 32 && ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+                 "im2col_nhwc: x must be 16-byte aligned with a pixel pitch multiple of 8");
+  const int64_t total = (int64_t)B * oh * ow * ks * ks * 4;
+  im2col_kernel<<<(unsigned)cdiv(total, (int64_t)256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)col, total, h, w, ks, stride, off, oh, ow);
+  DGTD_LAUNCH_CHECK("im2col_nhwc");
   return 0;
 }
 

@@ -75,7 +75,10 @@ struct TcParams {
   void* out;
   int64_t ldo;
   int splits = 1;         // split-K (weight gradients): split z handles k-blocks [z*kb_per_split, ...)
-  int kb_per_split = 0;   // and writes rows [z*M, (z+1)*M) of a (splits*M) x N partial buffer
+  int kb_per_split = 0;   // and writes rows [z*split_rows, ...) of a (splits*split_rows) x N partial buffer
+  int split_rows = 0;     // M rounded up to the 256-row pair tile
+  int mn_major = 0;       // 1: A is (K x M) and B is (K x N) row-major (operands read "transposed":
+                          //    the reduction runs over the ROWS of two activation matrices, no copy)
 };
 
 

@@ -146,8 +146,16 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kb = kb0; kb < kb1; ++kb) {
           bw::mbar_wait(&empty[stage], phase ^ 1);
           const uint32_t lbar = bw2::map_to_rank(&full[stage], 0);
-          bw2::tma_load_2d_2sm(&tmA, lbar, sA + stage * Cfg::A_BYTES, kb * BK, m0);
-          bw2::tma_load_2d_2sm(&tmB, lbar, sB + stage * Cfg::B_BYTES, kb * BK, n0);
+          if (p.mn_major) {   // {64 MN, 64 K-row} boxes, one 8 KB block per 64 columns
+            bw2::tma_load_2d_2sm(&tmA, lbar, sA + stage * Cfg::A_BYTES, m0, kb * BK);
+            bw2::tma_load_2d_2sm(&tmA, lbar, sA + stage * Cfg::A_BYTES + 8192, m0 + 64, kb * BK);
+#pragma unroll
+            for (int j = 0; j < BN / 128; ++j)
+              bw2::tma_load_2d_2sm(&tmB, lbar, sB + stage * Cfg::B_BYTES + j * 8192, n0 + 64 * j, kb * BK);
+          } else {
+            bw2::tma_load_2d_2sm(&tmA, lbar, sA + stage * Cfg::A_BYTES, kb * BK, m0);
+            bw2::tma_load_2d_2sm(&tmB, lbar, sB + stage * Cfg::B_BYTES, kb * BK, n0);
+          }
           if (leader) bw::mbar_arrive_expect_tx(&full[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
           else bw2::mbar_arrive_cluster(lbar);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -157,7 +165,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == 1) {
     if (leader && lane == 0) {
       // ===================== MMA issuer (leader CTA only) =====================
-      constexpr uint32_t idesc = bw::umma_idesc_bf16(256, BN);
+      const uint32_t idesc = bw::umma_idesc_bf16(256, BN) | (p.mn_major ? (3u << 15) : 0u);
+      const uint32_t kstep = p.mn_major ? 128u : 2u;   // 16 K rows x 128 B vs 16 elements x 2 B, in 16-byte units
       int stage = 0, iter = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++iter) {
@@ -171,11 +180,14 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kb = kb0; kb < kb1; ++kb) {
           bw::mbar_wait(&full[stage], phase);
           bw::tc_fence_after();
-          const uint64_t da = bw::umma_smem_desc_kmajor(bw::smem_u32(sA + stage * Cfg::A_BYTES), 128);
-          const uint64_t db = bw::umma_smem_desc_kmajor(bw::smem_u32(sB + stage * Cfg::B_BYTES), 128);
+          const uint32_t a_addr = bw::smem_u32(sA + stage * Cfg::A_BYTES), b_addr = bw::smem_u32(sB + stage * Cfg::B_BYTES);
+          const uint64_t da = p.mn_major ? bw::umma_smem_desc_mnmajor_sw128(a_addr, 8192, 1024)
+                                         : bw::umma_smem_desc_kmajor(a_addr, 128);
+          const uint64_t db = p.mn_major ? bw::umma_smem_desc_mnmajor_sw128(b_addr, 8192, 1024)
+                                         : bw::umma_smem_desc_kmajor(b_addr, 128);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            bw2::umma_bf16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, ((kb - kb0) | k) != 0);
+            bw2::umma_bf16_2sm(d_tmem, da + kstep * k, db + kstep * k, idesc, ((kb - kb0) | k) != 0);
           bw2::umma_commit_2sm(&empty[stage]);
           if (kb == kb1 - 1) bw2::umma_commit_2sm(&tfull[as]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -198,7 +210,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       bw::tc_fence_after();
       const uint32_t rel = bw2::map_to_rank(&tempty[as], 0);
       tc_epilogue_tile_tma<BN, ACT, OT, RESIDUAL>(p, &tmOut, &tmRes, tmem_base + as * BN, quad, half, lane,
-                                                  z * p.M + m_blk * 256 + (int)rank * BM + quad * 32, n_blk, stg, rbar,
+                                                  z * p.split_rows + m_blk * 256 + (int)rank * BM + quad * 32, n_blk, stg, rbar,
                                                   sbuf, [rel] { bw2::mbar_arrive_cluster(rel); });
     }
     if (lane == 0) bw::tma_store_wait_all<0>();   // all results are in global memory before exit
@@ -228,22 +240,33 @@ static int tc2_launch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* 
     configured = true;
   }
   CUtensorMap tmA, tmB;
-  {
-    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.M}, str[1] = {(uint64_t)lda * 2};
-    uint32_t box[2] = {64, 128};
-    int rc = make_tmap(&tmA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (p.mn_major) {   // A: (K rows) x M, B: (K rows) x N, row-major with pitches lda / ldb
+    uint64_t dimsA[2] = {(uint64_t)p.M, (uint64_t)p.K}, strA[1] = {(uint64_t)lda * 2};
+    uint64_t dimsB[2] = {(uint64_t)p.N, (uint64_t)p.K}, strB[1] = {(uint64_t)ldb * 2};
+    uint32_t box[2] = {64, 64};
+    int rc = make_tmap(&tmA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dimsA, strA, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-  }
-  {
-    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N}, str[1] = {(uint64_t)ldb * 2};
-    uint32_t box[2] = {64, (uint32_t)(BN / 2)};
-    int rc = make_tmap(&tmB, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = make_tmap(&tmB, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dimsB, strB, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
+  } else {
+    {
+      uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.M}, str[1] = {(uint64_t)lda * 2};
+      uint32_t box[2] = {64, 128};
+      int rc = make_tmap(&tmA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
+    {
+      uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N}, str[1] = {(uint64_t)ldb * 2};
+      uint32_t box[2] = {64, (uint32_t)(BN / 2)};
+      int rc = make_tmap(&tmB, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
   }
   CUtensorMap tmOut, tmRes;
   {
     constexpr bool BF = sizeof(OT) == 2;
-    uint64_t dims[2] = {(uint64_t)p.N, (uint64_t)p.M * (uint64_t)p.splits}, str[1] = {(uint64_t)p.ldo * sizeof(OT)};
+    const uint64_t out_rows = p.splits > 1 || p.split_rows > p.M ? (uint64_t)p.split_rows * p.splits : (uint64_t)p.M;
+    uint64_t dims[2] = {(uint64_t)p.N, out_rows}, str[1] = {(uint64_t)p.ldo * sizeof(OT)};
     uint32_t box[2] = {BF ? 64u : 32u, 32u};
     int rc = make_tmap(&tmOut, p.out, BF ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                        dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -293,11 +316,14 @@ int tc_gemm2_launch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B,
 }
 
 // Split-K partial products for weight gradients: partial[z] (M x N fp32) = A[:, Kz] . B[:, Kz]^T
+// partial: splits x roundup(M, 256) x N floats.  mn_major: A is (K x M), B is (K x N) row-major.
 int tc_gemm2_splitk(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B, int64_t ldb, float* partial, int M,
-                    int N, int K, int splits, cudaStream_t s) {
+                    int N, int K, int splits, int mn_major, cudaStream_t s) {
   TcParams p{};
   p.M = M; p.N = N; p.K = K; p.out = partial; p.ldo = N; p.rows_per_sample = 1;
   p.splits = splits;
+  p.split_rows = cdiv(M, 256) * 256;
+  p.mn_major = mn_major;
   const int num_kb = cdiv(K, 64);
   p.kb_per_split = cdiv(num_kb, splits);
   if ((int64_t)(splits - 1) * p.kb_per_split >= num_kb) {   // every split must own at least one k-block

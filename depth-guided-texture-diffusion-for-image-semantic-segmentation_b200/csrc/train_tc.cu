@@ -46,6 +46,50 @@ transpose_op_kernel(const ST* __restrict__ src, const __nv_bfloat16* __restrict_
     }
 }
 
+// Same element-wise work without the transposed copy: 8 consecutive columns per thread (16-byte accesses).
+__device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void load8f(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x; f[2 * i + 1] = t.y;
+  }
+}
+template <typename ST, int MODE>
+__global__ void __launch_bounds__(256)
+eltwise_op_kernel(const ST* __restrict__ src, const __nv_bfloat16* __restrict__ aux, __nv_bfloat16* __restrict__ dst,
+                  const float* __restrict__ keep, const float* __restrict__ gamma, int rows_per_sample, int64_t total8,
+                  int N) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const int64_t e0 = i * 8;
+  const int64_t m = e0 / N;
+  const int n = (int)(e0 - m * N);
+  float f[8];
+  load8f(src + e0, f);
+  if (MODE == 0) {
+    const float k = keep ? keep[m / rows_per_sample] : 1.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] *= gamma ? k * gamma[n + e] : k;
+  }
+  if (MODE == 1) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
+  }
+  if (MODE == 2) {
+    float a[8];
+    load8f(aux + e0, a);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] *= gelu_grad_f(a[e]);
+  }
+  store8(dst + e0, f);
+}
+
 // column sums of a bf16 matrix: part[blk][n], then sum over blocks
 __global__ void __launch_bounds__(256)
 colsum_bf16_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ part, int M, int N,
@@ -65,12 +109,12 @@ colsum_bf16_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restric
   }
 }
 __global__ void sum_parts_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int S,
-                                 int transpose_rows, int transpose_cols) {
+                                 int64_t part_stride, int transpose_rows, int transpose_cols) {
   // out[i] = sum_z part[z][i];  with transpose_rows > 0 the (rows x cols) result is written transposed
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float s = 0.f;
-  for (int z = 0; z < S; ++z) s += part[(int64_t)z * n + i];
+  for (int z = 0; z < S; ++z) s += part[(int64_t)z * part_stride + i];
   if (transpose_rows > 0) {
     const int64_t r = i / transpose_cols, c = i - r * transpose_cols;
     out[c * transpose_rows + r] = s;
@@ -80,7 +124,7 @@ __global__ void sum_parts_kernel(const float* __restrict__ part, float* __restri
 }
 
 int tc_gemm2_splitk(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B, int64_t ldb, float* partial, int M,
-                    int N, int K, int splits, cudaStream_t s);
+                    int N, int K, int splits, int mn_major, cudaStream_t s);
 
 }  // namespace dgtd
 
@@ -93,10 +137,29 @@ int dgtd_transpose_op(const void* src, const void* aux, void* dst, void* dstT, c
                       int rows_per_sample, int M, int N, int mode, dgtd_stream_t stream) {
   DGTD_CHECK_ARG(src && (dst || dstT) && M > 0 && N > 0 && mode >= 0 && mode <= 3, "transpose_op: bad args");
   DGTD_CHECK_ARG(mode != 2 || aux, "transpose_op: gelu backward needs the pre-activation");
-  dim3 grid(cdiv(N, 32), cdiv(M, 32)), block(32, 8);
-  DGTD_CHECK_ARG(grid.y <= 65535, "transpose_op: too many rows for one launch");
   cudaStream_t s = (cudaStream_t)stream;
   const int rps = rows_per_sample > 0 ? rows_per_sample : 1;
+  if (!dstT && N % 8 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) |
+                               reinterpret_cast<uintptr_t>(aux)) & 15) == 0) {
+    const int64_t total8 = (int64_t)M * N / 8;
+    const unsigned blocks = (unsigned)cdiv(total8, (int64_t)256);
+    __nv_bfloat16* d = (__nv_bfloat16*)dst;
+    if (mode == 0)
+      eltwise_op_kernel<float, 0><<<blocks, 256, 0, s>>>((const float*)src, nullptr, d, keep, gamma, rps, total8, N);
+    else if (mode == 1)
+      eltwise_op_kernel<__nv_bfloat16, 1><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)src, nullptr, d, nullptr, nullptr,
+                                                                  1, total8, N);
+    else if (mode == 2)
+      eltwise_op_kernel<__nv_bfloat16, 2><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)src, (const __nv_bfloat16*)aux, d,
+                                                                  nullptr, nullptr, 1, total8, N);
+    else
+      eltwise_op_kernel<__nv_bfloat16, 3><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)src, nullptr, d, nullptr, nullptr,
+                                                                  1, total8, N);
+    DGTD_LAUNCH_CHECK("transpose_op(eltwise)");
+    return 0;
+  }
+  dim3 grid(cdiv(N, 32), cdiv(M, 32)), block(32, 8);
+  DGTD_CHECK_ARG(grid.y <= 65535, "transpose_op: too many rows for one launch");
   if (mode == 0)
     transpose_op_kernel<float, 0><<<grid, block, 0, s>>>((const float*)src, nullptr, (__nv_bfloat16*)dst,
                                                           (__nv_bfloat16*)dstT, keep, gamma, rps, M, N);
@@ -122,13 +185,13 @@ int dgtd_colsum_bf16(const void* x, float* ws, float* out, int M, int N, dgtd_st
   const int nb = cdiv(M, 1024);
   colsum_bf16_partial_kernel<<<dim3(cdiv(N, 32), nb), 256, 0, s>>>((const __nv_bfloat16*)x, ws, M, N, 1024);
   DGTD_LAUNCH_CHECK("colsum_bf16");
-  sum_parts_kernel<<<cdiv(N, 256), 256, 0, s>>>(ws, out, N, nb, 0, 0);
+  sum_parts_kernel<<<cdiv(N, 256), 256, 0, s>>>(ws, out, N, nb, N, 0, 0);
   DGTD_LAUNCH_CHECK("colsum_bf16.reduce");
   return 0;
 }
 
 // out = aT[Mo, Kr] . bT[No, Kr]^T  (fp32), reduction over the long Kr axis split across CTA pairs.
-// transpose_out != 0 writes out as (No x Mo).  ws: splits*Mo*No floats (dgtd_wgrad_tc_ws_floats).
+// transpose_out != 0 writes out as (No x Mo).  ws: dgtd_wgrad_tc_ws_floats floats.
 static int wgrad_splits(int Mo, int No, int Kr) {
   const int tiles = cdiv(Mo, 256) * cdiv(No, No % 256 == 0 ? 256 : 128);
   int s = cdiv(148, tiles);
@@ -139,22 +202,41 @@ static int wgrad_splits(int Mo, int No, int Kr) {
   const int kbps = cdiv(kb, s);
   return cdiv(kb, kbps);   // no empty split
 }
-int dgtd_wgrad_tc_ws_floats(int Mo, int No, int Kr) { return wgrad_splits(Mo, No, Kr) * Mo * No; }
+int dgtd_wgrad_tc_ws_floats(int Mo, int No, int Kr) { return wgrad_splits(Mo, No, Kr) * cdiv(Mo, 256) * 256 * No; }
+
+static int wgrad_tc_run(const void* a, int64_t lda, const void* b, int64_t ldb, float* out, float* ws, int Mo, int No,
+                        int Kr, int transpose_out, int mn_major, cudaStream_t s) {
+  const int S = wgrad_splits(Mo, No, Kr);
+  int rc = tc_gemm2_splitk((const __nv_bfloat16*)a, lda, (const __nv_bfloat16*)b, ldb, ws, Mo, No, Kr, S, mn_major, s);
+  if (rc) return rc;
+  DGTD_LAUNCH_CHECK("wgrad_tc");
+  const int64_t n = (int64_t)Mo * No;
+  sum_parts_kernel<<<cdiv(n, 256), 256, 0, s>>>(ws, out, n, S, (int64_t)cdiv(Mo, 256) * 256 * No,
+                                                transpose_out ? Mo : 0, No);
+  DGTD_LAUNCH_CHECK("wgrad_tc.reduce");
+  return 0;
+}
 
 int dgtd_wgrad_tc(const void* aT, const void* bT, float* out, float* ws, int Mo, int No, int Kr, int transpose_out,
                   dgtd_stream_t stream) {
   DGTD_CHECK_ARG(aT && bT && out && ws, "wgrad_tc: null pointer");
-  DGTD_CHECK_ARG(Mo >= 256 && Mo % 256 == 0 && No >= 128 && No % 8 == 0 && Kr >= 64 && Kr % 8 == 0,
-                 "wgrad_tc: need Mo %% 256 == 0, No >= 128, Kr %% 8 == 0 (got %d, %d, %d)", Mo, No, Kr);
-  cudaStream_t s = (cudaStream_t)stream;
-  const int S = wgrad_splits(Mo, No, Kr);
-  int rc = tc_gemm2_splitk((const __nv_bfloat16*)aT, Kr, (const __nv_bfloat16*)bT, Kr, ws, Mo, No, Kr, S, s);
-  if (rc) return rc;
-  DGTD_LAUNCH_CHECK("wgrad_tc");
-  const int64_t n = (int64_t)Mo * No;
-  sum_parts_kernel<<<cdiv(n, 256), 256, 0, s>>>(ws, out, n, S, transpose_out ? Mo : 0, No);
-  DGTD_LAUNCH_CHECK("wgrad_tc.reduce");
-  return 0;
+  DGTD_CHECK_ARG(Mo >= 8 && No >= 8 && No % 8 == 0 && Kr >= 64 && Kr % 8 == 0,
+                 "wgrad_tc: need No %% 8 == 0, Kr %% 8 == 0, Kr >= 64 (got %d, %d, %d)", Mo, No, Kr);
+  return wgrad_tc_run(aT, Kr, bT, Kr, out, ws, Mo, No, Kr, transpose_out, 0, (cudaStream_t)stream);
+}
+
+// Same product from UN-transposed operands: out (Mo x No) = a[Kr, Mo]^T . b[Kr, No], a and b row-major
+// activation matrices (pitches lda / ldb elements, column slices allowed), read as MN-major UMMA operands.
+int dgtd_wgrad_tc_mn(const void* a, int lda, const void* b, int ldb, float* out, float* ws, int Mo, int No, int Kr,
+                     int transpose_out, dgtd_stream_t stream) {
+  DGTD_CHECK_ARG(a && b && out && ws, "wgrad_tc_mn: null pointer");
+  DGTD_CHECK_ARG(Mo >= 8 && No >= 8 && Mo % 8 == 0 && No % 8 == 0 && Kr >= 1 && lda >= Mo && ldb >= No && lda % 8 == 0 &&
+                     ldb % 8 == 0,
+                 "wgrad_tc_mn: need Mo, No, lda, ldb multiples of 8 (got Mo=%d No=%d Kr=%d lda=%d ldb=%d)", Mo, No, Kr,
+                 lda, ldb);
+  DGTD_CHECK_ARG(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0,
+                 "wgrad_tc_mn: operands must be 16-byte aligned");
+  return wgrad_tc_run(a, lda, b, ldb, out, ws, Mo, No, Kr, transpose_out, 1, (cudaStream_t)stream);
 }
 
 }  // extern "C"

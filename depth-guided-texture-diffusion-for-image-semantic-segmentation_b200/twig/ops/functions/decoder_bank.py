@@ -11,12 +11,12 @@ geometry:
   conv1 (batched) dW1 = im2col(emb)^T dh1;                               demb = sum_d conv(dh1_d, rot180(W1_d)^T)
 
 precision "fp32": exact CUDA-core GEMMs (simt_gemm.cuh);  "bf16": tcgen05 grouped implicit-GEMM convs for
-the forward and the input gradients, split-K tcgen05 GEMMs on transposed im2col operands for the weight
-gradients.  All arithmetic is in libdgtd_ops.so; torch does allocation, views, packing copies.
+the forward and the input gradients, split-K tcgen05 GEMMs reading im2col / gradient matrices as MN-major
+operands (no transposed copies) for the weight gradients.  All arithmetic is in libdgtd_ops.so; torch does allocation, views, packing copies.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 from torch.autograd import Function
@@ -113,41 +113,12 @@ def col2im(dcol: torch.Tensor, Ct: int, mask: Optional[torch.Tensor], out: torch
     return out
 
 
-_SCRATCH: Dict[Tuple, torch.Tensor] = {}
-
-
-def _zero_rows_scratch(dev: torch.device, rows: int, cols: int, tag: str) -> torch.Tensor:
-    """bf16 (rows, cols) buffer whose padding rows are zero: allocated (and zeroed) once per shape, the
-    live rows are fully rewritten by every use (stream ordered)."""
-    key = (dev, rows, cols, tag)
-    t = _SCRATCH.get(key)
-    if t is None:
-        if len(_SCRATCH) > 16:
-            _SCRATCH.clear()
-        t = torch.zeros(rows, cols, device=dev, dtype=torch.bfloat16)
-        _SCRATCH[key] = t
-    return t
-
-
-def im2col_t(x: torch.Tensor, ks: int, stride: int, off: int, out_hw: Tuple[int, int], rows_to: int = 0,
-             tag: str = "a") -> torch.Tensor:
-    """x: (B,h,w,32) bf16 slice (pixel pitch x.stride(2)) -> (max(rows_to, ks*ks*32), B*oh*ow) bf16."""
+def im2col(x: torch.Tensor, ks: int, stride: int, off: int, out_hw: Tuple[int, int]) -> torch.Tensor:
+    """x: (B,h,w,32) bf16 slice (pixel pitch x.stride(2)) -> (B*oh*ow, ks*ks*32) bf16, zero outside the map."""
     B, h, w = x.shape[0], x.shape[1], x.shape[2]
-    M = B * out_hw[0] * out_hw[1]
-    rows = ks * ks * PAD
-    out = (_zero_rows_scratch(x.device, rows_to, M, tag) if rows_to > rows
-           else torch.empty(rows, M, device=x.device, dtype=torch.bfloat16))
-    call("dgtd_im2col_t", x.data_ptr(), x.stride(2), ptr(out), B, h, w, ks, stride, off, out_hw[0], out_hw[1], stream())
-    return out
-
-
-def transpose_rows_padded(src: torch.Tensor, rows_to: int, tag: str) -> torch.Tensor:
-    """(M, N) bf16 -> (max(rows_to, N), M) bf16, padding rows zero."""
-    M, N = src.shape
-    if rows_to <= N:
-        return TF.transpose_op(src, 3)[1]
-    out = _zero_rows_scratch(src.device, rows_to, M, tag)
-    call("dgtd_transpose_op", ptr(src), None, None, ptr(out), None, None, 1, M, N, 3, stream())
+    out = torch.empty(B * out_hw[0] * out_hw[1], ks * ks * PAD, device=x.device, dtype=torch.bfloat16)
+    call("dgtd_im2col_nhwc", x.data_ptr(), x.stride(2), ptr(out), B, h, w, ks, stride, off, out_hw[0], out_hw[1],
+         stream())
     return out
 
 
@@ -156,10 +127,6 @@ def group_sum(x: torch.Tensor, groups: int, group_stride: int, C: int) -> torch.
     out = torch.empty(M, C, device=x.device, dtype=torch.float32)
     call("dgtd_group_sum", ptr(x), capi.dtype_code(x.dtype), ptr(out), M, groups, group_stride, C, stream())
     return out
-
-
-def _round_up(v: int, m: int) -> int:
-    return (v + m - 1) // m * m
 
 
 def bank_supported(src_hw: Tuple[int, int], grids: Sequence[Tuple[int, int]]) -> bool:
@@ -280,15 +247,6 @@ def _backward_fp32(emb, h1, h2, W, grads, geo, L, D):
     return demb, dparams
 
 
-def _wgrad_conv_slow(g16: torch.Tensor, x: torch.Tensor, E: int, ks, st, off, grid) -> torch.Tensor:
-    """Tiny token grids (rows not a multiple of 8 / fewer than 64): exact CUDA-core weight gradient on
-    fp32 copies.  x: (B,h,w,32) bf16 slice -> (E, ks*ks*32)."""
-    xf = x.float().contiguous()
-    B, h, w, _ = xf.shape
-    return TF.linear_wgrad(g16.float().contiguous(), xf, E, ks * ks * PAD,
-                           conv=(ks, h, w, PAD, PAD, grid[0], grid[1], st, off))
-
-
 def _backward_bf16(emb_pad, h1, h2, W, grads, geo, L, D):
     B, h, w, _ = emb_pad.shape
     M = B * h * w
@@ -303,40 +261,20 @@ def _backward_bf16(emb_pad, h1, h2, W, grads, geo, L, D):
         Ms = B * grid[0] * grid[1]
         g = grads[d].detach().reshape(Ms, E).to(bf).contiguous()
         h2_d = h2[..., d * PAD:(d + 1) * PAD]
-        KP = ks * ks * PAD
-        w3p = pad_taps_bf16(pack_conv3(w3_d) if ks == 3 else fold_conv3_bilinear(w3_d), L)   # (E, KP)
-        if Ms % 8 == 0 and Ms >= 64:
-            colT = im2col_t(h2_d, ks, st, off, grid, rows_to=_round_up(KP, 256), tag="c3a")
-            gT = transpose_rows_padded(g, max(128, E), tag="c3b")
-            o = TF.wgrad_tc(colT, gT)                                              # (KP_pad, E_pad)
-            dWp = o[:KP, :E].t().contiguous()
-            del colT, gT, o
-        else:
-            dWp = _wgrad_conv_slow(g, h2_d, E, ks, st, off, grid)
+        w3p = pad_taps_bf16(pack_conv3(w3_d) if ks == 3 else fold_conv3_bilinear(w3_d), L)   # (E, ks*ks*32)
+        dWp = TF.wgrad_tc_mn(g, im2col(h2_d, ks, st, off, grid))                      # (E, ks*ks*32) = g^T col
         dW3.append(_unpack_w3_grad(dWp, E, ks, PAD, L))
-        db3.append(TF.colsum_bf16(g) if Ms >= 1 else None)
-        dcol = OP.linear(g, w3p.t().contiguous(), None)                                # (Ms, KP) bf16
+        db3.append(TF.colsum_bf16(g))
+        dcol = OP.linear(g, w3p.t().contiguous(), None)                                # (Ms, ks*ks*32) bf16
         col2im(dcol, PAD, h2_d, dh2[..., d * PAD:(d + 1) * PAD], PAD, ks, st, off, grid)
         del dcol
-    # ---- conv2: weight gradient per decoder (4 decoders' output channels share one 128-row operand)
+    # ---- conv2: per-decoder weight gradient, the decoder's 32 gradient channels read as a column slice
     dh2_2d = dh2.view(M, D * PAD)
     db2 = TF.colsum_bf16(dh2_2d).view(D, PAD)[:, :L]
     dW2 = []
-    tc = M % 8 == 0 and M >= 64
-    if tc:
-        dh2T = transpose_rows_padded(dh2_2d, _round_up(D * PAD, 128), tag="c2b")
-        for d in range(D):
-            colT = im2col_t(h1[..., d * PAD:(d + 1) * PAD], 3, 1, -1, (h, w), rows_to=512, tag="c2a")
-            q = (d * PAD) // 128 * 128
-            o = TF.wgrad_tc(colT, dh2T[q:q + 128])                                     # (512, 128)
-            blk = o[:9 * PAD, d * PAD - q:d * PAD - q + PAD].view(3, 3, PAD, PAD)[:, :, :L, :L]
-            dW2.append(blk.permute(3, 2, 0, 1).contiguous())
-        del dh2T, colT, o
-    else:
-        for d in range(D):
-            o = _wgrad_conv_slow(dh2[..., d * PAD:(d + 1) * PAD].reshape(M, PAD), h1[..., d * PAD:(d + 1) * PAD],
-                                 PAD, 3, 1, -1, (h, w))
-            dW2.append(o.view(PAD, 3, 3, PAD)[:L, :, :, :L].permute(0, 3, 1, 2).contiguous())
+    for d in range(D):
+        o = TF.wgrad_tc_mn(dh2_2d[:, d * PAD:(d + 1) * PAD], im2col(h1[..., d * PAD:(d + 1) * PAD], 3, 1, -1, (h, w)))
+        dW2.append(o.view(PAD, 3, 3, PAD)[:L, :, :, :L].permute(0, 3, 1, 2).contiguous())   # (co, ci, 3, 3)
     # ---- conv2 input gradient (grouped tcgen05 conv with transposed / rotated taps) + ReLU mask of h1
     w2t = torch.cat([pad_taps_bf16(rot_t(W[3 * d + 1]), L, PAD) for d in range(D)], 0)
     dh1 = torch.empty_like(dh2)
@@ -346,13 +284,7 @@ def _backward_bf16(emb_pad, h1, h2, W, grads, geo, L, D):
     # ---- conv1: one weight-gradient GEMM for all decoders (shared input)
     dh1_2d = dh1.view(M, D * PAD)
     db1 = TF.colsum_bf16(dh1_2d).view(D, PAD)[:, :L]
-    if tc:
-        dh1T = transpose_rows_padded(dh1_2d, _round_up(D * PAD, 256), tag="c1a")
-        colT = im2col_t(emb_pad, 3, 1, -1, (h, w))                                       # (288, M)
-        o = TF.wgrad_tc(dh1T, colT)[:D * PAD]                                           # (D*32, 288)
-        del dh1T, colT
-    else:
-        o = _wgrad_conv_slow(dh1_2d, emb_pad, D * PAD, 3, 1, -1, (h, w))
+    o = TF.wgrad_tc_mn(dh1_2d, im2col(emb_pad, 3, 1, -1, (h, w)))                         # (D*32, 288)
     dW1 = o.view(D, PAD, 3, 3, PAD)[:, :L, :, :, :L].permute(0, 1, 4, 2, 3).contiguous()
     # ---- input gradient of the shared embedding: per-decoder grouped conv, then the sum over decoders
     w1t = torch.cat([pad_taps_bf16(rot_t(W[3 * d]), L, PAD) for d in range(D)], 0)

@@ -115,6 +115,19 @@ def wgrad_tc(aT, bT, transpose_out=False):
     return out
 
 
+def wgrad_tc_mn(a, b, transpose_out=False):
+    """(Mo x No) = a[Kr,Mo]^T @ b[Kr,No] on tcgen05 straight from row-major bf16 activations (column
+    slices allowed: stride(0) = pitch, stride(1) = 1); fp32 result (optionally transposed)."""
+    Kr, Mo = a.shape
+    No = b.shape[1]
+    assert b.shape[0] == Kr and a.stride(1) == 1 and b.stride(1) == 1
+    out = _empty((No, Mo) if transpose_out else (Mo, No), a)
+    ws = _empty((capi.load().dgtd_wgrad_tc_ws_floats(Mo, No, Kr),), a)
+    call("dgtd_wgrad_tc_mn", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), ptr(out), ptr(ws), Mo, No, Kr,
+         int(transpose_out), stream())
+    return out
+
+
 def colsum_bf16(x):
     M, N = x.shape
     ws = _empty(((M + 1023) // 1024 * N,), x)
@@ -156,34 +169,34 @@ class ConvNextBlockBf16Fn(Function):
         out = torch.empty_like(x)
         OP.linear_residual_(hid, w2b, b2, gamma, keep, h * w, x, out=out)
         ctx.eps = eps
-        ctx.save_for_backward(x, y, a, hpre, dwT, ln_w, w1b, w2, w2b, b2, gamma, keep)
+        ctx.save_for_backward(x, y, a, hpre, hid, dwT, ln_w, w1b, w2, b2, gamma, keep)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
-        x, y, a, hpre, dwT, ln_w, w1b, w2, w2b, b2, gamma, keep = ctx.saved_tensors
+        """Weight gradients read dY and X as they lie in memory (MN-major tcgen05 operands, split over the
+        pixel rows): no transposed copies; the layer-scale factor is folded into W2 for the input gradient."""
+        x, y, a, hpre, hid, dwT, ln_w, w1b, w2, b2, gamma, keep = ctx.saved_tensors
         g = _f32(g)
         B, h, w, C = x.shape
         rows, C4, M = h * w, 4 * C, B * h * w
         g2 = g.view(M, C)
         s = colsum(g2, C, keep, rows)
-        gs, gT = transpose_op(g2, 0, want_dst=True, want_T=True, keep=keep, gamma=gamma, rows_per_sample=rows)
-        _, hidT = transpose_op(hpre, 1)                                # gelu(hpre)^T  (4C, M)
-        G = wgrad_tc(hidT, gT, transpose_out=True)                     # (C, 4C) = (keep g)^T hid
-        del hidT, gT
+        gk, _ = transpose_op(g2, 0, want_dst=True, want_T=False, keep=keep, rows_per_sample=rows)   # bf16 keep*g
+        G = wgrad_tc_mn(gk, hid)                                       # (C, 4C) = (keep g)^T hid
         dW2, db2 = torch.empty_like(w2), _empty((C,), g)
         dgamma = _empty((C,), g) if gamma is not None else None
         call("dgtd_layer_scale_finalize", ptr(G), ptr(s), ptr(w2), ptr(b2), ptr(gamma), ptr(dW2), ptr(db2),
              ptr(dgamma), C, C4, stream())
-        dh = OP.linear(gs, w2b.t().contiguous(), None)                 # bf16 (M, 4C) = (keep gamma g) @ W2
-        dhpre, dhpreT = transpose_op(dh, 2, aux=hpre, want_dst=True, want_T=True)
-        del dh, gs
-        _, aT = transpose_op(a, 3)
-        dW1 = wgrad_tc(dhpreT, aT)                                     # (4C, C)
+        w2g = w2 if gamma is None else w2 * gamma[:, None]
+        dh = OP.linear(gk, w2g.t().to(torch.bfloat16).contiguous(), None)   # bf16 (M, 4C) = (keep g) @ (gamma W2)
+        dhpre, _ = transpose_op(dh, 2, aux=hpre, want_dst=True, want_T=False)
+        del dh, gk
+        dW1 = wgrad_tc_mn(dhpre, a)                                    # (4C, C)
         db1 = colsum_bf16(dhpre)
         da = OP.linear(dhpre, w1b.t().contiguous(), None, out_dtype=F32)   # fp32 (M, C)
-        del dhpre, dhpreT, aT
+        del dhpre
         dy, dln_w, dln_b = ln_rows_bwd(da, y, ln_w, ctx.eps)
         dx = dwconv7(dy.view(B, h, w, C), dwT.flip(0).contiguous(), None, add=g)
         ddwT, ddb = dwconv7_wgrad(x, dy.view(B, h, w, C))
@@ -212,9 +225,8 @@ class DownsampleBf16Fn(Function):
         B, h, wd, C = x.shape
         g = _f32(g)
         g2 = g.view(-1, 2 * C)
-        gs, gT = transpose_op(g2, 0, want_dst=True, want_T=True)
-        _, pT = transpose_op(p, 3)
-        dWp = wgrad_tc(gT, pT)                                         # (2C, 4C)
+        gs, _ = transpose_op(g2, 0, want_dst=True, want_T=False)
+        dWp = wgrad_tc_mn(gs, p)                                       # (2C, 4C)
         dW = dWp.view(2 * C, 2, 2, C).permute(0, 3, 1, 2).contiguous()
         db = colsum(g2, 2 * C)
         dp = OP.linear(gs, wpb.t().contiguous(), None, out_dtype=F32)  # (M', 4C) fp32

@@ -235,6 +235,11 @@ int dgtd_colsum_bf16(const void* x, float* ws, float* out, int M, int N, dgtd_st
 int dgtd_wgrad_tc(const void* aT, const void* bT, float* out, float* ws, int Mo, int No, int Kr, int transpose_out,
                   dgtd_stream_t stream);
 int dgtd_wgrad_tc_ws_floats(int Mo, int No, int Kr);
+/* Same product from UN-transposed operands: out (Mo x No) = a[Kr,Mo]^T . b[Kr,No], a / b row-major bf16
+ * activation matrices (pitches lda / ldb in elements; column slices allowed), consumed as MN-major tcgen05
+ * operands -- the weight gradient dW = dY^T X straight from dY and X.  ws as for dgtd_wgrad_tc. */
+int dgtd_wgrad_tc_mn(const void* a, int lda, const void* b, int ldb, float* out, float* ws, int Mo, int No, int Kr,
+                     int transpose_out, dgtd_stream_t stream);
 /* Decoder-bank backward, data-movement halves (ShapePropDecoder cod.py:1210-1226 + folded injection :1471).
  * col2im: out[b,iy,ix,c] (pixel pitch ldo) = mask > 0 ? sum over the conv taps that read input pixel
  * (iy,ix) of dcol[(b,oy,ox)][(ty*ks+tx)*Ct + c] : 0; mask (nullable, dtype of out, pitch ldm) is the
@@ -242,10 +247,10 @@ int dgtd_wgrad_tc_ws_floats(int Mo, int No, int Kr);
 int dgtd_col2im_nhwc(const void* dcol, int dcol_dtype, int ldc, int Ct, const void* mask, int ldm, void* out,
                      int out_dtype, int ldo, int B, int h, int w, int C, int ks, int stride, int off, int oh, int ow,
                      dgtd_stream_t stream);
-/* outT[(tap*32 + c)][m] = x[b, oy*stride+off+ty, ox*stride+off+tx, c] (bf16, 32-channel slice at x, pixel
- * pitch ldx, zero outside the map): transposed im2col, the K-major operand of dgtd_wgrad_tc. */
-int dgtd_im2col_t(const void* x, int ldx, void* outT, int B, int h, int w, int ks, int stride, int off, int oh, int ow,
-                  dgtd_stream_t stream);
+/* col[m][tap*32 + c] = x[b, oy*stride+off+ty, ox*stride+off+tx, c] (bf16, 32-channel slice at x, pixel
+ * pitch ldx, zero outside the map), m = (b*oh+oy)*ow+ox: row-major im2col, an operand of dgtd_wgrad_tc_mn. */
+int dgtd_im2col_nhwc(const void* x, int ldx, void* col, int B, int h, int w, int ks, int stride, int off, int oh,
+                     int ow, dgtd_stream_t stream);
 /* out[m][c] (fp32) = sum_g x[m][g*group_stride + c], c < C */
 int dgtd_group_sum(const void* x, int dtype, float* out, int64_t M, int groups, int group_stride, int C,
                    dgtd_stream_t stream);

@@ -115,3 +115,32 @@ def test_conv_nhwc_grouped_bf16(OP, B, h, w, G, Cout, ks, stride, off, relu):
         ref = ref.clamp_min(0) if relu else ref
         got = out[gi].permute(0, 3, 1, 2).double().cpu()
         assert rel(got, ref) <= 1e-4, (gi, rel(got, ref))
+
+
+@pytest.mark.parametrize("Mo,No,Kr,lda,ldb,tr", [
+    (512, 128, 4096, 512, 128, False),     # trunk shape (stage 0 pwconv)
+    (256, 1024, 2304, 256, 1024, True),
+    (288, 32, 2304, 288, 512, False),      # decoder conv2: 32-column slice of a 512-wide gradient
+    (32, 288, 2304, 512, 288, False),      # ... and with the slice as the A operand (narrower than one TMA box)
+    (512, 288, 1000, 512, 288, False),     # reduction length not a multiple of the 64-row k-block
+    (64, 320, 72, 64, 320, False),         # tiny token grid (12x12 x B... ) and Mo below one pair tile
+    (4096, 1024, 9216, 4096, 1024, False),
+])
+def test_wgrad_tc_mn_reads_untransposed_operands(Mo, No, Kr, lda, ldb, tr):
+    """out = a^T b with a, b row-major activations consumed as MN-major tcgen05 operands; fp32 torch
+    reference on the same bf16-rounded inputs: |err| <= 2e-3 * max|ref| (accumulation order only)."""
+    from dgtd_b200.twig.ops.functions import train_func as TF
+    g = torch.Generator().manual_seed(Mo + No + Kr)
+    A = torch.randn(Kr, lda, generator=g).to(torch.bfloat16).cuda()
+    Bm = torch.randn(Kr, ldb, generator=g).to(torch.bfloat16).cuda()
+    off_a, off_b = (64 if lda > Mo else 0), (64 if ldb > No else 0)
+    a, b = A[:, off_a:off_a + Mo], Bm[:, off_b:off_b + No]
+    got = TF.wgrad_tc_mn(a, b, transpose_out=tr)
+    ref = a.float().t() @ b.float()
+    if tr:
+        ref = ref.t()
+    assert got.shape == ref.shape
+    err = float((got - ref).abs().max() / ref.abs().max())
+    assert err <= 2e-3, err
+    got2 = TF.wgrad_tc_mn(a, b, transpose_out=tr)
+    assert torch.equal(got, got2)

@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
     ap.add_argument("--size", type=int, default=384)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--train-eager", action="store_true", help="training leg without CUDA graph capture (DDP when N > 1)")
     ap.add_argument("--cpu-sample", type=int, default=2, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-diffusion", action="store_true")
@@ -139,39 +140,52 @@ def diffusion_microbench(OP, dev, peaks, C=256, S=1024, steps=(1, 2, 4, 8)):
     return out
 
 
-def train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding, steps=3, warmup=1, precision="bf16"):
+def train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding, steps=5, warmup=2, precision="bf16"):
     """Forward + backward of the hot path (block-level autograd Functions; `precision` selects the exact
-    fp32 CUDA-core path or the bf16 tcgen05 path of the trunk) on `train-batch` images per
-    GPU; with N > 1 the parameter gradients are all-reduced by DistributedDataParallel (bucketed NCCL
-    all-reduce overlapped with backward -- the reference's own mechanism, cod.py:8,238)."""
+    fp32 CUDA-core path or the bf16 tcgen05 path) on `train-batch` images per GPU.  Default: the step is
+    captured in a CUDA graph and replayed (twig/graphs.py); with N > 1 the flat gradient buffer is
+    all-reduced over NCCL after every replay.  --train-eager: Python-issued launches, gradients reduced by
+    DistributedDataParallel (bucketed all-reduce overlapped with backward -- the reference's mechanism,
+    cod.py:8,238)."""
     import torch.distributed as dist
     import torch.nn as nn
-
-    class HotPath(nn.Module):
-        def __init__(self, enc, dec):
-            super().__init__()
-            self.prompt_encoder, self.prompt_decoder = enc, dec
-
-        def forward(self, image, depth):
-            _, e3, toks = TD.texture_prompts_train(self.prompt_encoder, self.prompt_decoder, image, depth,
-                                                           precision=precision)
-            # scalar stand-in for the downstream loss: every prompt tensor contributes
-            return sum(t.float().mean() for row in toks for t in row) + e3.mean()
+    from dgtd_b200.twig import graphs
 
     B, S = args.train_batch, args.size
-    model = HotPath(enc, dec).train()
-    if world > 1:
-        model = nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
     image, depth = common.synthetic_inputs(B, S, seed=100 + rank)
     image, depth = image.to(dev), depth.to(dev)
-    for p in model.parameters():
-        p.grad = None
+    enc.train(); dec.train()
+    n_grad = sum(p.numel() for p in list(enc.parameters()) + list(dec.parameters()) if p.requires_grad)
 
-    def one():
-        loss = model(image, depth)
-        loss.backward()
+    if args.train_eager:
+        class HotPath(nn.Module):
+            def __init__(self, enc, dec):
+                super().__init__()
+                self.prompt_encoder, self.prompt_decoder = enc, dec
+
+            def forward(self, image, depth):
+                return graphs.default_loss(*TD.texture_prompts_train(self.prompt_encoder, self.prompt_decoder, image,
+                                                                     depth, precision=precision))
+
+        model = HotPath(enc, dec).train()
+        if world > 1:
+            model = nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
         for p in model.parameters():
             p.grad = None
+
+        def one():
+            model(image, depth).backward()
+            for p in model.parameters():
+                p.grad = None
+        launch = "eager (Python-issued launches)"
+        reduce = "DistributedDataParallel bucketed NCCL all-reduce" if world > 1 else "none (1 GPU)"
+    else:
+        step = graphs.GraphedTrainStep(enc, dec, image, depth, precision=precision)
+
+        def one():
+            step()
+        launch = "CUDA graph replay of fwd+bwd"
+        reduce = "one NCCL all-reduce of the flat gradient buffer after the replay" if world > 1 else "none (1 GPU)"
 
     for _ in range(warmup):
         one()
@@ -185,12 +199,12 @@ def train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding, s
     b.record()
     torch.cuda.synchronize()
     t = sharding.max_over_ranks(a.elapsed_time(b) / 1e3, dev)
-    n_grad = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    for p in list(enc.parameters()) + list(dec.parameters()):
+        p.grad = None
     enc.eval(); dec.eval()
     return {"value": world * B * steps / t, "unit": UNIT, "batch_per_gpu": B, "steps": steps, "ms_per_step": t / steps * 1e3,
-            "precision": precision,
-            "grad_allreduce": "DistributedDataParallel bucketed NCCL all-reduce, %d fp32 grads" % n_grad if world > 1
-            else "none (1 GPU)"}
+            "precision": precision, "launch": launch,
+            "grad_allreduce": f"{reduce}, {n_grad} fp32 grads" if world > 1 else reduce}
 
 
 def cpu_model() -> str:

@@ -14,7 +14,7 @@
 
 namespace dgtd {
 
-template <int SY, int SX>
+template <int SY, int SX, bool ADD>
 __global__ void __launch_bounds__(SY * SX * 32, 2)
 dwconv7_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ wT,
                    const float* __restrict__ bias, const float* __restrict__ add, float* __restrict__ y, int h,
@@ -94,6 +94,21 @@ dwconv7_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restr
             acc[oy][pp] = fma2(w2[ky * 7 + kx], (kx & 1) ? po[pp + (kx >> 1)] : pe[pp + (kx >> 1)], acc[oy][pp]);
       }
     }
+    if (ADD) {
+      // residual operand: all 32 loads issued before the first dependent store (one round trip, not 32)
+      float av[4][8];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int oy = y0 + 4 * sy + a, ox = x0 + 8 * sx + j;
+          av[a][j] = (oy < h && ox < w) ? __ldg(add + (((int64_t)b * h + oy) * w + ox) * C + c) : 0.f;
+        }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp) acc[a][pp] = add2(acc[a][pp], pk2(av[a][2 * pp], av[a][2 * pp + 1]));
+    }
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
       const int oy = y0 + 4 * sy + a;
@@ -104,8 +119,8 @@ dwconv7_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restr
         up2(acc[a][pp], v0, v1);
         const int ox = x0 + 8 * sx + 2 * pp;
         const int64_t o = (((int64_t)b * h + oy) * w + ox) * C + c;
-        if (ox < w) y[o] = add ? v0 + add[o] : v0;
-        if (ox + 1 < w) y[o + C] = add ? v1 + add[o + C] : v1;
+        if (ox < w) y[o] = v0;
+        if (ox + 1 < w) y[o + C] = v1;
       }
     }
     __syncthreads();   // every warp is done with buffer i&1 before it is refilled
@@ -245,10 +260,11 @@ static int dw_launch(const CUtensorMap& tm, const float* wT, const float* bias, 
                      int h, int w, int C, cudaStream_t s) {
   constexpr int PH = 4 * SY + 6, PW = 8 * SX + 6;
   constexpr int SMEM = 2 * PH * PW * 128 + 128;
-  auto kern = dwconv7_tma_kernel<SY, SX>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e = cudaFuncSetAttribute(dwconv7_tma_kernel<SY, SX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(dwconv7_tma_kernel<SY, SX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) {
       set_error("dwconv7_tma: cannot opt in to %d B smem: %s", SMEM, cudaGetErrorString(e));
       return -2;
@@ -257,7 +273,10 @@ static int dw_launch(const CUtensorMap& tm, const float* wT, const float* bias, 
   }
   const int tiles_x = cdiv(w, 8 * SX), tiles_y = cdiv(h, 4 * SY);
   const int64_t blocks = (int64_t)B * tiles_x * tiles_y * (C / 128);
-  kern<<<(unsigned)blocks, SY * SX * 32, SMEM, s>>>(tm, wT, bias, add, y, h, w, C, tiles_x, tiles_y);
+  if (add)
+    dwconv7_tma_kernel<SY, SX, true><<<(unsigned)blocks, SY * SX * 32, SMEM, s>>>(tm, wT, bias, add, y, h, w, C, tiles_x, tiles_y);
+  else
+    dwconv7_tma_kernel<SY, SX, false><<<(unsigned)blocks, SY * SX * 32, SMEM, s>>>(tm, wT, bias, add, y, h, w, C, tiles_x, tiles_y);
   return 0;
 }
 

@@ -1,0 +1,77 @@
+"""CUDA-graph replay of one forward + backward pass of the hot path.
+
+A training step of the path is ~2000 short launches (36 ConvNeXt blocks x ~25 kernels each way, 16
+decoders); issued eagerly from Python the host falls behind the GPU (55 ms of launch work for 40 ms of
+kernels at 16 images).  The shapes of a training run are static, so the step is captured once and
+replayed: every kernel of libdgtd_ops.so takes its stream from the caller and allocates nothing, so the
+capture needs no special casing.
+
+Gradients live in ONE flat fp32 buffer (`.grad` of every parameter is a view into it): with data
+parallel training the whole gradient is reduced by a single NCCL all-reduce after the replay
+(354.7 MB for the hot path; cod.py:238 `MMDistributedDataParallel` does the same reduction in buckets).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+import torch.nn as nn
+
+from .model import texture_diffuser as TD
+
+
+def default_loss(emb1, emb3, tokens) -> torch.Tensor:
+    """Scalar stand-in for the downstream loss: every prompt tensor and embedding3 contribute."""
+    return sum(t.float().mean() for row in tokens for t in row) + emb3.float().mean()
+
+
+class GraphedTrainStep:
+    """step = GraphedTrainStep(enc, dec, image, depth); loss = step(image, depth) replays fwd + bwd.
+
+    After the call `p.grad` of every hot-path parameter holds this step's gradient (averaged over
+    `process_group` when given).  Inputs must keep the shape / dtype of the example tensors."""
+
+    def __init__(self, enc: nn.Module, dec: nn.Module, image: torch.Tensor, depth: torch.Tensor,
+                 loss_fn: Callable = default_loss, precision: Optional[str] = None, warmup: int = 3,
+                 process_group=None):
+        assert image.is_cuda and depth.is_cuda, "GraphedTrainStep needs CUDA tensors"
+        self.enc, self.dec, self.loss_fn, self.precision = enc, dec, loss_fn, precision
+        self.group = process_group
+        self.image, self.depth = image.detach().clone(), depth.detach().clone()
+        self.params = [p for p in list(enc.parameters()) + list(dec.parameters()) if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        self.flat_grad = torch.zeros(n, device=image.device, dtype=torch.float32)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):              # warm-up off the capture stream (allocator, lazy inits)
+            for _ in range(max(1, warmup)):
+                self._fwd_bwd()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._fwd_bwd()
+
+    def _fwd_bwd(self) -> torch.Tensor:
+        self.flat_grad.zero_()
+        out = TD.texture_prompts_train(self.enc, self.dec, self.image, self.depth, precision=self.precision)
+        loss = self.loss_fn(*out)
+        loss.backward()                            # accumulates in place into the flat buffer's views
+        return loss.detach()
+
+    def __call__(self, image: Optional[torch.Tensor] = None, depth: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if image is not None:
+            self.image.copy_(image, non_blocking=True)
+        if depth is not None:
+            self.depth.copy_(depth, non_blocking=True)
+        self.graph.replay()
+        if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                      and torch.distributed.get_world_size() > 1):
+            import torch.distributed as dist
+            dist.all_reduce(self.flat_grad, group=self.group)
+            self.flat_grad.div_(dist.get_world_size(self.group))
+        return self.loss

@@ -212,3 +212,43 @@ def test_decoder_bank_falls_back_per_decoder_for_non_power_of_two_grids():
     assert not DB.bank_supported((50, 50), TD.pvt_token_grids((200, 200)))
     assert DB.bank_supported((96, 96), TD.pvt_token_grids((384, 384)))
     assert DB.bank_supported((88, 88), TD.pvt_token_grids((352, 352)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_graphed_train_step_replays_the_eager_gradients(precision):
+    """CUDA-graph replay of fwd+bwd (twig/graphs.py) gives the gradients of the eager step bit for bit
+    (eval mode: no DropPath randomness; every reduction in the library has a fixed order), also after the
+    inputs and the weights changed between replays."""
+    TD = common.package()
+    from dgtd_b200.twig import graphs
+    enc, dec = TD.build_texture_diffuser(seed=0)
+    enc, dec = enc.cuda().eval(), dec.cuda().eval()
+    common.perturb_regressor_(enc)
+    S, B = 192, 2
+    image, depth = common.synthetic_inputs(B, S, seed=5)
+    image2, depth2 = common.synthetic_inputs(B, S, seed=6)
+    params = [p for p in list(enc.parameters()) + list(dec.parameters()) if p.requires_grad]
+
+    def eager(img, dep):
+        for p in params:
+            p.grad = None
+        graphs.default_loss(*TD.texture_prompts_train(enc, dec, img.cuda(), dep.cuda(), precision=precision)).backward()
+        return [None if p.grad is None else p.grad.clone() for p in params]
+
+    want1 = eager(image, depth)
+    step = graphs.GraphedTrainStep(enc, dec, image.cuda(), depth.cuda(), precision=precision)
+    step()
+    got1 = [p.grad.clone() for p in params]
+    with torch.no_grad():
+        for p in params:
+            p.mul_(1.01)                     # an "optimizer step": replays must read the new weights
+    step(image2.cuda(), depth2.cuda())
+    got2 = [p.grad.clone() for p in params]
+    want2 = eager(image2, depth2)
+    for want, got in ((want1, got1), (want2, got2)):
+        for w, g in zip(want, got):
+            if w is None:
+                assert float(g.abs().max()) == 0.0
+            else:
+                assert torch.equal(w, g)

@@ -137,7 +137,46 @@ def diffusion_microbench(OP, dev, peaks, C=256, S=1024, steps=(1, 2, 4, 8)):
     bb = (2 * C * 2 + 49 * 4) * S * S
     out["bf16_storage_T1"] = {"ms": ms, "alg_bytes": bb, "gbs": bb / (ms * 1e-3) / 1e9, "hbm_frac": bb / (ms * 1e-3) / 1e9 / hbm,
                               "tflops": 2.0 * 49 * C * S * S / (ms * 1e-3) / 1e12}
+    del wgt
+    out["w2_fused_regressor"] = diffusion_microbench_w2(OP, dev, xb, hbm, fma_roof, C, S)
     return out
+
+
+def diffusion_microbench_w2(OP, dev, xb, hbm, fma_roof, C, S):
+    """Weight mode W2: the model's per-channel weights sigmoid(Wr g + br) are
+    generated on chip from the 3-channel guide (49 GiB if materialised).  Algorithmic bytes per iteration
+    (2*C*s + 3*4)*H*W; algorithmic FLOPs 2*49*C*H*W (stencil) + C*49*14*H*W (regressor + sigmoid).  One
+    pass per iteration, weights regenerated every pass; the bound is the MUFU/FMA issue rate, not HBM."""
+    g = torch.Generator("cpu").manual_seed(1)
+    guide = torch.randn(1, 3, S, S, generator=g).to(dev)
+    reg_w = (torch.randn(C * 49, 3, generator=g) * 0.5).to(dev)
+    reg_b = torch.randn(C * 49, generator=g).to(dev)
+    mufu_roof = 148 * 16 * 1.965e9            # MUFU lane-ops/s (16 per SM per clock)
+    res = {"weights": "per-channel, generated on chip (wc=C)", "sweep": []}
+    x32 = xb.float()
+    cases = [("f32", x32, False, 1), ("f32", x32, False, 4), ("f32", x32, True, 1), ("bf16", xb, True, 1)]
+    for name, x, fast, T in cases:
+        es = 4 if name == "f32" else 2
+        for _ in range(2):
+            OP.message_passing_regress(x, guide, reg_w, reg_b, T, fast_sigmoid=fast)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(2):
+            OP.message_passing_regress(x, guide, reg_w, reg_b, T, fast_sigmoid=fast)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 2
+        nbytes = (2 * C * es + 12) * S * S
+        flops = (2.0 * 49 + 49 * 14) * C * S * S * T
+        mufu = (1 if fast else 2) * 49.0 * C * S * S * T
+        bound_ms = max(nbytes / (hbm * 1e9), flops / fma_roof, mufu / mufu_roof) * 1e3
+        res["sweep"].append({"storage": name, "sigmoid": "tanh.approx" if fast else "ex2+rcp", "T": T, "ms": ms,
+                             "alg_bytes_per_iter": nbytes, "gbs_per_iter": nbytes * T / (ms * 1e-3) / 1e9,
+                             "tflops": flops / (ms * 1e-3) / 1e12, "mufu_ms": mufu / mufu_roof * 1e3,
+                             "fma_ms": flops / fma_roof * 1e3, "hbm_ms": nbytes / (hbm * 1e9) * 1e3 * T,
+                             "roofline_ms": bound_ms, "frac_of_roofline": bound_ms / ms})
+    return res
 
 
 def train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding, steps=5, warmup=2, precision="bf16"):

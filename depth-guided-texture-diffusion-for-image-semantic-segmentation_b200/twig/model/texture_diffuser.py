@@ -531,8 +531,10 @@ class prompt_encoder(nn.Module):
         x = self.fft(image, self.freq_nums)                                            # no parameter upstream
         xx = OP.resize_nchw(x, (H, H), bilinear=False)                                 # nearest, :1295
         weights = self.propagation_weight_regressor(xx)                                # :1296
-        e1 = OP.conv1x1_nchw_autograd(cues.contiguous().float(), self.encoder1.weight, self.encoder1.bias, False)
-        d12 = OP.resize_bilinear_nchw_autograd(e1, (H, H))                             # :1298
+        # :1297-1298 with the two linear maps swapped (1x1 conv and bilinear resize commute, SURVEY.md
+        # appendix A): the 24-channel full-resolution tensor and its gradient are never materialised
+        c12 = OP.resize_bilinear_nchw_autograd(cues.contiguous().float(), (H, H))
+        d12 = OP.conv1x1_nchw_autograd(c12, self.encoder1.weight, self.encoder1.bias, False)
         mp = self.message_passing
         steps = H if mp.max_step < 0 else mp.max_step
         core = OP.message_passing_core(d12, weights, steps, 1e-5)

@@ -240,6 +240,24 @@ def message_passing_tiled(x: torch.Tensor, weight: torch.Tensor, steps: int, eps
     return out
 
 
+def message_passing_regress(x: torch.Tensor, guide: torch.Tensor, reg_w: torch.Tensor, reg_b: torch.Tensor,
+                            steps: int, eps: float = 1e-5, fast_sigmoid: bool = False) -> torch.Tensor:
+    """Large-map variant with the model's per-channel weights generated on chip: x (n,h,w,c) channels-last
+    storage (fp32|bf16), guide (n,3,h,w) fp32, reg_w (c*49,3[,1,1]), reg_b (c*49) -- the
+    ShapePropWeightRegressor parameters (cod.py:1051-1060)."""
+    check_cuda(x, guide, reg_w, reg_b)
+    n, h, w, c = x.shape
+    assert guide.shape == (n, 3, h, w) and reg_w.numel() == c * 49 * 3 and reg_b.numel() == c * 49
+    packed = torch.empty(c * 49, 4, device=x.device, dtype=torch.float32)
+    call("dgtd_pack_regressor", ptr(reg_w.detach().reshape(c * 49, 3).float().contiguous()),
+         ptr(reg_b.detach().float().contiguous()), ptr(packed), c, stream())
+    out = torch.empty_like(x)
+    tmp = torch.empty_like(x) if steps > 1 else None
+    call("dgtd_message_passing_regress_fwd", ptr(x), ptr(guide.contiguous().float()), ptr(packed), ptr(out), ptr(tmp),
+         n, h, w, c, steps, float(eps), capi.dtype_code(x.dtype), int(fast_sigmoid), stream())
+    return out
+
+
 # ------------------------------------------------------------------------------------------ helpers
 def conv1x1_nchw(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], sigmoid: bool = False):
     check_cuda(x, w, b)

@@ -85,6 +85,15 @@ int dgtd_message_passing_fwd(const float* x, const float* weight, float* out, fl
 int dgtd_message_passing_tiled_fwd(const void* x, const float* weight, void* out, void* tmp,
                                    int n, int h, int w, int c, int T, float eps, int dtype,
                                    dgtd_stream_t stream);
+/* Same operator with the MODEL's per-channel weights generated on chip (mode W2):
+ * W[c,k,p] = sigmoid(Wr[c*49+k,:] . guide[:,p] + br[c*49+k]) (ShapePropWeightRegressor, cod.py:1051-1060,
+ * 1296), normalised over the 49 taps (+eps, cod.py:1201) and applied as the 7x7 zero-padded stencil.
+ * x,out NHWC (n,h,w,c) fp32 | bf16 storage; guide (n,3,h,w) fp32 NCHW; packed = dgtd_pack_regressor(Wr, br)
+ * (c*49 float4).  fast_sigmoid != 0 uses tanh.approx (|err| <= 2.5e-4).  c multiple of 32. */
+int dgtd_pack_regressor(const float* wr, const float* br, float* packed, int c, dgtd_stream_t stream);
+int dgtd_message_passing_regress_fwd(const void* x, const float* guide, const float* packed, void* out, void* tmp,
+                                     int n, int h, int w, int c, int T, float eps, int dtype, int fast_sigmoid,
+                                     dgtd_stream_t stream);
 /* backward of the stand-alone operator: grad_out (n,c,h,w) -> grad_x (n,c,h,w) and
  * grad_weight (n,wc*49,h,w) (through the normalisation), from the saved states. */
 int dgtd_message_passing_bwd(const float* grad_out, const float* weight, const float* states,

@@ -102,6 +102,32 @@ def test_message_passing_tiled_large_map_variant(OP, n, h, w, c, T):
     check(got.permute(0, 3, 1, 2), ref, 1e-5)
 
 
+@pytest.mark.parametrize("n,h,w,c,T", [(1, 40, 70, 32, 1), (2, 17, 33, 64, 3), (1, 48, 48, 96, 2)])
+def test_message_passing_regress_generates_the_models_weights_on_chip(OP, n, h, w, c, T):
+    """W2 mode of the microbench: per-channel weights sigmoid(Wr g + br) generated inside the kernel ==
+    ShapePropWeightRegressor (cod.py:1051-1060) + MessagePassing core (cod.py:1190-1205) of the oracle.
+    Regressor scaled so that the weights are far from the uniform 0.5."""
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(n, c, h, w, generator=g)
+    guide = torch.randn(n, 3, h, w, generator=g)
+    reg_w = torch.randn(c * 49, 3, 1, 1, generator=g) * 0.8
+    reg_b = torch.randn(c * 49, generator=g)
+    wgt = O.regress_weights(guide.double(), reg_w.double(), reg_b.double())
+    ref = O.message_passing_core(x.double(), wgt, 7, T)
+    xc = x.permute(0, 2, 3, 1).contiguous().cuda()
+    got = OP.message_passing_regress(xc, guide.cuda(), reg_w.cuda(), reg_b.cuda(), T)
+    check(got.permute(0, 3, 1, 2), ref, 1e-5)
+    # tanh.approx sigmoid (one MUFU op per weight): stated tolerance 2e-3 of max|ref|
+    fast = OP.message_passing_regress(xc, guide.cuda(), reg_w.cuda(), reg_b.cuda(), T, fast_sigmoid=True)
+    check(fast.permute(0, 3, 1, 2), ref, 2e-3)
+    # bf16 storage / fp32 accumulate: one bf16 rounding per iteration
+    xb = x.to(torch.bfloat16)
+    refb = O.message_passing_core(xb.double(), wgt, 7, T)
+    gotb = OP.message_passing_regress(xb.permute(0, 2, 3, 1).contiguous().cuda(), guide.cuda(), reg_w.cuda(),
+                                      reg_b.cuda(), T, fast_sigmoid=True)
+    check(gotb.float().permute(0, 3, 1, 2), refb, 4e-3 * T + 2e-3)
+
+
 def test_message_passing_tiled_bf16_storage(OP):
     """bf16 storage / fp32 accumulate: exact on bf16-representable inputs up to the output rounding."""
     g = torch.Generator().manual_seed(22)

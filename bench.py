@@ -356,22 +356,29 @@ def run_ours(args):
     value = world * B * args.steps / t_max
 
     # ---- end to end: pinned host inputs -> H2D -> path -> D2H of the result ---------------------
-    res_h = torch.empty(B, 144, 512, dtype=torch.float32).pin_memory()   # last-stage prompt tokens
+    # (twig/pipeline.py: copy of batch i+1 and read-back of result i-1 overlap the compute of batch i;
+    #  every step's inputs cross PCIe inside the timed region)
+    from dgtd_b200.twig.pipeline import HostPipeline
+    res_h = [torch.empty(B, (S // 32) ** 2, 512, dtype=torch.float32).pin_memory() for _ in range(2)]   # last-stage prompt tokens
+    pipe = HostPipeline(enc, dec, precision=args.precision, want_embedding3=False, device=dev)
+    select = lambda e1, e3, toks: toks[3][2].float()
     e2e_steps = max(3, args.steps // 2)
+    for _ in pipe.run([(image_h, depth_h)] * 2, select, res_h):   # warm the pipeline's buffers
+        pass
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
-    for _ in range(e2e_steps):
-        img = image_h.to(dev, non_blocking=True)
-        dep = depth_h.to(dev, non_blocking=True)
-        _, _, toks = step(img, dep)
-        res_h.copy_(toks[3][2].float(), non_blocking=True)
+    last = None
+    for _, _, done in pipe.run([(image_h, depth_h)] * e2e_steps, select, res_h):
+        last = done
+    last.synchronize()
+    torch.cuda.current_stream().wait_event(last)
     t1.record()
     barrier()
     e2e = world * B * e2e_steps / sharding.max_over_ranks(t0.elapsed_time(t1) / 1e3, dev)
     h2d = image_h.numel() * 4 + depth_h.numel() * 4
-    d2h = res_h.numel() * 4
+    d2h = res_h[0].numel() * 4
 
     # ---- roofline of the dominant kernel family (tcgen05 GEMM), measured live with CUDA events ---
     roof = None

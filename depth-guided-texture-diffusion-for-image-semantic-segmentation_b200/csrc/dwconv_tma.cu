@@ -57,7 +57,7 @@ dwconv7_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restr
                       y0 - 3, b);
     }
     // taps duplicated into both halves of a 64-bit register: fma.rn.f32x2 then updates two
-    // horizontally adjacent output pixels per instruction (half the FMA issue slots)
+    // vertically adjacent output pixels per instruction (half the FMA issue slots)
     uint64_t w2[49];
 #pragma unroll
     for (int k = 0; k < 49; ++k) {
@@ -65,33 +65,34 @@ dwconv7_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restr
       w2[k] = pk2(t, t);
     }
     const float bc = bias ? __ldg(bias + c) : 0.f;
-    uint64_t acc[4][4];
+    // acc[q][j] = output pixels (row 2q, col j) and (row 2q+1, col j): the two halves of one f32x2 register.
+    // Pairing ROWS (not columns) means the matching input pair (in[iy][j+kx], in[iy+1][j+kx]) is two plain
+    // shared loads into the halves of a register pair for every kx -- no re-packing moves.
+    uint64_t acc[2][8];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int q = 0; q < 2; ++q)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[a][j] = pk2(bc, bc);
+      for (int j = 0; j < 8; ++j) acc[q][j] = pk2(bc, bc);
 
     bw::mbar_wait(&bar[i & 1], (i >> 1) & 1);
     const float* base = xs + (i & 1) * TILE_FLOATS + ((4 * sy) * PW + 8 * sx) * 32 + lane;
 #pragma unroll
-    for (int iy = 0; iy < 10; ++iy) {
-      float in[14];
+    for (int iy = 0; iy < 9; ++iy) {
+      uint64_t pr[14];   // (input row iy, input row iy+1) at the 14 columns of the sub-tile's halo
 #pragma unroll
-      for (int j = 0; j < 14; ++j) in[j] = base[(iy * PW + j) * 32];
-      uint64_t pe[7], po[6];   // (in[2m], in[2m+1]) and (in[2m+1], in[2m+2])
+      for (int j = 0; j < 14; ++j) {   // volatile: two fresh loads per pair (the compiler would otherwise reuse row
+        // iy+1 from the previous iteration and pay two moves per pair to re-pack it)
+        const volatile float* p0 = base + (iy * PW + j) * 32;
+        pr[j] = pk2(p0[0], p0[PW * 32]);
+      }
 #pragma unroll
-      for (int m = 0; m < 7; ++m) pe[m] = pk2(in[2 * m], in[2 * m + 1]);
-#pragma unroll
-      for (int m = 0; m < 6; ++m) po[m] = pk2(in[2 * m + 1], in[2 * m + 2]);
-#pragma unroll
-      for (int oy = 0; oy < 4; ++oy) {
-        const int ky = iy - oy;
+      for (int q = 0; q < 2; ++q) {
+        const int ky = iy - 2 * q;
         if (ky < 0 || ky >= 7) continue;
 #pragma unroll
         for (int kx = 0; kx < 7; ++kx)
 #pragma unroll
-          for (int pp = 0; pp < 4; ++pp)
-            acc[oy][pp] = fma2(w2[ky * 7 + kx], (kx & 1) ? po[pp + (kx >> 1)] : pe[pp + (kx >> 1)], acc[oy][pp]);
+          for (int j = 0; j < 8; ++j) acc[q][j] = fma2(w2[ky * 7 + kx], pr[j + kx], acc[q][j]);
       }
     }
     if (ADD) {
@@ -105,22 +106,36 @@ dwconv7_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restr
           av[a][j] = (oy < h && ox < w) ? __ldg(add + (((int64_t)b * h + oy) * w + ox) * C + c) : 0.f;
         }
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int q = 0; q < 2; ++q)
 #pragma unroll
-        for (int pp = 0; pp < 4; ++pp) acc[a][pp] = add2(acc[a][pp], pk2(av[a][2 * pp], av[a][2 * pp + 1]));
+        for (int j = 0; j < 8; ++j) acc[q][j] = add2(acc[q][j], pk2(av[2 * q][j], av[2 * q + 1][j]));
     }
+    {
+      const int oy0 = y0 + 4 * sy, ox0 = x0 + 8 * sx;
+      float* yp = y + (((int64_t)b * h + oy0) * w + ox0) * C + c;
+      const int rs = w * C;   // one image row; a sub-tile spans < 2^31 elements
+      if (oy0 + 4 <= h && ox0 + 8 <= w) {   // interior sub-tile (warp-uniform): no per-store predicates
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int oy = y0 + 4 * sy + a;
-      if (oy >= h) continue;
+        for (int q = 0; q < 2; ++q)
 #pragma unroll
-      for (int pp = 0; pp < 4; ++pp) {
-        float v0, v1;
-        up2(acc[a][pp], v0, v1);
-        const int ox = x0 + 8 * sx + 2 * pp;
-        const int64_t o = (((int64_t)b * h + oy) * w + ox) * C + c;
-        if (ox < w) y[o] = v0;
-        if (ox + 1 < w) y[o + C] = v1;
+          for (int j = 0; j < 8; ++j) {
+            float v0, v1;
+            up2(acc[q][j], v0, v1);
+            yp[(2 * q) * rs + j * C] = v0;
+            yp[(2 * q + 1) * rs + j * C] = v1;
+          }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float v0, v1;
+            up2(acc[q][j], v0, v1);
+            if (ox0 + j < w) {
+              if (oy0 + 2 * q < h) yp[(2 * q) * rs + j * C] = v0;
+              if (oy0 + 2 * q + 1 < h) yp[(2 * q + 1) * rs + j * C] = v1;
+            }
+          }
       }
     }
     __syncthreads();   // every warp is done with buffer i&1 before it is refilled

@@ -272,6 +272,58 @@ fusion_tail_kernel(const float* __restrict__ l0, const float* __restrict__ l1,
   }
 }
 
+// Same head with the 1x1 fusion conv already applied per level (it commutes with the bilinear up-sample and
+// is folded into the head projections on the host): out[p] = bias + sum_lv bilinear_up(z_lv)[p].
+// thread = (pixel, 4 channels); quads beyond C only zero-fill the padded bf16 copy.
+__global__ void __launch_bounds__(256)
+fusion_sum_kernel(const float* __restrict__ z0, const float* __restrict__ z1, const float* __restrict__ z2,
+                  const float* __restrict__ z3, int h0, int w0, int h1, int w1, int h2, int w2, int h3, int w3,
+                  const float* __restrict__ bias, float* __restrict__ out_nhwc, float* __restrict__ out_nchw,
+                  __nv_bfloat16* __restrict__ out_pad, int C, int Cpad, int quads, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cq = (int)(i % quads);
+  const int64_t p = i / quads;
+  const int c = cq * 4;
+  if (c >= C) {   // padding channels of the bf16 copy
+    if (out_pad && c < Cpad) store4(out_pad + p * Cpad + c, 0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  const int ox = (int)(p % w0);
+  const int64_t t = p / w0;
+  const int oy = (int)(t % h0), b = (int)(t / h0);
+  float4 acc = load4(bias + c);
+  {
+    const float4 v = load4(z0 + p * C + c);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+#pragma unroll
+  for (int lv = 1; lv < 4; ++lv) {
+    const float* src = lv == 1 ? z1 : lv == 2 ? z2 : z3;
+    const int hh = lv == 1 ? h1 : lv == 2 ? h2 : h3;
+    const int ww = lv == 1 ? w1 : lv == 2 ? w2 : w3;
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bilinear_src(oy, (float)hh / h0, hh, y0, y1, ly);
+    bilinear_src(ox, (float)ww / w0, ww, x0, x1, lx);
+    const float* sb = src + (int64_t)b * hh * ww * C + c;
+    const float4 a = load4(sb + ((int64_t)y0 * ww + x0) * C), bq = load4(sb + ((int64_t)y0 * ww + x1) * C);
+    const float4 cc = load4(sb + ((int64_t)y1 * ww + x0) * C), d = load4(sb + ((int64_t)y1 * ww + x1) * C);
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    acc.x += w00 * a.x + w01 * bq.x + w10 * cc.x + w11 * d.x;
+    acc.y += w00 * a.y + w01 * bq.y + w10 * cc.y + w11 * d.y;
+    acc.z += w00 * a.z + w01 * bq.z + w10 * cc.z + w11 * d.z;
+    acc.w += w00 * a.w + w01 * bq.w + w10 * cc.w + w11 * d.w;
+  }
+  if (out_nhwc) store4(out_nhwc + p * C + c, acc.x, acc.y, acc.z, acc.w);
+  if (out_pad) store4(out_pad + p * Cpad + c, acc.x, acc.y, acc.z, acc.w);
+  if (out_nchw) {
+    const int64_t hw = (int64_t)h0 * w0, r = p - (int64_t)b * hw;
+    float* o = out_nchw + ((int64_t)b * C + c) * hw + r;
+    o[0] = acc.x; o[hw] = acc.y; o[2 * hw] = acc.z; o[3 * hw] = acc.w;
+  }
+}
+
 // ------------------------------------------------------------------------------------ a11 resize
 template <typename IT, typename OT>
 __global__ void resize_nhwc_kernel(const IT* __restrict__ x, OT* __restrict__ out, int h, int w, int C,
@@ -437,6 +489,22 @@ int dgtd_fusion_head_fwd(const float* lv0, const float* lv1, const float* lv2, c
       lv0, lv1, lv2, lv3, hw[0], hw[1], hw[2], hw[3], hw[4], hw[5], hw[6], hw[7], wf, bf, out_nhwc,
       out_nchw, (__nv_bfloat16*)out_pad, Cpad, total);
   DGTD_LAUNCH_CHECK("fusion_head");
+  return 0;
+}
+
+int dgtd_fusion_sum_fwd(const float* z0, const float* z1, const float* z2, const float* z3, const int* hw,
+                        const float* bias, float* out_nhwc, float* out_nchw, void* out_pad, int Cpad, int B, int C,
+                        dgtd_stream_t stream) {
+  DGTD_CHECK_ARG(z0 && z1 && z2 && z3 && hw && bias, "fusion_sum: null pointer");
+  DGTD_CHECK_ARG(C > 0 && C % 4 == 0, "fusion_sum: C must be a multiple of 4");
+  DGTD_CHECK_ARG(out_nhwc || out_nchw || out_pad, "fusion_sum: no output requested");
+  DGTD_CHECK_ARG(!out_pad || (Cpad >= C && Cpad % 4 == 0), "fusion_sum: Cpad must be a multiple of 4 and >= C");
+  const int quads = (out_pad && Cpad > C ? Cpad : C) / 4;
+  const int64_t total = (int64_t)B * hw[0] * hw[1] * quads;
+  fusion_sum_kernel<<<(unsigned)cdiv(total, (int64_t)256), 256, 0, (cudaStream_t)stream>>>(
+      z0, z1, z2, z3, hw[0], hw[1], hw[2], hw[3], hw[4], hw[5], hw[6], hw[7], bias, out_nhwc, out_nchw,
+      (__nv_bfloat16*)out_pad, C, Cpad, quads, total);
+  DGTD_LAUNCH_CHECK("fusion_sum");
   return 0;
 }
 

@@ -223,30 +223,44 @@ dwconv7_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, 
   p[(int64_t)49 * C] = gsum;
 }
 
-// ---- stem patch gather (training forward) and its adjoint ------------------------------------------
-// patches[(b,oy,ox)][ci*16+ky*4+kx] = image[b,ci,4oy+ky,4ox+kx] + up(grid)[...]
+// ---- stem patch gather (training forward; bf16 operand of the tcgen05 stem GEMM) and its adjoint ----------
+// patches[(b,oy,ox)][ci*16+ky*4+kx] = image[b,ci,4oy+ky,4ox+kx] + up(grid)[...]; thread = 4 consecutive kx
+template <typename OT>
 __global__ void stem_patchify_kernel(const float* __restrict__ image, const float* __restrict__ grid, int G,
-                                     float* __restrict__ patches, int H, int W, int oh, int ow, int64_t total) {
+                                     OT* __restrict__ patches, int H, int W, int oh, int ow, int64_t total4) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int k = (int)(i % 48);
-  int64_t t = i / 48;
+  if (i >= total4) return;
+  const int k4 = (int)(i % 12);            // (ci, ky)
+  int64_t t = i / 12;
   const int ox = (int)(t % ow); t /= ow;
   const int oy = (int)(t % oh);
   const int b = (int)(t / oh);
-  const int ci = k >> 4, ky = (k >> 2) & 3, kx = k & 3;
-  const int iy = oy * 4 + ky, ix = ox * 4 + kx;
-  float v = image[(((int64_t)b * 3 + ci) * H + iy) * W + ix];
-  if (grid) {
-    int y0, y1, x0, x1;
-    float ly, lx;
-    bilinear_src(iy, (float)G / H, G, y0, y1, ly);
-    bilinear_src(ix, (float)G / W, G, x0, x1, lx);
-    const float* g = grid + ((int64_t)b * 3 + ci) * G * G;
-    v += (1.f - ly) * ((1.f - lx) * g[y0 * G + x0] + lx * g[y0 * G + x1]) +
-         ly * ((1.f - lx) * g[y1 * G + x0] + lx * g[y1 * G + x1]);
+  const int ci = k4 >> 2, ky = k4 & 3;
+  const int iy = oy * 4 + ky, ix0 = ox * 4;
+  const float* ip = image + (((int64_t)b * 3 + ci) * H + iy) * W + ix0;
+  float v[4];
+  if ((W & 3) == 0) {
+    const float4 q = *reinterpret_cast<const float4*>(ip);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  } else {
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx) v[kx] = ip[kx];
   }
-  patches[i] = v;
+  if (grid) {
+    int y0, y1;
+    float ly;
+    bilinear_src(iy, (float)G / H, G, y0, y1, ly);
+    const float* g = grid + ((int64_t)b * 3 + ci) * G * G;
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx) {
+      int x0, x1;
+      float lx;
+      bilinear_src(ix0 + kx, (float)G / W, G, x0, x1, lx);
+      v[kx] += (1.f - ly) * ((1.f - lx) * g[y0 * G + x0] + lx * g[y0 * G + x1]) +
+               ly * ((1.f - lx) * g[y1 * G + x0] + lx * g[y1 * G + x1]);
+    }
+  }
+  store4(patches + i * 4, v[0], v[1], v[2], v[3]);
 }
 // dimg[b,ci,iy,ix] = dpatches[(b,iy/4,ix/4)][ci*16+(iy%4)*4+ix%4]  (0 outside the covered area)
 __global__ void stem_unpatchify_kernel(const float* __restrict__ dp, float* __restrict__ dimg, int H, int W, int oh,
@@ -493,12 +507,17 @@ int dgtd_dwconv7_wgrad(const float* x, const float* dy, float* ws, float* dwT, f
   return 0;
 }
 
-int dgtd_stem_patchify(const float* image, const float* grid, int G, float* patches, int B, int H, int W,
+int dgtd_stem_patchify(const float* image, const float* grid, int G, void* patches, int out_dtype, int B, int H, int W,
                        dgtd_stream_t stream) {
   DGTD_CHECK_ARG(image && patches && B > 0 && H >= 4 && W >= 4, "stem_patchify: bad args");
   const int oh = H / 4, ow = W / 4;
-  const int64_t total = (int64_t)B * oh * ow * 48;
-  stem_patchify_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(image, grid, G, patches, H, W, oh, ow, total);
+  const int64_t total4 = (int64_t)B * oh * ow * 12;
+  if (out_dtype == DGTD_BF16)
+    stem_patchify_kernel<<<cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(image, grid, G, (__nv_bfloat16*)patches, H,
+                                                                              W, oh, ow, total4);
+  else
+    stem_patchify_kernel<<<cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(image, grid, G, (float*)patches, H, W, oh,
+                                                                              ow, total4);
   DGTD_LAUNCH_CHECK("stem_patchify");
   return 0;
 }

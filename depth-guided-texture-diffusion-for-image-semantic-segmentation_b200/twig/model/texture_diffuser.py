@@ -252,7 +252,14 @@ class ShapePropEncoder(nn.Module):
         pk = _packed(self)
         st_conv, st_ln = self.downsample_layers[0][0], self.downsample_layers[0][1]
         w0 = pk.get("stem", [st_conv.weight], lambda: st_conv.weight.detach().reshape(self.dims[0], 48).float().contiguous())
-        x = OP.stem(image, grid, w0, st_conv.bias.detach(), st_ln.weight.detach(), st_ln.bias.detach(), st_ln.eps)
+        if mode == BF16 and self.dims[0] % 128 == 0 and image.shape[-1] % 4 == 0:
+            # tcgen05 stem: bf16 patches (K = 48) x weights -> fp32, LayerNorm rows in place
+            w0b = pk.get("stem.bf16", [st_conv.weight], lambda: w0.to(torch.bfloat16))
+            B, _, H, W = image.shape
+            x = OP.linear(OP.stem_patches(image, grid, BF16), w0b, st_conv.bias.detach(), out_dtype=F32)
+            x = OP.ln_rows_(x, st_ln.weight.detach(), st_ln.bias.detach(), st_ln.eps).view(B, H // 4, W // 4, self.dims[0])
+        else:
+            x = OP.stem(image, grid, w0, st_conv.bias.detach(), st_ln.weight.detach(), st_ln.bias.detach(), st_ln.eps)
         outs = []
         for i in range(4):
             if i > 0:
@@ -272,19 +279,25 @@ class ShapePropEncoder(nn.Module):
         pk = _packed(self)
         B = outs[0].shape[0]
         levels, hw = [], []
+        L = self.out_dim
+        fw = self.fusion_conv.weight
         for i, o in enumerate(outs):
             conv = self.convs[i]
-            wl = pk.get(f"head{i}.{mode}", [conv.weight],
-                        lambda conv=conv: _as(conv.weight.detach().reshape(self.out_dim, -1), mode))
+            # fusion conv folded into the head projection (both 1x1, and a 1x1 conv commutes with the bilinear
+            # up-sample): z_i = x_i (Wf_i Wh_i)^T + Wf_i bh_i, so the 96 -> 24 product at full resolution is gone
+            wl = pk.get(f"headf{i}.{mode}", [conv.weight, fw],
+                        lambda conv=conv, i=i: _as(fw.detach().reshape(L, 4 * L)[:, i * L:(i + 1) * L].float()
+                                                   @ conv.weight.detach().reshape(L, -1).float(), mode))
+            bl = pk.get(f"headfb{i}", [conv.bias, fw],
+                        lambda conv=conv, i=i: (fw.detach().reshape(L, 4 * L)[:, i * L:(i + 1) * L].float()
+                                                @ conv.bias.detach().float()).contiguous())
             a = o.view(-1, o.shape[-1])
             if mode == BF16:       # tcgen05 projection (N=24): cast the fp32 stage output once
                 a = OP.cast(a, torch.bfloat16)
-            levels.append(OP.linear(a, wl, conv.bias.detach(), out_dtype=F32))
+            levels.append(OP.linear(a, wl, bl, out_dtype=F32))
             hw.append((o.shape[1], o.shape[2]))
-        wf = pk.get("fusion", [self.fusion_conv.weight],
-                    lambda: self.fusion_conv.weight.detach().reshape(self.out_dim, 4 * self.out_dim).float().contiguous())
-        return OP.fusion_head(levels, hw, wf, self.fusion_conv.bias.detach(), B, want_nhwc=True,
-                              want_nchw=want_nchw, pad_to=pad_to)
+        return OP.fusion_sum(levels, hw, self.fusion_conv.bias.detach(), B, want_nhwc=True, want_nchw=want_nchw,
+                             pad_to=pad_to)
 
     def _forward_train(self, image: torch.Tensor, grid: Optional[torch.Tensor], mode: int = F32) -> torch.Tensor:
         """Autograd-building path: returns embedding3 as NHWC (B,h0,w0,out_dim).  mode F32 = exact

@@ -47,6 +47,7 @@ SIGNATURES = {
     "dgtd_linear_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "dgtd_linear_residual_fwd": [_P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P],
     "dgtd_fusion_head_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "dgtd_fusion_sum_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "dgtd_conv_nhwc_fwd": [_P, _P, _P, _P] + [_I] * 15 + [_P],
     "dgtd_conv_nhwc_grouped_fwd": [_P, _P, _P, _P] + [_I] * 18 + [_L, _P],
     "dgtd_resize_nhwc_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
@@ -61,7 +62,7 @@ SIGNATURES = {
     "dgtd_ln_rows_bwd_ws_floats": [_L, _I],
     "dgtd_dwconv7_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "dgtd_dwconv7_wgrad": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
-    "dgtd_stem_patchify": [_P, _P, _I, _P, _I, _I, _I, _P],
+    "dgtd_stem_patchify": [_P, _P, _I, _P, _I, _I, _I, _I, _P],
     "dgtd_stem_unpatchify": [_P, _P, _I, _I, _I, _P],
     "dgtd_patchify2": [_P, _P, _I, _I, _I, _I, _P],
     "dgtd_unpatchify2": [_P, _P, _I, _I, _I, _I, _P],

@@ -20,7 +20,7 @@ from ..capi import ACT_GELU, ACT_NONE, ACT_RELU, BF16, F32, call, check_cuda, pt
 __all__ = [
     "surface_normals", "HighpassPlan", "fft_highpass", "diffusion_front", "MessagePassingFunction",
     "message_passing_core", "message_passing_tiled", "conv1x1_nchw_autograd", "resize_bilinear_nchw_autograd", "conv1x1_nchw", "resize_nchw", "layer_norm",
-    "stem", "ln_patchify", "dwconv7_ln", "dwconv7_ln_tma", "linear", "linear_residual_", "fusion_head", "conv_nhwc", "conv_nhwc_grouped",
+    "stem", "stem_patches", "ln_rows_", "fusion_sum", "ln_patchify", "dwconv7_ln", "dwconv7_ln_tma", "linear", "linear_residual_", "fusion_head", "conv_nhwc", "conv_nhwc_grouped",
     "resize_nhwc", "cast", "nhwc_to_nchw", "nchw_to_nhwc", "enable_gemm_profile", "collect_gemm_profile",
 ]
 
@@ -384,6 +384,42 @@ def fusion_head(levels: List[torch.Tensor], hw: List[Tuple[int, int]], wf, bf, B
     call("dgtd_fusion_head_fwd", ptr(levels[0]), ptr(levels[1]), ptr(levels[2]), ptr(levels[3]), hw_arr,
          ptr(wf), ptr(bf), ptr(nhwc), ptr(nchw), ptr(pad), pad_to, B, C, stream())
     return nhwc, nchw, pad
+
+
+def fusion_sum(levels: List[torch.Tensor], hw: List[Tuple[int, int]], bias, B: int, want_nhwc=True,
+               want_nchw=False, pad_to: int = 0):
+    """levels[i]: (B*h_i*w_i, C) fp32 with the fusion conv already folded in; out = bias + sum_i up(levels[i]).
+    Returns (nhwc, nchw, padded-bf16) tensors."""
+    check_cuda(*levels, bias)
+    C = levels[0].shape[-1]
+    dev = levels[0].device
+    h0, w0 = hw[0]
+    nhwc = torch.empty(B, h0, w0, C, device=dev, dtype=torch.float32) if want_nhwc else None
+    nchw = torch.empty(B, C, h0, w0, device=dev, dtype=torch.float32) if want_nchw else None
+    pad = torch.empty(B, h0, w0, pad_to, device=dev, dtype=torch.bfloat16) if pad_to else None
+    hw_arr = (capi.c_int * 8)(*[v for pair in hw for v in pair])
+    call("dgtd_fusion_sum_fwd", ptr(levels[0]), ptr(levels[1]), ptr(levels[2]), ptr(levels[3]), hw_arr,
+         ptr(bias), ptr(nhwc), ptr(nchw), ptr(pad), pad_to, B, C, stream())
+    return nhwc, nchw, pad
+
+
+def stem_patches(image: torch.Tensor, grid: Optional[torch.Tensor], out_dtype: int) -> torch.Tensor:
+    """(up(grid)+image) gathered as 4x4/4 patches: (B*(H/4)*(W/4), 48) rows ordered (ci,ky,kx)."""
+    check_cuda(image, grid)
+    B, _, H, W = image.shape
+    out = torch.empty(B * (H // 4) * (W // 4), 48, device=image.device, dtype=_tdtype(out_dtype))
+    call("dgtd_stem_patchify", ptr(image), ptr(grid), grid.shape[-1] if grid is not None else 0, ptr(out), out_dtype,
+         B, H, W, stream())
+    return out
+
+
+def ln_rows_(y: torch.Tensor, ln_w, ln_b, eps: float = 1e-6) -> torch.Tensor:
+    """In-place LayerNorm over the last dim of an fp32 tensor (each row is read into registers before it is
+    written); C a multiple of 128."""
+    check_cuda(y, ln_w, ln_b)
+    C = y.shape[-1]
+    call("dgtd_ln_rows_fwd", ptr(y), ptr(ln_w), ptr(ln_b), ptr(y), F32, y.numel() // C, C, float(eps), stream())
+    return y
 
 
 # ------------------------------------------------------------------------------------------ a10/a11

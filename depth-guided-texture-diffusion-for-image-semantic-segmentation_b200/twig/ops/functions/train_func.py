@@ -321,8 +321,8 @@ class StemFn(Function):
         w2, b, ln_w, ln_b = _f32(w).reshape(Cout, 48).contiguous(), _f32(b), _f32(ln_w), _f32(ln_b)
         oh, ow = H // 4, W // 4
         patches = _empty((B * oh * ow, 48), image)
-        call("dgtd_stem_patchify", ptr(image), ptr(grid), grid.shape[-1] if grid is not None else 0, ptr(patches), B,
-             H, W, stream())
+        call("dgtd_stem_patchify", ptr(image), ptr(grid), grid.shape[-1] if grid is not None else 0, ptr(patches), F32,
+             B, H, W, stream())
         pre = OP.linear(patches, w2, b)
         out = ln_rows(pre, ln_w, ln_b, eps).view(B, oh, ow, Cout)
         ctx.cfg = (B, H, W, Cout, eps, None if grid is None else tuple(grid.shape))

@@ -165,6 +165,11 @@ int dgtd_fusion_head_fwd(const float* lv0, const float* lv1, const float* lv2, c
                          const int* hw, const float* wf, const float* bf, float* out_nhwc,
                          float* out_nchw, void* out_pad, int Cpad, int B, int C,
                          dgtd_stream_t stream);
+/* Same head after folding the fusion conv into the four head projections (a 1x1 conv commutes with the
+ * bilinear up-sample): z_i (B*h_i*w_i, C) fp32 = x_i (Wf_i Wh_i)^T + Wf_i bh_i;  out = bias + sum_i up(z_i). */
+int dgtd_fusion_sum_fwd(const float* z0, const float* z1, const float* z2, const float* z3, const int* hw,
+                        const float* bias, float* out_nhwc, float* out_nchw, void* out_pad, int Cpad, int B, int C,
+                        dgtd_stream_t stream);
 
 /* ---- a10/a11: ShapePropDecoder convs (cod.py:1216-1222) + prompt injection (:1471) -------- */
 /* KxK conv as implicit GEMM on NHWC: x (B,h,w,ldx) -> out (B,oh,ow,ldo);
@@ -222,8 +227,8 @@ int dgtd_dwconv7_fwd(const float* x, const float* wT, const float* bias, const f
 int dgtd_dwconv7_wgrad(const float* x, const float* dy, float* ws, float* dwT, float* db, int B, int h, int w, int C,
                        dgtd_stream_t stream);
 /* stem input gather: patches[(b,oy,ox)][ci*16+ky*4+kx] = image + up(grid); and its adjoint */
-int dgtd_stem_patchify(const float* image, const float* grid, int G, float* patches, int B, int H, int W,
-                       dgtd_stream_t stream);
+int dgtd_stem_patchify(const float* image, const float* grid, int G, void* patches, int out_dtype, int B, int H,
+                       int W, dgtd_stream_t stream);
 int dgtd_stem_unpatchify(const float* dpatches, float* dimg, int B, int H, int W, dgtd_stream_t stream);
 /* 2x2/2 patch gather of an NHWC tensor (rows of 4C, order (dy,dx,c)) and its adjoint */
 int dgtd_patchify2(const float* x, float* out, int B, int h, int w, int C, dgtd_stream_t stream);

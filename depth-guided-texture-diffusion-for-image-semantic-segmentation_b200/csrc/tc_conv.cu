@@ -7,6 +7,7 @@
 // out-of-bounds = zero padding) into a 64B-swizzled K-major smem tile that tcgen05.mma consumes.
 // Groups (the 16 decoders of the path) are a grid dimension: group g reads channel slice
 // [32g, 32g+32) of x, weight rows [g*w_group_rows, ...) and writes out + g*out_group_stride.
+#include <stdlib.h>
 #include "blackwell.cuh"
 #include "common.cuh"
 
@@ -185,6 +186,255 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// 3x3 / stride 1 / pad 1 variant (decoder conv1, conv2 and the identity-grid conv3): ONE halo tile per
+// output tile.  The per-tap kernel above re-reads the input nine times from L2 (9 x 8 KB of A per 128
+// output pixels); with only 32 output channels per group that makes the grouped decoder convs L2-feed
+// bound.  Here the tile is 16 rows x 8 pixels and the producer loads the (16+2) x (8+2) pixel halo once
+// (11.25 KB, 64B-swizzled, zero fill = padding).  The A operand of tap (dy,dx) is the SAME shared-memory
+// tile read through a descriptor that starts (dy*10 + dx) pixels further and strides 10 pixels (640 B)
+// between 8-row groups: the 128 MMA rows (j, i) = (row, pixel) land on halo pixel (j+dy, i+dx).
+// The nine weight tiles of a (group, n-block) stay resident (double buffered across group changes);
+// tiles are ordered so that a CTA changes (group, n-block) at most groups*tiles_n times.
+constexpr int HALO_TW = 8, HALO_TH = 16, HALO_PW = HALO_TW + 2, HALO_PH = HALO_TH + 2;
+constexpr int HALO_BYTES = HALO_PH * HALO_PW * 64;          // 11520
+constexpr int HALO_STAGE = 12288;                           // 1024-aligned slot
+
+template <int BN>
+struct HaloCfg {
+  static constexpr int W_BYTES = 9 * BN * 64;               // all taps of one (group, n-block)
+  static constexpr int STAGES = BN >= 128 ? 4 : 8;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * HALO_STAGE + 2 * W_BYTES + 256 + 1024;
+};
+
+// K-major 64B-swizzle descriptor with an explicit 8-row-group pitch.  The start address is only 64-byte
+// aligned (one pixel), not aligned to the 512-byte swizzle pattern: measured on B200, the MMA unit applies
+// the XOR pattern to the absolute shared-memory address bits, i.e. exactly what TMA wrote, so the
+// descriptor's base_offset field stays 0 (setting it to (addr >> 7) & 7 gives wrong results).
+__device__ __forceinline__ uint64_t halo_desc(uint32_t addr, uint32_t sbo_bytes) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (4ull << 61);
+}
+
+template <int BN, int ACT, typename OT>
+__global__ void __launch_bounds__(256, 1)
+tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                    const ConvParams p) {
+  using Cfg = HaloCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + STAGES * HALO_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * HALO_STAGE + 2 * Cfg::W_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint64_t* wfull = bars + 2 * STAGES + 4;
+  uint64_t* wempty = bars + 2 * STAGES + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_img = p.tiles_x * p.tiles_y;
+  const int per_key = p.B * tiles_img;                      // tiles sharing one (group, n-block)
+  const int num_tiles = p.groups * p.tiles_n * per_key;
+
+  auto decode = [&](int tile, int& g, int& b, int& ty, int& tx, int& nb) {
+    tx = tile % p.tiles_x; tile /= p.tiles_x;
+    ty = tile % p.tiles_y; tile /= p.tiles_y;
+    b = tile % p.B; tile /= p.B;
+    nb = tile % p.tiles_n;
+    g = tile / p.tiles_n;
+  };
+
+  if (warp == 0 && lane == 0) {
+    bw::prefetch_tmap(&tmX);
+    bw::prefetch_tmap(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      bw::mbar_init(&full[i], 1);
+      bw::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      bw::mbar_init(&tfull[i], 1);
+      bw::mbar_init(&tempty[i], 128);
+      bw::mbar_init(&wfull[i], 1);
+      bw::mbar_init(&wempty[i], 1);
+    }
+    bw::fence_mbar_init();
+  }
+  if (warp == 2) bw::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  bw::tc_fence_before();
+  __syncthreads();
+  bw::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0, wcount = 0, last_key = -1;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int g, b, ty, tx, nb;
+        decode(tile, g, b, ty, tx, nb);
+        const int key = tile / per_key;
+        if (key != last_key) {   // new (group, n-block): its nine weight tiles into the other buffer
+          const int buf = wcount & 1;
+          bw::mbar_wait(&wempty[buf], ((wcount >> 1) & 1) ^ 1);
+          bw::mbar_arrive_expect_tx(&wfull[buf], Cfg::W_BYTES);
+#pragma unroll 1
+          for (int t = 0; t < 9; ++t)
+            bw::tma_load_2d(&tmW, &wfull[buf], sW + buf * Cfg::W_BYTES + t * BN * 64, t * 32,
+                            g * p.w_group_rows + nb * BN);
+          ++wcount;
+          last_key = key;
+        }
+        bw::mbar_wait(&empty[stage], phase ^ 1);
+        bw::mbar_arrive_expect_tx(&full[stage], HALO_BYTES);
+        bw::tma_load_4d(&tmX, &full[stage], sA + stage * HALO_STAGE, g * 32, tx * HALO_TW - 1, ty * HALO_TH - 1, b);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = bw::umma_idesc_bf16(128, BN);
+      int stage = 0, iter = 0, wcount = 0, last_key = -1, buf = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+        const int key = tile / per_key;
+        if (key != last_key) {
+          if (last_key >= 0) bw::umma_commit(&wempty[buf]);   // previous weights free once their MMAs retire
+          buf = wcount & 1;
+          bw::mbar_wait(&wfull[buf], (wcount >> 1) & 1);
+          ++wcount;
+          last_key = key;
+        }
+        const int as = iter & 1;
+        const uint32_t aphase = (iter >> 1) & 1;
+        bw::mbar_wait(&tempty[as], aphase ^ 1);
+        bw::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        bw::mbar_wait(&full[stage], phase);
+        bw::tc_fence_after();
+        const uint32_t a0 = bw::smem_u32(sA + stage * HALO_STAGE);
+        const uint32_t w0 = bw::smem_u32(sW + buf * Cfg::W_BYTES);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int dy = t / 3, dx = t - 3 * dy;
+          const uint64_t da = halo_desc(a0 + (dy * HALO_PW + dx) * 64, HALO_PW * 64);
+          const uint64_t db = bw::umma_smem_desc_kmajor(w0 + t * BN * 64, 64);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) bw::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (t | k) != 0);
+        }
+        bw::umma_commit(&empty[stage]);
+        bw::umma_commit(&tfull[as]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+      int g, b, ty, tx, nb;
+      decode(tile, g, b, ty, tx, nb);
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1;
+      bw::mbar_wait(&tfull[as], aphase);
+      bw::tc_fence_after();
+      const int r = ew * 32 + lane;                 // MMA row = (j, i): image row j, pixel i of the 16 x 8 tile
+      const int j = r >> 3, i = r & 7;
+      const int oy = ty * HALO_TH + j, ox = tx * HALO_TW + i;
+      const bool row_ok = oy < p.oh && ox < p.ow;
+      OT* orow = reinterpret_cast<OT*>(p.out) + (int64_t)g * p.out_group_stride +
+                 (((int64_t)b * p.oh + oy) * p.ow + ox) * p.ldo;
+      const float* bias = p.bias ? p.bias + g * p.w_group_rows : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        bw::tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN + c0, v);
+        bw::tmem_ld_wait();
+        const int col0 = nb * BN + c0;
+        if (row_ok && col0 < p.Cout) {
+#pragma unroll
+          for (int q = 0; q < 32; q += 8) {
+            if (col0 + q >= p.Cout) break;
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q + e]);
+            if (bias) {
+              float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + q));
+              float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + q + 4));
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            if (ACT == DGTD_ACT_RELU) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+            }
+            store4(orow + col0 + q, f[0], f[1], f[2], f[3]);
+            store4(orow + col0 + q + 4, f[4], f[5], f[6], f[7]);
+          }
+        }
+      }
+      bw::tc_fence_before();
+      bw::mbar_arrive(&tempty[as]);
+    }
+  }
+
+  bw::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    bw::tc_fence_after();
+    bw::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN, int ACT, typename OT>
+static int conv_halo_launch(const void* x, int B, int h, int wd, int ldx, const __nv_bfloat16* w, int Wrows,
+                            ConvParams p, cudaStream_t s) {
+  using Cfg = HaloCfg<BN>;
+  auto kern = tc_conv_halo_kernel<BN, ACT, OT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("tc_conv(halo): cannot opt in to %d B of shared memory: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return -2;
+    }
+    configured = true;
+  }
+  CUtensorMap tmX, tmW;
+  {
+    uint64_t dims[4] = {(uint64_t)ldx, (uint64_t)wd, (uint64_t)h, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)ldx * 2, (uint64_t)wd * ldx * 2, (uint64_t)h * wd * ldx * 2};
+    uint32_t box[4] = {32, HALO_PW, HALO_PH, 1};
+    int rc = make_tmap(&tmX, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)288, (uint64_t)Wrows}, str[1] = {(uint64_t)288 * 2};
+    uint32_t box[2] = {32, (uint32_t)BN};
+    int rc = make_tmap(&tmW, w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
+  p.TW = HALO_TW; p.TH = HALO_TH;
+  p.tiles_x = cdiv(p.ow, HALO_TW);
+  p.tiles_y = cdiv(p.oh, HALO_TH);
+  p.tiles_n = cdiv(p.Cout, BN);
+  int64_t tiles = (int64_t)p.groups * p.B * p.tiles_x * p.tiles_y * p.tiles_n;
+  int grid = tiles < sm_count() ? (int)tiles : sm_count();
+  kern<<<grid, 256, Cfg::SMEM_BYTES, s>>>(tmX, tmW, p);
+  return 0;
+}
+
+template <int ACT, typename OT>
+static int conv_halo_dispatch_bn(const void* x, int B, int h, int wd, int ldx, const __nv_bfloat16* w, int Wrows,
+                                 const ConvParams& p, cudaStream_t s) {
+  if (p.Cout <= 32) return conv_halo_launch<32, ACT, OT>(x, B, h, wd, ldx, w, Wrows, p, s);
+  if (p.Cout <= 64) return conv_halo_launch<64, ACT, OT>(x, B, h, wd, ldx, w, Wrows, p, s);
+  return conv_halo_launch<128, ACT, OT>(x, B, h, wd, ldx, w, Wrows, p, s);
+}
+
 static void pick_tile(int ow, int oh, int stride, int& TW, int& TH) {
   int lim = 256 / stride;
   if (lim > 32) lim = 32;
@@ -250,6 +500,16 @@ int tc_conv_nhwc(const void* x, const void* w, const float* bias, void* out, int
   p.B = B; p.oh = oh; p.ow = ow; p.Cout = Cout; p.ldo = ldo; p.ks = ks; p.stride = stride; p.off = off;
   p.groups = groups; p.w_group_rows = w_group_rows; p.out_group_stride = out_group_stride;
   p.bias = bias; p.out = out;
+  if (ks == 3 && stride == 1 && off == -1 && oh == h && ow == wd && !getenv("DGTD_CONV_NO_HALO")) {
+    const int Wrows = groups * w_group_rows;
+    const __nv_bfloat16* wp = (const __nv_bfloat16*)w;
+    if (dtype_out == DGTD_BF16) {
+      if (act == DGTD_ACT_RELU) return conv_halo_dispatch_bn<DGTD_ACT_RELU, __nv_bfloat16>(x, B, h, wd, ldx, wp, Wrows, p, s);
+      return conv_halo_dispatch_bn<DGTD_ACT_NONE, __nv_bfloat16>(x, B, h, wd, ldx, wp, Wrows, p, s);
+    }
+    if (act == DGTD_ACT_RELU) return conv_halo_dispatch_bn<DGTD_ACT_RELU, float>(x, B, h, wd, ldx, wp, Wrows, p, s);
+    return conv_halo_dispatch_bn<DGTD_ACT_NONE, float>(x, B, h, wd, ldx, wp, Wrows, p, s);
+  }
   pick_tile(ow, oh, stride, p.TW, p.TH);
   p.tiles_x = cdiv(ow, p.TW);
   p.tiles_y = cdiv(oh, p.TH);

@@ -35,17 +35,19 @@ def enable_gemm_profile(on: bool = True):
     return _PROFILE
 
 
-def collect_gemm_profile():
-    """(total algorithmic FLOPs, total milliseconds, launches) of the profiled tcgen05 GEMMs."""
+def collect_gemm_profile(min_n: int = 0, min_k: int = 0):
+    """(total algorithmic FLOPs, total milliseconds, launches) of the profiled tcgen05 GEMMs with
+    N >= min_n and K >= min_k."""
     torch.cuda.synchronize()
-    flops = sum(f for f, _, _ in _PROFILE["events"])
-    ms = sum(a.elapsed_time(b) for _, a, b in _PROFILE["events"])
-    return flops, ms, len(_PROFILE["events"])
+    ev = [e for e in _PROFILE["events"] if e[3] is None or (e[3][1] >= min_n and e[3][2] >= min_k)]
+    flops = sum(e[0] for e in ev)
+    ms = sum(e[1].elapsed_time(e[2]) for e in ev)
+    return flops, ms, len(ev)
 
 
 class _timed:
-    def __init__(self, flops: float, active: bool):
-        self.flops, self.active = flops, active and _PROFILE["on"]
+    def __init__(self, flops: float, active: bool, shape=None):
+        self.flops, self.active, self.shape = flops, active and _PROFILE["on"], shape
 
     def __enter__(self):
         if self.active:
@@ -56,7 +58,7 @@ class _timed:
     def __exit__(self, *exc):
         if self.active:
             self.b.record()
-            _PROFILE["events"].append((self.flops, self.a, self.b))
+            _PROFILE["events"].append((self.flops, self.a, self.b, self.shape))
 
 
 def _tdtype(code: int) -> torch.dtype:
@@ -348,7 +350,7 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: 
     if out is None:
         out = torch.empty(tuple(a.shape[:-1]) + (N,), device=a.device, dtype=_tdtype(dout))
     ldo = out.shape[-1]
-    with _timed(2.0 * M * N * K, din == BF16):
+    with _timed(2.0 * M * N * K, din == BF16, (M, N, K)):
         call("dgtd_linear_fwd", ptr(a), ptr(w), ptr(bias), ptr(out), M, N, K, ldo, din, dout, act, stream())
     return out
 
@@ -363,7 +365,7 @@ def linear_residual_(a: torch.Tensor, w: torch.Tensor, bias, gamma, keep: Option
     N = w.shape[0]
     assert residual.dtype == torch.float32 and residual.numel() == M * N
     out = residual if out is None else out
-    with _timed(2.0 * M * N * K, a.dtype == torch.bfloat16):
+    with _timed(2.0 * M * N * K, a.dtype == torch.bfloat16, (M, N, K)):
         call("dgtd_linear_residual_fwd", ptr(a), ptr(w), ptr(bias), ptr(gamma), ptr(keep), rows_per_sample,
              ptr(residual), ptr(out), M, N, K, capi.dtype_code(a.dtype), stream())
     return out

@@ -87,6 +87,7 @@ CONV_CASES = [  # (B, h, w, groups, Cout, ks, stride, off, relu)
     (3, 96, 96, 2, 512, 4, 8, 2, False),     # folded, ratio 8
     (1, 88, 88, 2, 64, 4, 2, -1, False),     # 352^2 input: 88 -> 44
     (1, 20, 28, 1, 40, 3, 1, -1, False),     # odd tile shapes / N tail
+    (2, 24, 40, 5, 32, 3, 1, -1, True),      # five groups: the resident weight tiles are swapped four times
 ]
 
 

@@ -205,7 +205,8 @@ struct HaloCfg {
   static constexpr int W_BYTES = 9 * BN * 64;               // all taps of one (group, n-block)
   static constexpr int STAGES = BN >= 128 ? 4 : 8;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * HALO_STAGE + 2 * W_BYTES + 256 + 1024;
+  static constexpr int STG_BYTES = 4 * 2 * 2048;            // per epilogue warp: two 32-row x 64-byte staging tiles
+  static constexpr int SMEM_BYTES = STAGES * HALO_STAGE + 2 * W_BYTES + STG_BYTES + 256 + 1024;
 };
 
 // K-major 64B-swizzle descriptor with an explicit 8-row-group pitch.  The start address is only 64-byte
@@ -219,13 +220,14 @@ __device__ __forceinline__ uint64_t halo_desc(uint32_t addr, uint32_t sbo_bytes)
 template <int BN, int ACT, typename OT>
 __global__ void __launch_bounds__(256, 1)
 tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                    const ConvParams p) {
+                    const __grid_constant__ CUtensorMap tmO, const ConvParams p) {
   using Cfg = HaloCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sW = smem + STAGES * HALO_STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * HALO_STAGE + 2 * Cfg::W_BYTES);
+  uint8_t* sStg = smem + STAGES * HALO_STAGE + 2 * Cfg::W_BYTES;      // 1024-aligned (all sizes above are)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + Cfg::STG_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
@@ -334,6 +336,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   } else if (warp >= 4) {
     const int ew = warp - 4;
     int iter = 0;
+    uint32_t sbuf = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
       int g, b, ty, tx, nb;
       decode(tile, g, b, ty, tx, nb);
@@ -345,23 +348,28 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const int j = r >> 3, i = r & 7;
       const int oy = ty * HALO_TH + j, ox = tx * HALO_TW + i;
       const bool row_ok = oy < p.oh && ox < p.ow;
-      OT* orow = reinterpret_cast<OT*>(p.out) + (int64_t)g * p.out_group_stride +
-                 (((int64_t)b * p.oh + oy) * p.ow + ox) * p.ldo;
       const float* bias = p.bias ? p.bias + g * p.w_group_rows : nullptr;
+      if (sizeof(OT) == 2) {
+        // bf16 results leave through a 64B-swizzled staging tile (32 rows = 4 image rows x 8 pixels, 64 B each)
+        // and ONE 5-D TMA store per 32 channels: full lines instead of 32 scattered 8-byte stores per lane;
+        // the tensor map clips tile rows / channels beyond the image.
+        uint8_t* stg = sStg + ew * 4096;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        bw::tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN + c0, v);
-        bw::tmem_ld_wait();
-        const int col0 = nb * BN + c0;
-        if (row_ok && col0 < p.Cout) {
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          bw::tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN + c0, v);
+          bw::tmem_ld_wait();
+          const int col0 = nb * BN + c0;
+          if (col0 >= p.Cout) break;
+          uint8_t* buf = stg + (sbuf & 1) * 2048;
+          if (lane == 0) bw::tma_store_wait_read<1>();   // the store that last read this buffer (two commits ago)
+          __syncwarp();
 #pragma unroll
           for (int q = 0; q < 32; q += 8) {
-            if (col0 + q >= p.Cout) break;
             float f[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q + e]);
-            if (bias) {
+            if (bias && col0 + q < p.Cout) {
               float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + q));
               float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + q + 4));
               f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
@@ -371,14 +379,58 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
             }
-            store4(orow + col0 + q, f[0], f[1], f[2], f[3]);
-            store4(orow + col0 + q + 4, f[4], f[5], f[6], f[7]);
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+            u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+            // 16-byte chunk (q/8) of row `lane` lives at chunk (q/8) ^ ((lane >> 1) & 3) of the 64-byte row
+            *reinterpret_cast<uint4*>(buf + lane * 64 + ((((q >> 3) ^ (lane >> 1)) & 3) << 4)) = u;
+          }
+          bw::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            bw::tma_store_5d(&tmO, buf, col0, tx * HALO_TW, ty * HALO_TH + ew * 4, b, g);
+            bw::tma_store_commit();
+          }
+          ++sbuf;
+        }
+      } else {
+        OT* orow = reinterpret_cast<OT*>(p.out) + (int64_t)g * p.out_group_stride +
+                   (((int64_t)b * p.oh + oy) * p.ow + ox) * p.ldo;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          bw::tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN + c0, v);
+          bw::tmem_ld_wait();
+          const int col0 = nb * BN + c0;
+          if (row_ok && col0 < p.Cout) {
+#pragma unroll
+            for (int q = 0; q < 32; q += 8) {
+              if (col0 + q >= p.Cout) break;
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q + e]);
+              if (bias) {
+                float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + q));
+                float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + q + 4));
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              }
+              if (ACT == DGTD_ACT_RELU) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+              }
+              store4(orow + col0 + q, f[0], f[1], f[2], f[3]);
+              store4(orow + col0 + q + 4, f[4], f[5], f[6], f[7]);
+            }
           }
         }
       }
       bw::tc_fence_before();
       bw::mbar_arrive(&tempty[as]);
     }
+    if (sizeof(OT) == 2 && lane == 0) bw::tma_store_wait_all<0>();   // results are in global memory before exit
   }
 
   bw::tc_fence_before();
@@ -417,13 +469,22 @@ static int conv_halo_launch(const void* x, int B, int h, int wd, int ldx, const 
     int rc = make_tmap(&tmW, w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
   }
+  CUtensorMap tmO = tmW;
+  if (sizeof(OT) == 2) {
+    uint64_t dims[5] = {(uint64_t)p.Cout, (uint64_t)p.ow, (uint64_t)p.oh, (uint64_t)p.B, (uint64_t)p.groups};
+    uint64_t str[4] = {(uint64_t)p.ldo * 2, (uint64_t)p.ow * p.ldo * 2, (uint64_t)p.oh * p.ow * p.ldo * 2,
+                       (uint64_t)(p.groups > 1 ? p.out_group_stride : (int64_t)p.B * p.oh * p.ow * p.ldo) * 2};
+    uint32_t box[5] = {32, HALO_TW, 4, 1, 1};
+    int rc = make_tmap(&tmO, p.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
   p.TW = HALO_TW; p.TH = HALO_TH;
   p.tiles_x = cdiv(p.ow, HALO_TW);
   p.tiles_y = cdiv(p.oh, HALO_TH);
   p.tiles_n = cdiv(p.Cout, BN);
   int64_t tiles = (int64_t)p.groups * p.B * p.tiles_x * p.tiles_y * p.tiles_n;
   int grid = tiles < sm_count() ? (int)tiles : sm_count();
-  kern<<<grid, 256, Cfg::SMEM_BYTES, s>>>(tmX, tmW, p);
+  kern<<<grid, 256, Cfg::SMEM_BYTES, s>>>(tmX, tmW, tmO, p);
   return 0;
 }
 

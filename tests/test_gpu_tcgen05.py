@@ -116,6 +116,13 @@ def test_conv_nhwc_grouped_bf16(OP, B, h, w, G, Cout, ks, stride, off, relu):
         ref = ref.clamp_min(0) if relu else ref
         got = out[gi].permute(0, 3, 1, 2).double().cpu()
         assert rel(got, ref) <= 1e-4, (gi, rel(got, ref))
+    # bf16 output (the decoder activations): TMA-store epilogue of the halo kernel; one output rounding
+    outb = torch.full((G, B, oh, ow, Cout), float("nan"), dtype=torch.bfloat16).cuda()
+    OP.conv_nhwc_grouped(x.cuda(), wt.reshape(G * Cout, ks * ks * 32).cuda().contiguous(), bias.reshape(-1).cuda(),
+                         32, (oh, ow), ks, stride, off, ACT_RELU if relu else ACT_NONE, outb, Cout, Cout, G, 32,
+                         Cout, B * oh * ow * Cout)
+    assert torch.isfinite(outb.float()).all()
+    assert rel(outb.float().cpu().double(), out.cpu().double()) <= 5e-3
 
 
 @pytest.mark.parametrize("Mo,No,Kr,lda,ldb,tr", [

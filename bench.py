@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-diffusion", action="store_true")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-highres", action="store_true")
     ap.add_argument("--train-batch", type=int, default=16, help="images per GPU per training step (configs[2])")
     return ap.parse_args()
 
@@ -139,7 +140,46 @@ def diffusion_microbench(OP, dev, peaks, C=256, S=1024, steps=(1, 2, 4, 8)):
                               "tflops": 2.0 * 49 * C * S * S / (ms * 1e-3) / 1e12}
     del wgt
     out["w2_fused_regressor"] = diffusion_microbench_w2(OP, dev, xb, hbm, fma_roof, C, S)
+    out["cpu_port"] = diffusion_microbench_cpu()
     return out
+
+
+def diffusion_microbench_cpu(C=256, S=256, T=1):
+    """The same operator through the oracle port on the host cores at a REDUCED size (the reference's
+    unfold formulation needs 49x the state; 1024^2 would be 49 GiB): element-iterations per second so that it
+    can be set beside the GPU sweep (1024^2 x 256 x T elements per call there)."""
+    from oracle import texture_diffuser_ref as O
+    g = torch.Generator("cpu").manual_seed(0)
+    x = torch.randn(1, C, S, S, generator=g)
+    wgt = torch.rand(1, 49, S, S, generator=g)
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        O.message_passing_core(x, wgt, 7, T)
+        t0 = time.perf_counter()
+        O.message_passing_core(x, wgt, 7, T)
+        dt = time.perf_counter() - t0
+    return {"shape": [1, C, S, S], "T": T, "seconds": dt, "elements_per_s": C * S * S * T / dt,
+            "cores": os.cpu_count() or 1, "kind": "port (oracle.message_passing_core, fp32 torch CPU)"}
+
+
+def highres_bench(TD, enc, dec, dev, world, rank, args, common, sharding, S=768, total=8, steps=5):
+    """BASELINE configs[4]: high-resolution inference, 8 images of 768^2 sharded by image over the GPUs
+    (8 / N per GPU, no collective); images/s of the whole job, device time, max over ranks."""
+    B = max(1, total // world)
+    image, depth = common.synthetic_inputs(B, S, seed=200 + rank)
+    image, depth = image.to(dev), depth.to(dev)
+    for _ in range(2):
+        TD.texture_prompts(enc, dec, image, depth, precision=args.precision, want_embedding3=False)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        TD.texture_prompts(enc, dec, image, depth, precision=args.precision, want_embedding3=False)
+    b.record()
+    torch.cuda.synchronize()
+    t = sharding.max_over_ranks(a.elapsed_time(b) / 1e3, dev)
+    return {"value": world * B * steps / t, "unit": "images/s", "size": S, "batch_per_gpu": B, "ms_per_step": t / steps * 1e3,
+            "sharding": "by image, no collective"}
 
 
 def diffusion_microbench_w2(OP, dev, xb, hbm, fma_roof, C, S):
@@ -238,12 +278,23 @@ def train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding, s
     b.record()
     torch.cuda.synchronize()
     t = sharding.max_over_ranks(a.elapsed_time(b) / 1e3, dev)
+    allreduce_ms = None
+    if world > 1 and not args.train_eager:      # exposed time of the gradient reduction (it follows the replay)
+        c, d = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); dist.barrier()
+        c.record()
+        for _ in range(steps):
+            dist.all_reduce(step.flat_grad)
+        d.record()
+        torch.cuda.synchronize()
+        allreduce_ms = sharding.max_over_ranks(c.elapsed_time(d) / 1e3, dev) / steps * 1e3
     for p in list(enc.parameters()) + list(dec.parameters()):
         p.grad = None
     enc.eval(); dec.eval()
     return {"value": world * B * steps / t, "unit": UNIT, "batch_per_gpu": B, "steps": steps, "ms_per_step": t / steps * 1e3,
             "precision": precision, "launch": launch,
-            "grad_allreduce": f"{reduce}, {n_grad} fp32 grads" if world > 1 else reduce}
+            "grad_allreduce": f"{reduce}, {n_grad} fp32 grads" if world > 1 else reduce,
+            "allreduce_exposed_ms": allreduce_ms}
 
 
 def cpu_model() -> str:
@@ -393,29 +444,49 @@ def run_ours(args):
             for _ in range(2):
                 step(image, depth)
             torch.cuda.synchronize()
-            flops, ms, n = OP.collect_gemm_profile(min_n=128, min_k=128)   # pointwise + down-sample GEMMs of the trunk
+            # dominant kernel instance: tc_gemm2_kernel on the large pointwise GEMMs (N, K >= 512: stages 2-3,
+            # 62 of the 75 trunk GEMMs and ~80% of the step's tensor FLOPs); the short-K stage-0/1 GEMMs are
+            # bound by their 600 MB of hidden-activation traffic / the GELU epilogue, not by the tensor pipe
+            flops, ms, n = OP.collect_gemm_profile(min_n=512, min_k=512)
+            fa, msa, na = OP.collect_gemm_profile(min_n=128, min_k=128)
             OP.enable_gemm_profile(False)
             peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
             ach = flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
             roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     "traffic": 271.1e6, "traffic_note": "DRAM bytes of one stage-2 pwconv2 launch (M=36864,N=512,K=2048) "
                     "from profiles/r1_ncu_full_stage2.md; algorithmic bytes of that launch 302 MB",
-                    "kernel": "tc_gemm2_kernel (tcgen05 cta_group::2): the 72 pointwise + 3 down-sample GEMMs of a step "
-                              "(N, K >= 128; 98% of the path's tensor FLOPs)",
+                    "kernel": "tc_gemm2_kernel (tcgen05 cta_group::2) on the stage-2/3 pointwise GEMMs (N, K >= 512)",
                     "launches_timed": n, "avg_launch_ms": ms / max(n, 1),
+                    "all_trunk_gemms": {"achieved": fa / (msa * 1e-3) / 1e12 if msa > 0 else 0.0, "launches": na,
+                                        "note": "incl. the memory/epilogue-bound stage-0/1 shapes (K = 128, 256)"},
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"}
 
     # ---- fwd+bwd (BASELINE configs[2]: SOD training, batch 16/GPU, 384^2, data parallel) ----------
     train = None
     if not args.no_train:
-        train = train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding, precision="bf16")
-        train["fp32_exact"] = train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding, steps=2,
-                                          precision="fp32")
+        # auxiliary legs never take the headline line down with them: a failure is reported in place
+        try:
+            train = train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding, precision="bf16")
+            train["fp32_exact"] = train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding, steps=2,
+                                              precision="fp32")
+        except Exception as e:   # noqa: BLE001
+            train = dict(train or {}, error=f"{type(e).__name__}: {e}"[:300])
+
+    # ---- high-resolution inference (BASELINE configs[4]: B = 8 at 768^2, sharded by image) --------
+    highres = None
+    if not args.no_highres:
+        try:
+            highres = highres_bench(TD, enc, dec, dev, world, rank, args, common, sharding)
+        except Exception as e:   # noqa: BLE001
+            highres = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     # ---- diffusion microbench (BASELINE configs[3]): MessagePassing core, 1024^2 x 256, shared weights
     diff = None
     if rank == 0 and not args.no_diffusion:
-        diff = diffusion_microbench(OP, dev, peaks if rank == 0 else {})
+        try:
+            diff = diffusion_microbench(OP, dev, peaks if rank == 0 else {})
+        except Exception as e:   # noqa: BLE001
+            diff = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -434,7 +505,7 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "result": "stage-4 prompt tokens of the last block (B,144,512) fp32"},
             "gpu_launches": int(launches), "clocks": clocks.summary(),
-            "roofline": roof, "cpu_baseline": cpu, "train_fwd_bwd": train, "diffusion_microbench": diff,
+            "roofline": roof, "cpu_baseline": cpu, "train_fwd_bwd": train, "highres_768": highres, "diffusion_microbench": diff,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -73,6 +73,10 @@ SIGNATURES = {
     "dgtd_wgrad_tc_ws_floats": [_I, _I, _I],
     "dgtd_wgrad_tc_mn": [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _P],
     "dgtd_ln_rows_fwd": [_P, _P, _P, _P, _I, _L, _I, _F, _P],
+    "dgtd_ln_tokens_fwd": [_P, _P, _I, _P, _P, _P, _P, _I, _L, _I, _F, _P],
+    "dgtd_patchify_tokens_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "dgtd_dwconv3_gelu_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "dgtd_attention_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "dgtd_col2im_nhwc": [_P, _I, _I, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "dgtd_im2col_nhwc": [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "dgtd_group_sum": [_P, _I, _P, _L, _I, _I, _I, _P],

@@ -281,6 +281,23 @@ int dgtd_nhwc_to_nchw_fwd(const void* x, float* out, int B, int h, int w, int C,
 int dgtd_nchw_to_nhwc_fwd(const float* x, void* out, int B, int h, int w, int C, int ldo,
                           int dtype_out, dgtd_stream_t stream);
 
+/* ---- PVT-v2 blocks consuming the prompts (cod.py:824-961, 1455-1509): non-GEMM pieces ----
+ * ln_tokens: out = LayerNorm_C(x + add) * ln_w + ln_b per token row; sum_out (nullable fp32) = x + add
+ * (`x + prompt[i]`, cod.py:1472, fused with norm1 :958).  add nullable, fp32 | bf16; out fp32 | bf16. */
+int dgtd_ln_tokens_fwd(const float* x, const void* add, int add_dtype, float* sum_out, const float* ln_w,
+                       const float* ln_b, void* out, int out_dtype, int64_t rows, int C, float eps,
+                       dgtd_stream_t stream);
+/* spatial-reduction conv (k = stride = sr, cod.py:887,903) as a gather: out[(b,oy,ox)][(ty*sr+tx)*C + c] */
+int dgtd_patchify_tokens_fwd(const void* x, void* out, int dtype, int B, int h, int w, int C, int sr,
+                             dgtd_stream_t stream);
+/* Mlp.dwconv + act (cod.py:852-854): depthwise 3x3 pad 1 + bias + GELU(erf) on (B,h,w,C) tokens; wT (9,C) */
+int dgtd_dwconv3_gelu_fwd(const void* x, const float* wT, const float* bias, void* out, int dtype, int B, int h, int w,
+                          int C, dgtd_stream_t stream);
+/* Attention core (cod.py:911-915), head_dim 64: q (B*N, heads*64), kv (B*Nk, 2*heads*64) [k | v], out like q;
+ * softmax(scale * q k^T) v in fp32 with an online softmax over key tiles. */
+int dgtd_attention_fwd(const void* q, const void* kv, void* out, int dtype, int B, int N, int Nk, int heads,
+                       float scale, dgtd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,3 +92,25 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     """max|a-b| / max|b| (the parity metric of SURVEY.md 8c)."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def fill_params_(module, seed: int = 0) -> None:
+    """Constructor-independent parameter recipe (used for the PVT backbone fixtures): every tensor of the
+    state dict is drawn from its own generator seeded by (seed, crc32(name)), so the reference classes and
+    the mirror classes get identical values whatever their constructors did to the global RNG.
+    LayerNorm-like weights ~ 1 + 0.1 N(0,1), biases ~ 0.1 N(0,1) (non-zero on purpose), matrices / conv
+    kernels ~ N(0, 1/sqrt(fan_in))."""
+    import zlib
+    with torch.no_grad():
+        for name, t in sorted(module.state_dict().items()):
+            if not t.dtype.is_floating_point:
+                continue
+            g = torch.Generator("cpu").manual_seed((seed * 1000003 + zlib.crc32(name.encode())) % (2 ** 31))
+            r = torch.randn(t.shape, generator=g, dtype=torch.float32)
+            if t.dim() == 1:
+                is_scale = name.endswith("weight") or name.endswith("gamma")
+                v = 1.0 + 0.1 * r if is_scale else 0.1 * r
+            else:
+                fan_in = t[0].numel()
+                v = r / max(1.0, fan_in) ** 0.5
+            t.copy_(v.to(t.dtype))

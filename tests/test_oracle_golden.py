@@ -110,3 +110,26 @@ def test_full_path_against_reference(name, S, w20):
         close(common.subsample(k, v), t(fx[k + ".sub"]), 1e-9)
         mom = common.moments(v)
         assert np.allclose(mom, fx[k + ".mom"], rtol=1e-9, atol=1e-12), k
+
+
+def test_pvt_backbone_oracle_matches_reference_golden():
+    """oracle/pvt_ref.py (with the texture-prompt oracle inside) on the mirror module's
+    state dict == the unmodified reference `pvt_v2_b2.forward_features` fixture (float64, 1e-9)."""
+    import os
+    import numpy as np
+    from oracle import pvt_ref as P
+    common.package()
+    from dgtd_b200.twig.model import pvt
+    g = np.load(os.path.join(common.GOLDEN, "pvt_128.npz"))
+    S, B = int(g["S"]), int(g["B"])
+    net = pvt.pvt_v2_b2().eval()
+    common.fill_params_(net, seed=0)
+    sd = {k: v.detach().double() for k, v in net.state_dict().items()}
+    image, depth = common.synthetic_inputs(B, S, seed=7)
+    with torch.no_grad():
+        _, outs = P.forward_features(image.double(), depth.double(), sd)
+    for s, o in enumerate(outs):
+        ref = torch.from_numpy(g[f"out{s}"])
+        err = float((o[:, ::4, ::2, ::2] - ref).abs().max() / ref.abs().max())
+        assert err <= 1e-9, (s, err)
+        assert np.allclose(common.moments(o), g[f"out{s}_moments"], rtol=1e-9)

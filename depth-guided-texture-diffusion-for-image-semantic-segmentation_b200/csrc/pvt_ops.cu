@@ -87,34 +87,100 @@ __global__ void patchify_tokens_kernel(const T* __restrict__ x, T* __restrict__ 
   store4(out + i * 4, v.x, v.y, v.z, v.w);
 }
 
-// depthwise 3x3 (pad 1) + bias + GELU(erf) on NHWC tokens; wT is (9, C); thread = 4 channels of one pixel
+// depthwise 3x3 (pad 1) + bias + GELU on NHWC tokens; wT is (9, C).
+// thread = 8 channels x 4 consecutive pixels of one row: the 3 x 6 input window is loaded once (16-byte loads
+// for bf16) and feeds 4 outputs, the 72 taps stay in registers.  bf16 storage uses the polynomial GELU of the
+// GEMM epilogues (|err| <= 2.8e-5), fp32 storage the exact erf form.
+__device__ __forceinline__ float gelu_poly(float x) {
+  const float xc = fminf(fmaxf(x, -4.5f), 4.5f);
+  const float t = xc * xc;
+  float q = -1.400070736e-12f;
+  q = fmaf(q, t, 1.697307069e-10f);
+  q = fmaf(q, t, -9.193762573e-09f);
+  q = fmaf(q, t, 2.958901695e-07f);
+  q = fmaf(q, t, -6.365260363e-06f);
+  q = fmaf(q, t, 9.787139965e-05f);
+  q = fmaf(q, t, -1.122678685e-03f);
+  q = fmaf(q, t, 9.833185488e-03f);
+  q = fmaf(q, t, -6.633705714e-02f);
+  q = fmaf(q, t, 3.988837948e-01f);
+  return x * fminf(fmaxf(fmaf(xc, q, 0.5f), 0.f), 1.f);
+}
+__device__ __forceinline__ void ld8(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x; f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void st8(float* p, const float (&f)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&f)[8]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(f[4], f[5]), d = __floats2bfloat162_rn(f[6], f[7]);
+  uint4 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+  u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
 template <typename T>
-__global__ void dwconv3_gelu_kernel(const T* __restrict__ x, const float* __restrict__ wT, const float* __restrict__ bias,
-                                    T* __restrict__ out, int h, int w, int C, int64_t total) {
+__global__ void __launch_bounds__(256)
+dwconv3_gelu_kernel(const T* __restrict__ x, const float* __restrict__ wT, const float* __restrict__ bias,
+                    T* __restrict__ out, int h, int w, int C, int64_t total) {
+  constexpr int PX = 4;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int cq = C >> 2;
-  const int c = (int)(i % cq) * 4;
-  int64_t t = i / cq;
-  const int ox = (int)(t % w); t /= w;
+  const int co = C >> 3;
+  const int c = (int)(i % co) * 8;
+  int64_t t = i / co;
+  const int wq = (w + PX - 1) / PX;
+  const int ox0 = (int)(t % wq) * PX; t /= wq;
   const int oy = (int)(t % h);
   const int b = (int)(t / h);
-  float4 acc = *reinterpret_cast<const float4*>(bias + c);
+  float k[9][8], acc[PX][8], bs[8];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) ld8(wT + j * C + c, k[j]);
+  ld8(bias + c, bs);
+#pragma unroll
+  for (int p = 0; p < PX; ++p)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[p][e] = bs[e];
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     const int iy = oy + ky - 1;
     if ((unsigned)iy >= (unsigned)h) continue;
+    const T* row = x + (((int64_t)b * h + iy) * w) * C + c;
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int ix = ox + kx - 1;
+    for (int j = 0; j < PX + 2; ++j) {   // input column ox0 - 1 + j feeds outputs p = j - kx, kx in 0..2
+      const int ix = ox0 - 1 + j;
       if ((unsigned)ix >= (unsigned)w) continue;
-      const float4 v = ld4<T>(x + (((int64_t)b * h + iy) * w + ix) * C + c);
-      const float4 k = *reinterpret_cast<const float4*>(wT + (ky * 3 + kx) * C + c);
-      acc.x = fmaf(v.x, k.x, acc.x); acc.y = fmaf(v.y, k.y, acc.y);
-      acc.z = fmaf(v.z, k.z, acc.z); acc.w = fmaf(v.w, k.w, acc.w);
+      float v[8];
+      ld8(row + (int64_t)ix * C, v);
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int p = j - kx;
+        if (p < 0 || p >= PX) continue;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[p][e] = fmaf(v[e], k[ky * 3 + kx][e], acc[p][e]);
+      }
     }
   }
-  store4(out + i * 4, gelu_erf(acc.x), gelu_erf(acc.y), gelu_erf(acc.z), gelu_erf(acc.w));
+#pragma unroll
+  for (int p = 0; p < PX; ++p) {
+    if (ox0 + p >= w) break;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[p][e] = sizeof(T) == 2 ? gelu_poly(acc[p][e]) : gelu_erf(acc[p][e]);
+    st8(out + (((int64_t)b * h + oy) * w + ox0 + p) * C + c, acc[p]);
+  }
 }
 
 // Attention core, head_dim = 64, fp32 math with an online softmax over key tiles of 64.
@@ -203,6 +269,151 @@ attention_kernel(const T* __restrict__ q, const T* __restrict__ kv, T* __restric
   }
 }
 
+
+// ---- bf16 attention on the warp-level tensor-core path (mma.sync m16n8k16, fp32 accumulate) -----------------
+// K/V sets are tiny (144 keys x 64 channels per head), so the whole product is two small GEMMs per 16-query
+// warp tile with an online softmax in between (flash-attention register layout: the S accumulators of two
+// adjacent key tiles ARE the A fragment of the P.V product).  CTA = 64 queries of one (image, head), 4 warps;
+// keys stream through shared memory in tiles of 48 (144 = 3 x 48; 72-element row pitch = conflict-free ldmatrix).
+constexpr int FA_TK = 48, FA_PITCH = 72, FA_QB = 64;
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(128)
+attention_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kv,
+                     __nv_bfloat16* __restrict__ out, int N, int Nk, int C, float scale) {
+  __shared__ __align__(16) __nv_bfloat16 Ks[FA_TK][FA_PITCH];
+  __shared__ __align__(16) __nv_bfloat16 Vs[FA_TK][FA_PITCH];
+  const int hd = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int qrow0 = blockIdx.x * FA_QB + warp * 16 + g, qrow1 = qrow0 + 8;   // the two query rows of this thread
+
+  // Q fragments (A operand of S = Q K^T), pre-scaled: 4 k-steps over d = 64
+  uint32_t qa[4][4];
+  {
+    const __nv_bfloat16* q0 = q + ((int64_t)b * N + min(qrow0, N - 1)) * C + hd * 64;
+    const __nv_bfloat16* q1 = q + ((int64_t)b * N + min(qrow1, N - 1)) * C + hd * 64;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int c0 = ks * 16 + t4 * 2;
+      const float2 a0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(q0 + c0));
+      const float2 a1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(q1 + c0));
+      const float2 a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(q0 + c0 + 8));
+      const float2 a3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(q1 + c0 + 8));
+      qa[ks][0] = pack_bf16(a0.x * scale, a0.y * scale);
+      qa[ks][1] = pack_bf16(a1.x * scale, a1.y * scale);
+      qa[ks][2] = pack_bf16(a2.x * scale, a2.y * scale);
+      qa[ks][3] = pack_bf16(a3.x * scale, a3.y * scale);
+    }
+  }
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[j][e] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+  const __nv_bfloat16* kvb = kv + (int64_t)b * Nk * 2 * C + hd * 64;
+  for (int k0 = 0; k0 < Nk; k0 += FA_TK) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < FA_TK * 8; i += 128) {   // 16-byte chunks; keys beyond Nk are zero
+      const int key = i >> 3, ch = (i & 7) * 8;
+      uint4 kk = make_uint4(0u, 0u, 0u, 0u), vv = kk;
+      if (k0 + key < Nk) {
+        kk = *reinterpret_cast<const uint4*>(kvb + (int64_t)(k0 + key) * 2 * C + ch);
+        vv = *reinterpret_cast<const uint4*>(kvb + (int64_t)(k0 + key) * 2 * C + C + ch);
+      }
+      *reinterpret_cast<uint4*>(&Ks[key][ch]) = kk;
+      *reinterpret_cast<uint4*>(&Vs[key][ch]) = vv;
+    }
+    __syncthreads();
+
+    // S = Q K^T for 6 key tiles of 8
+    float sacc[6][4];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sacc[j][e] = 0.f;
+#pragma unroll
+      for (int kp = 0; kp < 2; ++kp) {   // one ldmatrix.x4 = B fragments of two k-steps (32 channels)
+        uint32_t kb[4];
+        ldsm_x4(kb, &Ks[j * 8 + (lane & 7)][kp * 32 + (lane >> 3) * 8]);
+        mma_bf16_16816(sacc[j], qa[kp * 2], kb[0], kb[1]);
+        mma_bf16_16816(sacc[j], qa[kp * 2 + 1], kb[2], kb[3]);
+      }
+    }
+    // mask keys beyond Nk, online softmax (rows g and g + 8)
+    float tm0 = -INFINITY, tm1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const int key = k0 + j * 8 + t4 * 2;
+      if (key >= Nk) { sacc[j][0] = -INFINITY; sacc[j][2] = -INFINITY; }
+      if (key + 1 >= Nk) { sacc[j][1] = -INFINITY; sacc[j][3] = -INFINITY; }
+      tm0 = fmaxf(tm0, fmaxf(sacc[j][0], sacc[j][1]));
+      tm1 = fmaxf(tm1, fmaxf(sacc[j][2], sacc[j][3]));
+    }
+    tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 1)); tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 2));
+    tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 1)); tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 2));
+    const float mn0 = fmaxf(m0, tm0), mn1 = fmaxf(m1, tm1);
+    const float c0 = __expf(m0 - mn0), c1 = __expf(m1 - mn1);
+    float ps0 = 0.f, ps1 = 0.f;
+    uint32_t pa[3][4];   // P as A fragments of the three 16-key k-steps
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const float p0 = __expf(sacc[j][0] - mn0), p1 = __expf(sacc[j][1] - mn0);
+      const float p2 = __expf(sacc[j][2] - mn1), p3 = __expf(sacc[j][3] - mn1);
+      ps0 += p0 + p1; ps1 += p2 + p3;
+      pa[j >> 1][(j & 1) * 2] = pack_bf16(p0, p1);
+      pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2, p3);
+    }
+    ps0 += __shfl_xor_sync(0xffffffffu, ps0, 1); ps0 += __shfl_xor_sync(0xffffffffu, ps0, 2);
+    ps1 += __shfl_xor_sync(0xffffffffu, ps1, 1); ps1 += __shfl_xor_sync(0xffffffffu, ps1, 2);
+    l0 = l0 * c0 + ps0; l1 = l1 * c1 + ps1;
+    m0 = mn0; m1 = mn1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1; }
+    // O += P V : 3 k-steps of 16 keys x 8 channel tiles of 8 (ldmatrix.trans serves two channel tiles)
+#pragma unroll
+    for (int ks = 0; ks < 3; ++ks) {
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        uint32_t vb[4];
+        ldsm_x4_t(vb, &Vs[ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][jp * 16 + (lane >> 4) * 8]);
+        mma_bf16_16816(o[jp * 2], pa[ks], vb[0], vb[1]);
+        mma_bf16_16816(o[jp * 2 + 1], pa[ks], vb[2], vb[3]);
+      }
+    }
+  }
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int col = hd * 64 + j * 8 + t4 * 2;
+    if (qrow0 < N)
+      *reinterpret_cast<uint32_t*>(out + ((int64_t)b * N + qrow0) * C + col) = pack_bf16(o[j][0] * i0, o[j][1] * i0);
+    if (qrow1 < N)
+      *reinterpret_cast<uint32_t*>(out + ((int64_t)b * N + qrow1) * C + col) = pack_bf16(o[j][2] * i1, o[j][3] * i1);
+  }
+}
+
 }  // namespace dgtd
 
 using namespace dgtd;
@@ -258,8 +469,8 @@ int dgtd_patchify_tokens_fwd(const void* x, void* out, int dtype, int B, int h, 
 
 int dgtd_dwconv3_gelu_fwd(const void* x, const float* wT, const float* bias, void* out, int dtype, int B, int h, int w,
                           int C, dgtd_stream_t stream) {
-  DGTD_CHECK_ARG(x && wT && bias && out && B > 0 && h > 0 && w > 0 && C % 4 == 0, "dwconv3_gelu: bad args");
-  const int64_t total = (int64_t)B * h * w * (C / 4);
+  DGTD_CHECK_ARG(x && wT && bias && out && B > 0 && h > 0 && w > 0 && C % 8 == 0, "dwconv3_gelu: bad args (C % 8)");
+  const int64_t total = (int64_t)B * h * ((w + 3) / 4) * (C / 8);
   const unsigned blocks = (unsigned)cdiv(total, (int64_t)256);
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == DGTD_BF16)
@@ -278,9 +489,9 @@ int dgtd_attention_fwd(const void* q, const void* kv, void* out, int dtype, int 
   const int C = heads * ATT_D;   // head_dim 64 (pvt_v2: 64/1, 128/2, 320/5, 512/8)
   dim3 grid(cdiv(N, ATT_QB), heads, B);
   cudaStream_t s = (cudaStream_t)stream;
-  if (dtype == DGTD_BF16)
-    attention_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)kv, (__nv_bfloat16*)out, N, Nk,
-                                          C, scale);
+  if (dtype == DGTD_BF16)   // tensor-core path (scores rounded to bf16 before P.V, fp32 accumulate)
+    attention_mma_kernel<<<dim3(cdiv(N, FA_QB), heads, B), 128, 0, s>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)kv,
+                                                                        (__nv_bfloat16*)out, N, Nk, C, scale);
   else if (dtype == DGTD_F32)
     attention_kernel<<<grid, 256, 0, s>>>((const float*)q, (const float*)kv, (float*)out, N, Nk, C, scale);
   else DGTD_CHECK_ARG(false, "attention: bad dtype %d", dtype);

@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--no-diffusion", action="store_true")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-highres", action="store_true")
+    ap.add_argument("--no-backbone", action="store_true")
     ap.add_argument("--train-batch", type=int, default=16, help="images per GPU per training step (configs[2])")
     return ap.parse_args()
 
@@ -160,6 +161,35 @@ def diffusion_microbench_cpu(C=256, S=256, T=1):
         dt = time.perf_counter() - t0
     return {"shape": [1, C, S, S], "T": T, "seconds": dt, "elements_per_s": C * S * S * T / dt,
             "cores": os.cpu_count() or 1, "kind": "port (oracle.message_passing_core, fp32 torch CPU)"}
+
+
+def backbone_bench(TD, dev, world, rank, args, common, sharding, steps=5):
+    """SURVEY.md 8f-1 (next row): the whole `pvt_v2_b2.forward_features` (cod.py:1455-1509) -- the hot path plus
+    the 16 PVT-v2 blocks that consume the prompts -- batch `--batch` per GPU, images/s of the job."""
+    from dgtd_b200.twig.model import pvt
+    net = pvt.pvt_v2_b2().eval()
+    common.fill_params_(net, seed=0)
+    net = net.to(dev)
+    TD.set_precision(net, args.precision)
+    B, S = args.batch, args.size
+    image, depth = common.synthetic_inputs(B, S, seed=300 + rank)
+    image, depth = image.to(dev), depth.to(dev)
+    for _ in range(2):
+        net.forward_features(image, depth)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        net.forward_features(image, depth)
+    b.record()
+    torch.cuda.synchronize()
+    t = sharding.max_over_ranks(a.elapsed_time(b) / 1e3, dev)
+    del net
+    torch.cuda.empty_cache()
+    return {"value": world * B * steps / t, "unit": "images/s", "batch_per_gpu": B, "size": S, "ms_per_step": t / steps * 1e3,
+            "precision": args.precision,
+            "what": "pvt_v2_b2.forward_features = texture-diffusion hot path + 4 patch embeds + 16 PVT-v2 blocks "
+                    "(spatial-reduction attention on mma.sync, Mix-FFN on tcgen05 GEMMs)"}
 
 
 def highres_bench(TD, enc, dec, dev, world, rank, args, common, sharding, S=768, total=8, steps=5):
@@ -480,6 +510,14 @@ def run_ours(args):
         except Exception as e:   # noqa: BLE001
             highres = {"error": f"{type(e).__name__}: {e}"[:300]}
 
+    # ---- next row 8f-1: the full backbone that consumes the prompts ----------------------------------
+    backbone = None
+    if not args.no_backbone:
+        try:
+            backbone = backbone_bench(TD, dev, world, rank, args, common, sharding)
+        except Exception as e:   # noqa: BLE001
+            backbone = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     # ---- diffusion microbench (BASELINE configs[3]): MessagePassing core, 1024^2 x 256, shared weights
     diff = None
     if rank == 0 and not args.no_diffusion:
@@ -505,7 +543,8 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "result": "stage-4 prompt tokens of the last block (B,144,512) fp32"},
             "gpu_launches": int(launches), "clocks": clocks.summary(),
-            "roofline": roof, "cpu_baseline": cpu, "train_fwd_bwd": train, "highres_768": highres, "diffusion_microbench": diff,
+            "roofline": roof, "cpu_baseline": cpu, "train_fwd_bwd": train, "highres_768": highres, "backbone_forward_features": backbone,
+            "diffusion_microbench": diff,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -44,18 +44,20 @@ col2im_kernel(const IT* __restrict__ dcol, int ldc, int Ct, const OT* __restrict
   store1(out + pix * ldo + c, acc);
 }
 
-// col[m][tap*32 + c] = x[b, oy*stride+off+ty, ox*stride+off+tx, c]   (zero outside the map),
-// m = (b*oh + oy)*ow + ox, c < 32: the row-major im2col matrix that dgtd_wgrad_tc_mn consumes as an
-// MN-major operand.  Thread = 8 channels (one 16-byte load and store).
+// col[m][tap*C + c] = x[b, oy*stride+off+ty, ox*stride+off+tx, c]   (zero outside the map),
+// m = (b*oh + oy)*ow + ox, c < C (C a multiple of 8): the row-major im2col matrix -- an MN-major operand of
+// dgtd_wgrad_tc_mn (decoder weight gradients, C = 32) or the A operand of a patch-embed GEMM.
+// Thread = 8 channels (one 16-byte load and store).
 __global__ void __launch_bounds__(256)
 im2col_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ col, int64_t total, int h,
-              int w, int ks, int stride, int off, int oh, int ow) {
+              int w, int C, int ks, int stride, int off, int oh, int ow) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int chunk = (int)(i & 3);
+  const int cq = C >> 3;
+  const int chunk = (int)(i % cq);
   const int taps = ks * ks;
-  const int tap = (int)((i >> 2) % taps);
-  const int64_t m = (i >> 2) / taps;
+  const int tap = (int)((i / cq) % taps);
+  const int64_t m = (i / cq) / taps;
   const int ty = tap / ks, tx = tap - ty * ks;
   const int ox = (int)(m % ow);
   const int64_t r = m / ow;
@@ -65,7 +67,7 @@ im2col_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __res
   uint4 v = make_uint4(0u, 0u, 0u, 0u);
   if ((unsigned)iy < (unsigned)h && (unsigned)ix < (unsigned)w)
     v = *reinterpret_cast<const uint4*>(x + (((int64_t)b * h + iy) * w + ix) * ldx + chunk * 8);
-  *reinterpret_cast<uint4*>(col + (m * taps + tap) * 32 + chunk * 8) = v;
+  *reinterpret_cast<uint4*>(col + (m * taps + tap) * C + chunk * 8) = v;
 }
 
 // out[m][c] = sum_g x[m][g*gs + c], c < C   (input gradients of the decoders' first convs, summed over decoders)
@@ -109,17 +111,17 @@ int dgtd_col2im_nhwc(const void* dcol, int dcol_dtype, int ldc, int Ct, const vo
   return 0;
 }
 
-// x: NHWC bf16, the 32-channel slice starting at the pointer (pixel pitch ldx, multiple of 8, 16-byte
-// aligned); col: (B*oh*ow) rows x (ks*ks*32)
-int dgtd_im2col_nhwc(const void* x, int ldx, void* col, int B, int h, int w, int ks, int stride, int off, int oh,
+// x: NHWC bf16, the C-channel slice starting at the pointer (pixel pitch ldx, multiple of 8, 16-byte aligned);
+// col: (B*oh*ow) rows x (ks*ks*C)
+int dgtd_im2col_nhwc(const void* x, int ldx, void* col, int B, int h, int w, int C, int ks, int stride, int off, int oh,
                      int ow, dgtd_stream_t stream) {
   DGTD_CHECK_ARG(x && col && B > 0 && h > 0 && w > 0 && ks >= 1 && ks <= 8 && stride >= 1 && oh > 0 && ow > 0,
                  "im2col_nhwc: bad args");
-  DGTD_CHECK_ARG(ldx >= 32 && ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
-                 "im2col_nhwc: x must be 16-byte aligned with a pixel pitch multiple of 8");
-  const int64_t total = (int64_t)B * oh * ow * ks * ks * 4;
+  DGTD_CHECK_ARG(C >= 8 && C % 8 == 0 && ldx >= C && ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+                 "im2col_nhwc: C and the pixel pitch must be multiples of 8, x 16-byte aligned");
+  const int64_t total = (int64_t)B * oh * ow * ks * ks * (C / 8);
   im2col_kernel<<<(unsigned)cdiv(total, (int64_t)256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)col, total, h, w, ks, stride, off, oh, ow);
+      (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)col, total, h, w, C, ks, stride, off, oh, ow);
   DGTD_LAUNCH_CHECK("im2col_nhwc");
   return 0;
 }

@@ -5,7 +5,7 @@
 //   patchify       spatial-reduction conv k = stride = sr as a patch gather + GEMM (cod.py:887,903)
 //   attention      softmax(q k^T / sqrt(d)) v with N_kv <= a few hundred keys (cod.py:911-915), fp32 math
 //   dwconv3_gelu   Mlp's depthwise 3x3 + GELU(erf) on the hidden tokens (cod.py:852-854, 1520-1531)
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace dgtd {
 
@@ -21,44 +21,54 @@ __device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16* p) {
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
-// One warp per token row.  sum_out (nullable, fp32) receives x + add; out = LN(x + add) * w + b.
-template <typename AT, typename OT, int VPL>
+// LPR lanes per token row (32 / LPR rows per warp: narrow stage-1 rows of 64 channels use half a warp each).
+// sum_out (nullable, fp32) receives x + add; out = LN(x + add) * w + b.
+template <int LPR>
+__device__ __forceinline__ float seg_sum(float v) {
+#pragma unroll
+  for (int off = LPR / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+template <typename AT, typename OT, int VPL, int LPR>
 __global__ void __launch_bounds__(256)
 ln_tokens_kernel(const float* __restrict__ x, const AT* __restrict__ add, float* __restrict__ sum_out,
                  const float* __restrict__ ln_w, const float* __restrict__ ln_b, OT* __restrict__ out, int64_t rows,
                  int C, float eps) {
-  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int lane = threadIdx.x & 31;
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & (LPR - 1);
+  int64_t row = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW + ((threadIdx.x & 31) / LPR);
+  const bool live = row < rows;
+  if (!live) row = rows - 1;            // keep the whole warp in the shuffles; stores are predicated
   const int nq = C >> 2;
   float4 v[VPL];
   float s = 0.f;
 #pragma unroll
   for (int j = 0; j < VPL; ++j) {
-    const int q = j * 32 + lane;
+    const int q = j * LPR + lane;
     if (q < nq) {
       v[j] = *reinterpret_cast<const float4*>(x + row * C + q * 4);
       if (add) {
         const float4 a = ld4<AT>(add + row * C + q * 4);
         v[j].x += a.x; v[j].y += a.y; v[j].z += a.z; v[j].w += a.w;
       }
-      if (sum_out) *reinterpret_cast<float4*>(sum_out + row * C + q * 4) = v[j];
+      if (sum_out && live) *reinterpret_cast<float4*>(sum_out + row * C + q * 4) = v[j];
       s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
     }
   }
-  const float mean = warp_sum(s) / C;
+  const float mean = seg_sum<LPR>(s) / C;
   float qq = 0.f;
 #pragma unroll
   for (int j = 0; j < VPL; ++j) {
-    if (j * 32 + lane < nq) {
+    if (j * LPR + lane < nq) {
       const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
       qq += (a * a + b * b) + (c * c + d * d);
     }
   }
-  const float rstd = 1.0f / sqrtf(warp_sum(qq) / C + eps);
+  const float rstd = 1.0f / sqrtf(seg_sum<LPR>(qq) / C + eps);
+  if (!live) return;
 #pragma unroll
   for (int j = 0; j < VPL; ++j) {
-    const int q = j * 32 + lane;
+    const int q = j * LPR + lane;
     if (q < nq) {
       const float4 g = *reinterpret_cast<const float4*>(ln_w + q * 4), be = *reinterpret_cast<const float4*>(ln_b + q * 4);
       store4(out + row * C + q * 4, (v[j].x - mean) * rstd * g.x + be.x, (v[j].y - mean) * rstd * g.y + be.y,
@@ -89,23 +99,8 @@ __global__ void patchify_tokens_kernel(const T* __restrict__ x, T* __restrict__ 
 
 // depthwise 3x3 (pad 1) + bias + GELU on NHWC tokens; wT is (9, C).
 // thread = 8 channels x 4 consecutive pixels of one row: the 3 x 6 input window is loaded once (16-byte loads
-// for bf16) and feeds 4 outputs, the 72 taps stay in registers.  bf16 storage uses the polynomial GELU of the
-// GEMM epilogues (|err| <= 2.8e-5), fp32 storage the exact erf form.
-__device__ __forceinline__ float gelu_poly(float x) {
-  const float xc = fminf(fmaxf(x, -4.5f), 4.5f);
-  const float t = xc * xc;
-  float q = -1.400070736e-12f;
-  q = fmaf(q, t, 1.697307069e-10f);
-  q = fmaf(q, t, -9.193762573e-09f);
-  q = fmaf(q, t, 2.958901695e-07f);
-  q = fmaf(q, t, -6.365260363e-06f);
-  q = fmaf(q, t, 9.787139965e-05f);
-  q = fmaf(q, t, -1.122678685e-03f);
-  q = fmaf(q, t, 9.833185488e-03f);
-  q = fmaf(q, t, -6.633705714e-02f);
-  q = fmaf(q, t, 3.988837948e-01f);
-  return x * fminf(fmaxf(fmaf(xc, q, 0.5f), 0.f), 1.f);
-}
+// for bf16) and feeds 4 outputs.  bf16 storage uses the packed polynomial GELU of the GEMM epilogues
+// (|err| <= 2.8e-5), fp32 storage the exact erf form.
 __device__ __forceinline__ void ld8(const float* p, float (&f)[8]) {
   const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
   f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
@@ -132,54 +127,86 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&f)[8]) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
+// CTA = 64 channels (8 threads x 8 channels) x 32 groups of 4 pixels; the 9 x 64 taps of the CTA's channel group
+// sit in shared memory and are re-read per kernel row (24 registers instead of 72).
 template <typename T>
 __global__ void __launch_bounds__(256)
 dwconv3_gelu_kernel(const T* __restrict__ x, const float* __restrict__ wT, const float* __restrict__ bias,
-                    T* __restrict__ out, int h, int w, int C, int64_t total) {
+                    T* __restrict__ out, int h, int w, int C, int64_t groups_total) {
   constexpr int PX = 4;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int co = C >> 3;
-  const int c = (int)(i % co) * 8;
-  int64_t t = i / co;
+  __shared__ __align__(16) float ws[10][64];   // 9 taps + bias
+  const int c0 = blockIdx.x * 64;
+  for (int i = threadIdx.x; i < 640; i += 256) {
+    const int j = i >> 6, cc = i & 63;
+    ws[j][cc] = c0 + cc < C ? (j < 9 ? wT[j * C + c0 + cc] : bias[c0 + cc]) : 0.f;
+  }
+  __syncthreads();
+  const int co = (threadIdx.x & 7) * 8;
+  const int c = c0 + co;
+  int64_t t = (int64_t)blockIdx.y * 32 + (threadIdx.x >> 3);
+  if (t >= groups_total || c >= C) return;
   const int wq = (w + PX - 1) / PX;
   const int ox0 = (int)(t % wq) * PX; t /= wq;
   const int oy = (int)(t % h);
   const int b = (int)(t / h);
-  float k[9][8], acc[PX][8], bs[8];
+  // packed f32x2 arithmetic: 8 channels = 4 register pairs (half the FMA / GELU issue slots)
+  uint64_t acc[PX][4];
+  {
+    float bs[8];
+    ld8(&ws[9][co], bs);
 #pragma unroll
-  for (int j = 0; j < 9; ++j) ld8(wT + j * C + c, k[j]);
-  ld8(bias + c, bs);
+    for (int p = 0; p < PX; ++p)
 #pragma unroll
-  for (int p = 0; p < PX; ++p)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[p][e] = bs[e];
+      for (int e = 0; e < 4; ++e) acc[p][e] = pk2(bs[2 * e], bs[2 * e + 1]);
+  }
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     const int iy = oy + ky - 1;
     if ((unsigned)iy >= (unsigned)h) continue;
+    uint64_t k[3][4];
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      float kf[8];
+      ld8(&ws[ky * 3 + kx][co], kf);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) k[kx][e] = pk2(kf[2 * e], kf[2 * e + 1]);
+    }
     const T* row = x + (((int64_t)b * h + iy) * w) * C + c;
+    // all six column loads of the row are issued back to back (clamped address, zeroed afterwards): no
+    // branch between them, so they overlap instead of paying one memory round trip each
+    float vf[PX + 2][8];
+#pragma unroll
+    for (int j = 0; j < PX + 2; ++j) {
+      const int ix = ox0 - 1 + j;
+      ld8(row + (int64_t)min(max(ix, 0), w - 1) * C, vf[j]);
+    }
 #pragma unroll
     for (int j = 0; j < PX + 2; ++j) {   // input column ox0 - 1 + j feeds outputs p = j - kx, kx in 0..2
       const int ix = ox0 - 1 + j;
-      if ((unsigned)ix >= (unsigned)w) continue;
-      float v[8];
-      ld8(row + (int64_t)ix * C, v);
+      const float ok = (unsigned)ix < (unsigned)w ? 1.f : 0.f;
+      uint64_t v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = pk2(vf[j][2 * e] * ok, vf[j][2 * e + 1] * ok);
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
         const int p = j - kx;
         if (p < 0 || p >= PX) continue;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[p][e] = fmaf(v[e], k[ky * 3 + kx][e], acc[p][e]);
+        for (int e = 0; e < 4; ++e) acc[p][e] = fma2(v[e], k[kx][e], acc[p][e]);
       }
     }
   }
 #pragma unroll
   for (int p = 0; p < PX; ++p) {
     if (ox0 + p >= w) break;
+    float r[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[p][e] = sizeof(T) == 2 ? gelu_poly(acc[p][e]) : gelu_erf(acc[p][e]);
-    st8(out + (((int64_t)b * h + oy) * w + ox0 + p) * C + c, acc[p]);
+    for (int e = 0; e < 4; ++e) {
+      up2(acc[p][e], r[2 * e], r[2 * e + 1]);
+      if (sizeof(T) == 2) gelu_fast2(r[2 * e], r[2 * e + 1]);
+      else { r[2 * e] = gelu_erf(r[2 * e]); r[2 * e + 1] = gelu_erf(r[2 * e + 1]); }
+    }
+    st8(out + (((int64_t)b * h + oy) * w + ox0 + p) * C + c, r);
   }
 }
 
@@ -428,14 +455,15 @@ int dgtd_ln_tokens_fwd(const float* x, const void* add, int add_dtype, float* su
   DGTD_CHECK_ARG(!add || add_dtype == DGTD_F32 || add_dtype == DGTD_BF16, "ln_tokens: bad add dtype");
   DGTD_CHECK_ARG(out_dtype == DGTD_F32 || out_dtype == DGTD_BF16, "ln_tokens: bad out dtype");
   cudaStream_t s = (cudaStream_t)stream;
-  const unsigned blocks = (unsigned)cdiv(rows, (int64_t)8);
-#define DGTD_LNT(AT, OT, V)                                                                                       \
-  ln_tokens_kernel<AT, OT, V><<<blocks, 256, 0, s>>>(x, (const AT*)add, sum_out, ln_w, ln_b, (OT*)out, rows, C, eps)
+#define DGTD_LNT(AT, OT, V, L)                                                                                    \
+  ln_tokens_kernel<AT, OT, V, L><<<(unsigned)cdiv(rows, (int64_t)(8 * (32 / L))), 256, 0, s>>>(                     \
+      x, (const AT*)add, sum_out, ln_w, ln_b, (OT*)out, rows, C, eps)
 #define DGTD_LNT_V(AT, OT)                         \
   do {                                             \
-    if (C <= 128) DGTD_LNT(AT, OT, 1);             \
-    else if (C <= 512) DGTD_LNT(AT, OT, 4);        \
-    else DGTD_LNT(AT, OT, 16);                     \
+    if (C <= 64) DGTD_LNT(AT, OT, 1, 16);          \
+    else if (C <= 128) DGTD_LNT(AT, OT, 1, 32);    \
+    else if (C <= 512) DGTD_LNT(AT, OT, 4, 32);    \
+    else DGTD_LNT(AT, OT, 16, 32);                 \
   } while (0)
   const bool abf = add && add_dtype == DGTD_BF16;
   if (out_dtype == DGTD_BF16) {
@@ -470,8 +498,9 @@ int dgtd_patchify_tokens_fwd(const void* x, void* out, int dtype, int B, int h, 
 int dgtd_dwconv3_gelu_fwd(const void* x, const float* wT, const float* bias, void* out, int dtype, int B, int h, int w,
                           int C, dgtd_stream_t stream) {
   DGTD_CHECK_ARG(x && wT && bias && out && B > 0 && h > 0 && w > 0 && C % 8 == 0, "dwconv3_gelu: bad args (C % 8)");
-  const int64_t total = (int64_t)B * h * ((w + 3) / 4) * (C / 8);
-  const unsigned blocks = (unsigned)cdiv(total, (int64_t)256);
+  const int64_t total = (int64_t)B * h * ((w + 3) / 4);   // groups of 4 pixels
+  DGTD_CHECK_ARG(cdiv(total, (int64_t)32) <= 65535, "dwconv3_gelu: too many pixels for one launch");
+  dim3 blocks(cdiv(C, 64), (unsigned)cdiv(total, (int64_t)32));
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == DGTD_BF16)
     dwconv3_gelu_kernel<<<blocks, 256, 0, s>>>((const __nv_bfloat16*)x, wT, bias, (__nv_bfloat16*)out, h, w, C, total);

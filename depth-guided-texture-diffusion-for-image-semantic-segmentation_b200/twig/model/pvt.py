@@ -194,29 +194,39 @@ class OverlapPatchEmbed(nn.Module):
         self.norm = nn.LayerNorm(embed_dim)
         self.apply(_init_like_reference)
 
-    def _forward_nhwc(self, x: torch.Tensor) -> Tuple[torch.Tensor, int, int]:
-        """x (B,H,W,Cin) fp32 -> tokens (B, H'*W', C) fp32 (exact CUDA-core implicit GEMM + LayerNorm)."""
+    def _forward_nhwc(self, x: torch.Tensor, mode: int = F32) -> Tuple[torch.Tensor, int, int]:
+        """x (B,H,W,Cin) fp32 -> tokens (B, H'*W', C) fp32.  Exact mode: CUDA-core implicit GEMM; bf16 mode:
+        bf16 im2col (tap-major) + tcgen05 GEMM.  LayerNorm rows (eps of nn.LayerNorm) in fp32 either way."""
         B, H, W, Cin = x.shape
         k, s = self.patch_size[0], self.stride
         Cout = self.proj.out_channels
-        cin4 = (Cin + 3) // 4 * 4
-        if cin4 != Cin:                         # RGB input: pad to 4 channels (zero weights for the pad)
-            xp = torch.zeros(B, H, W, cin4, device=x.device, dtype=torch.float32)
-            xp[..., :Cin].copy_(x)
-            x = xp
+        unit = 8 if mode == BF16 else 4
+        cp = (Cin + unit - 1) // unit * unit
+        if cp != Cin or mode == BF16:             # RGB input: zero-pad the channels; bf16 mode: down-cast
+            xp = torch.zeros(B, H, W, cp, device=x.device, dtype=torch.bfloat16 if mode == BF16 else torch.float32) \
+                if cp != Cin else None
+            if xp is None:
+                x = OP.cast(x, torch.bfloat16)
+            else:
+                xp[..., :Cin].copy_(x)
+                x = xp
 
         def pack():
-            w = torch.zeros(Cout, k, k, cin4, device=self.proj.weight.device, dtype=torch.float32)
+            w = torch.zeros(Cout, k, k, cp, device=self.proj.weight.device, dtype=torch.float32)
             w[..., :Cin] = self.proj.weight.detach().float().permute(0, 2, 3, 1)
-            return w.reshape(Cout, k * k * cin4).contiguous()
-        wp = _packed(self).get("proj", [self.proj.weight], pack)
+            return _as(w.reshape(Cout, k * k * cp), mode)
+        wp = _packed(self).get(f"proj.{mode}.{cp}", [self.proj.weight], pack)
         oh, ow = (H + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
-        y = OP.conv_nhwc(x, wp, _f(self.proj.bias), cin4, (oh, ow), k, s, -(k // 2))
+        if mode == BF16:
+            from ..ops.functions.decoder_bank import im2col
+            y = OP.linear(im2col(x, k, s, -(k // 2), (oh, ow)), wp, _f(self.proj.bias), out_dtype=F32)
+        else:
+            y = OP.conv_nhwc(x, wp, _f(self.proj.bias), cp, (oh, ow), k, s, -(k // 2))
         t, _ = PF.ln_tokens(y.view(B, oh * ow, Cout), _f(self.norm.weight), _f(self.norm.bias), self.norm.eps, F32)
         return t, oh, ow
 
     def forward(self, x):
-        return self._forward_nhwc(OP.nchw_to_nhwc(x.detach().float().contiguous()))
+        return self._forward_nhwc(OP.nchw_to_nhwc(x.detach().float().contiguous()), _mode(self))
 
 
 class PyramidVisionTransformerImpr(nn.Module):
@@ -269,7 +279,7 @@ class PyramidVisionTransformerImpr(nn.Module):
         outs: List[torch.Tensor] = []
         cur = OP.nchw_to_nhwc(image)
         for s in range(4):
-            t, H, W = getattr(self, f"patch_embed{s + 1}")._forward_nhwc(cur)
+            t, H, W = getattr(self, f"patch_embed{s + 1}")._forward_nhwc(cur, mode)
             for i, blk in enumerate(getattr(self, f"block{s + 1}")):
                 t = blk._forward_tokens(t, tokens[s][i].reshape(t.shape), H, W, mode)
             norm = getattr(self, f"norm{s + 1}")

@@ -114,10 +114,11 @@ def col2im(dcol: torch.Tensor, Ct: int, mask: Optional[torch.Tensor], out: torch
 
 
 def im2col(x: torch.Tensor, ks: int, stride: int, off: int, out_hw: Tuple[int, int]) -> torch.Tensor:
-    """x: (B,h,w,32) bf16 slice (pixel pitch x.stride(2)) -> (B*oh*ow, ks*ks*32) bf16, zero outside the map."""
-    B, h, w = x.shape[0], x.shape[1], x.shape[2]
-    out = torch.empty(B * out_hw[0] * out_hw[1], ks * ks * PAD, device=x.device, dtype=torch.bfloat16)
-    call("dgtd_im2col_nhwc", x.data_ptr(), x.stride(2), ptr(out), B, h, w, ks, stride, off, out_hw[0], out_hw[1],
+    """x: (B,h,w,C) bf16 (C % 8 == 0; may be a channel slice, pixel pitch x.stride(2)) ->
+    (B*oh*ow, ks*ks*C) bf16 tap-major, zero outside the map."""
+    B, h, w, C = x.shape
+    out = torch.empty(B * out_hw[0] * out_hw[1], ks * ks * C, device=x.device, dtype=torch.bfloat16)
+    call("dgtd_im2col_nhwc", x.data_ptr(), x.stride(2), ptr(out), B, h, w, C, ks, stride, off, out_hw[0], out_hw[1],
          stream())
     return out
 

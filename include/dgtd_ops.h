@@ -261,9 +261,10 @@ int dgtd_wgrad_tc_mn(const void* a, int lda, const void* b, int ldb, float* out,
 int dgtd_col2im_nhwc(const void* dcol, int dcol_dtype, int ldc, int Ct, const void* mask, int ldm, void* out,
                      int out_dtype, int ldo, int B, int h, int w, int C, int ks, int stride, int off, int oh, int ow,
                      dgtd_stream_t stream);
-/* col[m][tap*32 + c] = x[b, oy*stride+off+ty, ox*stride+off+tx, c] (bf16, 32-channel slice at x, pixel
- * pitch ldx, zero outside the map), m = (b*oh+oy)*ow+ox: row-major im2col, an operand of dgtd_wgrad_tc_mn. */
-int dgtd_im2col_nhwc(const void* x, int ldx, void* col, int B, int h, int w, int ks, int stride, int off, int oh,
+/* col[m][tap*C + c] = x[b, oy*stride+off+ty, ox*stride+off+tx, c] (bf16, C-channel slice at x, pixel pitch
+ * ldx, zero outside the map), m = (b*oh+oy)*ow+ox: row-major im2col -- an operand of dgtd_wgrad_tc_mn
+ * (decoder gradients, C = 32) or the A operand of a patch-embed GEMM (OverlapPatchEmbed, cod.py:976). */
+int dgtd_im2col_nhwc(const void* x, int ldx, void* col, int B, int h, int w, int C, int ks, int stride, int off, int oh,
                      int ow, dgtd_stream_t stream);
 /* out[m][c] (fp32) = sum_g x[m][g*group_stride + c], c < C */
 int dgtd_group_sum(const void* x, int dtype, float* out, int64_t M, int groups, int group_stride, int C,

@@ -239,7 +239,19 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_img = p.tiles_x * p.tiles_y;
   const int per_key = p.B * tiles_img;                      // tiles sharing one (group, n-block)
-  const int num_tiles = p.groups * p.tiles_n * per_key;
+  // Work assignment: a CTA owns ONE (group, n-block) key (its nine weight tiles are loaded once) and walks the
+  // images in order together with the CTAs of the other keys, so that the pixel rows of an image -- which
+  // interleave the channel slices of all groups -- are consumed by all groups while they are in L2.
+  const int keys = p.groups * p.tiles_n;
+  const int kmod = keys < (int)gridDim.x ? keys : (int)gridDim.x;    // keys in flight
+  const int nct = keys < (int)gridDim.x ? (int)gridDim.x / keys : 1; // CTAs sharing a key
+  const int key0 = (int)blockIdx.x % kmod, ci = (int)blockIdx.x / kmod;
+  const int per_cta = ci < nct ? (per_key - ci + nct - 1) / nct : 0;
+  const int n_total = per_cta * ((keys - key0 + kmod - 1) / kmod);
+  auto tile_of = [&](int n) {
+    const int kk = n / per_cta, tt = n - kk * per_cta;
+    return (key0 + kk * kmod) * per_key + ci + tt * nct;
+  };
 
   auto decode = [&](int tile, int& g, int& b, int& ty, int& tx, int& nb) {
     tx = tile % p.tiles_x; tile /= p.tiles_x;
@@ -276,7 +288,8 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     if (lane == 0) {
       int stage = 0, wcount = 0, last_key = -1;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int n = 0; n < n_total; ++n) {
+        const int tile = tile_of(n);
         int g, b, ty, tx, nb;
         decode(tile, g, b, ty, tx, nb);
         const int key = tile / per_key;
@@ -302,7 +315,8 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       constexpr uint32_t idesc = bw::umma_idesc_bf16(128, BN);
       int stage = 0, iter = 0, wcount = 0, last_key = -1, buf = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+      for (int n = 0; n < n_total; ++n, ++iter) {
+        const int tile = tile_of(n);
         const int key = tile / per_key;
         if (key != last_key) {
           if (last_key >= 0) bw::umma_commit(&wempty[buf]);   // previous weights free once their MMAs retire
@@ -337,7 +351,8 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const int ew = warp - 4;
     int iter = 0;
     uint32_t sbuf = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+    for (int n = 0; n < n_total; ++n, ++iter) {
+      const int tile = tile_of(n);
       int g, b, ty, tx, nb;
       decode(tile, g, b, ty, tx, nb);
       const int as = iter & 1;
@@ -482,8 +497,11 @@ static int conv_halo_launch(const void* x, int B, int h, int wd, int ldx, const 
   p.tiles_x = cdiv(p.ow, HALO_TW);
   p.tiles_y = cdiv(p.oh, HALO_TH);
   p.tiles_n = cdiv(p.Cout, BN);
-  int64_t tiles = (int64_t)p.groups * p.B * p.tiles_x * p.tiles_y * p.tiles_n;
-  int grid = tiles < sm_count() ? (int)tiles : sm_count();
+  const int keys = p.groups * p.tiles_n;
+  const int64_t per_key = (int64_t)p.B * p.tiles_x * p.tiles_y;
+  int nct = keys < sm_count() ? sm_count() / keys : 1;
+  if (nct > per_key) nct = (int)per_key;
+  const int grid = keys < sm_count() ? keys * nct : sm_count();
   kern<<<grid, 256, Cfg::SMEM_BYTES, s>>>(tmX, tmW, tmO, p);
   return 0;
 }

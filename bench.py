@@ -192,6 +192,39 @@ def backbone_bench(TD, dev, world, rank, args, common, sharding, steps=5):
                     "(spatial-reduction attention on mma.sync, Mix-FFN on tcgen05 GEMMs)"}
 
 
+def loss_bench(dev, peaks, common, B=16, S=384, steps=10):
+    """SURVEY.md 8f-3 (next row): structure loss + deep supervision (cod.py:75-84, 135-141) forward + backward on
+    five B x 1 x S x S logit maps.  Pure bandwidth: the weight map is computed once (8 B/pixel), each of the
+    four weighted maps reads 12 B/pixel forward and moves 16 B/pixel backward."""
+    from dgtd_b200.twig.model import losses as M
+    preds, gts = common.loss_inputs(B, S, S, seed=1)
+    g = torch.Generator("cpu").manual_seed(2)
+    P1 = [(2.0 * torch.randn(B, 1, S, S, generator=g)).to(dev).requires_grad_(True) for _ in range(4)]
+    P2 = preds.to(dev).requires_grad_(True)
+    label = gts.to(dev)
+
+    def one():
+        loss = M.deep_supervision_loss(P1, P2, label)
+        loss.backward()
+        for t in P1 + [P2]:
+            t.grad = None
+    for _ in range(3):
+        one()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        one()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    nbytes = B * S * S * (8 + 4 * (12 + 16))
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    return {"ms": ms, "images_per_s": B / (ms * 1e-3), "alg_bytes": nbytes, "gbs": nbytes / (ms * 1e-3) / 1e9,
+            "hbm_frac": nbytes / (ms * 1e-3) / 1e9 / hbm, "batch": B, "size": S,
+            "note": "5 supervised maps, fwd + bwd, 12 launches; latency-bound at this size (labels and logits fit in L2)"}
+
+
 def highres_bench(TD, enc, dec, dev, world, rank, args, common, sharding, S=768, total=8, steps=5):
     """BASELINE configs[4]: high-resolution inference, 8 images of 768^2 sharded by image over the GPUs
     (8 / N per GPU, no collective); images/s of the whole job, device time, max over ranks."""
@@ -518,6 +551,13 @@ def run_ours(args):
         except Exception as e:   # noqa: BLE001
             backbone = {"error": f"{type(e).__name__}: {e}"[:300]}
 
+    loss_leg = None
+    if rank == 0 and not args.no_backbone:
+        try:
+            loss_leg = loss_bench(dev, peaks if rank == 0 else {}, common)
+        except Exception as e:   # noqa: BLE001
+            loss_leg = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     # ---- diffusion microbench (BASELINE configs[3]): MessagePassing core, 1024^2 x 256, shared weights
     diff = None
     if rank == 0 and not args.no_diffusion:
@@ -543,7 +583,7 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "result": "stage-4 prompt tokens of the last block (B,144,512) fp32"},
             "gpu_launches": int(launches), "clocks": clocks.summary(),
-            "roofline": roof, "cpu_baseline": cpu, "train_fwd_bwd": train, "highres_768": highres, "backbone_forward_features": backbone,
+            "roofline": roof, "cpu_baseline": cpu, "train_fwd_bwd": train, "highres_768": highres, "backbone_forward_features": backbone, "structure_loss": loss_leg,
             "diffusion_microbench": diff,
         }
         print(json.dumps(line), flush=True)

@@ -77,6 +77,10 @@ SIGNATURES = {
     "dgtd_patchify_tokens_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "dgtd_dwconv3_gelu_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "dgtd_attention_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "dgtd_boundary_weight_fwd": [_P, _P, _I, _I, _I, _P],
+    "dgtd_structure_loss_ws_floats": [_I, _L],
+    "dgtd_structure_loss_fwd": [_P, _P, _P, _P, _P, _P, _I, _L, _P],
+    "dgtd_structure_loss_bwd": [_P, _P, _P, _P, _P, _P, _I, _L, _P],
     "dgtd_col2im_nhwc": [_P, _I, _I, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "dgtd_im2col_nhwc": [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "dgtd_group_sum": [_P, _I, _P, _L, _I, _I, _I, _P],

@@ -299,6 +299,16 @@ int dgtd_dwconv3_gelu_fwd(const void* x, const float* wT, const float* bias, voi
 int dgtd_attention_fwd(const void* q, const void* kv, void* out, int dtype, int B, int N, int Nk, int heads,
                        float scale, dgtd_stream_t stream);
 
+/* ---- structure loss (cod.cal_loss, cod.py:75-84) ------------------------------------------
+ * weit = 1 + 5 |avgpool31x31(gt) - gt| (zero padding, divisor 961); depends on the label only. */
+int dgtd_boundary_weight_fwd(const float* gt, float* weit, int planes, int H, int W, dgtd_stream_t stream);
+/* loss[0] = mean over planes of wbce + wiou; sums (planes x 4) = (sum w*bce, sum w, I, U) saved for backward */
+int dgtd_structure_loss_ws_floats(int planes, int64_t HW);
+int dgtd_structure_loss_fwd(const float* preds, const float* gt, const float* weit, float* ws, float* sums, float* loss,
+                            int planes, int64_t HW, dgtd_stream_t stream);
+int dgtd_structure_loss_bwd(const float* preds, const float* gt, const float* weit, const float* sums,
+                            const float* grad_out, float* dpreds, int planes, int64_t HW, dgtd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,3 +114,17 @@ def fill_params_(module, seed: int = 0) -> None:
                 fan_in = t[0].numel()
                 v = r / max(1.0, fan_in) ** 0.5
             t.copy_(v.to(t.dtype))
+
+
+def loss_inputs(B: int, H: int, W: int, seed: int = 0):
+    """Logits ~ 3 N(0,1) and a blobby binary-ish ground truth (rectangles + soft edge) for the structure loss."""
+    g = torch.Generator("cpu").manual_seed(seed)
+    preds = 3.0 * torch.randn(B, 1, H, W, generator=g)
+    gts = torch.zeros(B, 1, H, W)
+    for b in range(B):
+        for _ in range(3):
+            y0, x0 = int(torch.randint(0, H - 8, (1,), generator=g)), int(torch.randint(0, W - 8, (1,), generator=g))
+            hh, ww = int(torch.randint(4, H // 2, (1,), generator=g)), int(torch.randint(4, W // 2, (1,), generator=g))
+            gts[b, 0, y0:y0 + hh, x0:x0 + ww] = 1.0
+    gts = (gts + 0.1 * torch.rand(B, 1, H, W, generator=g)).clamp(0, 1)
+    return preds, gts

@@ -133,3 +133,18 @@ def test_pvt_backbone_oracle_matches_reference_golden():
         err = float((o[:, ::4, ::2, ::2] - ref).abs().max() / ref.abs().max())
         assert err <= 1e-9, (s, err)
         assert np.allclose(common.moments(o), g[f"out{s}_moments"], rtol=1e-9)
+
+
+def test_structure_loss_oracle_matches_reference_golden():
+    """oracle/loss_ref.py == `cod.cal_loss` fixture (value and autograd gradient, float64)."""
+    import os
+    import numpy as np
+    from oracle import loss_ref as L
+    g = np.load(os.path.join(common.GOLDEN, "loss_small.npz"))
+    for tag, shape in (("a", (2, 48, 64)), ("b", (3, 40, 40))):
+        preds, gts = common.loss_inputs(*shape, seed=ord(tag))
+        p = preds.double().requires_grad_(True)
+        loss = L.structure_loss(p, gts.double())
+        (gr,) = torch.autograd.grad(loss, p)
+        assert abs(float(loss.detach()) - float(g[f"{tag}_loss"])) <= 1e-12
+        assert float((gr - torch.from_numpy(g[f"{tag}_grad"])).abs().max()) <= 1e-13

@@ -246,19 +246,23 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   const int kmod = keys < (int)gridDim.x ? keys : (int)gridDim.x;    // keys in flight
   const int nct = keys < (int)gridDim.x ? (int)gridDim.x / keys : 1; // CTAs sharing a key
   const int key0 = (int)blockIdx.x % kmod, ci = (int)blockIdx.x / kmod;
-  const int per_cta = ci < nct ? (per_key - ci + nct - 1) / nct : 0;
-  const int n_total = per_cta * ((keys - key0 + kmod - 1) / kmod);
-  auto tile_of = [&](int n) {
-    const int kk = n / per_cta, tt = n - kk * per_cta;
-    return (key0 + kk * kmod) * per_key + ci + tt * nct;
+  const int per_cta = ci < nct ? (per_key - ci + nct - 1) / nct : 0;   // positions of a key walked by this CTA
+  // Division-free walk (the single producer / MMA threads are latency chains: a handful of integer divisions per
+  // tile cost more than the eighteen MMAs of a 32-column tile): position pos = ci + tt*nct within a key,
+  // (tx, ty, b) advanced incrementally.
+  struct Walk {
+    int key, g, nb, tt, tx, ty, b;
   };
-
-  auto decode = [&](int tile, int& g, int& b, int& ty, int& tx, int& nb) {
-    tx = tile % p.tiles_x; tile /= p.tiles_x;
-    ty = tile % p.tiles_y; tile /= p.tiles_y;
-    b = tile % p.B; tile /= p.B;
-    nb = tile % p.tiles_n;
-    g = tile / p.tiles_n;
+  auto walk_begin = [&](Walk& wk, int key) {
+    wk.key = key; wk.g = key / p.tiles_n; wk.nb = key - wk.g * p.tiles_n; wk.tt = 0;
+    wk.tx = ci % p.tiles_x;
+    const int r = ci / p.tiles_x;
+    wk.ty = r % p.tiles_y; wk.b = r / p.tiles_y;
+  };
+  auto walk_next = [&](Walk& wk) {
+    ++wk.tt;
+    wk.tx += nct;
+    while (wk.tx >= p.tiles_x) { wk.tx -= p.tiles_x; if (++wk.ty == p.tiles_y) { wk.ty = 0; ++wk.b; } }
   };
 
   if (warp == 0 && lane == 0) {
@@ -286,75 +290,74 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 
   if (warp == 0) {
     if (lane == 0) {
-      int stage = 0, wcount = 0, last_key = -1;
+      int stage = 0, wcount = 0;
       uint32_t phase = 0;
-      for (int n = 0; n < n_total; ++n) {
-        const int tile = tile_of(n);
-        int g, b, ty, tx, nb;
-        decode(tile, g, b, ty, tx, nb);
-        const int key = tile / per_key;
-        if (key != last_key) {   // new (group, n-block): its nine weight tiles into the other buffer
+      Walk wk;
+      for (int key = key0; key < keys && per_cta > 0; key += kmod) {
+        walk_begin(wk, key);
+        {   // the nine weight tiles of this (group, n-block) into the other buffer
           const int buf = wcount & 1;
           bw::mbar_wait(&wempty[buf], ((wcount >> 1) & 1) ^ 1);
           bw::mbar_arrive_expect_tx(&wfull[buf], Cfg::W_BYTES);
 #pragma unroll 1
           for (int t = 0; t < 9; ++t)
             bw::tma_load_2d(&tmW, &wfull[buf], sW + buf * Cfg::W_BYTES + t * BN * 64, t * 32,
-                            g * p.w_group_rows + nb * BN);
+                            wk.g * p.w_group_rows + wk.nb * BN);
           ++wcount;
-          last_key = key;
         }
-        bw::mbar_wait(&empty[stage], phase ^ 1);
-        bw::mbar_arrive_expect_tx(&full[stage], HALO_BYTES);
-        bw::tma_load_4d(&tmX, &full[stage], sA + stage * HALO_STAGE, g * 32, tx * HALO_TW - 1, ty * HALO_TH - 1, b);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        for (; wk.tt < per_cta; walk_next(wk)) {
+          bw::mbar_wait(&empty[stage], phase ^ 1);
+          bw::mbar_arrive_expect_tx(&full[stage], HALO_BYTES);
+          bw::tma_load_4d(&tmX, &full[stage], sA + stage * HALO_STAGE, wk.g * 32, wk.tx * HALO_TW - 1,
+                          wk.ty * HALO_TH - 1, wk.b);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = bw::umma_idesc_bf16(128, BN);
-      int stage = 0, iter = 0, wcount = 0, last_key = -1, buf = 0;
+      int stage = 0, iter = 0, wcount = 0, buf = 0;
       uint32_t phase = 0;
-      for (int n = 0; n < n_total; ++n, ++iter) {
-        const int tile = tile_of(n);
-        const int key = tile / per_key;
-        if (key != last_key) {
-          if (last_key >= 0) bw::umma_commit(&wempty[buf]);   // previous weights free once their MMAs retire
-          buf = wcount & 1;
-          bw::mbar_wait(&wfull[buf], (wcount >> 1) & 1);
-          ++wcount;
-          last_key = key;
-        }
-        const int as = iter & 1;
-        const uint32_t aphase = (iter >> 1) & 1;
-        bw::mbar_wait(&tempty[as], aphase ^ 1);
-        bw::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
-        bw::mbar_wait(&full[stage], phase);
-        bw::tc_fence_after();
-        const uint32_t a0 = bw::smem_u32(sA + stage * HALO_STAGE);
-        const uint32_t w0 = bw::smem_u32(sW + buf * Cfg::W_BYTES);
+      const uint64_t da_base = halo_desc(bw::smem_u32(sA), HALO_PW * 64);
+      const uint64_t db_base = bw::umma_smem_desc_kmajor(bw::smem_u32(sW), 64);
+      for (int key = key0; key < keys && per_cta > 0; key += kmod) {
+        if (wcount > 0) bw::umma_commit(&wempty[buf]);   // previous weights free once their MMAs retire
+        buf = wcount & 1;
+        bw::mbar_wait(&wfull[buf], (wcount >> 1) & 1);
+        ++wcount;
+        const uint64_t db0 = db_base + (uint64_t)((buf * Cfg::W_BYTES) >> 4);
+        for (int tt = 0; tt < per_cta; ++tt, ++iter) {
+          const int as = iter & 1;
+          const uint32_t aphase = (iter >> 1) & 1;
+          bw::mbar_wait(&tempty[as], aphase ^ 1);
+          bw::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + as * BN;
+          bw::mbar_wait(&full[stage], phase);
+          bw::tc_fence_after();
+          const uint64_t da0 = da_base + (uint64_t)((stage * HALO_STAGE) >> 4);
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const int dy = t / 3, dx = t - 3 * dy;
-          const uint64_t da = halo_desc(a0 + (dy * HALO_PW + dx) * 64, HALO_PW * 64);
-          const uint64_t db = bw::umma_smem_desc_kmajor(w0 + t * BN * 64, 64);
+          for (int t = 0; t < 9; ++t) {
+            const int dy = t / 3, dx = t - 3 * dy;
+            const uint64_t da = da0 + (uint64_t)(((dy * HALO_PW + dx) * 64) >> 4);   // descriptor address field: 16-byte units
+            const uint64_t db = db0 + (uint64_t)((t * BN * 64) >> 4);
 #pragma unroll
-          for (int k = 0; k < 2; ++k) bw::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (t | k) != 0);
+            for (int k = 0; k < 2; ++k) bw::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (t | k) != 0);
+          }
+          bw::umma_commit(&empty[stage]);
+          bw::umma_commit(&tfull[as]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        bw::umma_commit(&empty[stage]);
-        bw::umma_commit(&tfull[as]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
     const int ew = warp - 4;
     int iter = 0;
     uint32_t sbuf = 0;
-    for (int n = 0; n < n_total; ++n, ++iter) {
-      const int tile = tile_of(n);
-      int g, b, ty, tx, nb;
-      decode(tile, g, b, ty, tx, nb);
+    Walk wk;
+    for (int key = key0; key < keys && per_cta > 0; key += kmod)
+    for (walk_begin(wk, key); wk.tt < per_cta; walk_next(wk), ++iter) {
+      const int g = wk.g, b = wk.b, ty = wk.ty, tx = wk.tx, nb = wk.nb;
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
       bw::mbar_wait(&tfull[as], aphase);

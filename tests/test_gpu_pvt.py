@@ -96,3 +96,93 @@ def test_attention_kernel_key_tails_and_bf16():
     qb, kvb = q.to(torch.bfloat16), kv.to(torch.bfloat16)
     gotb = PF.attention(qb.cuda(), kvb.cuda(), B, N, Nk, heads)
     assert rel(gotb.float().cpu(), ref(qb.float(), kvb.float())) <= 8e-3      # one bf16 rounding of the output
+
+
+# ---- shape sweeps of the new token operators against plain torch (float64) --------------------------------
+from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
+
+_SET = dict(max_examples=12, deadline=None, suppress_health_check=list(HealthCheck))
+
+
+@settings(**_SET)
+@given(rows=st.integers(1, 70), c4=st.sampled_from([4, 16, 32, 80, 128, 160, 512]), with_add=st.booleans(),
+       bf16_out=st.booleans())
+def test_sweep_ln_tokens(rows, c4, with_add, bf16_out):
+    common.package()
+    from dgtd_b200.twig.ops.functions import pvt_func as PF
+    from dgtd_b200.twig.ops.capi import BF16, F32
+    C = c4 * 4 if c4 <= 128 else c4      # 16 .. 512 channels (and the 640-wide case below)
+    g = torch.Generator().manual_seed(rows * 1000 + C)
+    x = torch.randn(rows, C, generator=g) * 2 + 0.5
+    add = torch.randn(rows, C, generator=g) if with_add else None
+    w, b = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    out, s = PF.ln_tokens(x.cuda(), w.cuda(), b.cuda(), 1e-6, BF16 if bf16_out else F32,
+                          add=add.cuda() if with_add else None, want_sum=True)
+    xs = x.double() + (add.double() if with_add else 0)
+    ref = torch.nn.functional.layer_norm(xs, (C,), w.double(), b.double(), 1e-6)
+    assert rel(s.cpu(), xs) <= 1e-6
+    assert rel(out.float().cpu(), ref) <= (8e-3 if bf16_out else 1e-5)
+
+
+@settings(**_SET)
+@given(B=st.integers(1, 2), h=st.integers(1, 9), w=st.integers(1, 11), c8=st.sampled_from([1, 3, 8, 9, 40]))
+def test_sweep_dwconv3_gelu(B, h, w, c8):
+    common.package()
+    from dgtd_b200.twig.ops.functions import pvt_func as PF
+    C = 8 * c8
+    g = torch.Generator().manual_seed(B * 7919 + h * 131 + w * 17 + C)
+    x = torch.randn(B, h, w, C, generator=g)
+    wt = torch.randn(C, 1, 3, 3, generator=g) * 0.4
+    bias = torch.randn(C, generator=g)
+    ref = torch.nn.functional.gelu(torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), wt.double(), bias.double(),
+                                                              padding=1, groups=C)).permute(0, 2, 3, 1)
+    wT = wt.reshape(C, 9).t().contiguous()
+    got = PF.dwconv3_gelu(x.cuda(), wT.cuda(), bias.cuda())
+    assert rel(got.cpu(), ref) <= 1e-5
+    gotb = PF.dwconv3_gelu(x.to(torch.bfloat16).cuda(), wT.cuda(), bias.cuda())
+    refb = torch.nn.functional.gelu(torch.nn.functional.conv2d(x.to(torch.bfloat16).double().permute(0, 3, 1, 2), wt.double(),
+                                                               bias.double(), padding=1, groups=C)).permute(0, 2, 3, 1)
+    assert rel(gotb.float().cpu(), refb) <= 8e-3
+
+
+@settings(**_SET)
+@given(B=st.integers(1, 2), N=st.integers(1, 130), Nk=st.integers(1, 150), heads=st.integers(1, 3))
+def test_sweep_attention_fp32_and_bf16(B, N, Nk, heads):
+    common.package()
+    from dgtd_b200.twig.ops.functions import pvt_func as PF
+    g = torch.Generator().manual_seed(B + 10 * N + 1000 * Nk + heads)
+    q = torch.randn(B * N, heads * 64, generator=g)
+    kv = torch.randn(B * Nk, 2 * heads * 64, generator=g)
+
+    def ref(q, kv):
+        qh = q.double().view(B, N, heads, 64).permute(0, 2, 1, 3)
+        k = kv.double()[:, :heads * 64].reshape(B, Nk, heads, 64).permute(0, 2, 1, 3)
+        v = kv.double()[:, heads * 64:].reshape(B, Nk, heads, 64).permute(0, 2, 1, 3)
+        return (torch.softmax(qh @ k.transpose(-1, -2) / 8.0, -1) @ v).permute(0, 2, 1, 3).reshape(B * N, heads * 64)
+    assert rel(PF.attention(q.cuda(), kv.cuda(), B, N, Nk, heads).cpu(), ref(q, kv)) <= 1e-5
+    qb, kvb = q.to(torch.bfloat16), kv.to(torch.bfloat16)
+    assert rel(PF.attention(qb.cuda(), kvb.cuda(), B, N, Nk, heads).float().cpu(), ref(qb.float(), kvb.float())) <= 1e-2
+
+
+def test_backbone_at_352_and_batch_consistency(net):
+    """352^2 (token grids 88/44/22/11, 121 keys: not a multiple of the 48-key tile) in fp32 vs the oracle; bf16
+    batch of 3 == the same images one by one (no cross-sample coupling)."""
+    from dgtd_b200.twig.model.texture_diffuser import set_precision
+    set_precision(net, "fp32")
+    sd = {k: v.detach().double().cpu() for k, v in net.state_dict().items()}
+    image, depth = common.synthetic_inputs(1, 352, seed=21)
+    with torch.no_grad():
+        _, want = P.forward_features(image.double(), depth.double(), sd)
+    _, outs = net.forward_features(image.cuda(), depth.cuda())
+    for s in range(4):
+        assert rel(outs[s].cpu(), want[s]) <= 1e-4, (s, rel(outs[s].cpu(), want[s]))
+    set_precision(net, "bf16")
+    imgs = [common.synthetic_inputs(1, 128, seed=30 + i) for i in range(3)]
+    image = torch.cat([a for a, _ in imgs]).cuda()
+    depth = torch.cat([d for _, d in imgs]).cuda()
+    _, batch = net.forward_features(image, depth)
+    for i in range(3):
+        _, one = net.forward_features(image[i:i + 1], depth[i:i + 1])
+        for s in range(4):
+            assert rel(batch[s][i:i + 1].cpu(), one[s].cpu()) <= 2e-2
+    set_precision(net, None)

@@ -96,6 +96,74 @@ struct EpiHighpass {
   }
 };
 
+
+// ---- tensor-core variant (bf16 mode of the path): the two projector products as tcgen05 GEMMs over ALL planes,
+// fp32-accurate through a two-term bf16 split of both operands:
+//     x = x_hi + x_lo,  A = A_hi + A_lo   ->   x A  ~=  x_hi A_hi + x_hi A_lo + x_lo A_hi     (|err| ~ 2^-16 |x||A|)
+// accumulated in fp32 by the residual epilogue of the GEMM.  The second product contracts over image rows, so
+// the intermediate is transposed per plane (fused with its split) and the result comes out transposed; the
+// finishing kernel transposes back while applying the rank-2 imaginary term, the subtraction and |.|.
+__global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, int64_t n4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = *reinterpret_cast<const float4*>(x + i * 4);
+  const float f[4] = {v.x, v.y, v.z, v.w};
+  float h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    h[e] = __bfloat162float(__float2bfloat16_rn(f[e]));
+    l[e] = f[e] - h[e];
+  }
+  store4(hi + i * 4, h[0], h[1], h[2], h[3]);
+  store4(lo + i * 4, l[0], l[1], l[2], l[3]);
+}
+// per plane (R x C fp32) -> (C x R) bf16 hi / lo
+__global__ void __launch_bounds__(256)
+transpose_split_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                       int R, int C) {
+  __shared__ float tile[32][33];
+  const int64_t pb = (int64_t)blockIdx.z * R * C;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8)
+    tile[i][tx] = (r0 + i < R && c0 + tx < C) ? t[pb + (int64_t)(r0 + i) * C + c0 + tx] : 0.f;
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (c < C && r < R) {
+      const float v = tile[tx][i];
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      hi[pb + (int64_t)c * R + r] = h;
+      lo[pb + (int64_t)c * R + r] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+// out[p][i][j] = | x[p][i][j] - yt[p][j][i] + (u_i * sin_w[j] + t_i * cos_w[j]) |   (EpiHighpass, transposed input)
+__global__ void __launch_bounds__(256)
+highpass_finish_kernel(const float* __restrict__ x, const float* __restrict__ yt, const float* __restrict__ sc_h,
+                       const float* __restrict__ sc_w, const float* __restrict__ coef, float* __restrict__ out, int H,
+                       int W) {
+  __shared__ float tile[32][33];
+  const int pl = blockIdx.z;
+  const int64_t pb = (int64_t)pl * H * W;
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int k = ty; k < 32; k += 8)   // yt rows = j, columns = i
+    tile[k][tx] = (j0 + k < W && i0 + tx < H) ? yt[pb + (int64_t)(j0 + k) * H + i0 + tx] : 0.f;
+  __syncthreads();
+  const float4 q = load4(coef + pl * 4);
+  for (int k = ty; k < 32; k += 8) {
+    const int i = i0 + k, j = j0 + tx;
+    if (i < H && j < W) {
+      const float sa = sc_h[i], ca = sc_h[H + i];
+      const float u = sa * q.x - ca * q.z, t = ca * q.w - sa * q.y;
+      const int64_t o = pb + (int64_t)i * W + j;
+      out[o] = fabsf(x[o] - tile[tx][k] + (u * sc_w[j] + t * sc_w[W + j]));
+    }
+  }
+}
+
 }  // namespace dgtd
 
 using namespace dgtd;
@@ -138,6 +206,43 @@ int dgtd_fft_highpass_fwd(const float* x, const float* Ph, const float* Pw, cons
     launch_simt_gemm<true, false>(al, bl, ep, H, W, H, planes, s);
     DGTD_LAUNCH_CHECK("fft_highpass.cols");
   }
+  return 0;
+}
+
+// bf16-mode variant on the tcgen05 GEMMs (see above).  P*_hi / P*_lo: bf16 split of the projectors (H x H, W x W);
+// zeros: max(H, W) fp32 zeros (bias operand of the accumulating GEMMs); ws_hi / ws_lo: planes*H*W bf16 each,
+// ws_f32: planes*H*W fp32; coef: planes*4.
+int dgtd_fft_highpass_tc_fwd(const float* x, const void* Ph_hi, const void* Ph_lo, const void* Pw_hi, const void* Pw_lo,
+                             const float* sc_h, const float* sc_w, const float* zeros, void* ws_hi, void* ws_lo,
+                             float* ws_f32, float* coef, float* out, int planes, int H, int W, dgtd_stream_t stream) {
+  DGTD_CHECK_ARG(x && Ph_hi && Ph_lo && Pw_hi && Pw_lo && sc_h && sc_w && zeros && ws_hi && ws_lo && ws_f32 && coef && out,
+                 "fft_highpass_tc: null pointer");
+  DGTD_CHECK_ARG(planes > 0 && planes <= 65535 && H > 0 && W > 0 && (W % 8) == 0 && (H % 8) == 0,
+                 "fft_highpass_tc: H and W must be multiples of 8 (got %dx%d)", H, W);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n = (int64_t)planes * H * W;
+  __nv_bfloat16* hi = (__nv_bfloat16*)ws_hi;
+  __nv_bfloat16* lo = (__nv_bfloat16*)ws_lo;
+  imag_coef_kernel<<<planes, 256, 0, s>>>(x, sc_h, sc_w, coef, H, W);
+  DGTD_LAUNCH_CHECK("fft_highpass_tc.coef");
+  split_bf16_kernel<<<(unsigned)cdiv(n / 4, (int64_t)256), 256, 0, s>>>(x, hi, lo, n / 4);
+  DGTD_LAUNCH_CHECK("fft_highpass_tc.split");
+  int rc;
+  // T[(p,i), j] = sum_k x[(p,i), k] A_w[j, k]
+  const int R = planes * H;
+  if ((rc = dgtd_linear_fwd(hi, Pw_hi, nullptr, ws_f32, R, W, W, W, DGTD_BF16, DGTD_F32, DGTD_ACT_NONE, stream))) return rc;
+  if ((rc = dgtd_linear_residual_fwd(hi, Pw_lo, zeros, nullptr, nullptr, 1, ws_f32, ws_f32, R, W, W, DGTD_BF16, stream))) return rc;
+  if ((rc = dgtd_linear_residual_fwd(lo, Pw_hi, zeros, nullptr, nullptr, 1, ws_f32, ws_f32, R, W, W, DGTD_BF16, stream))) return rc;
+  // per plane transpose (+ split): Tt[(p,j), i] = T[(p,i), j]
+  transpose_split_kernel<<<dim3(cdiv(W, 32), cdiv(H, 32), planes), 256, 0, s>>>(ws_f32, hi, lo, H, W);
+  DGTD_LAUNCH_CHECK("fft_highpass_tc.transpose");
+  // Yt[(p,j), i'] = sum_i Tt[(p,j), i] A_h[i', i]
+  const int R2 = planes * W;
+  if ((rc = dgtd_linear_fwd(hi, Ph_hi, nullptr, ws_f32, R2, H, H, H, DGTD_BF16, DGTD_F32, DGTD_ACT_NONE, stream))) return rc;
+  if ((rc = dgtd_linear_residual_fwd(hi, Ph_lo, zeros, nullptr, nullptr, 1, ws_f32, ws_f32, R2, H, H, DGTD_BF16, stream))) return rc;
+  if ((rc = dgtd_linear_residual_fwd(lo, Ph_hi, zeros, nullptr, nullptr, 1, ws_f32, ws_f32, R2, H, H, DGTD_BF16, stream))) return rc;
+  highpass_finish_kernel<<<dim3(cdiv(W, 32), cdiv(H, 32), planes), 256, 0, s>>>(x, ws_f32, sc_h, sc_w, coef, out, H, W);
+  DGTD_LAUNCH_CHECK("fft_highpass_tc.finish");
   return 0;
 }
 

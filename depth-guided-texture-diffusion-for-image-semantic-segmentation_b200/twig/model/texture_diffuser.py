@@ -521,7 +521,8 @@ class prompt_encoder(nn.Module):
         H = 12                                                                    # cod.py:1283
         image = image.contiguous().float()
         cues = cues.contiguous().float()
-        x = self.fft(image, self.freq_nums)                                       # :1288
+        # :1288; bf16 mode: the projector products on tcgen05 (two-term bf16 split, fp32-accurate)
+        x = OP.fft_highpass(image, self.freq_nums, tensor_cores=(mode == BF16))
         reg = self.propagation_weight_regressor.reg
         mp = self.message_passing
         pk = _packed(self)

@@ -103,12 +103,32 @@ class HighpassPlan:
         return plan
 
 
-def fft_highpass(x: torch.Tensor, rate: float = 0.3) -> torch.Tensor:
-    """|x - lowpass(x)| per plane, the operator of cod.py:1256-1271.  No gradient."""
+def _split_bf16(t: torch.Tensor):
+    hi = t.to(torch.bfloat16)
+    return hi.contiguous(), (t - hi.float()).to(torch.bfloat16).contiguous()
+
+
+def fft_highpass(x: torch.Tensor, rate: float = 0.3, tensor_cores: bool = False) -> torch.Tensor:
+    """|x - lowpass(x)| per plane, the operator of cod.py:1256-1271.  No gradient.
+    tensor_cores=True: projector products on tcgen05 with a two-term bf16 split (fp32-accurate, ~1e-5)."""
     check_cuda(x)
     assert x.dtype == torch.float32 and x.dim() == 4
     B, C, H, W = x.shape
     plan = HighpassPlan.get(H, W, rate, x.device)
+    if tensor_cores and H % 8 == 0 and W % 8 == 0:
+        if not hasattr(plan, "tc"):
+            ph, pw = _split_bf16(plan.Ph), (_split_bf16(plan.Pw) if plan.Pw is not plan.Ph else None)
+            plan.tc = (ph, pw or ph, torch.zeros(max(H, W), device=x.device, dtype=torch.float32))
+        (ph_hi, ph_lo), (pw_hi, pw_lo), zeros = plan.tc
+        n = x.numel()
+        ws_hi = torch.empty(n, device=x.device, dtype=torch.bfloat16)
+        ws_lo = torch.empty(n, device=x.device, dtype=torch.bfloat16)
+        ws_f = torch.empty(n, device=x.device, dtype=torch.float32)
+        coef = torch.empty(B * C * 4, device=x.device, dtype=torch.float32)
+        out = torch.empty_like(x)
+        call("dgtd_fft_highpass_tc_fwd", ptr(x), ptr(ph_hi), ptr(ph_lo), ptr(pw_hi), ptr(pw_lo), ptr(plan.sc_h),
+             ptr(plan.sc_w), ptr(zeros), ptr(ws_hi), ptr(ws_lo), ptr(ws_f), ptr(coef), ptr(out), B * C, H, W, stream())
+        return out
     tmp = torch.empty_like(x)
     coef = torch.empty(B * C * 4, device=x.device, dtype=torch.float32)
     out = torch.empty_like(x)

@@ -60,6 +60,13 @@ int dgtd_lowpass_projector(float* P, float* sc, int n, int line, dgtd_stream_t s
 int dgtd_fft_highpass_fwd(const float* x, const float* Ph, const float* Pw, const float* sc_h,
                           const float* sc_w, float* tmp, float* coef, float* out, int planes,
                           int H, int W, dgtd_stream_t stream);
+/* Same operator with the two projector products on the tcgen05 GEMMs (bf16 mode of the path), fp32-accurate
+ * through a two-term bf16 split of both operands (x_hi A_hi + x_hi A_lo + x_lo A_hi, fp32 accumulation).
+ * P*_hi / P*_lo: bf16 split of the projectors; zeros: max(H,W) fp32 zeros; ws_hi / ws_lo: planes*H*W bf16,
+ * ws_f32: planes*H*W fp32.  H, W multiples of 8. */
+int dgtd_fft_highpass_tc_fwd(const float* x, const void* Ph_hi, const void* Ph_lo, const void* Pw_hi, const void* Pw_lo,
+                             const float* sc_h, const float* sc_w, const float* zeros, void* ws_hi, void* ws_lo,
+                             float* ws_f32, float* coef, float* out, int planes, int H, int W, dgtd_stream_t stream);
 
 /* ---- a3..a6 fused: cod.py:1295-1298 + MessagePassing.forward :1189-1206 ------------------- */
 /* nearest GxG sample of emb1 -> regressor 1x1 conv (3 -> C*49) + sigmoid -> random-walk

@@ -43,7 +43,8 @@ def test_linear_bf16_fp32_out(OP, M, N, K):
     assert rel(got, ref) <= 1e-4
 
 
-@pytest.mark.parametrize("M,N,K", [(300, 512, 128), (5000, 2048, 512)])
+@pytest.mark.parametrize("M,N,K", [(300, 512, 128), (5000, 2048, 512), (20000, 2048, 512), (19100, 1280, 320),
+                                   (38000, 1024, 256)])   # the last three: more row blocks than CTA pairs
 def test_linear_bf16_gelu_bf16_out(OP, M, N, K):
     a, w, b = operands(M, N, K, seed=1)
     ref = O.gelu_erf(a.double() @ w.double().t() + b.double())

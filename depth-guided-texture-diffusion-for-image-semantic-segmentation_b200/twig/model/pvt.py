@@ -265,9 +265,8 @@ class PyramidVisionTransformerImpr(nn.Module):
         self.batch = 0
 
     @torch.no_grad()
-    def forward_features(self, x, depth):
-        """cod.py:1455-1509 -> (embedding1, [(B, C_s, H_s, W_s) fp32]).  `depth` may be the reference's list of
-        (1,H,W) maps or a (B,1,H,W) tensor."""
+    def _forward_features_nhwc(self, x, depth):
+        """cod.py:1455-1509 with the stage maps left in NHWC (B, H_s, W_s, C_s) fp32 for the decoder kernels."""
         self.batch += 1
         if isinstance(depth, (list, tuple)):
             depth = torch.stack([d.reshape(1, *d.shape[-2:]) for d in depth], 0)
@@ -285,8 +284,15 @@ class PyramidVisionTransformerImpr(nn.Module):
             norm = getattr(self, f"norm{s + 1}")
             o, _ = PF.ln_tokens(t, _f(norm.weight), _f(norm.bias), norm.eps, F32)
             cur = o.view(B, H, W, -1)
-            outs.append(OP.nhwc_to_nchw(cur))
+            outs.append(cur)
         return emb1, outs
+
+    @torch.no_grad()
+    def forward_features(self, x, depth):
+        """cod.py:1455-1509 -> (embedding1, [(B, C_s, H_s, W_s) fp32]).  `depth` may be the reference's list of
+        (1,H,W) maps or a (B,1,H,W) tensor."""
+        emb1, outs = self._forward_features_nhwc(x, depth)
+        return emb1, [OP.nhwc_to_nchw(o) for o in outs]
 
     def forward(self, x, depth):
         return self.forward_features(x, depth)

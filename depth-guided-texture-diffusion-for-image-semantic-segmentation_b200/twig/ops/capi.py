@@ -88,6 +88,15 @@ SIGNATURES = {
     "dgtd_cast_fwd": [_P, _P, _L, _I, _I, _P],
     "dgtd_nhwc_to_nchw_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "dgtd_nchw_to_nhwc_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "dgtd_conv_nhwc_affine_fwd": [_P, _P, _P, _P, _P, _P, _I, _P] + [_I] * 12 + [_P],
+    "dgtd_channel_sums_chunks": [_I],
+    "dgtd_channel_sums_fwd": [_P, _I, _P, _I, _I, _I, _P],
+    "dgtd_channel_gate_fwd": [_P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P],
+    "dgtd_gated_sum_fwd": [_P, _I, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P],
+    "dgtd_resize_nhwc_ld_fwd": [_P, _I, _P, _I] + [_I] * 7 + [_P],
+    "dgtd_copy_channels_fwd": [_P, _I, _P, _I, _L, _I, _P],
+    "dgtd_head1_fwd": [_P, _I, _P, _P, _P, _L, _I, _I, _P],
+    "dgtd_sigmoid_fwd": [_P, _P, _L, _P],
 }
 _RESTYPES = {"dgtd_last_error": c_char_p, "dgtd_launch_count": c_int64}
 

@@ -316,6 +316,39 @@ int dgtd_structure_loss_fwd(const float* preds, const float* gt, const float* we
 int dgtd_structure_loss_bwd(const float* preds, const float* gt, const float* weit, const float* sums,
                             const float* grad_out, float* dpreds, int planes, int64_t HW, dgtd_stream_t stream);
 
+/* ---- Hitnet iterative decoder (cod.py:685-807), NHWC fp32, inference semantics -----------
+ * BasicConv2d / CAB convs (cod.py:355-368, 434-451): out[m, n] = prelu(scale[n] * conv(x)[m, n] + shift[n])
+ * + residual[m, n]; scale/shift = the folded eval-mode BatchNorm (nullable), prelu = the ONE shared slope of
+ * nn.PReLU() (nullable), residual nullable (row pitch ldr).  x / out may be channel slices of wider tensors
+ * (pixel pitches ldx / ldo), which is how torch.cat (cod.py:778,785,789,791) is realised.  w packed
+ * (Cout, ks*ks*Cin) tap-major; input pixel = o*stride + off + tap, zero outside. */
+int dgtd_conv_nhwc_affine_fwd(const float* x, const float* w, const float* scale, const float* shift,
+                              const float* prelu, const float* residual, int ldr, float* out, int B, int h, int wd,
+                              int Cin, int ldx, int oh, int ow, int Cout, int ldo, int ks, int stride, int off,
+                              dgtd_stream_t stream);
+/* CALayer / SAM gates (cod.py:413-429, 454-506): fixed-order partial channel sums of x (B, hw, C | pitch ldx)
+ * -> partial (B, chunks, C), chunks = dgtd_channel_sums_chunks(hw); then
+ * gate[b, o] = sigmoid(sum_j W2[o, j] relu(sum_c W1[j, c] mean[b, c])), W1 (Cr, C), W2 (Co, Cr). */
+int dgtd_channel_sums_chunks(int hw);
+int dgtd_channel_sums_fwd(const float* x, int ldx, float* partial, int B, int hw, int C, dgtd_stream_t stream);
+int dgtd_channel_gate_fwd(const float* partial, int nchunks, int hw, const float* w1, const float* w2, float* gate,
+                          int B, int C, int Cr, int Co, dgtd_stream_t stream);
+/* out = a * ga[b, c] * sa[b] + b * gb[b, c] * sb[b]  (ga, sa, b, gb, sb nullable): CAB tail `res * y + x`
+ * (cod.py:447-450) and the SAM fusion (cod.py:487-503). */
+int dgtd_gated_sum_fwd(const float* a, int lda, const float* ga, const float* sa, const float* b, int ldb,
+                       const float* gb, const float* sb, float* out, int ldo, int B, int hw, int C,
+                       dgtd_stream_t stream);
+/* bilinear resize NHWC with pixel pitches, both conventions (nn.Upsample(align_corners=True), cod.py:709,733,737) */
+int dgtd_resize_nhwc_ld_fwd(const float* x, int ldx, float* out, int ldo, int B, int h, int w, int C, int oh, int ow,
+                            int align_corners, dgtd_stream_t stream);
+/* out[row, 0:C] = x[row, 0:C] between tensors of different pixel pitch (the other operand of torch.cat) */
+int dgtd_copy_channels_fwd(const float* x, int ldx, float* out, int ldo, int64_t rows, int C, dgtd_stream_t stream);
+/* out_CFM / out_SAM (cod.py:710-711,793,803): out[row] (+)= bias[0] + sum_c x[row, c] w[c] */
+int dgtd_head1_fwd(const float* x, int ldx, const float* w, const float* bias, float* out, int64_t rows, int C,
+                   int accumulate, dgtd_stream_t stream);
+/* `output.sigmoid()` of the predict mode (cod.py:212,217) */
+int dgtd_sigmoid_fwd(const float* x, float* out, int64_t n, dgtd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -107,13 +107,25 @@ def fill_params_(module, seed: int = 0) -> None:
                 continue
             g = torch.Generator("cpu").manual_seed((seed * 1000003 + zlib.crc32(name.encode())) % (2 ** 31))
             r = torch.randn(t.shape, generator=g, dtype=torch.float32)
-            if t.dim() == 1:
+            if name.endswith("running_var"):
+                v = (1.0 + 0.3 * r).abs() + 0.05          # BatchNorm variance: positive, not all ~1
+            elif t.dim() == 1 and t.numel() == 1:
+                v = torch.full(t.shape, 0.2)               # the shared nn.PReLU() slope (cod.py:686)
+            elif t.dim() == 1:
                 is_scale = name.endswith("weight") or name.endswith("gamma")
                 v = 1.0 + 0.1 * r if is_scale else 0.1 * r
             else:
                 fan_in = t[0].numel()
                 v = r / max(1.0, fan_in) ** 0.5
             t.copy_(v.to(t.dtype))
+
+
+def hitnet_fixture_params_(net, seed: int = 0) -> None:
+    """`fill_params_` + a shift of the CFM head bias so that the predict logits straddle zero (with the plain
+    recipe every logit of the 128^2 fixture is negative and the binarised masks would be trivially empty)."""
+    fill_params_(net, seed=seed)
+    with torch.no_grad():
+        net.out_CFM.bias.add_(3.3)
 
 
 def loss_inputs(B: int, H: int, W: int, seed: int = 0):

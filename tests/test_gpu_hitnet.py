@@ -1,0 +1,189 @@
+"""the Hitnet iterative decoder + the `cod` predict head on the CUDA path, against the golden
+fixture from the unmodified reference (tests/golden/hitnet_128.npz) and the float64 oracle.  This is where the
+north-star mask criterion is checked: binarised masks identical to the reference's in fp32 mode, Hamming
+distance reported (and bounded by the reference's own bf16-autocast distance) in bf16 mode."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import common
+from oracle import hitnet_ref as H
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def net():
+    common.package()
+    from dgtd_b200.twig.model import hitnet
+    m = hitnet.Hitnet().eval()
+    common.hitnet_fixture_params_(m, seed=0)
+    return m.cuda()
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(common.GOLDEN, "hitnet_128.npz"))
+
+
+def test_state_dict_keys(net):
+    sd = net.state_dict()
+    assert len(sd) == 879                       # == the reference's Hitnet (checked key by key at authoring time)
+    # the ONE shared PReLU slope of the default constructor argument (cod.py:686)
+    slopes = {sd[k].data_ptr() for k in sd if k.endswith("body.1.weight")}
+    assert len(slopes) == 1
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_forward_matches_reference_golden(net, golden, precision):
+    from dgtd_b200.twig.model.texture_diffuser import set_precision
+    S, B = int(golden["S"]), int(golden["B"])
+    image, depth = common.synthetic_inputs(B, S, seed=7)
+    set_precision(net, precision)
+    try:
+        emb1, P1, P2 = net(image.cuda(), depth.cuda())
+    finally:
+        set_precision(net, None)
+    assert len(P1) == 4 and all(tuple(p.shape) == (B, 1, S, S) for p in P1) and tuple(P2.shape) == (B, 1, S, S)
+    # fp32: 1e-4; bf16: no worse than 2x the reference's own bf16-autocast error
+    tol = 1e-4 if precision == "fp32" else max(2.0 * float(golden["ref_bf16_relerr"]), 2e-2)
+    for i, p in enumerate(P1):
+        e = rel(p[:, :, ::2, ::2].cpu(), torch.from_numpy(golden[f"P1_{i}"]))
+        assert e <= tol, (precision, i, e, tol)
+    e = rel(P2[:, :, ::2, ::2].cpu(), torch.from_numpy(golden["P2"]))
+    assert e <= tol, (precision, "P2", e, tol)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_predict_masks_match_reference(net, golden, precision):
+    """cod.py:148-149 + binarisation at 0.5 and at binary_thresh = 0.2 (cod.yml:47)."""
+    from dgtd_b200.twig.model.texture_diffuser import set_precision
+    S, B = int(golden["S"]), int(golden["B"])
+    image, depth = common.synthetic_inputs(B, S, seed=7)
+    set_precision(net, precision)
+    try:
+        _, logits = net.predict_logits(image.cuda(), depth.cuda(), (S, S))
+    finally:
+        set_precision(net, None)
+    ref = torch.from_numpy(golden["logits"])
+    got = logits.cpu().double()
+    err = rel(got, ref)
+    report = {"precision": precision, "logit_rel_err": err}
+    for thr, key in ((0.5, "mask50"), (0.2, "mask20")):
+        cut = math.log(thr / (1 - thr))
+        ref_mask = np.unpackbits(golden[key])[:ref.numel()].reshape(ref.shape).astype(bool)
+        assert np.array_equal(ref_mask, (torch.sigmoid(ref) > thr).numpy())
+        got_mask = (got > cut).numpy()
+        ham = int((got_mask != ref_mask).sum())
+        report[f"hamming_{key}"] = ham
+        if precision == "fp32":
+            assert err <= 1e-4, err
+            # identical masks; a bit may only differ where the reference logit is within the fp32 error of the cut
+            band = (ref - cut).abs().numpy() <= 1e-4 * float(ref.abs().max())
+            assert int(((got_mask != ref_mask) & ~band).sum()) == 0
+            assert ham <= int(band.sum())
+        else:
+            ref_ham = int(golden[f"ref_bf16_hamming_{key}"])
+            assert ham <= max(2 * ref_ham, int(0.02 * ref.numel())), (key, ham, ref_ham)
+    print("mask parity:", report)
+
+
+def _sd64(m):
+    return {k: v.detach().double().cpu() for k, v in m.state_dict().items() if v.dtype.is_floating_point}
+
+
+def test_decoder_modules_against_the_oracle(net):
+    """CAB / BasicConv2d (1x1, 3x3, 8x8 stride 4) / SAM forwards (reference signatures, NCHW in and out) vs the
+    float64 restatement, non-square maps, batch > 1 (the gates are per image)."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(3, 64, 20, 12, generator=g)
+    got = net.decoder_level1[0](x.cuda())
+    ref = H.cab(x.double(), _sd64(net.decoder_level1[0]))
+    assert rel(got.cpu(), ref) <= 1e-5
+    x = torch.randn(2, 96, 9, 14, generator=g)
+    got = net.decoder_level2[1](x.cuda())
+    assert rel(got.cpu(), H.cab(x.double(), _sd64(net.decoder_level2[1]))) <= 1e-5
+    x = torch.randn(2, 64, 24, 16, generator=g)
+    got = net.compress_out(x.cuda())
+    ref = H.basic_conv(x.double(), _sd64(net.compress_out), stride=4, padding=2)
+    assert got.shape == ref.shape and rel(got.cpu(), ref) <= 1e-5
+    x = torch.randn(2, 96, 10, 7, generator=g)
+    assert rel(net.conv4(x.cuda()).cpu(), H.basic_conv(x.double(), _sd64(net.conv4), padding=1)) <= 1e-5
+    x = torch.randn(2, 512, 5, 4, generator=g)
+    assert rel(net.Translayer4_1(x.cuda()).cpu(), H.basic_conv(x.double(), _sd64(net.Translayer4_1))) <= 1e-5
+    a, b = torch.randn(3, 32, 11, 6, generator=g), torch.randn(3, 32, 11, 6, generator=g)
+    assert rel(net.SAM(a.cuda(), b.cuda()).cpu(), H.sam(a.double(), b.double(), _sd64(net.SAM))) <= 1e-5
+
+
+@pytest.mark.parametrize("align", [True, False])
+def test_resize_both_conventions(align):
+    common.package()
+    from dgtd_b200.twig.ops.functions import hitnet_func as HF
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 7, 5, 8, generator=g)                       # NHWC
+    for size in ((14, 10), (3, 2), (28, 20), (7, 5)):
+        got = HF.resize_ld(x.cuda(), size, align).cpu()
+        ref = H.resize_bilinear(x.permute(0, 3, 1, 2).double(), size[0], size[1], align).permute(0, 2, 3, 1)
+        assert rel(got, ref) <= 1e-6, (align, size)
+    # writing into a channel slice of a wider tensor (the torch.cat operand)
+    wide = torch.zeros(2, 14, 10, 24, device="cuda")
+    HF.resize_ld(x.cuda(), (14, 10), align, out=wide[..., 8:16])
+    ref = H.resize_bilinear(x.permute(0, 3, 1, 2).double(), 14, 10, align).permute(0, 2, 3, 1)
+    assert rel(wide[..., 8:16].cpu(), ref) <= 1e-6 and float(wide[..., :8].abs().max()) == 0 and float(wide[..., 16:].abs().max()) == 0
+
+
+def test_decode_against_the_oracle_on_random_features(net):
+    """The decoder alone (4 feedback iterations) on random backbone maps of a non-square image."""
+    g = torch.Generator().manual_seed(9)
+    B, h, w = 2, 8, 6                                              # stride-32 grid
+    feats = [torch.randn(B, c, h * s, w * s, generator=g) for c, s in ((64, 8), (128, 4), (320, 2), (512, 1))]
+    p = _sd64(net)
+    ref_preds, ref_p2 = H.decode([f.double() for f in feats], p)
+    nhwc = [f.permute(0, 2, 3, 1).contiguous().cuda() for f in feats]
+    preds, p2, _ = net.decode(nhwc)
+    for a, b in zip(list(preds) + [p2], list(ref_preds) + [ref_p2]):
+        assert a.shape == b.shape and rel(a.cpu(), b) <= 1e-4, rel(a.cpu(), b)
+
+
+def test_train_mode_raises_instead_of_falling_back(net):
+    net.train()
+    try:
+        with pytest.raises(NotImplementedError):
+            net.conv4(torch.randn(1, 96, 4, 4, device="cuda"))
+    finally:
+        net.eval()
+
+
+def test_cod_modes(golden):
+    common.package()
+    from dgtd_b200.twig.model import hitnet
+    from dgtd_b200.twig.model.texture_diffuser import set_precision
+    m = hitnet.cod(win_size=22, filter_ratio=0.9, using_sam=True, using_depth=True, finetune=True, binary_thresh=0.2,
+                   pretrain_sam=None, head=None).eval()
+    common.hitnet_fixture_params_(m.hitnet, seed=0)
+    m = m.cuda()
+    set_precision(m, "fp32")
+    S, B = int(golden["S"]), int(golden["B"])
+    image, depth = common.synthetic_inputs(B, S, seed=7)
+    label = (torch.rand(B, 1, S, S, generator=torch.Generator().manual_seed(1)) > 0.5).float().cuda()
+    depth_list = [d for d in depth.cuda()]                        # the reference passes a list of (1,S,S) maps
+    out = m(None, image.cuda(), label, depth_list, mode="tensor")
+    assert rel(out.cpu(), torch.from_numpy(golden["logits"])) <= 1e-4
+    prob, lab = m(None, image.cuda(), label, depth_list, mode="predict")
+    assert lab is label and rel(prob.cpu(), torch.sigmoid(torch.from_numpy(golden["logits"]))) <= 1e-4
+    loss = m(None, image.cuda(), label, depth_list, mode="loss")["loss"]
+    # deep supervision of cod.py:135-141 (without the gradient-free SSIM constant) from the oracle's structure loss
+    from oracle import loss_ref as L
+    p = _sd64(m.hitnet)
+    _, P1, P2 = H.hitnet_forward(image.double(), depth.double(), p)
+    ref = L.deep_supervision_loss(P1, P2, label.cpu().double())
+    assert abs(float(loss) - float(ref)) <= 1e-4 * abs(float(ref))
+    with pytest.raises(NotImplementedError):
+        m(None, image.cuda(), label, depth_list, mode="nope")

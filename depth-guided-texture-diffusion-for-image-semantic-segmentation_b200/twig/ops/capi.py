@@ -97,8 +97,10 @@ SIGNATURES = {
     "dgtd_copy_channels_fwd": [_P, _I, _P, _I, _L, _I, _P],
     "dgtd_head1_fwd": [_P, _I, _P, _P, _P, _L, _I, _I, _P],
     "dgtd_sigmoid_fwd": [_P, _P, _L, _P],
+    "dgtd_sod_metrics_ws_bytes": [_I, _I, _I],
+    "dgtd_sod_metrics_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],
 }
-_RESTYPES = {"dgtd_last_error": c_char_p, "dgtd_launch_count": c_int64}
+_RESTYPES = {"dgtd_last_error": c_char_p, "dgtd_launch_count": c_int64, "dgtd_sod_metrics_ws_bytes": c_int64}
 
 _lib: Optional[ctypes.CDLL] = None
 

@@ -349,6 +349,15 @@ int dgtd_head1_fwd(const float* x, int ldx, const float* w, const float* bias, f
 /* `output.sigmoid()` of the predict mode (cod.py:212,217) */
 int dgtd_sigmoid_fwd(const float* x, float* out, int64_t n, dgtd_stream_t stream);
 
+/* ---- evaluation metrics (twig/metric/MAE.py:18-36, Smeasure.py:18-36 + pysodmetrics 1.3.1) ----
+ * pred, gt (B,1,H,W) fp32 in [0,1] as the `predict` mode returns them (cod.py:217).  Quantises both like the
+ * wrappers do (`(x * 255).astype(np.uint8)`, gt > 128), min-max normalises the prediction per image and writes
+ * out[b] = {MAE, S-measure (alpha = 0.5)} in float64, from exact integer moments (bit-stable).  ws: 256-byte
+ * aligned scratch of dgtd_sod_metrics_ws_bytes(B, H, W). */
+int64_t dgtd_sod_metrics_ws_bytes(int B, int H, int W);
+int dgtd_sod_metrics_fwd(const float* pred, const float* gt, void* ws, double* out, int B, int H, int W,
+                         dgtd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

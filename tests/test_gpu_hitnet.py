@@ -187,3 +187,34 @@ def test_cod_modes(golden):
     assert abs(float(loss) - float(ref)) <= 1e-4 * abs(float(ref))
     with pytest.raises(NotImplementedError):
         m(None, image.cuda(), label, depth_list, mode="nope")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_smeasure_and_mae_deltas_against_the_reference_prediction(net, golden, precision):
+    """North-star report: S-measure / MAE of the new path's prediction next to those of the reference's prediction
+    (golden logits) on the same synthetic label, through the GPU metrics and through the oracle metrics."""
+    import warnings
+    from dgtd_b200.twig.metric import sod_metrics
+    from dgtd_b200.twig.model.texture_diffuser import set_precision
+    from dgtd_b200.twig.ops.functions import hitnet_func as HF
+    from oracle import metrics_ref as M
+    S, B = int(golden["S"]), int(golden["B"])
+    image, depth = common.synthetic_inputs(B, S, seed=7)
+    label = torch.zeros(B, 1, S, S)
+    label[:, :, S // 4: 3 * S // 4, S // 8: S // 2] = 1.0
+    set_precision(net, precision)
+    try:
+        _, logits = net.predict_logits(image.cuda(), depth.cuda(), (S, S))
+    finally:
+        set_precision(net, None)
+    ours = sod_metrics(HF.sigmoid(logits), label.cuda()).cpu().numpy()
+    ref_prob = torch.sigmoid(torch.from_numpy(golden["logits"]).float())
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = np.array([(M.mae_one(p, g), M.smeasure_one(p, g))
+                        for p, g in zip(M.quantise(ref_prob.numpy()), M.quantise(label.numpy()))])
+    d_mae, d_sm = np.abs(ours[:, 0] - ref[:, 0]).max(), np.abs(ours[:, 1] - ref[:, 1]).max()
+    print(f"metric deltas [{precision}]: |dMAE| = {d_mae:.3e}, |dS| = {d_sm:.3e}  (reference MAE {ref[:, 0].mean():.4f}, "
+          f"S {ref[:, 1].mean():.4f})")
+    tol = 1e-4 if precision == "fp32" else 1e-2
+    assert d_mae <= tol and d_sm <= tol, (d_mae, d_sm)

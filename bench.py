@@ -192,6 +192,62 @@ def backbone_bench(TD, dev, world, rank, args, common, sharding, steps=5):
                     "(spatial-reduction attention on mma.sync, Mix-FFN on tcgen05 GEMMs)"}
 
 
+def full_model_bench(TD, dev, world, rank, args, common, sharding, steps=5):
+    """SURVEY.md 8f-2 / 8f-4 (next rows): the whole `cod` model in predict mode (cod.py:147-217 without the PNG side
+    effects) -- backbone with the texture prompts, Hitnet iterative decoder (exact fp32 kernels), sigmoid -- and
+    the MAE / S-measure evaluation of the batch (twig/metric), batch `--batch` per GPU, images/s of the job."""
+    from dgtd_b200.twig.metric import sod_metrics
+    from dgtd_b200.twig.model import hitnet
+    from dgtd_b200.twig.ops import capi
+    net = hitnet.cod(win_size=22, filter_ratio=0.9, using_sam=True, using_depth=True, finetune=True,
+                     binary_thresh=0.2, pretrain_sam=None, head=None).eval()
+    common.hitnet_fixture_params_(net.hitnet, seed=0)
+    net = net.to(dev)
+    TD.set_precision(net, args.precision)
+    B, S = args.batch, args.size
+    image, depth = common.synthetic_inputs(B, S, seed=400 + rank)
+    image, depth = image.to(dev), depth.to(dev)
+    label = (torch.rand(B, 1, S, S, generator=torch.Generator("cpu").manual_seed(5)) > 0.5).float().to(dev)
+
+    def timed(fn, n):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = capi.launch_count()
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n, (capi.launch_count() - l0) // n
+    ms, launches = timed(lambda: net(None, image, label, depth, mode="predict"), steps)
+    t = sharding.max_over_ranks(ms / 1e3, dev)
+    _, feats = net.hitnet.backbone._forward_features_nhwc(image, depth)
+    dec_ms, dec_launches = timed(lambda: net.hitnet.decode(feats, want_stage_preds=False), steps)
+    prob, _ = net(None, image, label, depth, mode="predict")
+    met_ms, _ = timed(lambda: sod_metrics(prob, label), 10)
+    vals = sod_metrics(prob, label).mean(0).tolist()
+    del net
+    torch.cuda.empty_cache()
+    # decoder FLOPs per image on the stride-8 grid g = S/8 (cod.py:752-805): 2 CABs x 2 conv3 at 64 ch on (2g)^2,
+    # per iteration 2x2 conv3 at 32 ch on (g/4)^2, 64 ch on (g/2)^2, 96 ch on g^2, conv4 96->32, compress 8x8
+    g = S // 8
+    per_iter = 4 * 2 * 9 * (32 * 32 * (g // 4) ** 2 + 64 * 64 * (g // 2) ** 2 + 96 * 96 * g * g) + 2 * 9 * 96 * 32 * g * g
+    flops = 4 * 2 * 9 * 64 * 64 * (2 * g) ** 2 + 4 * per_iter + 3 * 2 * 64 * 64 * 32 * (g // 4) ** 2
+    return {"value": world * B / t, "unit": "images/s", "batch_per_gpu": B, "size": S, "ms_per_step": t * 1e3,
+            "precision": (f"{args.precision} (decoder: bf16 im2col + tcgen05 GEMM, fp32 accumulate / activations)"
+                          if args.precision == "bf16" else "fp32 (exact CUDA-core implicit GEMMs)"),
+            "launches_per_step": int(launches),
+            "decoder_ms": dec_ms, "decoder_launches": int(dec_launches),
+            "decoder_gflop_per_image": flops / 1e9, "decoder_tflops": flops * B / (dec_ms * 1e-3) / 1e12,
+            "metrics_ms": met_ms, "metrics_gbs": B * S * S * (8 + 2 + 2) / (met_ms * 1e-3) / 1e9,
+            "metrics_note": "MAE + S-measure of the batch: 8 B/pixel read + 2 B/pixel written in pass 1, 2 B/pixel read in pass 2",
+            "mae_smeasure_vs_random_label": vals,
+            "what": "cod.forward(mode='predict'): pvt_v2_b2 backbone with the texture prompts + Hitnet decoder "
+                    "(4 feedback iterations) + sigmoid"}
+
+
 def loss_bench(dev, peaks, common, B=16, S=384, steps=10):
     """SURVEY.md 8f-3 (next row): structure loss + deep supervision (cod.py:75-84, 135-141) forward + backward on
     five B x 1 x S x S logit maps.  Pure bandwidth: the weight map is computed once (8 B/pixel), each of the
@@ -551,6 +607,12 @@ def run_ours(args):
         except Exception as e:   # noqa: BLE001
             backbone = {"error": f"{type(e).__name__}: {e}"[:300]}
 
+    full_model = None
+    if not args.no_backbone:
+        try:
+            full_model = full_model_bench(TD, dev, world, rank, args, common, sharding)
+        except Exception as e:  # noqa: BLE001
+            full_model = {"error": f"{type(e).__name__}: {e}"[:300]}
     loss_leg = None
     if rank == 0 and not args.no_backbone:
         try:
@@ -583,7 +645,7 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "result": "stage-4 prompt tokens of the last block (B,144,512) fp32"},
             "gpu_launches": int(launches), "clocks": clocks.summary(),
-            "roofline": roof, "cpu_baseline": cpu, "train_fwd_bwd": train, "highres_768": highres, "backbone_forward_features": backbone, "structure_loss": loss_leg,
+            "roofline": roof, "cpu_baseline": cpu, "train_fwd_bwd": train, "highres_768": highres, "backbone_forward_features": backbone, "full_model_predict": full_model, "structure_loss": loss_leg,
             "diffusion_microbench": diff,
         }
         print(json.dumps(line), flush=True)

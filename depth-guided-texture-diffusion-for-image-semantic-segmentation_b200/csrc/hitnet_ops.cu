@@ -208,6 +208,45 @@ __global__ void __launch_bounds__(256) head1_kernel(const float* __restrict__ x,
   }
 }
 
+// bf16 mode: operand of the tcgen05 GEMM.  col[m, (tap, c)] = bf16(prelu(x[b, oy*stride+off+ty, ox*stride+off+tx, c])),
+// zero outside the image; 8 channels (one 16-byte store) per thread, consecutive threads walk K.
+__global__ void __launch_bounds__(256) im2col_act_kernel(const float* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ col,
+                                                         const float* __restrict__ prelu, int64_t total, int h, int w, int C,
+                                                         int ks, int stride, int off, int oh, int ow) {
+  const int cg = C >> 3, taps = ks * ks;
+  const float a = prelu ? __ldg(prelu) : 1.0f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cg);
+    int64_t t = i / cg;
+    const int tap = (int)(t % taps);
+    const int64_t m = t / taps;
+    const int ox = (int)(m % ow);
+    const int64_t t2 = m / ow;
+    const int oy = (int)(t2 % oh);
+    const int b = (int)(t2 / oh);
+    const int ty = tap / ks, tx = tap - ty * ks;
+    const int iy = oy * stride + off + ty, ix = ox * stride + off + tx;
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    if ((unsigned)iy < (unsigned)h && (unsigned)ix < (unsigned)w) {
+      const float* src = x + ((int64_t)(b * h + iy) * w + ix) * ldx + c8 * 8;
+      v0 = load4(src);
+      v1 = load4(src + 4);
+      if (prelu) {
+        v0.x = v0.x >= 0.f ? v0.x : v0.x * a; v0.y = v0.y >= 0.f ? v0.y : v0.y * a;
+        v0.z = v0.z >= 0.f ? v0.z : v0.z * a; v0.w = v0.w >= 0.f ? v0.w : v0.w * a;
+        v1.x = v1.x >= 0.f ? v1.x : v1.x * a; v1.y = v1.y >= 0.f ? v1.y : v1.y * a;
+        v1.z = v1.z >= 0.f ? v1.z : v1.z * a; v1.w = v1.w >= 0.f ? v1.w : v1.w * a;
+      }
+    }
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(v0.x, v0.y), p1 = __floats2bfloat162_rn(v0.z, v0.w);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(v1.x, v1.y), p3 = __floats2bfloat162_rn(v1.z, v1.w);
+    uint4 pk;
+    pk.x = *reinterpret_cast<unsigned int*>(&p0); pk.y = *reinterpret_cast<unsigned int*>(&p1);
+    pk.z = *reinterpret_cast<unsigned int*>(&p2); pk.w = *reinterpret_cast<unsigned int*>(&p3);
+    *reinterpret_cast<uint4*>(col + i * 8) = pk;
+  }
+}
+
 __global__ void __launch_bounds__(256) sigmoid_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = sigmoidf_acc(x[i]);
@@ -314,6 +353,19 @@ int dgtd_head1_fwd(const float* x, int ldx, const float* w, const float* bias, f
   const int64_t threads = rows * 8;
   head1_kernel<<<cdiv(threads, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, w, bias, out, rows, C, accumulate);
   DGTD_LAUNCH_CHECK("head1");
+  return 0;
+}
+
+int dgtd_im2col_act_fwd(const float* x, int ldx, void* col, const float* prelu, int B, int h, int w, int C, int ks,
+                        int stride, int off, int oh, int ow, dgtd_stream_t stream) {
+  DGTD_CHECK_ARG(x && col && B > 0 && h > 0 && w > 0 && ks >= 1 && stride >= 1 && oh > 0 && ow > 0, "im2col_act: bad args");
+  DGTD_CHECK_ARG(C >= 8 && C % 8 == 0 && ldx >= C && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(col) & 15) == 0,
+                 "im2col_act: C multiple of 8, pitch multiple of 4, 16-byte aligned pointers");
+  const int64_t total = (int64_t)B * oh * ow * ks * ks * (C / 8);
+  im2col_act_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(x, ldx, (__nv_bfloat16*)col, prelu, total, h, w, C, ks,
+                                                                      stride, off, oh, ow);
+  DGTD_LAUNCH_CHECK("im2col_act");
   return 0;
 }
 

@@ -3,7 +3,9 @@
 
 Same class names, constructor signatures and attribute names as the reference (identical ``state_dict`` keys,
 including the never-executed `ca` / `sa` members and the ONE `nn.PReLU()` slope that the default constructor
-argument shares between all CABs); every forward runs on libdgtd_ops.so (csrc/hitnet_ops.cu), NHWC fp32.
+argument shares between all CABs); every forward runs on libdgtd_ops.so (csrc/hitnet_ops.cu), NHWC fp32 activations.  fp32 mode = exact CUDA-core
+implicit GEMMs (the mask-parity path); bf16 mode (`set_precision` / autocast, like the hot path) = bf16 im2col
+operand + tcgen05 GEMM with the BatchNorm scale folded into the weights, fp32 accumulation and fp32 outputs.
 Inference semantics only in this round: BatchNorm uses its running statistics (folded into the conv epilogue),
 there is no autograd graph through the decoder, and `train()` mode raises.
 
@@ -19,8 +21,9 @@ import torch.nn as nn
 
 from ..ops.functions import hitnet_func as HF
 from ..ops.functions import texture_diffusion_func as OP
+from ..ops.capi import BF16
 from .pvt import pvt_v2_b2
-from .texture_diffuser import _packed
+from .texture_diffuser import _mode, _packed
 
 __all__ = ["BasicConv2d", "ChannelAttention", "SpatialAttention", "CALayer", "CAB", "SAM", "Hitnet", "cod"]
 
@@ -70,6 +73,10 @@ class BasicConv2d(nn.Module):
         k, s, p = self.conv.kernel_size[0], self.conv.stride[0], self.conv.padding[0]
         oh = (x.shape[1] + 2 * p - k) // s + 1
         ow = (x.shape[2] + 2 * p - k) // s + 1
+        if _mode(self) == BF16:
+            wb = _packed(self).get("fold_bf16", [self.conv.weight, self.bn.weight, self.bn.running_var],
+                                   lambda: (w * scale[:, None]).to(torch.bfloat16).contiguous())
+            return HF.conv_affine_tc(x, wb, (oh, ow), k, s, -p, shift=shift, out=out)
         return HF.conv_affine(x, w, (oh, ow), k, s, -p, scale=scale, shift=shift, out=out)
 
     def forward(self, x):
@@ -150,8 +157,14 @@ class CAB(nn.Module):
         k = c0.kernel_size[0]
         hw = (x.shape[1], x.shape[2])
         slope = act.weight.detach().float()
-        r = HF.conv_affine(x, w0, hw, k, 1, -(k // 2), prelu=slope)
-        r = HF.conv_affine(r, w2, hw, k, 1, -(k // 2))
+        if _mode(self) == BF16:
+            b0, b2 = _packed(self).get("w_bf16", [c0.weight, c2.weight],
+                                       lambda: (w0.to(torch.bfloat16).contiguous(), w2.to(torch.bfloat16).contiguous()))
+            r = HF.conv_affine_tc(x, b0, hw, k, 1, -(k // 2))
+            r = HF.conv_affine_tc(r, b2, hw, k, 1, -(k // 2), prelu_in=slope)
+        else:
+            r = HF.conv_affine(x, w0, hw, k, 1, -(k // 2), prelu=slope)
+            r = HF.conv_affine(r, w2, hw, k, 1, -(k // 2))
         return HF.gated_sum(r, ga=self.CA._gate(r), b=x, out=out)
 
     def forward(self, x):

@@ -11,7 +11,7 @@ import torch
 from .. import capi
 from ..capi import call, check_cuda, ptr, stream
 
-__all__ = ["conv_affine", "channel_sums", "channel_gate", "gated_sum", "resize_ld", "copy_channels", "head1", "sigmoid"]
+__all__ = ["conv_affine", "conv_affine_tc", "channel_sums", "channel_gate", "gated_sum", "resize_ld", "copy_channels", "head1", "sigmoid"]
 
 
 def _on_cuda(*tensors: Optional[torch.Tensor]) -> None:
@@ -48,6 +48,41 @@ def conv_affine(x: torch.Tensor, w: torch.Tensor, out_hw: Tuple[int, int], ks: i
     call("dgtd_conv_nhwc_affine_fwd", x.data_ptr(), ptr(w), ptr(scale), ptr(shift), ptr(prelu), ptr(residual),
          _pitch(residual) if residual is not None else 0, out.data_ptr(), B, h, wd, Cin, _pitch(x), oh, ow, Cout,
          _pitch(out), ks, stride, off, stream())
+    return out
+
+
+_COL = {}
+
+
+def _col_scratch(device: torch.device, numel: int) -> torch.Tensor:
+    """bf16 im2col operand, reused by every conv of the decoder (stream-ordered producer / consumer pairs)."""
+    buf = _COL.get(device)
+    if buf is None or buf.numel() < numel:
+        buf = _COL[device] = torch.empty(numel, device=device, dtype=torch.bfloat16)
+    return buf
+
+
+def conv_affine_tc(x: torch.Tensor, w: torch.Tensor, out_hw: Tuple[int, int], ks: int, stride: int, off: int,
+                   shift: Optional[torch.Tensor] = None, prelu_in: Optional[torch.Tensor] = None,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bf16 tensor-core form: conv(prelu_in(x)) * scale + shift with the scale already folded into `w`
+    ((Cout, ks*ks*Cin) bf16, tap-major).  The PReLU of a CAB (cod.py:440-442) is applied to the INPUT of its
+    second conv while the operand is gathered, so the first conv's epilogue stays a plain store."""
+    check_cuda(w, shift, prelu_in)
+    _on_cuda(x, out)
+    B, h, wd, Cin = x.shape
+    Cout, K = w.shape
+    assert K == ks * ks * Cin and w.dtype == torch.bfloat16
+    oh, ow = out_hw
+    M = B * oh * ow
+    if out is None:
+        out = torch.empty(B, oh, ow, Cout, device=x.device, dtype=torch.float32)
+    assert out.shape == (B, oh, ow, Cout)
+    col = _col_scratch(x.device, M * K)
+    call("dgtd_im2col_act_fwd", x.data_ptr(), _pitch(x), ptr(col), ptr(prelu_in), B, h, wd, Cin, ks, stride, off, oh, ow,
+         stream())
+    call("dgtd_linear_fwd", ptr(col), ptr(w), ptr(shift), out.data_ptr(), M, Cout, K, _pitch(out), capi.BF16, capi.F32,
+         capi.ACT_NONE, stream())
     return out
 
 

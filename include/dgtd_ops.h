@@ -346,6 +346,10 @@ int dgtd_copy_channels_fwd(const float* x, int ldx, float* out, int ldo, int64_t
 /* out_CFM / out_SAM (cod.py:710-711,793,803): out[row] (+)= bias[0] + sum_c x[row, c] w[c] */
 int dgtd_head1_fwd(const float* x, int ldx, const float* w, const float* bias, float* out, int64_t rows, int C,
                    int accumulate, dgtd_stream_t stream);
+/* bf16 mode of the decoder convs: col (B*oh*ow, ks*ks*C) bf16 = im2col of prelu(x) (prelu nullable), the A operand
+ * of dgtd_linear_fwd (tcgen05) whose weights carry the folded BatchNorm scale and whose bias is the BN shift. */
+int dgtd_im2col_act_fwd(const float* x, int ldx, void* col, const float* prelu, int B, int h, int w, int C, int ks,
+                        int stride, int off, int oh, int ow, dgtd_stream_t stream);
 /* `output.sigmoid()` of the predict mode (cod.py:212,217) */
 int dgtd_sigmoid_fwd(const float* x, float* out, int64_t n, dgtd_stream_t stream);
 

@@ -218,3 +218,28 @@ def test_smeasure_and_mae_deltas_against_the_reference_prediction(net, golden, p
           f"S {ref[:, 1].mean():.4f})")
     tol = 1e-4 if precision == "fp32" else 1e-2
     assert d_mae <= tol and d_sm <= tol, (d_mae, d_sm)
+
+
+def test_bf16_tensor_core_decoder_convs(net):
+    """bf16 mode of the decoder: im2col(bf16) + tcgen05 GEMM with folded BatchNorm; against the float64 oracle on the
+    same parameters.  Stated tolerance 2e-2 relative (bf16 operands, fp32 accumulation, K up to 4096)."""
+    from dgtd_b200.twig.model.texture_diffuser import set_precision
+    g = torch.Generator().manual_seed(13)
+    set_precision(net, "bf16")
+    try:
+        x = torch.randn(3, 96, 12, 20, generator=g)
+        e = rel(net.decoder_level2[0](x.cuda()).cpu(), H.cab(x.double(), _sd64(net.decoder_level2[0])))
+        assert e <= 2e-2, e
+        x = torch.randn(2, 64, 24, 16, generator=g)
+        e = rel(net.compress_out(x.cuda()).cpu(), H.basic_conv(x.double(), _sd64(net.compress_out), stride=4, padding=2))
+        assert e <= 2e-2, e
+        x = torch.randn(2, 320, 6, 5, generator=g)
+        e = rel(net.Translayer3_1(x.cuda()).cpu(), H.basic_conv(x.double(), _sd64(net.Translayer3_1)))
+        assert e <= 2e-2, e
+        feats = [torch.randn(2, c, 8 * s, 6 * s, generator=g) for c, s in ((64, 8), (128, 4), (320, 2), (512, 1))]
+        ref_preds, ref_p2 = H.decode([f.double() for f in feats], _sd64(net))
+        preds, p2, _ = net.decode([f.permute(0, 2, 3, 1).contiguous().cuda() for f in feats])
+        for a, b in zip(list(preds) + [p2], list(ref_preds) + [ref_p2]):
+            assert rel(a.cpu(), b) <= 3e-2, rel(a.cpu(), b)
+    finally:
+        set_precision(net, None)

@@ -228,6 +228,23 @@ def full_model_bench(TD, dev, world, rank, args, common, sharding, steps=5):
     prob, _ = net(None, image, label, depth, mode="predict")
     met_ms, _ = timed(lambda: sod_metrics(prob, label), 10)
     vals = sod_metrics(prob, label).mean(0).tolist()
+    cpu_port = None
+    if rank == 0 and not args.no_cpu_baseline:
+        # the reference's CPU path for the same model: oracle port (pinned to the unmodified Hitnet), fp32, all host
+        # threads, a bounded sample of 2 images of the same size
+        from oracle import hitnet_ref as HR
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        p32 = {k: v.detach().float().cpu() for k, v in net.hitnet.state_dict().items() if v.dtype.is_floating_point}
+        ci, cd = common.synthetic_inputs(2, S, seed=400)
+        with torch.no_grad():
+            HR.hitnet_forward(ci[:1], cd[:1], p32)
+            t0 = time.perf_counter()
+            _, cp1, cp2 = HR.hitnet_forward(ci, cd, p32)
+            HR.predict_logits(cp1, cp2, (S, S))
+            dt = time.perf_counter() - t0
+        cpu_port = {"value": 2 / dt, "unit": "images/s", "cores": cores, "kind": "port",
+                    "sample": f"2 images {S}x{S}, fp32 torch CPU, {cpu_model()}"}
     del net
     torch.cuda.empty_cache()
     # decoder FLOPs per image on the stride-8 grid g = S/8 (cod.py:752-805): 2 CABs x 2 conv3 at 64 ch on (2g)^2,
@@ -243,7 +260,7 @@ def full_model_bench(TD, dev, world, rank, args, common, sharding, steps=5):
             "decoder_gflop_per_image": flops / 1e9, "decoder_tflops": flops * B / (dec_ms * 1e-3) / 1e12,
             "metrics_ms": met_ms, "metrics_gbs": B * S * S * (8 + 2 + 2) / (met_ms * 1e-3) / 1e9,
             "metrics_note": "MAE + S-measure of the batch: 8 B/pixel read + 2 B/pixel written in pass 1, 2 B/pixel read in pass 2",
-            "mae_smeasure_vs_random_label": vals,
+            "mae_smeasure_vs_random_label": vals, "cpu_baseline": cpu_port,
             "what": "cod.forward(mode='predict'): pvt_v2_b2 backbone with the texture prompts + Hitnet decoder "
                     "(4 feedback iterations) + sigmoid"}
 

@@ -247,6 +247,34 @@ __global__ void __launch_bounds__(256) im2col_act_kernel(const float* __restrict
   }
 }
 
+// bf16 operand of the implicit 3x3 conv: out[pixel, 0:Cp] = bf16(prelu(x[pixel, 0:C])), channels C..Cp-1 zero
+__global__ void __launch_bounds__(256) cast_pad_act_kernel(const float* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ out,
+                                                           const float* __restrict__ prelu, int64_t total, int C, int Cp) {
+  const int cg = Cp >> 3;
+  const float a = prelu ? __ldg(prelu) : 1.0f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cg) * 8;
+    const int64_t row = i / cg;
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    if (c < C) {
+      v0 = load4(x + row * ldx + c);
+      v1 = load4(x + row * ldx + c + 4);
+      if (prelu) {
+        v0.x = v0.x >= 0.f ? v0.x : v0.x * a; v0.y = v0.y >= 0.f ? v0.y : v0.y * a;
+        v0.z = v0.z >= 0.f ? v0.z : v0.z * a; v0.w = v0.w >= 0.f ? v0.w : v0.w * a;
+        v1.x = v1.x >= 0.f ? v1.x : v1.x * a; v1.y = v1.y >= 0.f ? v1.y : v1.y * a;
+        v1.z = v1.z >= 0.f ? v1.z : v1.z * a; v1.w = v1.w >= 0.f ? v1.w : v1.w * a;
+      }
+    }
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(v0.x, v0.y), p1 = __floats2bfloat162_rn(v0.z, v0.w);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(v1.x, v1.y), p3 = __floats2bfloat162_rn(v1.z, v1.w);
+    uint4 pk;
+    pk.x = *reinterpret_cast<unsigned int*>(&p0); pk.y = *reinterpret_cast<unsigned int*>(&p1);
+    pk.z = *reinterpret_cast<unsigned int*>(&p2); pk.w = *reinterpret_cast<unsigned int*>(&p3);
+    *reinterpret_cast<uint4*>(out + i * 8) = pk;
+  }
+}
+
 __global__ void __launch_bounds__(256) sigmoid_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = sigmoidf_acc(x[i]);
@@ -366,6 +394,18 @@ int dgtd_im2col_act_fwd(const float* x, int ldx, void* col, const float* prelu, 
   im2col_act_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(x, ldx, (__nv_bfloat16*)col, prelu, total, h, w, C, ks,
                                                                       stride, off, oh, ow);
   DGTD_LAUNCH_CHECK("im2col_act");
+  return 0;
+}
+
+int dgtd_cast_pad_act_fwd(const float* x, int ldx, void* out, const float* prelu, int64_t rows, int C, int Cp,
+                          dgtd_stream_t stream) {
+  DGTD_CHECK_ARG(x && out && rows > 0, "cast_pad_act: bad args");
+  DGTD_CHECK_ARG(C >= 8 && C % 8 == 0 && Cp >= C && Cp % 8 == 0 && ldx >= C && ldx % 4 == 0 &&
+                     (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                 "cast_pad_act: C, Cp multiples of 8, pitch multiple of 4, 16-byte aligned pointers");
+  const int64_t total = rows * (Cp / 8);
+  cast_pad_act_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(x, ldx, (__nv_bfloat16*)out, prelu, total, C, Cp);
+  DGTD_LAUNCH_CHECK("cast_pad_act");
   return 0;
 }
 

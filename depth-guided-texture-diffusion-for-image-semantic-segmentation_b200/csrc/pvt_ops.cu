@@ -143,12 +143,17 @@ dwconv3_gelu_kernel(const T* __restrict__ x, const float* __restrict__ wT, const
   __syncthreads();
   const int co = (threadIdx.x & 7) * 8;
   const int c = c0 + co;
-  int64_t t = (int64_t)blockIdx.y * 32 + (threadIdx.x >> 3);
-  if (t >= groups_total || c >= C) return;
-  const int wq = (w + PX - 1) / PX;
-  const int ox0 = (int)(t % wq) * PX; t /= wq;
-  const int oy = (int)(t % h);
-  const int b = (int)(t / h);
+  // CTA = one 8-row x 16-pixel patch (32 groups of 4 pixels, 4 across x 8 down): the rows oy-1 / oy+1 a thread
+  // needs are the rows its neighbours in the CTA read anyway, so the vertical re-reads hit L1 instead of L2
+  // (10 input rows per 8 output rows instead of 3 per 1).
+  const int g = threadIdx.x >> 3;
+  const int patches_x = (w + 15) / 16, patches_y = (h + 7) / 8;
+  int t = blockIdx.y;
+  const int ox0 = ((t % patches_x) * 4 + (g & 3)) * PX; t /= patches_x;
+  const int oy = (t % patches_y) * 8 + (g >> 2);
+  const int b = t / patches_y;
+  if (ox0 >= w || oy >= h || c >= C) return;
+  (void)groups_total;
   // packed f32x2 arithmetic: 8 channels = 4 register pairs (half the FMA / GELU issue slots)
   uint64_t acc[PX][4];
   {
@@ -498,9 +503,9 @@ int dgtd_patchify_tokens_fwd(const void* x, void* out, int dtype, int B, int h, 
 int dgtd_dwconv3_gelu_fwd(const void* x, const float* wT, const float* bias, void* out, int dtype, int B, int h, int w,
                           int C, dgtd_stream_t stream) {
   DGTD_CHECK_ARG(x && wT && bias && out && B > 0 && h > 0 && w > 0 && C % 8 == 0, "dwconv3_gelu: bad args (C % 8)");
-  const int64_t total = (int64_t)B * h * ((w + 3) / 4);   // groups of 4 pixels
-  DGTD_CHECK_ARG(cdiv(total, (int64_t)32) <= 65535, "dwconv3_gelu: too many pixels for one launch");
-  dim3 blocks(cdiv(C, 64), (unsigned)cdiv(total, (int64_t)32));
+  const int64_t total = (int64_t)B * cdiv(h, 8) * cdiv(w, 16);   // 8 x 16 pixel patches
+  DGTD_CHECK_ARG(total <= 65535, "dwconv3_gelu: too many pixels for one launch");
+  dim3 blocks(cdiv(C, 64), (unsigned)total);
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == DGTD_BF16)
     dwconv3_gelu_kernel<<<blocks, 256, 0, s>>>((const __nv_bfloat16*)x, wT, bias, (__nv_bfloat16*)out, h, w, C, total);

@@ -79,6 +79,10 @@ struct TcParams {
   int split_rows = 0;     // M rounded up to the 256-row pair tile
   int mn_major = 0;       // 1: A is (K x M) and B is (K x N) row-major (operands read "transposed":
                           //    the reduction runs over the ROWS of two activation matrices, no copy)
+  // implicit 3x3 / stride 1 / pad 1 convolution (tc_gemm_kernel<..., CONV3 = true>): the A operand of k-block
+  // (tap, 64-channel chunk) is one 4-D TMA box {64 ch, 16 px, 8 rows, 1 image} of the NHWC input shifted by the
+  // tap (zero fill outside the image = padding); M tiles are 8 x 16 pixel patches.
+  int cv_h = 0, cv_w = 0, cv_chunks = 0, cv_tiles_x = 0, cv_tiles_y = 0;
 };
 
 

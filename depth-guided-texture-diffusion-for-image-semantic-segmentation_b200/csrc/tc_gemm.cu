@@ -78,7 +78,7 @@ struct TcCfg {
   static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + 1024;  // +align slack
 };
 
-template <int BN, int ACT, typename OT, bool RESIDUAL>
+template <int BN, int ACT, typename OT, bool RESIDUAL, bool CONV3 = false>
 __global__ void __launch_bounds__(384, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcParams p) {
@@ -96,7 +96,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.tiles_m * p.tiles_n;
-  const int num_kb = (p.K + BK - 1) / BK;
+  const int num_kb = CONV3 ? 9 * p.cv_chunks : (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
     bw::prefetch_tmap(&tmA);
@@ -126,10 +126,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
+        int img = 0, oy0 = 0, ox0 = 0;
+        if (CONV3) {   // m_blk = (image, patch row, patch column)
+          const int px = m_blk % p.cv_tiles_x, t = m_blk / p.cv_tiles_x;
+          ox0 = px * 16; oy0 = (t % p.cv_tiles_y) * 8; img = t / p.cv_tiles_y;
+        }
+        int tap = 0, chunk = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           bw::mbar_wait(&empty[stage], phase ^ 1);
           bw::mbar_arrive_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_BYTES);
-          bw::tma_load_2d(&tmA, &full[stage], sA + stage * Cfg::A_BYTES, kb * BK, m_blk * BM);
+          if (CONV3) {
+            const int dy = tap / 3, dx = tap - dy * 3;
+            bw::tma_load_4d(&tmA, &full[stage], sA + stage * Cfg::A_BYTES, chunk * BK, ox0 + dx - 1, oy0 + dy - 1, img);
+            if (++chunk == p.cv_chunks) { chunk = 0; ++tap; }
+          } else {
+            bw::tma_load_2d(&tmA, &full[stage], sA + stage * Cfg::A_BYTES, kb * BK, m_blk * BM);
+          }
           bw::tma_load_2d(&tmB, &full[stage], sB + stage * Cfg::B_BYTES, kb * BK, n_blk * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -174,8 +186,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       bw::mbar_wait(&tfull[as], aphase);
       bw::tc_fence_after();
       uint64_t* rel = &tempty[as];
-      tc_epilogue_tile<BN, ACT, OT, RESIDUAL>(p, tmem_base + as * BN, quad, half, lane,
-                                              m_blk * BM + quad * 32 + lane, n_blk,
+      int row = m_blk * BM + quad * 32 + lane;
+      if (CONV3) {   // accumulator row r = pixel (r / 16, r % 16) of the patch -> NHWC pixel index, or masked
+        const int px = m_blk % p.cv_tiles_x, t = m_blk / p.cv_tiles_x;
+        const int r = quad * 32 + lane;
+        const int oy = (t % p.cv_tiles_y) * 8 + (r >> 4), ox = px * 16 + (r & 15);
+        row = (oy < p.cv_h && ox < p.cv_w) ? ((t / p.cv_tiles_y) * p.cv_h + oy) * p.cv_w + ox : p.M;
+      }
+      tc_epilogue_tile<BN, ACT, OT, RESIDUAL>(p, tmem_base + as * BN, quad, half, lane, row, n_blk,
                                               [rel] { bw::mbar_arrive(rel); });
     }
   }
@@ -232,6 +250,53 @@ static int tc_dispatch_bn(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat
   if (p.N % 256 == 0 && (int64_t)cdiv(p.M, 128) * (p.N / 256) >= sm_count())
     return tc_launch<256, ACT, OT, RESIDUAL>(A, lda, B, ldb, p, s);
   return tc_launch<128, ACT, OT, RESIDUAL>(A, lda, B, ldb, p, s);
+}
+
+// 3x3 / stride 1 / pad 1 convolution as an implicit GEMM: x (B, h, w, Cp) bf16 with Cp a multiple of 64,
+// weights (Cout, 9 * Cp) bf16 tap-major, out (B*h*w, ldo) fp32 = conv + bias.
+template <int BN>
+static int tc_conv3_launch(const __nv_bfloat16* x, const __nv_bfloat16* w, TcParams p, int B, int Cp, cudaStream_t s) {
+  using Cfg = TcCfg<BN>;
+  auto kern = tc_gemm_kernel<BN, DGTD_ACT_NONE, float, false, true>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("tc_conv3: cannot opt in to %d B of shared memory: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return -2;
+    }
+    configured = true;
+  }
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)Cp, (uint64_t)p.cv_w, (uint64_t)p.cv_h, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)Cp * 2, (uint64_t)p.cv_w * Cp * 2, (uint64_t)p.cv_h * p.cv_w * Cp * 2};
+    uint32_t box[4] = {64, 16, 8, 1};
+    int rc = make_tmap(&tmA, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N}, str[1] = {(uint64_t)p.K * 2};
+    uint32_t box[2] = {64, (uint32_t)BN};
+    int rc = make_tmap(&tmB, w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  p.tiles_m = B * p.cv_tiles_y * p.cv_tiles_x;
+  p.tiles_n = cdiv(p.N, BN);
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, 384, Cfg::SMEM_BYTES, s>>>(tmA, tmB, p);
+  return 0;
+}
+
+int tc_conv3(const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, float* out, int B, int h, int wd,
+             int Cp, int Cout, int64_t ldo, cudaStream_t s) {
+  TcParams p{};
+  p.M = B * h * wd; p.N = Cout; p.K = 9 * Cp; p.bias = bias; p.out = out; p.ldo = ldo; p.rows_per_sample = 1;
+  p.cv_h = h; p.cv_w = wd; p.cv_chunks = Cp / 64; p.cv_tiles_x = cdiv(wd, 16); p.cv_tiles_y = cdiv(h, 8);
+  if (Cout <= 32) return tc_conv3_launch<32>(x, w, p, B, Cp, s);
+  if (Cout <= 64) return tc_conv3_launch<64>(x, w, p, B, Cp, s);
+  return tc_conv3_launch<128>(x, w, p, B, Cp, s);
 }
 
 int tc_linear(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B, int64_t ldb, const float* bias,
@@ -306,6 +371,24 @@ int dgtd_linear_fwd(const void* a, const void* w, const float* bias, void* out, 
   }
 #undef DGTD_SIMT_LIN
   DGTD_LAUNCH_CHECK("linear(fp32)");
+  return 0;
+}
+
+int dgtd_conv3x3_tc_fwd(const void* x, const void* w, const float* bias, float* out, int B, int h, int wd, int Cp,
+                        int Cout, int ldo, dgtd_stream_t stream) {
+  DGTD_CHECK_ARG(x && w && out, "conv3x3_tc: null pointer");
+  DGTD_CHECK_ARG(B > 0 && h > 0 && wd > 0 && Cp > 0 && Cp % 64 == 0 && Cout > 0 && Cout % 8 == 0 && Cout <= 128 &&
+                     ldo >= Cout && ldo % 4 == 0,
+                 "conv3x3_tc: Cp must be a multiple of 64, Cout a multiple of 8 and <= 128 (B=%d h=%d w=%d Cp=%d Cout=%d)",
+                 B, h, wd, Cp, Cout);
+  DGTD_CHECK_ARG((int64_t)B * h * wd < (1ll << 31), "conv3x3_tc: too many pixels");
+  DGTD_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 127) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                 "conv3x3_tc: x must be 128-byte aligned, w / out 16-byte aligned");
+  int rc = tc_conv3((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias, out, B, h, wd, Cp, Cout, ldo,
+                    (cudaStream_t)stream);
+  if (rc) return rc;
+  DGTD_LAUNCH_CHECK("conv3x3_tc");
   return 0;
 }
 

@@ -4,8 +4,9 @@
 Same class names, constructor signatures and attribute names as the reference (identical ``state_dict`` keys,
 including the never-executed `ca` / `sa` members and the ONE `nn.PReLU()` slope that the default constructor
 argument shares between all CABs); every forward runs on libdgtd_ops.so (csrc/hitnet_ops.cu), NHWC fp32 activations.  fp32 mode = exact CUDA-core
-implicit GEMMs (the mask-parity path); bf16 mode (`set_precision` / autocast, like the hot path) = bf16 im2col
-operand + tcgen05 GEMM with the BatchNorm scale folded into the weights, fp32 accumulation and fp32 outputs.
+implicit GEMMs (the mask-parity path); bf16 mode (`set_precision` / autocast, like the hot path) = tcgen05: the 3x3
+convs as implicit GEMMs (one shifted 4-D TMA box per tap, nothing materialised), the 1x1 / 8x8-stride-4 convs
+through a bf16 im2col operand; BatchNorm scale folded into the weights, fp32 accumulation and fp32 outputs.
 Inference semantics only in this round: BatchNorm uses its running statistics (folded into the conv epilogue),
 there is no autograd graph through the decoder, and `train()` mode raises.
 
@@ -36,6 +37,19 @@ def conv(in_channels, out_channels, kernel_size, bias=False, stride=1):
 def _tap_major(w: torch.Tensor) -> torch.Tensor:
     """(O, I, kh, kw) -> (O, kh*kw*I): the K order of the implicit-GEMM loader."""
     return w.detach().float().permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+
+
+def _tap_major_padded_bf16(w: torch.Tensor, scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(O, I, 3, 3) -> (O, 9 * Cp) bf16, input channels zero-padded to Cp = roundup(I, 64) (one or two 128-byte
+    TMA rows per tap), optional per-output-channel scale (folded BatchNorm)."""
+    O, I = w.shape[0], w.shape[1]
+    Cp = (I + 63) // 64 * 64
+    t = w.detach().float().permute(0, 2, 3, 1)
+    if scale is not None:
+        t = t * scale[:, None, None, None]
+    out = torch.zeros(O, 3, 3, Cp, device=w.device, dtype=torch.float32)
+    out[..., :I] = t
+    return out.reshape(O, 9 * Cp).to(torch.bfloat16).contiguous()
 
 
 def _no_training(m: nn.Module) -> None:
@@ -74,6 +88,10 @@ class BasicConv2d(nn.Module):
         oh = (x.shape[1] + 2 * p - k) // s + 1
         ow = (x.shape[2] + 2 * p - k) // s + 1
         if _mode(self) == BF16:
+            if (k, s, p) == (3, 1, 1):
+                wb = _packed(self).get("fold_bf16p", [self.conv.weight, self.bn.weight, self.bn.running_var],
+                                       lambda: _tap_major_padded_bf16(self.conv.weight, scale))
+                return HF.conv3_tc(x, wb, shift=shift, out=out)
             wb = _packed(self).get("fold_bf16", [self.conv.weight, self.bn.weight, self.bn.running_var],
                                    lambda: (w * scale[:, None]).to(torch.bfloat16).contiguous())
             return HF.conv_affine_tc(x, wb, (oh, ow), k, s, -p, shift=shift, out=out)
@@ -157,7 +175,12 @@ class CAB(nn.Module):
         k = c0.kernel_size[0]
         hw = (x.shape[1], x.shape[2])
         slope = act.weight.detach().float()
-        if _mode(self) == BF16:
+        if _mode(self) == BF16 and k == 3:
+            b0, b2 = _packed(self).get("w_bf16p", [c0.weight, c2.weight],
+                                       lambda: (_tap_major_padded_bf16(c0.weight), _tap_major_padded_bf16(c2.weight)))
+            r = HF.conv3_tc(x, b0)
+            r = HF.conv3_tc(r, b2, prelu_in=slope)
+        elif _mode(self) == BF16:
             b0, b2 = _packed(self).get("w_bf16", [c0.weight, c2.weight],
                                        lambda: (w0.to(torch.bfloat16).contiguous(), w2.to(torch.bfloat16).contiguous()))
             r = HF.conv_affine_tc(x, b0, hw, k, 1, -(k // 2))

@@ -97,6 +97,8 @@ SIGNATURES = {
     "dgtd_copy_channels_fwd": [_P, _I, _P, _I, _L, _I, _P],
     "dgtd_head1_fwd": [_P, _I, _P, _P, _P, _L, _I, _I, _P],
     "dgtd_sigmoid_fwd": [_P, _P, _L, _P],
+    "dgtd_cast_pad_act_fwd": [_P, _I, _P, _P, _L, _I, _I, _P],
+    "dgtd_conv3x3_tc_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "dgtd_im2col_act_fwd": [_P, _I, _P, _P] + [_I] * 9 + [_P],
     "dgtd_sod_metrics_ws_bytes": [_I, _I, _I],
     "dgtd_sod_metrics_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],

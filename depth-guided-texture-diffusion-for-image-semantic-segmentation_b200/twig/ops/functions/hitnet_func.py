@@ -11,7 +11,7 @@ import torch
 from .. import capi
 from ..capi import call, check_cuda, ptr, stream
 
-__all__ = ["conv_affine", "conv_affine_tc", "channel_sums", "channel_gate", "gated_sum", "resize_ld", "copy_channels", "head1", "sigmoid"]
+__all__ = ["conv_affine", "conv_affine_tc", "conv3_tc", "channel_sums", "channel_gate", "gated_sum", "resize_ld", "copy_channels", "head1", "sigmoid"]
 
 
 def _on_cuda(*tensors: Optional[torch.Tensor]) -> None:
@@ -83,6 +83,31 @@ def conv_affine_tc(x: torch.Tensor, w: torch.Tensor, out_hw: Tuple[int, int], ks
          stream())
     call("dgtd_linear_fwd", ptr(col), ptr(w), ptr(shift), out.data_ptr(), M, Cout, K, _pitch(out), capi.BF16, capi.F32,
          capi.ACT_NONE, stream())
+    return out
+
+
+_XB = {}
+
+
+def conv3_tc(x: torch.Tensor, w: torch.Tensor, shift: Optional[torch.Tensor] = None,
+             prelu_in: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """3x3 / stride 1 / pad 1 conv as an implicit tcgen05 GEMM (no im2col in HBM): conv(prelu_in(x)) + shift.
+    `w` (Cout, 9 * Cp) bf16 tap-major with the input channels zero-padded to Cp = roundup(Cin, 64)."""
+    check_cuda(w, shift, prelu_in)
+    _on_cuda(x, out)
+    B, h, wd, Cin = x.shape
+    Cout = w.shape[0]
+    Cp = (Cin + 63) // 64 * 64
+    assert w.shape[1] == 9 * Cp and w.dtype == torch.bfloat16
+    if out is None:
+        out = torch.empty(B, h, wd, Cout, device=x.device, dtype=torch.float32)
+    assert out.shape == (B, h, wd, Cout)
+    n = B * h * wd * Cp
+    xb = _XB.get(x.device)
+    if xb is None or xb.numel() < n:
+        xb = _XB[x.device] = torch.empty(n, device=x.device, dtype=torch.bfloat16)
+    call("dgtd_cast_pad_act_fwd", x.data_ptr(), _pitch(x), ptr(xb), ptr(prelu_in), B * h * wd, Cin, Cp, stream())
+    call("dgtd_conv3x3_tc_fwd", ptr(xb), ptr(w), ptr(shift), out.data_ptr(), B, h, wd, Cp, Cout, _pitch(out), stream())
     return out
 
 

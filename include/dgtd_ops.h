@@ -350,6 +350,15 @@ int dgtd_head1_fwd(const float* x, int ldx, const float* w, const float* bias, f
  * of dgtd_linear_fwd (tcgen05) whose weights carry the folded BatchNorm scale and whose bias is the BN shift. */
 int dgtd_im2col_act_fwd(const float* x, int ldx, void* col, const float* prelu, int B, int h, int w, int C, int ks,
                         int stride, int off, int oh, int ow, dgtd_stream_t stream);
+/* 3x3 / stride 1 / pad 1 conv of the CABs and conv4 as an implicit tcgen05 GEMM (no im2col in HBM): x (B,h,w,Cp)
+ * bf16 from dgtd_cast_pad_act_fwd (= bf16(prelu(x)), channels zero-padded to Cp, a multiple of 64); the A operand
+ * of k-block (tap, 64-channel chunk) is ONE 4-D TMA box {64 ch, 16 px, 8 rows} shifted by the tap, zero fill outside
+ * the image = the padding; w (Cout, 9*Cp) bf16 tap-major (BatchNorm scale folded in); out (B*h*w, ldo) fp32
+ * = conv + bias. */
+int dgtd_cast_pad_act_fwd(const float* x, int ldx, void* out, const float* prelu, int64_t rows, int C, int Cp,
+                          dgtd_stream_t stream);
+int dgtd_conv3x3_tc_fwd(const void* x, const void* w, const float* bias, float* out, int B, int h, int wd, int Cp,
+                        int Cout, int ldo, dgtd_stream_t stream);
 /* `output.sigmoid()` of the predict mode (cod.py:212,217) */
 int dgtd_sigmoid_fwd(const float* x, float* out, int64_t n, dgtd_stream_t stream);
 

@@ -243,3 +243,28 @@ def test_bf16_tensor_core_decoder_convs(net):
             assert rel(a.cpu(), b) <= 3e-2, rel(a.cpu(), b)
     finally:
         set_precision(net, None)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 24, 16, 64), (1, 96, 11, 23, 96), (3, 32, 12, 12, 32), (2, 96, 48, 48, 32),
+                                   (1, 64, 7, 5, 64)])
+def test_implicit_conv3x3_tcgen05(shape):
+    """dgtd_conv3x3_tc_fwd (shifted TMA boxes, zero fill = padding, masked partial patches) against a float64
+    conv on the same bf16-rounded operands: <= 1e-4 (only the fp32 accumulation order differs); also into a
+    channel slice of a wider output."""
+    common.package()
+    from dgtd_b200.twig.model.hitnet import _tap_major_padded_bf16
+    from dgtd_b200.twig.ops.functions import hitnet_func as HF
+    B, Cin, h, w, Cout = shape
+    g = torch.Generator().manual_seed(h * w + Cin)
+    x = torch.randn(B, Cin, h, w, generator=g)
+    wt = torch.randn(Cout, Cin, 3, 3, generator=g) / (3.0 * Cin ** 0.5)
+    shift = torch.randn(Cout, generator=g)
+    slope = torch.tensor([0.2])
+    xq = torch.where(x >= 0, x, 0.2 * x).to(torch.bfloat16).double()
+    wq = wt.to(torch.bfloat16).double()
+    ref = torch.nn.functional.conv2d(xq, wq, shift.double(), padding=1).permute(0, 2, 3, 1)
+    wide = torch.full((B, h, w, Cout + 32), 7.0, device="cuda")
+    HF.conv3_tc(x.permute(0, 2, 3, 1).contiguous().cuda(), _tap_major_padded_bf16(wt.cuda()), shift=shift.cuda(),
+                prelu_in=slope.cuda(), out=wide[..., 16:16 + Cout])
+    assert rel(wide[..., 16:16 + Cout].cpu(), ref) <= 1e-4
+    assert float((wide[..., :16] - 7.0).abs().max()) == 0 and float((wide[..., 16 + Cout:] - 7.0).abs().max()) == 0

@@ -164,6 +164,49 @@ dwconv3_gelu_kernel(const T* __restrict__ x, const float* __restrict__ wT, const
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[p][e] = pk2(bs[2 * e], bs[2 * e + 1]);
   }
+  if constexpr (sizeof(T) == 2) {
+    // bf16 storage: all 18 window loads (16 bytes each, packed) are issued before any arithmetic -- 288 bytes in
+    // flight per thread instead of 96 -- with clamped addresses; out-of-image taps are zeroed on the packed words.
+    uint4 raw[3][PX + 2];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = min(max(oy + ky - 1, 0), h - 1);
+      const T* row = x + (((int64_t)b * h + iy) * w) * C + c;
+#pragma unroll
+      for (int j = 0; j < PX + 2; ++j)
+        raw[ky][j] = __ldg(reinterpret_cast<const uint4*>(row + (int64_t)min(max(ox0 - 1 + j, 0), w - 1) * C));
+    }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const bool rok = (unsigned)(oy + ky - 1) < (unsigned)h;
+      uint64_t k[3][4];
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        float kf[8];
+        ld8(&ws[ky * 3 + kx][co], kf);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) k[kx][e] = pk2(kf[2 * e], kf[2 * e + 1]);
+      }
+#pragma unroll
+      for (int j = 0; j < PX + 2; ++j) {
+        const bool ok = rok && (unsigned)(ox0 - 1 + j) < (unsigned)w;
+        const uint32_t u[4] = {raw[ky][j].x, raw[ky][j].y, raw[ky][j].z, raw[ky][j].w};
+        uint64_t v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {   // bf16 pair -> fp32 pair: low half << 16, high half masked
+          const uint32_t q = ok ? u[e] : 0u;
+          v[e] = pk2(__uint_as_float(q << 16), __uint_as_float(q & 0xffff0000u));
+        }
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int p = j - kx;
+          if (p < 0 || p >= PX) continue;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[p][e] = fma2(v[e], k[kx][e], acc[p][e]);
+        }
+      }
+    }
+  } else {
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     const int iy = oy + ky - 1;
@@ -200,6 +243,7 @@ dwconv3_gelu_kernel(const T* __restrict__ x, const float* __restrict__ wT, const
         for (int e = 0; e < 4; ++e) acc[p][e] = fma2(v[e], k[kx][e], acc[p][e]);
       }
     }
+  }
   }
 #pragma unroll
   for (int p = 0; p < PX; ++p) {

@@ -55,6 +55,18 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, D* __restrict__
     if (p < HW && c < ldo) out[((int64_t)b * HW + p) * ldo + c] = from_float<D>(c < C ? t[threadIdx.x][i] : 0.f);
   }
 }
+// few channels (the RGB image in front of the first patch embed): thread = pixel, the C plane reads are coalesced
+// and a warp's writes are one contiguous run of 32 * ldo values
+template <typename D>
+__global__ void nchw_to_nhwc_small_kernel(const float* __restrict__ x, D* __restrict__ out, int HW, int C, int ldo,
+                                          int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t b = i / HW;
+  const int p = (int)(i - b * HW);
+  for (int c = 0; c < ldo; ++c)
+    out[i * ldo + c] = from_float<D>(c < C ? x[(b * C + c) * HW + p] : 0.f);
+}
 }  // namespace dgtd
 
 using namespace dgtd;
@@ -104,6 +116,16 @@ int dgtd_nchw_to_nhwc_fwd(const float* x, void* out, int B, int h, int w, int C,
   DGTD_CHECK_ARG(x && out && B > 0 && h > 0 && w > 0 && C > 0 && ldo >= C, "nchw_to_nhwc: bad args");
   dim3 grid(cdiv(h * w, 32), cdiv(ldo, 32), B), block(32, 8);
   cudaStream_t s = (cudaStream_t)stream;
+  if (ldo <= 8) {
+    const int64_t total = (int64_t)B * h * w;
+    if (dtype_out == DGTD_F32)
+      nchw_to_nhwc_small_kernel<<<(unsigned)cdiv(total, (int64_t)256), 256, 0, s>>>(x, (float*)out, h * w, C, ldo, total);
+    else
+      nchw_to_nhwc_small_kernel<<<(unsigned)cdiv(total, (int64_t)256), 256, 0, s>>>(x, (__nv_bfloat16*)out, h * w, C, ldo,
+                                                                                   total);
+    DGTD_LAUNCH_CHECK("nchw_to_nhwc");
+    return 0;
+  }
   if (dtype_out == DGTD_F32)
     nchw_to_nhwc_kernel<<<grid, block, 0, s>>>(x, (float*)out, h * w, C, ldo);
   else

@@ -33,18 +33,26 @@ class GraphedTrainStep:
 
     def __init__(self, enc: nn.Module, dec: nn.Module, image: torch.Tensor, depth: torch.Tensor,
                  loss_fn: Callable = default_loss, precision: Optional[str] = None, warmup: int = 3,
-                 process_group=None):
+                 process_group=None, flat_grad: Optional[torch.Tensor] = None):
         assert image.is_cuda and depth.is_cuda, "GraphedTrainStep needs CUDA tensors"
         self.enc, self.dec, self.loss_fn, self.precision = enc, dec, loss_fn, precision
         self.group = process_group
         self.image, self.depth = image.detach().clone(), depth.detach().clone()
         self.params = [p for p in list(enc.parameters()) + list(dec.parameters()) if p.requires_grad]
         n = sum(p.numel() for p in self.params)
-        self.flat_grad = torch.zeros(n, device=image.device, dtype=torch.float32)
-        off = 0
-        for p in self.params:
-            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        if flat_grad is None:
+            self.flat_grad = torch.zeros(n, device=image.device, dtype=torch.float32)
+            off = 0
+            for p in self.params:
+                p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+                off += p.numel()
+        else:   # an optimizer (twig/optim.py::FusedAdamW) already owns the flat buffer and bound the views
+            assert flat_grad.numel() == n and flat_grad.dtype == torch.float32
+            self.flat_grad = flat_grad
+            off = 0
+            for p in self.params:
+                assert p.grad is not None and p.grad.data_ptr() == flat_grad.data_ptr() + 4 * off
+                off += p.numel()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):              # warm-up off the capture stream (allocator, lazy inits)

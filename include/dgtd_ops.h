@@ -371,6 +371,16 @@ int64_t dgtd_sod_metrics_ws_bytes(int B, int H, int W);
 int dgtd_sod_metrics_fwd(const float* pred, const float* gt, void* ws, double* out, int B, int H, int W,
                          dgtd_stream_t stream);
 
+/* ---- optimizer step of the training configuration (config/sod.yml:56-76; torch.optim.AdamW semantics) ----------
+ * One launch over flat fp32 buffers p, g, m, v (the hot path's gradients already live in one flat buffer,
+ * twig/graphs.py).  table: nslices entries of dgtd_adamw_slice_bytes() bytes = {int64 off; int32 n (<= 4096);
+ * float lr; float weight_decay; int32 pad} -- one per slice of one parameter, which is how the per-prefix lr
+ * multipliers of paramwise_cfg.custom_keys are applied.  g is multiplied by grad_scale first (1 / world size after
+ * a sum all-reduce).  step = 1-based step count for the bias corrections. */
+int dgtd_adamw_slice_bytes(void);
+int dgtd_adamw_step(float* p, const float* g, float* m, float* v, const void* table, int nslices, float beta1, float beta2,
+                    float eps, int step, float grad_scale, dgtd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,9 +63,11 @@ def main(S=128, B=2):
         bf16_err = rel(lh, logits)
     rec = {"S": np.array(S), "B": np.array(B), "ref_f32_relerr": np.array(f32_err),
            "ref_bf16_relerr": np.array(bf16_err)}
+    sub = 2 if S <= 128 else 8
     for i, t in enumerate(P1):
-        rec[f"P1_{i}"] = t[:, :, ::2, ::2].numpy()
-    rec["P2"] = P2[:, :, ::2, ::2].numpy()
+        rec[f"P1_{i}"] = t[:, :, ::sub, ::sub].numpy()
+    rec["P2"] = P2[:, :, ::sub, ::sub].numpy()
+    rec["sub"] = np.array(sub)
     rec["logits"] = logits.numpy().astype(np.float64)
     for thr, key in ((0.5, "mask50"), (0.2, "mask20")):
         rec[key] = np.packbits(masks(logits, thr))
@@ -85,3 +87,4 @@ def main(S=128, B=2):
 
 if __name__ == "__main__":
     main()
+    main(S=352, B=1)        # BASELINE configs[0]: COD forward, batch 1, 352 x 352

@@ -131,3 +131,17 @@ def test_no_cpu_fallback():
         TD.texture_prompts(enc, dec, image, depth)
     with pytest.raises(RuntimeError, match="CUDA tensors only"):
         TD.MessagePassing(24)(torch.randn(1, 24, 12, 12), torch.rand(1, 1176, 12, 12))
+
+
+def test_paramwise_options_follow_the_custom_keys_of_the_training_config():
+    """config/sod.yml:62-76 through mmengine's rule (longest matching key wins)."""
+    import common
+    common.package()
+    from dgtd_b200.twig.optim import SOD_CUSTOM_KEYS, paramwise_options
+    f = lambda n: paramwise_options(n, 5e-4, 0.1, SOD_CUSTOM_KEYS)  # noqa: E731
+    assert f("hitnet.backbone.prompt_encoder.encoder2.stages.2.5.pwconv1.weight") == (5e-4 * 0.02, 0.1)
+    assert f("hitnet.backbone.prompt_encoder.encoder2.downsample_layers.1.1.weight") == (5e-4 * 0.02, 0.1)
+    assert f("hitnet.backbone.prompt_encoder.message_passing.conv.weight") == (5e-4 * 0.2, 0.1)
+    assert f("hitnet.backbone.block1.0.attn.q.weight") == (5e-4 * 0.2, 0.1)
+    assert f("hitnet.decoder_level1.0.body.0.weight") == (5e-4, 0.1)
+    assert paramwise_options("x", 1.0, 0.5, None) == (1.0, 0.5)

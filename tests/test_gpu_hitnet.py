@@ -28,9 +28,10 @@ def net():
     return m.cuda()
 
 
-@pytest.fixture(scope="module")
-def golden():
-    return np.load(os.path.join(common.GOLDEN, "hitnet_128.npz"))
+@pytest.fixture(scope="module", params=["hitnet_128.npz", "hitnet_352.npz"])
+def golden(request):
+    """128^2 x 2 images, and BASELINE configs[0] (COD forward, batch 1, 352 x 352)."""
+    return np.load(os.path.join(common.GOLDEN, request.param))
 
 
 def test_state_dict_keys(net):
@@ -54,10 +55,11 @@ def test_forward_matches_reference_golden(net, golden, precision):
     assert len(P1) == 4 and all(tuple(p.shape) == (B, 1, S, S) for p in P1) and tuple(P2.shape) == (B, 1, S, S)
     # fp32: 1e-4; bf16: no worse than 2x the reference's own bf16-autocast error
     tol = 1e-4 if precision == "fp32" else max(2.0 * float(golden["ref_bf16_relerr"]), 2e-2)
+    sub = int(golden["sub"])
     for i, p in enumerate(P1):
-        e = rel(p[:, :, ::2, ::2].cpu(), torch.from_numpy(golden[f"P1_{i}"]))
+        e = rel(p[:, :, ::sub, ::sub].cpu(), torch.from_numpy(golden[f"P1_{i}"]))
         assert e <= tol, (precision, i, e, tol)
-    e = rel(P2[:, :, ::2, ::2].cpu(), torch.from_numpy(golden["P2"]))
+    e = rel(P2[:, :, ::sub, ::sub].cpu(), torch.from_numpy(golden["P2"]))
     assert e <= tol, (precision, "P2", e, tol)
 
 
@@ -161,7 +163,8 @@ def test_train_mode_raises_instead_of_falling_back(net):
         net.eval()
 
 
-def test_cod_modes(golden):
+def test_cod_modes():
+    golden = np.load(os.path.join(common.GOLDEN, "hitnet_128.npz"))
     common.package()
     from dgtd_b200.twig.model import hitnet
     from dgtd_b200.twig.model.texture_diffuser import set_precision

@@ -228,6 +228,20 @@ def full_model_bench(TD, dev, world, rank, args, common, sharding, steps=5):
     prob, _ = net(None, image, label, depth, mode="predict")
     met_ms, _ = timed(lambda: sod_metrics(prob, label), 10)
     vals = sod_metrics(prob, label).mean(0).tolist()
+    # small-batch serving latency: eager (Python-issued launches) against the captured predict step
+    latency = None
+    if rank == 0:
+        try:
+            from dgtd_b200.twig import graphs
+            li, ld = image[:1].contiguous(), depth[:1].contiguous()
+            eager_ms, _ = timed(lambda: net.hitnet.predict_logits(li, ld, (S, S)), 10)
+            run = graphs.GraphedPredict(net, li, ld)
+            graph_ms, _ = timed(lambda: run(), 20)
+            latency = {"batch": 1, "eager_ms": eager_ms, "graph_replay_ms": graph_ms,
+                       "note": "cod.forward(mode='tensor') at batch 1: the eager path is bound by issuing ~630 launches"}
+            del run
+        except Exception as e:  # noqa: BLE001
+            latency = {"error": f"{type(e).__name__}: {e}"[:300]}
     cpu_port = None
     if rank == 0 and not args.no_cpu_baseline:
         # the reference's CPU path for the same model: oracle port (pinned to the unmodified Hitnet), fp32, all host
@@ -260,7 +274,7 @@ def full_model_bench(TD, dev, world, rank, args, common, sharding, steps=5):
             "decoder_gflop_per_image": flops / 1e9, "decoder_tflops": flops * B / (dec_ms * 1e-3) / 1e12,
             "metrics_ms": met_ms, "metrics_gbs": B * S * S * (8 + 2 + 2) / (met_ms * 1e-3) / 1e9,
             "metrics_note": "MAE + S-measure of the batch: 8 B/pixel read + 2 B/pixel written in pass 1, 2 B/pixel read in pass 2",
-            "mae_smeasure_vs_random_label": vals, "cpu_baseline": cpu_port,
+            "mae_smeasure_vs_random_label": vals, "cpu_baseline": cpu_port, "latency_batch1": latency,
             "what": "cod.forward(mode='predict'): pvt_v2_b2 backbone with the texture prompts + Hitnet decoder "
                     "(4 feedback iterations) + sigmoid"}
 

@@ -83,3 +83,45 @@ class GraphedTrainStep:
             dist.all_reduce(self.flat_grad, group=self.group)
             self.flat_grad.div_(dist.get_world_size(self.group))
         return self.loss
+
+
+class GraphedPredict:
+    """Low-latency serving of the whole model: `cod.forward(mode='tensor')` (cod.py:147-149) captured once for a
+    fixed batch shape and replayed.
+
+        run = GraphedPredict(model, image, depth)        # model = twig.model.hitnet.cod(...).eval()
+        logits = run(next_image, next_depth)             # (B,1,H,W) fp32; valid until the next call
+
+    One predict step is ~630 short launches; at batch 1 the GPU work is shorter than the time Python needs to issue
+    them, so the eager path is launch-bound.  The replay removes that: inputs are copied into the captured
+    buffers, the result is a captured buffer too (clone it if it must outlive the next call)."""
+
+    def __init__(self, model: nn.Module, image: torch.Tensor, depth: torch.Tensor, warmup: int = 2):
+        assert image.is_cuda and depth.is_cuda, "GraphedPredict needs CUDA tensors"
+        assert not model.training, "GraphedPredict captures the eval-mode forward"
+        self.model = model
+        self.image, self.depth = image.detach().clone(), depth.detach().clone()
+        self.size = tuple(image.shape[-2:])
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                    # warm-up off the capture stream (weight shadows, scratch)
+            for _ in range(max(1, warmup)):
+                self._forward()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.logits = self._forward()
+
+    @torch.no_grad()
+    def _forward(self) -> torch.Tensor:
+        _, out = self.model.hitnet.predict_logits(self.image, self.depth, self.size)
+        return out
+
+    def __call__(self, image: Optional[torch.Tensor] = None, depth: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if image is not None:
+            self.image.copy_(image, non_blocking=True)
+        if depth is not None:
+            self.depth.copy_(depth, non_blocking=True)
+        self.graph.replay()
+        return self.logits

@@ -271,3 +271,26 @@ def test_implicit_conv3x3_tcgen05(shape):
                 prelu_in=slope.cuda(), out=wide[..., 16:16 + Cout])
     assert rel(wide[..., 16:16 + Cout].cpu(), ref) <= 1e-4
     assert float((wide[..., :16] - 7.0).abs().max()) == 0 and float((wide[..., 16 + Cout:] - 7.0).abs().max()) == 0
+
+
+def test_graphed_predict_is_bit_identical_to_the_eager_forward():
+    """twig/graphs.py::GraphedPredict: the captured predict step replayed on new inputs equals the eager call bit
+    for bit (every kernel takes the caller's stream, nothing allocates behind torch's back)."""
+    common.package()
+    from dgtd_b200.twig import graphs
+    from dgtd_b200.twig.model import hitnet
+    from dgtd_b200.twig.model.texture_diffuser import set_precision
+    m = hitnet.cod(binary_thresh=0.2).eval()
+    common.hitnet_fixture_params_(m.hitnet, seed=0)
+    m = m.cuda()
+    for precision in ("fp32", "bf16"):
+        set_precision(m, precision)
+        image, depth = common.synthetic_inputs(2, 128, seed=21)
+        run = graphs.GraphedPredict(m, image.cuda(), depth.cuda())
+        image2, depth2 = common.synthetic_inputs(2, 128, seed=22)
+        got = run(image2.cuda(), depth2.cuda()).clone()
+        _, want = m.hitnet.predict_logits(image2.cuda(), depth2.cuda(), (128, 128))
+        assert torch.equal(got, want), precision
+        got1 = run(image.cuda(), depth.cuda()).clone()
+        _, want1 = m.hitnet.predict_logits(image.cuda(), depth.cuda(), (128, 128))
+        assert torch.equal(got1, want1) and not torch.equal(got1, got)

@@ -21,6 +21,7 @@ struct MetricWs {
   long long* part1;   // [B][chunks][NS1]
   int* info;          // [B][4] = dmin, R, x, y
   unsigned long long* part2;  // [B][chunks][NS2]
+  unsigned int* part3;        // [B][chunks][512]: 256-bin histograms of the re-quantised prediction, fg | bg
 };
 
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -35,6 +36,7 @@ static MetricWs carve(void* ws, int B, int H, int W, size_t* total) {
   m.part1 = (long long*)(base + off); off = align256(off + B * chunks * NS1 * sizeof(long long));
   m.info = (int*)(base + off); off = align256(off + (size_t)B * 4 * sizeof(int));
   m.part2 = (unsigned long long*)(base + off); off = align256(off + B * chunks * NS2 * sizeof(unsigned long long));
+  m.part3 = (unsigned int*)(base + off); off = align256(off + B * chunks * 512 * sizeof(unsigned int));
   if (total) *total = off;
   return m;
 }
@@ -224,6 +226,94 @@ __global__ void metric_final_kernel(MetricWs m, int nchunks, int B, int H, int W
   out[b * 2 + 1] = sm;
 }
 
+// F- / E-measure (pysodmetrics `Fmeasure.cal_pr`, `Emeasure.cal_em_with_cumsumhistogram`): both are functions of the
+// foreground / background histograms of the min-max normalised prediction re-quantised to uint8.  The library
+// does that re-quantisation in float64 -- (u/255 - min/255) / (max/255 - min/255) * 255, truncated -- and a value
+// that lands on an integer can fall either side of it, so the 256-entry map is evaluated with the same IEEE
+// operations in the same order (explicit round-to-nearest intrinsics: no contraction).
+__global__ void __launch_bounds__(256) metric_hist_kernel(MetricWs m, int H, int W) {
+  __shared__ unsigned int hist[512];
+  __shared__ unsigned char lut[256];
+  const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+  const int dmin = m.info[b * 4 + 0], R = m.info[b * 4 + 1];
+  {
+    const int u = threadIdx.x;
+    const double p0 = __ddiv_rn((double)u, 255.0);
+    const double mn = __ddiv_rn((double)dmin, 255.0), mx = __ddiv_rn((double)(dmin + R), 255.0);
+    // dmin = 0, R = 255 is both the constant-prediction convention of metric_info_kernel (no normalisation) and
+    // the full-range case, where (p0 - 0) / (1 - 0) == p0 exactly
+    const double p = (dmin == 0 && R == 255) ? p0 : __ddiv_rn(__dsub_rn(p0, mn), __dsub_rn(mx, mn));
+    const int q = (u >= dmin && u <= dmin + R) ? (int)__dmul_rn(p, 255.0) : 0;
+    lut[u] = (unsigned char)q;
+    hist[u] = 0u;
+    hist[256 + u] = 0u;
+  }
+  __syncthreads();
+  const int r0 = chunk * MROWS, r1 = min(H, r0 + MROWS);
+  const int64_t img = (int64_t)b * H * W;
+  for (int i = r0 * W + threadIdx.x; i < r1 * W; i += 256)
+    atomicAdd(&hist[(m.gu8[img + i] ? 0 : 256) + lut[m.pu8[img + i]]], 1u);   // integer: exact in any order
+  __syncthreads();
+  unsigned int* o = m.part3 + ((int64_t)b * nchunks + chunk) * 512;
+  o[threadIdx.x] = hist[threadIdx.x];
+  o[256 + threadIdx.x] = hist[256 + threadIdx.x];
+}
+
+// curves[b][0][i] = changeable F-measure, curves[b][1][i] = E-measure at threshold 255 - i (the library's order)
+__global__ void __launch_bounds__(256) metric_curves_kernel(MetricWs m, int nchunks, int H, int W, double* __restrict__ curves) {
+  __shared__ double cf[256], cb[256];
+  const int b = blockIdx.x, t = threadIdx.x;
+  unsigned long long f = 0, g = 0;
+  for (int c = 0; c < nchunks; ++c) {
+    const unsigned int* o = m.part3 + ((int64_t)b * nchunks + c) * 512;
+    f += o[255 - t];          // flipped: entry t holds bin 255 - t
+    g += o[256 + 255 - t];
+  }
+  cf[t] = (double)f;
+  cb[t] = (double)g;
+  __syncthreads();
+  if (t == 0) {               // cumulative sums (exact: integers below 2^53)
+    for (int i = 1; i < 256; ++i) { cf[i] += cf[i - 1]; cb[i] += cb[i - 1]; }
+  }
+  __syncthreads();
+  const double eps = 2.220446049250313e-16;
+  const double size = (double)H * (double)W, gt_fg = cf[255];
+  const double fg_fg = cf[t], fg_bg = cb[t];
+  // Fmeasure.cal_pr, beta^2 = 0.3
+  {
+    double ps = fg_fg + fg_bg;
+    if (ps == 0.0) ps = 1.0;
+    const double T = gt_fg > 1.0 ? gt_fg : 1.0;
+    const double prec = fg_fg / ps, rec = fg_fg / T;
+    const double num = 1.3 * prec * rec;
+    const double den = num == 0.0 ? 1.0 : 0.3 * prec + rec;
+    curves[((int64_t)b * 2 + 0) * 256 + t] = num / den;
+  }
+  // Emeasure.cal_em_with_cumsumhistogram
+  {
+    const double pred_fg = fg_fg + fg_bg, pred_bg = size - pred_fg;
+    double total;
+    if (gt_fg == 0.0) {
+      total = pred_bg;
+    } else if (gt_fg == size) {
+      total = pred_fg;
+    } else {
+      const double bg_fg = gt_fg - fg_fg, bg_bg = pred_bg - bg_fg;
+      const double mp = pred_fg / size, mg = gt_fg / size;
+      const double a[2] = {1.0 - mp, 0.0 - mp}, c[2] = {1.0 - mg, 0.0 - mg};
+      const double numel[4] = {fg_fg, fg_bg, bg_fg, bg_bg};
+      total = 0.0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double x = a[i >> 1], y = c[i & 1];
+        const double align = 2.0 * (x * y) / (x * x + y * y + eps);
+        total += (align + 1.0) * (align + 1.0) / 4.0 * numel[i];
+      }
+    }
+    curves[((int64_t)b * 2 + 1) * 256 + t] = total / (size - 1.0 + eps);
+  }
+}
+
 }  // namespace dgtd
 using namespace dgtd;
 
@@ -236,8 +326,8 @@ int64_t dgtd_sod_metrics_ws_bytes(int B, int H, int W) {
   return (int64_t)total;
 }
 
-int dgtd_sod_metrics_fwd(const float* pred, const float* gt, void* ws, double* out, int B, int H, int W,
-                         dgtd_stream_t stream) {
+int dgtd_sod_metrics_fwd(const float* pred, const float* gt, void* ws, double* out, double* curves, int B, int H,
+                         int W, dgtd_stream_t stream) {
   DGTD_CHECK_ARG(pred && gt && ws && out, "sod_metrics: null pointer");
   DGTD_CHECK_ARG(B > 0 && H > 1 && W > 1 && (int64_t)H * W < (1ll << 28), "sod_metrics: bad shape");
   DGTD_CHECK_ARG(((uintptr_t)ws & 255) == 0, "sod_metrics: workspace must be 256-byte aligned");
@@ -252,6 +342,12 @@ int dgtd_sod_metrics_fwd(const float* pred, const float* gt, void* ws, double* o
   DGTD_LAUNCH_CHECK("sod_metrics(moments)");
   metric_final_kernel<<<cdiv(B, 32), 32, 0, s>>>(m, nchunks, B, H, W, out);
   DGTD_LAUNCH_CHECK("sod_metrics(final)");
+  if (curves) {
+    metric_hist_kernel<<<dim3(nchunks, B), 256, 0, s>>>(m, H, W);
+    DGTD_LAUNCH_CHECK("sod_metrics(hist)");
+    metric_curves_kernel<<<B, 256, 0, s>>>(m, nchunks, H, W, curves);
+    DGTD_LAUNCH_CHECK("sod_metrics(curves)");
+  }
   return 0;
 }
 

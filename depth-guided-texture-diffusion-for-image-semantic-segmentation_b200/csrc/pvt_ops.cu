@@ -165,20 +165,30 @@ dwconv3_gelu_kernel(const T* __restrict__ x, const float* __restrict__ wT, const
       for (int e = 0; e < 4; ++e) acc[p][e] = pk2(bs[2 * e], bs[2 * e + 1]);
   }
   if constexpr (sizeof(T) == 2) {
-    // bf16 storage: all 18 window loads (16 bytes each, packed) are issued before any arithmetic -- 288 bytes in
-    // flight per thread instead of 96 -- with clamped addresses; out-of-image taps are zeroed on the packed words.
-    uint4 raw[3][PX + 2];
+    // bf16 storage.  Addressing is hoisted: six clamped column offsets (shared by the three rows) and three clamped
+    // row pointers; a warp is one 16-pixel row of the patch, so the row test is warp-uniform (a skipped row costs
+    // nothing) and only the two outer columns of the 6-wide window can fall outside the image in a full group --
+    // the masks are applied to those packed words only.
+    int coff[PX + 2];
+#pragma unroll
+    for (int j = 0; j < PX + 2; ++j) coff[j] = min(max(ox0 - 1 + j, 0), w - 1) * C;
+    const bool partial = ox0 + PX > w;            // last group of a row when w is not a multiple of 4
+    const bool left_ok = ox0 > 0, right_ok = ox0 + PX < w;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
-      const int iy = min(max(oy + ky - 1, 0), h - 1);
+      const int iy = oy + ky - 1;
+      if ((unsigned)iy >= (unsigned)h) continue;  // warp-uniform
       const T* row = x + (((int64_t)b * h + iy) * w) * C + c;
+      uint4 raw[PX + 2];
 #pragma unroll
-      for (int j = 0; j < PX + 2; ++j)
-        raw[ky][j] = __ldg(reinterpret_cast<const uint4*>(row + (int64_t)min(max(ox0 - 1 + j, 0), w - 1) * C));
-    }
+      for (int j = 0; j < PX + 2; ++j) raw[j] = __ldg(reinterpret_cast<const uint4*>(row + coff[j]));
+      if (!left_ok) raw[0] = make_uint4(0u, 0u, 0u, 0u);
+      if (!right_ok) raw[PX + 1] = make_uint4(0u, 0u, 0u, 0u);
+      if (partial) {
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const bool rok = (unsigned)(oy + ky - 1) < (unsigned)h;
+        for (int j = 1; j <= PX; ++j)
+          if (ox0 - 1 + j >= w) raw[j] = make_uint4(0u, 0u, 0u, 0u);
+      }
       uint64_t k[3][4];
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
@@ -189,14 +199,11 @@ dwconv3_gelu_kernel(const T* __restrict__ x, const float* __restrict__ wT, const
       }
 #pragma unroll
       for (int j = 0; j < PX + 2; ++j) {
-        const bool ok = rok && (unsigned)(ox0 - 1 + j) < (unsigned)w;
-        const uint32_t u[4] = {raw[ky][j].x, raw[ky][j].y, raw[ky][j].z, raw[ky][j].w};
+        const uint32_t u[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
         uint64_t v[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {   // bf16 pair -> fp32 pair: low half << 16, high half masked
-          const uint32_t q = ok ? u[e] : 0u;
-          v[e] = pk2(__uint_as_float(q << 16), __uint_as_float(q & 0xffff0000u));
-        }
+        for (int e = 0; e < 4; ++e)   // bf16 pair -> fp32 pair: low half << 16, high half masked
+          v[e] = pk2(__uint_as_float(u[e] << 16), __uint_as_float(u[e] & 0xffff0000u));
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
           const int p = j - kx;

@@ -103,7 +103,7 @@ SIGNATURES = {
     "dgtd_adamw_slice_bytes": [],
     "dgtd_adamw_step": [_P, _P, _P, _P, _P, _I, _F, _F, _F, _I, _F, _P],
     "dgtd_sod_metrics_ws_bytes": [_I, _I, _I],
-    "dgtd_sod_metrics_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],
+    "dgtd_sod_metrics_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
 }
 _RESTYPES = {"dgtd_last_error": c_char_p, "dgtd_launch_count": c_int64, "dgtd_sod_metrics_ws_bytes": c_int64}
 

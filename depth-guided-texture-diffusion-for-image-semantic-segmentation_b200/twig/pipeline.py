@@ -23,19 +23,23 @@ class HostPipeline:
     round-robin.  Yields (index, host_tensor, done_event); the host tensor is valid after
     done_event.synchronize()."""
 
-    def __init__(self, enc: nn.Module, dec: nn.Module, precision: Optional[str] = None,
-                 want_embedding3: bool = False, device: Optional[torch.device] = None):
+    def __init__(self, enc: Optional[nn.Module], dec: Optional[nn.Module], precision: Optional[str] = None,
+                 want_embedding3: bool = False, device: Optional[torch.device] = None,
+                 forward: Optional[Callable] = None):
+        """`forward(*device_tensors) -> tuple` replaces the hot-path call (e.g. the whole model in predict mode
+        followed by the metric kernels); a batch may then be any tuple of pinned host tensors."""
         self.enc, self.dec, self.precision, self.want_e3 = enc, dec, precision, want_embedding3
+        self.forward = forward
         self.device = device or next(enc.parameters()).device
         self.copy_stream = torch.cuda.Stream(self.device)
         self.out_stream = torch.cuda.Stream(self.device)
         self._bufs = None
 
-    def _buffers(self, image_h: torch.Tensor, depth_h: torch.Tensor):
-        key = (tuple(image_h.shape), tuple(depth_h.shape), image_h.dtype, depth_h.dtype)
+    def _buffers(self, *host: torch.Tensor):
+        key = tuple((tuple(t.shape), t.dtype) for t in host)
         if self._bufs is None or self._bufs[0] != key:
             mk = lambda t: torch.empty(t.shape, device=self.device, dtype=t.dtype)
-            self._bufs = (key, [(mk(image_h), mk(depth_h)) for _ in range(2)],
+            self._bufs = (key, [tuple(mk(t) for t in host) for _ in range(2)],
                           [torch.cuda.Event() for _ in range(2)],    # H2D of slot done
                           [torch.cuda.Event() for _ in range(2)])    # compute finished reading slot
         return self._bufs[1], self._bufs[2], self._bufs[3]
@@ -54,8 +58,8 @@ class HostPipeline:
             with torch.cuda.stream(self.copy_stream):
                 if used[slot]:
                     self.copy_stream.wait_event(free[slot])
-                bufs[slot][0].copy_(pair[0], non_blocking=True)
-                bufs[slot][1].copy_(pair[1], non_blocking=True)
+                for dst, src in zip(bufs[slot], pair):
+                    dst.copy_(src, non_blocking=True)
                 ready[slot].record(self.copy_stream)
             used[slot] = True
 
@@ -67,8 +71,11 @@ class HostPipeline:
             if nxt is not None:
                 submit(slot ^ 1, nxt)                      # overlaps with the compute of batch i
             compute.wait_event(ready[slot])
-            out = TD.texture_prompts(self.enc, self.dec, bufs[slot][0], bufs[slot][1], precision=self.precision,
-                                     want_embedding3=self.want_e3)
+            if self.forward is not None:
+                out = self.forward(*bufs[slot])
+            else:
+                out = TD.texture_prompts(self.enc, self.dec, bufs[slot][0], bufs[slot][1], precision=self.precision,
+                                         want_embedding3=self.want_e3)
             free[slot].record(compute)
             res = select(*out)
             computed = torch.cuda.Event()

@@ -362,14 +362,17 @@ int dgtd_conv3x3_tc_fwd(const void* x, const void* w, const float* bias, float* 
 /* `output.sigmoid()` of the predict mode (cod.py:212,217) */
 int dgtd_sigmoid_fwd(const float* x, float* out, int64_t n, dgtd_stream_t stream);
 
-/* ---- evaluation metrics (twig/metric/MAE.py:18-36, Smeasure.py:18-36 + pysodmetrics 1.3.1) ----
+/* ---- evaluation metrics (twig/metric/{MAE,Smeasure,Fmeasure,Emeasure}.py:18-36 + pysodmetrics
+ * 1.3.1) -- the four evaluators of config/cod.yml:123-128 / sod.yml:85-89.
  * pred, gt (B,1,H,W) fp32 in [0,1] as the `predict` mode returns them (cod.py:217).  Quantises both like the
  * wrappers do (`(x * 255).astype(np.uint8)`, gt > 128), min-max normalises the prediction per image and writes
- * out[b] = {MAE, S-measure (alpha = 0.5)} in float64, from exact integer moments (bit-stable).  ws: 256-byte
- * aligned scratch of dgtd_sod_metrics_ws_bytes(B, H, W). */
+ * out[b] = {MAE, S-measure (alpha = 0.5)} in float64, from exact integer moments (bit-stable).  curves (nullable):
+ * (B, 2, 256) float64 = per image the changeable F-measure (beta^2 = 0.3) and the E-measure at the 256 thresholds
+ * (entry i = threshold 255 - i, the library's order), from exact fg / bg histograms of the re-quantised prediction.
+ * ws: 256-byte aligned scratch of dgtd_sod_metrics_ws_bytes(B, H, W). */
 int64_t dgtd_sod_metrics_ws_bytes(int B, int H, int W);
-int dgtd_sod_metrics_fwd(const float* pred, const float* gt, void* ws, double* out, int B, int H, int W,
-                         dgtd_stream_t stream);
+int dgtd_sod_metrics_fwd(const float* pred, const float* gt, void* ws, double* out, double* curves, int B, int H,
+                         int W, dgtd_stream_t stream);
 
 /* ---- optimizer step of the training configuration (config/sod.yml:56-76; torch.optim.AdamW semantics) ----------
  * One launch over flat fp32 buffers p, g, m, v (the hot path's gradients already live in one flat buffer,

@@ -11,6 +11,8 @@ float64 and anchors on the reference's own call sites:
                                   evaluator.step per image -> the batch records the evaluator's RUNNING mean
                                   over all images seen so far; compute_metrics = mean of those records
   twig/metric/MAE.py:18-36        the same wrapper around the MAE evaluator
+  twig/metric/Fmeasure.py:18-36   `get_results()["fm"]["curve"].max()`: max over the 256 thresholds of the mean
+  twig/metric/Emeasure.py:18-36   changeable F / E curve over all images seen so far, recorded per batch
 
 **Parity unpinned**: the reference holds no golden vectors for the metrics and the library cannot be run here;
 tests/test_oracle_metrics.py pins this restatement on hand-computable cases only (empty / full ground truth,
@@ -96,6 +98,81 @@ def smeasure_one(pred_u8: np.ndarray, gt_u8: np.ndarray, alpha: float = 0.5) -> 
     if y == 1:
         return float(np.mean(pred))
     return max(0.0, alpha * _object(pred, gt) + (1 - alpha) * _region(pred, gt))
+
+
+BETA = 0.3
+
+
+def _cum_hists(pred: np.ndarray, gt: np.ndarray):
+    """`cal_pr` / `cal_em_with_cumsumhistogram`: the normalised prediction is re-quantised to uint8 and the
+    foreground / background counts at the 256 thresholds are flipped cumulative histograms
+    (entry i = number of pixels with value >= 255 - i)."""
+    q = (pred * 255).astype(np.uint8)
+    bins = np.linspace(0, 256, 257)
+    fg_hist, _ = np.histogram(q[gt], bins=bins)
+    bg_hist, _ = np.histogram(q[~gt], bins=bins)
+    return np.cumsum(np.flip(fg_hist)), np.cumsum(np.flip(bg_hist))
+
+
+def fmeasure_curve_one(pred_u8: np.ndarray, gt_u8: np.ndarray, beta: float = BETA) -> np.ndarray:
+    """pysodmetrics `Fmeasure.cal_pr` -> changeable F-measure at the 256 thresholds (beta^2 = 0.3)."""
+    pred, gt = prepare(pred_u8, gt_u8)
+    fg_w, bg_w = _cum_hists(pred, gt)
+    tps = fg_w
+    ps = fg_w + bg_w
+    ps = np.where(ps == 0, 1, ps)
+    t = max(np.count_nonzero(gt), 1)
+    precisions = tps / ps
+    recalls = tps / t
+    numerator = (1 + beta) * precisions * recalls
+    denominator = np.where(numerator == 0, 1, beta * precisions + recalls)
+    return numerator / denominator
+
+
+def emeasure_curve_one(pred_u8: np.ndarray, gt_u8: np.ndarray) -> np.ndarray:
+    """pysodmetrics `Emeasure.cal_em_with_cumsumhistogram`: enhanced-alignment measure at the 256 thresholds."""
+    pred, gt = prepare(pred_u8, gt_u8)
+    size = gt.shape[0] * gt.shape[1]
+    gt_fg = np.count_nonzero(gt)
+    fg_fg, fg_bg = _cum_hists(pred, gt)
+    pred_fg = fg_fg + fg_bg
+    pred_bg = size - pred_fg
+    if gt_fg == 0:
+        total = pred_bg.astype(np.float64)
+    elif gt_fg == size:
+        total = pred_fg.astype(np.float64)
+    else:
+        bg_fg = gt_fg - fg_fg
+        bg_bg = pred_bg - bg_fg
+        mean_pred = pred_fg / size
+        mean_gt = gt_fg / size
+        combos = [(1 - mean_pred, 1 - mean_gt), (1 - mean_pred, 0 - mean_gt),
+                  (0 - mean_pred, 1 - mean_gt), (0 - mean_pred, 0 - mean_gt)]
+        total = np.zeros(256, np.float64)
+        parts = np.empty((4, 256), np.float64)
+        for i, (numel, (a, b)) in enumerate(zip([fg_fg, fg_bg, bg_fg, bg_bg], combos)):
+            align = 2 * (a * b) / (a ** 2 + b ** 2 + EPS)
+            parts[i] = (align + 1) ** 2 / 4 * numel
+        total = parts.sum(axis=0)
+    return total / (size - 1 + EPS)
+
+
+class RunningCurveMetric:
+    """Fmeasure.py:18-36 / Emeasure.py:18-36: per batch record max over thresholds of the MEAN curve over all
+    images seen so far (`get_results()[..]["curve"].max()`); compute_metrics = mean of the records."""
+
+    def __init__(self, fn):
+        self.fn = fn
+        self.curves: List[np.ndarray] = []
+        self.results: List[float] = []
+
+    def process(self, pred, gt) -> None:
+        for p, g in zip(quantise(pred), quantise(gt)):
+            self.curves.append(self.fn(p, g))
+        self.results.append(float(np.mean(np.array(self.curves, dtype=np.float64), axis=0).max()))
+
+    def compute_metrics(self) -> float:
+        return sum(self.results) / len(self.results)
 
 
 def quantise(t) -> np.ndarray:

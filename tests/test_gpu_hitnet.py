@@ -294,3 +294,36 @@ def test_graphed_predict_is_bit_identical_to_the_eager_forward():
         got1 = run(image.cuda(), depth.cuda()).clone()
         _, want1 = m.hitnet.predict_logits(image.cuda(), depth.cuda(), (128, 128))
         assert torch.equal(got1, want1) and not torch.equal(got1, got)
+
+
+def test_host_pipeline_with_the_full_model_and_metrics():
+    """twig/pipeline.py with a `forward` callable: pinned image + depth + label in, per-image (MAE, S-measure) out,
+    equal to the direct calls batch by batch."""
+    common.package()
+    from dgtd_b200.twig.metric import sod_metrics
+    from dgtd_b200.twig.model import hitnet
+    from dgtd_b200.twig.model.texture_diffuser import set_precision
+    from dgtd_b200.twig.pipeline import HostPipeline
+    m = hitnet.cod(binary_thresh=0.2).eval()
+    common.hitnet_fixture_params_(m.hitnet, seed=0)
+    m = m.cuda()
+    set_precision(m, "bf16")
+    batches = []
+    for seed in range(3):
+        image, depth = common.synthetic_inputs(2, 128, seed=30 + seed)
+        label = (torch.rand(2, 1, 128, 128, generator=torch.Generator().manual_seed(seed)) > 0.6).float()
+        batches.append(tuple(t.pin_memory() for t in (image, depth, label)))
+
+    def fwd(im, dp, lb):
+        prob, _ = m(None, im, lb, dp, mode="predict")
+        return (sod_metrics(prob, lb),)
+    outs = [torch.empty(2, 2, dtype=torch.float64).pin_memory() for _ in range(2)]
+    pipe = HostPipeline(None, None, device=torch.device("cuda:0"), forward=fwd)
+    got = []
+    for i, host, done in pipe.run(iter(batches), lambda v: v, outs):
+        done.synchronize()
+        got.append(host.clone())
+    assert len(got) == 3
+    for (im, dp, lb), g in zip(batches, got):
+        want = fwd(im.cuda(), dp.cuda(), lb.cuda())[0].cpu()
+        assert torch.equal(g, want)

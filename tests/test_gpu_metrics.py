@@ -91,3 +91,58 @@ def test_bit_stable_across_batch_composition():
     a = sod_metrics(pred.cuda(), gt.cuda()).cpu()
     b = torch.cat([sod_metrics(pred[i:i + 1].cuda(), gt[i:i + 1].cuda()).cpu() for i in range(4)])
     assert torch.equal(a, b)
+
+
+def _oracle_curves(pred, gt):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return np.array([[M.fmeasure_curve_one(p, g), M.emeasure_curve_one(p, g)]
+                         for p, g in zip(M.quantise(pred.numpy()), M.quantise(gt.numpy()))])
+
+
+@pytest.mark.parametrize("shape", [(3, 64, 48), (2, 384, 384), (4, 37, 53)])
+def test_f_and_e_measure_curves_match_the_oracle(shape):
+    common.package()
+    from dgtd_b200.twig.metric import sod_metrics
+    B, H, W = shape
+    pred, gt = _blobs(B, H, W, seed=H * W)
+    vals, cur = sod_metrics(pred.cuda(), gt.cuda(), curves=True)
+    ref = _oracle_curves(pred, gt)
+    assert cur.shape == (B, 2, 256)
+    assert np.abs(cur.cpu().numpy() - ref).max() <= 1e-12
+    assert np.abs(vals.cpu().numpy() - _oracle(pred, gt)).max() <= 1e-12
+
+
+def test_curve_edge_cases_and_requantisation():
+    """Empty / full ground truth, constant prediction, perfect / inverted prediction, and narrow prediction ranges
+    (where the float64 re-quantisation `(p * 255).astype(uint8)` lands on or next to integers)."""
+    common.package()
+    from dgtd_b200.twig.metric import sod_metrics
+    H, W = 24, 40
+    g = torch.Generator().manual_seed(0)
+    rnd = torch.rand(1, 1, H, W, generator=g)
+    blob = torch.zeros(1, 1, H, W)
+    blob[..., 6:18, 10:30] = 1.0
+    cases = [(rnd, torch.zeros(1, 1, H, W)), (rnd, torch.ones(1, 1, H, W)), (torch.full((1, 1, H, W), 0.2), blob),
+             (blob.clone(), blob), (1 - blob, blob)]
+    for lo, hi in ((0.1, 0.9), (0.3, 0.31), (0.0, 0.4), (0.52, 1.0), (0.2, 0.2 + 3 / 255), (0.11, 0.77)):
+        cases.append((lo + (hi - lo) * torch.rand(1, 1, H, W, generator=g), blob))
+    pred = torch.cat([c[0] for c in cases])
+    gt = torch.cat([c[1] for c in cases])
+    _, cur = sod_metrics(pred.cuda(), gt.cuda(), curves=True)
+    assert np.abs(cur.cpu().numpy() - _oracle_curves(pred, gt)).max() <= 1e-12
+
+
+def test_curve_wrappers_follow_the_reference_protocol():
+    common.package()
+    from dgtd_b200.twig.metric import Emeasure, Fmeasure
+    fm, em = Fmeasure(), Emeasure()
+    ofm, oem = M.RunningCurveMetric(M.fmeasure_curve_one), M.RunningCurveMetric(M.emeasure_curve_one)
+    for seed in range(3):
+        pred, gt = _blobs(2, 32, 32, seed)
+        for m in (fm, em):
+            m.process(None, (pred.cuda(), gt.cuda()))
+        ofm.process(pred.numpy(), gt.numpy())
+        oem.process(pred.numpy(), gt.numpy())
+    assert abs(fm.evaluate()["Fmeasure"] - ofm.compute_metrics()) < 1e-12
+    assert abs(em.evaluate()["Emeasure"] - oem.compute_metrics()) < 1e-12

@@ -93,3 +93,41 @@ def test_running_mean_quirk_of_the_wrappers():
         per_image += [M.mae_one(a, b) for a, b in zip(M.quantise(p), M.quantise(g))]
     running = [np.mean(per_image[:2]), np.mean(per_image[:4]), np.mean(per_image[:6])]
     assert abs(m.compute_metrics() - np.mean(running)) < 1e-15
+
+
+def test_fmeasure_and_emeasure_curves_on_hand_cases():
+    gt = np.zeros((10, 10), np.uint8)
+    gt[2:6, 3:8] = 255                                       # 20 foreground pixels
+    f = M.fmeasure_curve_one(gt.copy(), gt)
+    e = M.emeasure_curve_one(gt.copy(), gt)
+    # perfect binary prediction: every threshold 1..255 reproduces gt -> precision = recall = 1 -> F = 1; the
+    # threshold 0 (last entry: value >= 0) marks everything foreground -> precision 0.2
+    assert np.allclose(f[:255], 1.0) and abs(f[255] - 1.3 * 0.2 / (0.3 * 0.2 + 1.0)) < 1e-12
+    # E-measure of a perfectly aligned map: every pixel scores 1 -> size / (size - 1)
+    assert np.allclose(e[:255], 100 / 99.0)
+    # inverted prediction: no true positives at thresholds > 0 -> F = 0
+    fi = M.fmeasure_curve_one(255 - gt, gt)
+    assert np.allclose(fi[:255], 0.0)
+    # empty ground truth: E counts the predicted background
+    rng = np.random.default_rng(2)
+    pred = rng.integers(0, 256, (10, 10)).astype(np.uint8)
+    e0 = M.emeasure_curve_one(pred, np.zeros_like(pred))
+    p, _ = M.prepare(pred, np.zeros_like(pred))
+    q = (p * 255).astype(np.uint8)
+    want = np.array([(q < 255 - i).sum() for i in range(256)]) / (100 - 1 + M.EPS)
+    assert np.allclose(e0, want)
+    # a threshold-by-threshold brute force of both curves on random data
+    gtr = (rng.random((12, 9)) > 0.6).astype(np.uint8) * 255
+    pr = rng.integers(0, 256, (12, 9)).astype(np.uint8)
+    p, g = M.prepare(pr, gtr)
+    q = (p * 255).astype(np.uint8)
+    fc, ec = M.fmeasure_curve_one(pr, gtr), M.emeasure_curve_one(pr, gtr)
+    for i in (0, 17, 128, 200, 255):
+        b = q >= 255 - i
+        tp = (b & g).sum()
+        prec, rec = tp / max(b.sum(), 1), tp / max(g.sum(), 1)
+        num = 1.3 * prec * rec
+        assert abs(fc[i] - (num / (0.3 * prec + rec) if num else 0.0)) < 1e-12
+        a, c = b - b.mean(), g - g.mean()
+        align = 2 * a * c / (a * a + c * c + M.EPS)
+        assert abs(ec[i] - ((align + 1) ** 2 / 4).sum() / (g.size - 1 + M.EPS)) < 1e-9

@@ -327,3 +327,89 @@ def test_host_pipeline_with_the_full_model_and_metrics():
     for (im, dp, lb), g in zip(batches, got):
         want = fwd(im.cuda(), dp.cuda(), lb.cuda())[0].cpu()
         assert torch.equal(g, want)
+
+
+# ---- randomized shape sweeps (hypothesis), oracle = float64 torch on the same inputs ---------------------------
+from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
+
+_SET = dict(max_examples=12, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+
+
+@settings(**_SET)
+@given(B=st.integers(1, 3), cin=st.sampled_from([4, 8, 32, 96]), cout=st.sampled_from([4, 32, 64, 96]),
+       h=st.integers(3, 19), w=st.integers(3, 21), cfg=st.sampled_from([(1, 1, 0), (3, 1, 1), (8, 4, 2), (3, 2, 1)]),
+       pre=st.booleans(), res=st.booleans(), seed=st.integers(0, 1000))
+def test_sweep_conv_affine(B, cin, cout, h, w, cfg, pre, res, seed):
+    """fp32 implicit GEMM with folded-BN / PReLU / residual epilogue, strided output slice."""
+    common.package()
+    from dgtd_b200.twig.ops.functions import hitnet_func as HF
+    k, s, p = cfg
+    if h + 2 * p < k or w + 2 * p < k:
+        return
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / (k * cin ** 0.5)
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g)
+    slope = torch.tensor([0.25])
+    ref = torch.nn.functional.conv2d(x.double(), wt.double(), None, stride=s, padding=p)
+    ref = ref * scale.double()[None, :, None, None] + shift.double()[None, :, None, None]
+    if pre:
+        ref = torch.where(ref >= 0, ref, 0.25 * ref)
+    oh, ow = ref.shape[2], ref.shape[3]
+    r = torch.randn(B, oh, ow, cout, generator=g)
+    if res:
+        ref = ref + r.permute(0, 3, 1, 2).double()
+    wide = torch.zeros(B, oh, ow, cout + 8, device="cuda")
+    HF.conv_affine(x.permute(0, 2, 3, 1).contiguous().cuda(), wt.permute(0, 2, 3, 1).reshape(cout, -1).contiguous().cuda(),
+                   (oh, ow), k, s, -p, scale=scale.cuda(), shift=shift.cuda(), prelu=slope.cuda() if pre else None,
+                   residual=r.cuda() if res else None, out=wide[..., 4:4 + cout])
+    assert rel(wide[..., 4:4 + cout].cpu().permute(0, 3, 1, 2), ref) <= 1e-5
+    assert float(wide[..., :4].abs().max()) == 0 and float(wide[..., 4 + cout:].abs().max()) == 0
+
+
+@settings(**_SET)
+@given(B=st.integers(1, 4), C=st.sampled_from([4, 32, 64, 96]), h=st.integers(1, 40), w=st.integers(1, 40),
+       red=st.sampled_from([2, 4, 16]), seed=st.integers(0, 1000))
+def test_sweep_gates_and_gated_sum(B, C, h, w, red, seed):
+    """channel sums -> gate MLP -> res * gate * scalar + x, against float64."""
+    common.package()
+    from dgtd_b200.twig.ops.functions import hitnet_func as HF
+    g = torch.Generator().manual_seed(seed)
+    cr = max(1, C // red)
+    a, b_ = torch.randn(B, h, w, C, generator=g), torch.randn(B, h, w, C, generator=g)
+    w1, w2 = torch.randn(cr, C, generator=g), torch.randn(C, cr, generator=g)
+    w3 = torch.randn(1, cr, generator=g)
+    part, hw = HF.channel_sums(a.cuda())
+    gate = HF.channel_gate(part, hw, w1.cuda(), w2.cuda())
+    scal = HF.channel_gate(part, hw, w1.cuda(), w3.cuda())
+    mean = a.double().mean(dim=(1, 2))
+    hid = torch.relu(mean @ w1.double().t())
+    gref, sref = torch.sigmoid(hid @ w2.double().t()), torch.sigmoid(hid @ w3.double().t())
+    assert rel(gate.cpu(), gref) <= 1e-5 and rel(scal.cpu(), sref) <= 1e-5
+    out = HF.gated_sum(a.cuda(), ga=gate, sa=scal.reshape(-1), b=b_.cuda())
+    ref = a.double() * gref[:, None, None, :] * sref[:, None, None, :] + b_.double()
+    assert rel(out.cpu(), ref) <= 1e-5
+
+
+@settings(**_SET)
+@given(B=st.integers(1, 3), h=st.integers(1, 50), w=st.integers(2, 70), thr=st.floats(0.05, 0.95),
+       seed=st.integers(0, 1000))
+def test_sweep_metrics(B, h, w, thr, seed):
+    """All four evaluators on random maps of random size against the numpy restatement."""
+    import warnings
+    from oracle import metrics_ref as M
+    common.package()
+    from dgtd_b200.twig.metric import sod_metrics
+    if h < 2:
+        h = 2
+    g = torch.Generator().manual_seed(seed)
+    pred = torch.rand(B, 1, h, w, generator=g)
+    gt = (torch.rand(B, 1, h, w, generator=g) > thr).float()
+    vals, cur = sod_metrics(pred.cuda(), gt.cuda(), curves=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for i, (p, q) in enumerate(zip(M.quantise(pred.numpy()), M.quantise(gt.numpy()))):
+            assert abs(float(vals[i, 0]) - M.mae_one(p, q)) <= 1e-12
+            assert abs(float(vals[i, 1]) - M.smeasure_one(p, q)) <= 1e-12
+            assert np.abs(cur[i, 0].cpu().numpy() - M.fmeasure_curve_one(p, q)).max() <= 1e-12
+            assert np.abs(cur[i, 1].cpu().numpy() - M.emeasure_curve_one(p, q)).max() <= 1e-12

@@ -413,3 +413,19 @@ def test_sweep_metrics(B, h, w, thr, seed):
             assert abs(float(vals[i, 1]) - M.smeasure_one(p, q)) <= 1e-12
             assert np.abs(cur[i, 0].cpu().numpy() - M.fmeasure_curve_one(p, q)).max() <= 1e-12
             assert np.abs(cur[i, 1].cpu().numpy() - M.emeasure_curve_one(p, q)).max() <= 1e-12
+
+
+def test_highres_768_full_model_modes_agree(net):
+    """BASELINE configs[4] geometry (768 x 768: 192 / 96 / 48 / 24 token grids, 576 reduced keys): the predict path
+    runs end to end and the bf16 tensor-core mode stays within the bf16 tolerance of the exact fp32 mode."""
+    from dgtd_b200.twig.model.texture_diffuser import set_precision
+    image, depth = common.synthetic_inputs(1, 768, seed=5)
+    out = {}
+    for precision in ("fp32", "bf16"):
+        set_precision(net, precision)
+        try:
+            _, out[precision] = net.predict_logits(image.cuda(), depth.cuda(), (768, 768))
+        finally:
+            set_precision(net, None)
+    assert tuple(out["fp32"].shape) == (1, 1, 768, 768) and torch.isfinite(out["fp32"]).all()
+    assert rel(out["bf16"].cpu(), out["fp32"].cpu()) <= 6e-2

@@ -263,12 +263,12 @@ class Hitnet(nn.Module):
 
     @torch.no_grad()
     def decode(self, feats: Sequence[torch.Tensor], iterations: int = 4, want_stage_preds: bool = True
-               ) -> Tuple[List[torch.Tensor], torch.Tensor, torch.Tensor]:
+               ) -> Tuple[List[torch.Tensor], Optional[torch.Tensor], Tuple[torch.Tensor, torch.Tensor]]:
         """cod.py:752-805 on the four NHWC backbone maps.
 
-        Returns (stage predictions [(B,1,8h,8w)] (empty when not wanted), SAM prediction (B,1,8h,8w),
-        low-resolution sum `out_CFM(cfm_last) + out_SAM(sam)` (B,1,h,w) whose x8 up-sample is the predict logit map,
-        bilinear interpolation being linear)."""
+        Returns (stage predictions [(B,1,8h,8w)] (empty when not wanted), SAM prediction (B,1,8h,8w) (None when not
+        wanted), (out_CFM(cfm_last), out_SAM(sam)) on the stride-8 grid (B,1,h,w): the x8 up-sample of their sum is
+        the predict logit map, bilinear interpolation being linear)."""
         _no_training(self)
         x1, x2, x3, x4 = feats
         B, ch = x1.shape[0], self.channel

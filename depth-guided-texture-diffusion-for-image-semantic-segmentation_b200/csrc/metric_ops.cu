@@ -96,9 +96,9 @@ __global__ void __launch_bounds__(256) metric_quantise_kernel(const float* __res
 }
 
 // per image: min-max normalisation constants (`_prepare_data`) and the centroid split (`Smeasure.centroid`)
-__global__ void metric_info_kernel(MetricWs m, int nchunks, int H, int W) {
+__global__ void metric_info_kernel(MetricWs m, int nchunks, int B, int H, int W) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= gridDim.x * blockDim.x) return;
+  if (b >= B) return;
   const long long* p = m.part1 + (int64_t)b * nchunks * NS1;
   long long a = 255, c = 0, n = 0, sr = 0, sc = 0;
   for (int k = 0; k < nchunks; ++k) {
@@ -336,7 +336,7 @@ int dgtd_sod_metrics_fwd(const float* pred, const float* gt, void* ws, double* o
   const int nchunks = cdiv(H, MROWS);
   metric_quantise_kernel<<<dim3(nchunks, B), 256, 0, s>>>(pred, gt, m, H, W);
   DGTD_LAUNCH_CHECK("sod_metrics(quantise)");
-  metric_info_kernel<<<B, 1, 0, s>>>(m, nchunks, H, W);
+  metric_info_kernel<<<cdiv(B, 32), 32, 0, s>>>(m, nchunks, B, H, W);
   DGTD_LAUNCH_CHECK("sod_metrics(info)");
   metric_moments_kernel<<<dim3(nchunks, B), 256, 0, s>>>(m, H, W);
   DGTD_LAUNCH_CHECK("sod_metrics(moments)");

@@ -132,7 +132,7 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&f)[8]) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 dwconv3_gelu_kernel(const T* __restrict__ x, const float* __restrict__ wT, const float* __restrict__ bias,
-                    T* __restrict__ out, int h, int w, int C, int64_t groups_total) {
+                    T* __restrict__ out, int h, int w, int C) {
   constexpr int PX = 4;
   __shared__ __align__(16) float ws[10][64];   // 9 taps + bias
   const int c0 = blockIdx.x * 64;
@@ -153,7 +153,6 @@ dwconv3_gelu_kernel(const T* __restrict__ x, const float* __restrict__ wT, const
   const int oy = (t % patches_y) * 8 + (g >> 2);
   const int b = t / patches_y;
   if (ox0 >= w || oy >= h || c >= C) return;
-  (void)groups_total;
   // packed f32x2 arithmetic: 8 channels = 4 register pairs (half the FMA / GELU issue slots)
   uint64_t acc[PX][4];
   {
@@ -559,9 +558,9 @@ int dgtd_dwconv3_gelu_fwd(const void* x, const float* wT, const float* bias, voi
   dim3 blocks(cdiv(C, 64), (unsigned)total);
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == DGTD_BF16)
-    dwconv3_gelu_kernel<<<blocks, 256, 0, s>>>((const __nv_bfloat16*)x, wT, bias, (__nv_bfloat16*)out, h, w, C, total);
+    dwconv3_gelu_kernel<<<blocks, 256, 0, s>>>((const __nv_bfloat16*)x, wT, bias, (__nv_bfloat16*)out, h, w, C);
   else if (dtype == DGTD_F32)
-    dwconv3_gelu_kernel<<<blocks, 256, 0, s>>>((const float*)x, wT, bias, (float*)out, h, w, C, total);
+    dwconv3_gelu_kernel<<<blocks, 256, 0, s>>>((const float*)x, wT, bias, (float*)out, h, w, C);
   else DGTD_CHECK_ARG(false, "dwconv3_gelu: bad dtype %d", dtype);
   DGTD_LAUNCH_CHECK("dwconv3_gelu");
   return 0;

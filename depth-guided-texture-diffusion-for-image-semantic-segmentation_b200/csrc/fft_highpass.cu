@@ -38,13 +38,20 @@ __global__ void projector_fill_kernel(float* __restrict__ P, int n) {
 }
 
 // coef[z] = {Qcc, Qcs, Qsc, Qss} / (H*W),  Qcs = sum_{b,c} cos_h[b] x[b,c] sin_w[c], ...
+// Two levels so that the reduction fills the GPU at any batch (one CTA per plane left 3 CTAs at batch 1 and two
+// uneven waves at batch 64: 237 us for 113 MB): COEF_CHUNKS CTAs per plane write partial sums, a second kernel adds
+// them in a fixed order (bit-stable) and normalises.
+constexpr int COEF_CHUNKS = 16;
 __global__ void __launch_bounds__(256)
-imag_coef_kernel(const float* __restrict__ x, const float* __restrict__ sc_h,
-                 const float* __restrict__ sc_w, float* __restrict__ coef, int H, int W) {
+imag_coef_partial_kernel(const float* __restrict__ x, const float* __restrict__ sc_h, const float* __restrict__ sc_w,
+                         float* __restrict__ partial, int H, int W) {
   __shared__ float red[4][8];
-  const float* p = x + (int64_t)blockIdx.x * H * W;
+  const int plane = blockIdx.y, chunk = blockIdx.x;
+  const int total = H * W, len = (total + COEF_CHUNKS - 1) / COEF_CHUNKS;
+  const int i0 = chunk * len, i1 = min(total, i0 + len);
+  const float* p = x + (int64_t)plane * total;
   float q[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int i = threadIdx.x; i < H * W; i += 256) {
+  for (int i = i0 + threadIdx.x; i < i1; i += 256) {
     int r = i / W, c = i - r * W;
     float v = p[i];
     float sh = sc_h[r], ch = sc_h[H + r], sw = sc_w[c], cw = sc_w[W + c];
@@ -63,8 +70,27 @@ imag_coef_kernel(const float* __restrict__ x, const float* __restrict__ sc_h,
   if (threadIdx.x < 4) {
     float s = 0.f;
     for (int i = 0; i < 8; ++i) s += red[threadIdx.x][i];
-    coef[blockIdx.x * 4 + threadIdx.x] = s / ((float)H * (float)W);
+    partial[((int64_t)plane * COEF_CHUNKS + chunk) * 4 + threadIdx.x] = s;
   }
+}
+
+__global__ void imag_coef_final_kernel(const float* __restrict__ partial, float* __restrict__ coef, int n, float hw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // i = plane * 4 + j
+  if (i >= n) return;
+  const int plane = i >> 2, j = i & 3;
+  float s = 0.f;
+  for (int k = 0; k < COEF_CHUNKS; ++k) s += partial[((int64_t)plane * COEF_CHUNKS + k) * 4 + j];
+  coef[i] = s / hw;
+}
+
+// `scratch`: >= planes * COEF_CHUNKS * 4 floats that nothing reads before the next kernel of the caller overwrites it
+static int launch_imag_coef(const float* x, const float* sc_h, const float* sc_w, float* scratch, float* coef, int planes,
+                            int H, int W, cudaStream_t s) {
+  imag_coef_partial_kernel<<<dim3(COEF_CHUNKS, planes), 256, 0, s>>>(x, sc_h, sc_w, scratch, H, W);
+  DGTD_LAUNCH_CHECK("fft_highpass.coef(partial)");
+  imag_coef_final_kernel<<<cdiv(planes * 4, 256), 256, 0, s>>>(scratch, coef, planes * 4, (float)H * (float)W);
+  DGTD_LAUNCH_CHECK("fft_highpass.coef");
+  return 0;
 }
 
 struct EpiStore {
@@ -190,8 +216,10 @@ int dgtd_fft_highpass_fwd(const float* x, const float* Ph, const float* Pw, cons
                  "fft_highpass: H and W must be multiples of 4 (got %dx%d)", H, W);
   DGTD_CHECK_ARG(planes <= 65535, "fft_highpass: too many planes");
   cudaStream_t s = (cudaStream_t)stream;
-  imag_coef_kernel<<<planes, 256, 0, s>>>(x, sc_h, sc_w, coef, H, W);
-  DGTD_LAUNCH_CHECK("fft_highpass.coef");
+  {  // partial sums live in `tmp` until the first GEMM overwrites it (H*W >= 64 floats per plane)
+    int rc0 = launch_imag_coef(x, sc_h, sc_w, tmp, coef, planes, H, W, s);
+    if (rc0) return rc0;
+  }
   {  // tmp = x . A_w^T over all (plane,row) rows at once
     RowMajorLoader al{x, W, 0, planes * H, W};
     RowMajorLoader bl{Pw, W, 0, W, W};
@@ -223,8 +251,10 @@ int dgtd_fft_highpass_tc_fwd(const float* x, const void* Ph_hi, const void* Ph_l
   const int64_t n = (int64_t)planes * H * W;
   __nv_bfloat16* hi = (__nv_bfloat16*)ws_hi;
   __nv_bfloat16* lo = (__nv_bfloat16*)ws_lo;
-  imag_coef_kernel<<<planes, 256, 0, s>>>(x, sc_h, sc_w, coef, H, W);
-  DGTD_LAUNCH_CHECK("fft_highpass_tc.coef");
+  {  // partial sums live in ws_f32 until the first GEMM overwrites it
+    int rc0 = launch_imag_coef(x, sc_h, sc_w, ws_f32, coef, planes, H, W, s);
+    if (rc0) return rc0;
+  }
   split_bf16_kernel<<<(unsigned)cdiv(n / 4, (int64_t)256), 256, 0, s>>>(x, hi, lo, n / 4);
   DGTD_LAUNCH_CHECK("fft_highpass_tc.split");
   int rc;

@@ -227,6 +227,7 @@ def full_model_bench(TD, dev, world, rank, args, common, sharding, steps=5):
     dec_ms, dec_launches = timed(lambda: net.hitnet.decode(feats, want_stage_preds=False), steps)
     prob, _ = net(None, image, label, depth, mode="predict")
     met_ms, _ = timed(lambda: sod_metrics(prob, label), 10)
+    met4_ms, _ = timed(lambda: sod_metrics(prob, label, curves=True), 10)
     vals = sod_metrics(prob, label).mean(0).tolist()
     # BASELINE configs[4] for the whole model: 8 images of 768^2 sharded by image, no collective
     hi = None
@@ -246,11 +247,12 @@ def full_model_bench(TD, dev, world, rank, args, common, sharding, steps=5):
         from dgtd_b200.twig.pipeline import HostPipeline
         nb = steps + 2
         host = [tuple(t.cpu().pin_memory() for t in (image, depth, label)) for _ in range(2)]
-        outs = [torch.empty(B, 2, dtype=torch.float64).pin_memory() for _ in range(2)]
+        outs = [torch.empty(B, 2 + 2 * 256, dtype=torch.float64).pin_memory() for _ in range(2)]
 
-        def fwd(im, dp, lb):
+        def fwd(im, dp, lb):      # all four evaluators of cod.yml:123-128: (MAE, S) + the F / E curves per image
             prob_, _ = net(None, im, lb, dp, mode="predict")
-            return (sod_metrics(prob_, lb),)
+            vals_, cur_ = sod_metrics(prob_, lb, curves=True)
+            return (torch.cat([vals_, cur_.reshape(B, -1)], dim=1),)
         pipe = HostPipeline(None, None, device=dev, forward=fwd)
         for _ in pipe.run((host[i & 1] for i in range(2)), lambda m: m, outs):
             pass
@@ -264,7 +266,7 @@ def full_model_bench(TD, dev, world, rank, args, common, sharding, steps=5):
         e2e = {"value": world * B * nb / dt, "unit": "images/s",
                "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in host[0])),
                "d2h_bytes_per_step": int(outs[0].numel() * 8),
-               "what": "pinned host image + depth + label -> predict -> MAE / S-measure -> 16 bytes per image back"}
+               "what": "pinned host image + depth + label -> predict -> MAE / S-measure / F- and E-measure curves -> 4 KB per image back"}
     except Exception as e:  # noqa: BLE001
         e2e = {"error": f"{type(e).__name__}: {e}"[:300]}
     # small-batch serving latency: eager (Python-issued launches) against the captured predict step
@@ -311,7 +313,7 @@ def full_model_bench(TD, dev, world, rank, args, common, sharding, steps=5):
             "launches_per_step": int(launches),
             "decoder_ms": dec_ms, "decoder_launches": int(dec_launches),
             "decoder_gflop_per_image": flops / 1e9, "decoder_tflops": flops * B / (dec_ms * 1e-3) / 1e12,
-            "metrics_ms": met_ms, "metrics_gbs": B * S * S * (8 + 2 + 2) / (met_ms * 1e-3) / 1e9,
+            "metrics_ms": met_ms, "metrics_all_four_ms": met4_ms, "metrics_gbs": B * S * S * (8 + 2 + 2) / (met_ms * 1e-3) / 1e9,
             "metrics_note": "MAE + S-measure of the batch: 8 B/pixel read + 2 B/pixel written in pass 1, 2 B/pixel read in pass 2",
             "mae_smeasure_vs_random_label": vals, "cpu_baseline": cpu_port, "latency_batch1": latency, "e2e": e2e, "highres_768": hi,
             "what": "cod.forward(mode='predict'): pvt_v2_b2 backbone with the texture prompts + Hitnet decoder "

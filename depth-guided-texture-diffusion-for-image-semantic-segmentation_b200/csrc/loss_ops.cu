@@ -121,6 +121,108 @@ __global__ void structure_loss_bwd_kernel(const float* __restrict__ p, const flo
 
 using namespace dgtd;
 
+
+// ---- SSIM constant of the training loss (cod.py:142-144, SSIM :316-351) ---------------------------------------
+// loss_3 = mean( clamp((1 - SSIM(x, y)) / 2, 0, 1) ), x = (embedding1 - min) / (max - min + 1e-8) with the min / max
+// taken over the WHOLE batch tensor (cod.py:143), y = the input image; 3x3 means over a reflection-padded window.
+// No parameter is upstream of it (embedding1 is the parameter-free FFT high-pass), so it has no backward.
+// Two fixed-order reduction levels (min/max, then the sum): bit-stable.
+namespace dgtd {
+constexpr int SSIM_THREADS = 256, SSIM_PER_CTA = 4096;
+
+__global__ void __launch_bounds__(SSIM_THREADS) minmax_partial_kernel(const float* __restrict__ x, int64_t n,
+                                                                      float* __restrict__ part) {
+  __shared__ float smin[8], smax[8];
+  float lo = INFINITY, hi = -INFINITY;
+  const int64_t i0 = (int64_t)blockIdx.x * SSIM_PER_CTA;
+  for (int64_t i = i0 + threadIdx.x; i < min(n, i0 + SSIM_PER_CTA); i += SSIM_THREADS) {
+    const float v = x[i];
+    lo = fminf(lo, v);
+    hi = fmaxf(hi, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { lo = fminf(lo, smin[w]); hi = fmaxf(hi, smax[w]); }
+    part[2 * blockIdx.x] = fminf(lo, smin[0]);
+    part[2 * blockIdx.x + 1] = fmaxf(hi, smax[0]);
+  }
+}
+
+__global__ void minmax_final_kernel(const float* __restrict__ part, int nblk, float* __restrict__ mm) {
+  __shared__ float smin[8], smax[8];
+  float lo = INFINITY, hi = -INFINITY;
+  for (int i = threadIdx.x; i < nblk; i += blockDim.x) { lo = fminf(lo, part[2 * i]); hi = fmaxf(hi, part[2 * i + 1]); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < 8; ++w) { lo = fminf(lo, smin[w]); hi = fmaxf(hi, smax[w]); }
+    mm[0] = lo;
+    mm[1] = hi;
+  }
+}
+
+__device__ __forceinline__ int reflect1(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
+
+__global__ void __launch_bounds__(SSIM_THREADS) ssim_partial_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                                    const float* __restrict__ mm, int H, int W, int64_t n,
+                                                                    float* __restrict__ part) {
+  __shared__ float red[8];
+  const float lo = mm[0], inv = 1.0f / (mm[1] - mm[0] + 1e-8f);
+  const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+  float acc = 0.f;
+  const int64_t i0 = (int64_t)blockIdx.x * SSIM_PER_CTA;
+  for (int64_t i = i0 + threadIdx.x; i < min(n, i0 + SSIM_PER_CTA); i += SSIM_THREADS) {
+    const int c = (int)(i % W);
+    const int64_t t = i / W;
+    const int r = (int)(t % H);
+    const int64_t plane = (t / H) * H * W;
+    float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int64_t row = plane + (int64_t)reflect1(r + dy, H) * W;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int64_t j = row + reflect1(c + dx, W);
+        const float a = (x[j] - lo) * inv, b = y[j];
+        sx += a; sy += b; sxx += a * a; syy += b * b; sxy += a * b;
+      }
+    }
+    const float mx = sx / 9.f, my = sy / 9.f;
+    const float vx = sxx / 9.f - mx * mx, vy = syy / 9.f - my * my, vxy = sxy / 9.f - mx * my;
+    const float num = (2.f * mx * my + C1) * (2.f * vxy + C2), den = (mx * mx + my * my + C1) * (vx + vy + C2);
+    acc += fminf(fmaxf((1.f - num / den) * 0.5f, 0.f), 1.f);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    part[blockIdx.x] = s;
+  }
+}
+
+__global__ void sum_final_kernel(const float* __restrict__ part, int nblk, float scale, float* __restrict__ out) {
+  // one thread: fixed order, double accumulation (nblk is a few thousand)
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < nblk; ++i) s += (double)part[i];
+    out[0] = (float)(s * (double)scale);
+  }
+}
+}  // namespace dgtd
+
 extern "C" {
 
 int dgtd_boundary_weight_fwd(const float* gt, float* weit, int planes, int H, int W, dgtd_stream_t stream) {
@@ -153,6 +255,30 @@ int dgtd_structure_loss_bwd(const float* preds, const float* gt, const float* we
   structure_loss_bwd_kernel<<<(unsigned)cdiv(total, (int64_t)256), 256, 0, (cudaStream_t)stream>>>(
       preds, gt, weit, sums, grad_out, dpreds, HW, planes, total);
   DGTD_LAUNCH_CHECK("structure_loss_bwd");
+  return 0;
+}
+
+
+int dgtd_ssim_loss_ws_floats(int64_t n) { return n > 0 ? (int)(3 * ((n + dgtd::SSIM_PER_CTA - 1) / dgtd::SSIM_PER_CTA) + 2) : 0; }
+
+int dgtd_ssim_loss_fwd(const float* emb1, const float* image, float* ws, float* out, int planes, int H, int W,
+                       dgtd_stream_t stream) {
+  DGTD_CHECK_ARG(emb1 && image && ws && out, "ssim_loss: null pointer");
+  DGTD_CHECK_ARG(planes > 0 && H >= 2 && W >= 2, "ssim_loss: bad shape (reflection padding needs H, W >= 2)");
+  const int64_t n = (int64_t)planes * H * W;
+  const int nblk = (int)((n + dgtd::SSIM_PER_CTA - 1) / dgtd::SSIM_PER_CTA);
+  cudaStream_t s = (cudaStream_t)stream;
+  float* part_mm = ws;                 // [nblk][2]
+  float* mm = ws + 2 * (int64_t)nblk;  // [2]
+  float* part_s = mm + 2;              // [nblk]
+  dgtd::minmax_partial_kernel<<<nblk, dgtd::SSIM_THREADS, 0, s>>>(emb1, n, part_mm);
+  DGTD_LAUNCH_CHECK("ssim_loss(minmax)");
+  dgtd::minmax_final_kernel<<<1, 256, 0, s>>>(part_mm, nblk, mm);
+  DGTD_LAUNCH_CHECK("ssim_loss(minmax final)");
+  dgtd::ssim_partial_kernel<<<nblk, dgtd::SSIM_THREADS, 0, s>>>(emb1, image, mm, H, W, n, part_s);
+  DGTD_LAUNCH_CHECK("ssim_loss(ssim)");
+  dgtd::sum_final_kernel<<<1, 32, 0, s>>>(part_s, nblk, 1.0f / (float)n, out);
+  DGTD_LAUNCH_CHECK("ssim_loss(sum)");
   return 0;
 }
 

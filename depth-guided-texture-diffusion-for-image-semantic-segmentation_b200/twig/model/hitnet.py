@@ -354,8 +354,8 @@ class cod(nn.Module):
     """cod.py:36-222 (the reference derives from mmengine's BaseModel; the runner is out of scope).
 
     `forward(raw, input, label, depth, mode)`: 'predict' -> (sigmoid(output), label) like cod.py:217 without the
-    PNG side effects; 'tensor' -> output logits; 'loss' -> {'loss': value} (forward value only, no autograd
-    graph through the decoder in this round; the SSIM constant of cod.py:143-145 is not included)."""
+    PNG side effects; 'tensor' -> output logits; 'loss' -> {'loss': loss_p1 + loss_P2 + loss_3} of cod.py:135-146
+    (forward value only: no autograd graph through the decoder in this round)."""
 
     def __init__(self, win_size=None, filter_ratio=None, using_depth=None, using_sam=None, finetune=None,
                  binary_thresh=None, pretrain_sam=None, head=None):
@@ -379,9 +379,9 @@ class cod(nn.Module):
                 return output
             return _sigmoid(output), label
         if mode == 'loss':
-            from .losses import deep_supervision_loss
-            _, P1, P2 = self.hitnet(input, depth)
-            return {'loss': deep_supervision_loss(P1, P2, label.float().contiguous())}
+            from .losses import total_loss
+            emb1, P1, P2 = self.hitnet(input, depth)
+            return {'loss': total_loss(emb1, P1, P2, input, label.float().contiguous())}
         raise NotImplementedError(f'Unsupported mode {mode}')
 
 

@@ -3,7 +3,8 @@
 `cal_loss(preds, gts)` has the reference's signature and value; `boundary_weight(gts)` exposes the
 label-only weight map so that a step computes it once for its five supervised maps
 (`deep_supervision_loss`).  The SSIM term of cod.py:142-144 has no gradient path to any parameter
-(embedding1 comes from the parameter-free FFT high-pass) and is not part of this module.
+(embedding1 comes from the parameter-free FFT high-pass): `ssim_constant(embedding1, image)` returns its value
+(forward only) and `total_loss` is the reference's `loss_p1 + loss_P2 + loss_3`.
 """
 from __future__ import annotations
 
@@ -16,7 +17,8 @@ from torch.autograd.function import once_differentiable
 from ..ops import capi
 from ..ops.capi import call, check_cuda, ptr, stream
 
-__all__ = ["boundary_weight", "cal_loss", "deep_supervision_loss", "StructureLossFunction"]
+__all__ = ["boundary_weight", "cal_loss", "deep_supervision_loss", "ssim_constant", "total_loss",
+           "StructureLossFunction"]
 
 
 def boundary_weight(gts: torch.Tensor) -> torch.Tensor:
@@ -70,3 +72,24 @@ def deep_supervision_loss(P1: Sequence[torch.Tensor], P2: torch.Tensor, label: t
         if it > 0:                      # it = 0 carries weight 0 in the reference
             loss = loss + (gamma * it) * cal_loss(out, label, weit)
     return loss
+
+
+@torch.no_grad()
+def ssim_constant(embedding1: torch.Tensor, image: torch.Tensor) -> torch.Tensor:
+    """cod.py:143-144: `ssim((e - e.min()) / (e.max() - e.min() + 1e-8), input)` with `SSIM` of cod.py:316-351.
+    Value only: nothing trainable is upstream of embedding1."""
+    e = embedding1.detach().contiguous().float()
+    y = image.detach().contiguous().float()
+    check_cuda(e, y)
+    assert e.shape == y.shape and e.dim() == 4, (tuple(e.shape), tuple(y.shape))
+    B, C, H, W = e.shape
+    ws = torch.empty(capi.load().dgtd_ssim_loss_ws_floats(e.numel()), device=e.device, dtype=torch.float32)
+    out = torch.empty(1, device=e.device, dtype=torch.float32)
+    call("dgtd_ssim_loss_fwd", ptr(e), ptr(y), ptr(ws), ptr(out), B * C, H, W, stream())
+    return out.reshape(())
+
+
+def total_loss(embedding1: torch.Tensor, P1: Sequence[torch.Tensor], P2: torch.Tensor, image: torch.Tensor,
+               label: torch.Tensor) -> torch.Tensor:
+    """cod.py:135-146: loss_p1 + loss_P2 + loss_3 (the SSIM constant enters the value, not the gradient)."""
+    return deep_supervision_loss(P1, P2, label) + ssim_constant(embedding1, image)

@@ -100,6 +100,8 @@ SIGNATURES = {
     "dgtd_cast_pad_act_fwd": [_P, _I, _P, _P, _L, _I, _I, _P],
     "dgtd_conv3x3_tc_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "dgtd_im2col_act_fwd": [_P, _I, _P, _P] + [_I] * 9 + [_P],
+    "dgtd_ssim_loss_ws_floats": [_L],
+    "dgtd_ssim_loss_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],
     "dgtd_adamw_slice_bytes": [],
     "dgtd_adamw_step": [_P, _P, _P, _P, _P, _I, _F, _F, _F, _I, _F, _P],
     "dgtd_sod_metrics_ws_bytes": [_I, _I, _I],

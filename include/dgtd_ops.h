@@ -316,6 +316,13 @@ int dgtd_structure_loss_fwd(const float* preds, const float* gt, const float* we
 int dgtd_structure_loss_bwd(const float* preds, const float* gt, const float* weit, const float* sums,
                             const float* grad_out, float* dpreds, int planes, int64_t HW, dgtd_stream_t stream);
 
+/* SSIM constant of the training loss (cod.py:142-144, SSIM :316-351): out[0] = mean(clamp((1 - SSIM(x, y)) / 2, 0, 1)),
+ * x = (emb1 - min) / (max - min + 1e-8) with min / max over the whole (planes, H, W) batch tensor, y = image; 3x3
+ * means over reflection-padded windows.  No backward (no parameter upstream).  ws: dgtd_ssim_loss_ws_floats(n). */
+int dgtd_ssim_loss_ws_floats(int64_t n);
+int dgtd_ssim_loss_fwd(const float* emb1, const float* image, float* ws, float* out, int planes, int H, int W,
+                       dgtd_stream_t stream);
+
 /* ---- Hitnet iterative decoder (cod.py:685-807), NHWC fp32, inference semantics -----------
  * BasicConv2d / CAB convs (cod.py:355-368, 434-451): out[m, n] = prelu(scale[n] * conv(x)[m, n] + shift[n])
  * + residual[m, n]; scale/shift = the folded eval-mode BatchNorm (nullable), prelu = the ONE shared slope of

@@ -46,3 +46,31 @@ def deep_supervision_loss(P1: Sequence[torch.Tensor], P2: torch.Tensor, label: t
     for it, out in enumerate(P1):
         loss = loss + (gamma * it) * structure_loss(out, label)
     return loss
+
+
+def ssim_constant(embedding1: torch.Tensor, image: torch.Tensor) -> torch.Tensor:
+    """cod.py:143-144 + `SSIM._ssim` (cod.py:333-348): batch-wide min-max normalisation of embedding1, 3x3 means over
+    reflection-padded windows written as nine shifted slices, mean of clamp((1 - SSIM) / 2, 0, 1)."""
+    x = (embedding1 - embedding1.min()) / (embedding1.max() - embedding1.min() + 1e-8)
+    y = image
+
+    def mean3(t):
+        H, W = t.shape[-2:]
+        ry = [1] + list(range(H)) + [H - 2]
+        rx = [1] + list(range(W)) + [W - 2]
+        p = t[..., ry, :][..., :, rx]
+        acc = torch.zeros_like(t)
+        for dy in range(3):
+            for dx in range(3):
+                acc = acc + p[..., dy:dy + H, dx:dx + W]
+        return acc / 9.0
+    mx, my = mean3(x), mean3(y)
+    vx, vy, vxy = mean3(x * x) - mx * mx, mean3(y * y) - my * my, mean3(x * y) - mx * my
+    num = (2 * mx * my + 0.01 ** 2) * (2 * vxy + 0.03 ** 2)
+    den = (mx * mx + my * my + 0.01 ** 2) * (vx + vy + 0.03 ** 2)
+    return torch.clamp((1 - num / den) / 2, 0, 1).mean()
+
+
+def total_loss(embedding1, P1, P2, image, label, gamma: float = 0.2):
+    """cod.py:135-146."""
+    return deep_supervision_loss(P1, P2, label, gamma) + ssim_constant(embedding1, image)

@@ -32,6 +32,15 @@ def main():
         assert abs(float((mine - ref).detach())) < 1e-12 and float((g - g2).abs().max()) < 1e-14
         rec[f"{tag}_loss"] = np.array(float(ref.detach()))
         rec[f"{tag}_grad"] = g.numpy()
+    # SSIM constant (cod.py:142-144, SSIM :316-351) and the full `cod.forward(mode='loss')` combination
+    g = torch.Generator().manual_seed(5)
+    emb = torch.rand(2, 3, 40, 56, generator=g, dtype=torch.float64) * 0.7
+    img = torch.randn(2, 3, 40, 56, generator=g, dtype=torch.float64)
+    ssim = m.SSIM()
+    e_n = (emb - emb.min()) / (emb.max() - emb.min() + 1e-8)
+    ref = ssim(e_n, img)
+    assert abs(float(ref - L.ssim_constant(emb, img))) < 1e-13
+    rec["ssim_emb"], rec["ssim_img"], rec["ssim_value"] = emb.numpy(), img.numpy(), np.array(float(ref))
     np.savez_compressed(os.path.join(OUT, "loss_small.npz"), **rec)
     print({k: (v.shape if v.ndim else float(v)) for k, v in rec.items()})
 

@@ -182,11 +182,11 @@ def test_cod_modes():
     prob, lab = m(None, image.cuda(), label, depth_list, mode="predict")
     assert lab is label and rel(prob.cpu(), torch.sigmoid(torch.from_numpy(golden["logits"]))) <= 1e-4
     loss = m(None, image.cuda(), label, depth_list, mode="loss")["loss"]
-    # deep supervision of cod.py:135-141 (without the gradient-free SSIM constant) from the oracle's structure loss
+    # the whole training loss of cod.py:135-146 (deep supervision + the SSIM constant) from the oracle
     from oracle import loss_ref as L
     p = _sd64(m.hitnet)
-    _, P1, P2 = H.hitnet_forward(image.double(), depth.double(), p)
-    ref = L.deep_supervision_loss(P1, P2, label.cpu().double())
+    e1, P1, P2 = H.hitnet_forward(image.double(), depth.double(), p)
+    ref = L.total_loss(e1, P1, P2, image.double(), label.cpu().double())
     assert abs(float(loss) - float(ref)) <= 1e-4 * abs(float(ref))
     with pytest.raises(NotImplementedError):
         m(None, image.cuda(), label, depth_list, mode="nope")

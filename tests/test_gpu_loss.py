@@ -65,3 +65,25 @@ def test_deep_supervision_sum():
     assert leaves[0].grad is None and gr[0] is None or float(gr[0].abs().max()) == 0.0   # it = 0 has weight 0
     for a, b in zip(leaves[1:], gr[1:]):
         assert float((a.grad.cpu().double() - b).abs().max() / b.abs().max()) <= 1e-4
+
+
+def test_ssim_constant_matches_the_reference_golden_and_the_oracle():
+    """cod.py:142-144 / SSIM :316-351: value recorded from the unmodified reference, plus a full-size case vs the
+    oracle (batch-wide min-max, reflection padding at every border)."""
+    import os
+    import numpy as np
+    from oracle import loss_ref as L
+    common.package()
+    from dgtd_b200.twig.model import losses as M
+    g = np.load(os.path.join(common.GOLDEN, "loss_small.npz"))
+    emb, img = torch.from_numpy(g["ssim_emb"]), torch.from_numpy(g["ssim_img"])
+    got = float(M.ssim_constant(emb.float().cuda(), img.float().cuda()))
+    assert abs(got - float(g["ssim_value"])) <= 1e-5 * float(g["ssim_value"])
+    gen = torch.Generator().manual_seed(9)
+    e = torch.rand(3, 3, 384, 352, generator=gen) * 2 - 0.3
+    y = torch.randn(3, 3, 384, 352, generator=gen)
+    got = float(M.ssim_constant(e.cuda(), y.cuda()))
+    want = float(L.ssim_constant(e.double(), y.double()))
+    assert abs(got - want) <= 1e-5 * want
+    a = M.ssim_constant(e.cuda(), y.cuda())
+    assert float(a) == got                      # fixed-order reductions: bit-stable

@@ -148,3 +148,15 @@ def test_structure_loss_oracle_matches_reference_golden():
         (gr,) = torch.autograd.grad(loss, p)
         assert abs(float(loss.detach()) - float(g[f"{tag}_loss"])) <= 1e-12
         assert float((gr - torch.from_numpy(g[f"{tag}_grad"])).abs().max()) <= 1e-13
+
+
+def test_ssim_constant_oracle_matches_reference_golden():
+    """oracle/loss_ref.ssim_constant against the value recorded from the unmodified `SSIM` module (cod.py:316-351)."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import loss_ref as L
+    import common
+    g = np.load(os.path.join(common.GOLDEN, "loss_small.npz"))
+    v = L.ssim_constant(torch.from_numpy(g["ssim_emb"]), torch.from_numpy(g["ssim_img"]))
+    assert abs(float(v) - float(g["ssim_value"])) < 1e-13

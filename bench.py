@@ -65,6 +65,24 @@ class ClockSampler:
         self.index, self.rows, self.stop, self.th = index, [], threading.Event(), None
 
     def _run(self):
+        # NVML in-process (a sample every ~5 ms, so that a 10-step timed region of ~140 ms yields a real median);
+        # the nvidia-smi subprocess (~100 ms per query) is the fallback when the binding is unavailable
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = [0x8, 0x40, 0x20, 0x4]   # HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap
+            while not self.stop.is_set():
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                r = int(get_reasons(h))
+                self.rows.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b in bits])
+                self.stop.wait(0.005)
+            return
+        except Exception:
+            pass
         while not self.stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",

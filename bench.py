@@ -3,7 +3,7 @@
 at 384^2).
 
     python bench.py [--gpus N --steps K --warmup W]            # our arm (N>1: under torchrun)
-    python bench.py --impl reference [...]                      # CPU arm (oracle port of the reference)
+    python bench.py --impl reference [...]                      # CPU arm: the unmodified reference module (oracle/_ref)
 
 One "step" = one pass of the hot path (prompt_encoder + 16 ShapePropDecoders + injection layout,
 cod.py:1467-1505 minus the PVT blocks) over one batch of synthetic RGB-D input.  Workload =
@@ -45,7 +45,8 @@ def parse():
     ap.add_argument("--size", type=int, default=384)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--train-eager", action="store_true", help="training leg without CUDA graph capture (DDP when N > 1)")
-    ap.add_argument("--cpu-sample", type=int, default=2, help="images per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="images per CPU-baseline step")
+    ap.add_argument("--no-eager-reference", action="store_true", help="skip the reference-eager-on-GPU baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-diffusion", action="store_true")
     ap.add_argument("--no-train", action="store_true")
@@ -538,25 +539,130 @@ def cpu_model() -> str:
 
 
 def cpu_reference_rate(size: int, images: int, steps: int, warmup: int):
-    """The reference algorithm on the host cores (oracle port, fp32, all threads): images/s."""
+    """The reference's own CPU implementation of the hot path on the host cores, fp32, all threads: the
+    UNMODIFIED module staged by oracle/make_ref.py (`kind: "reference"`; cod.py:1467-1505 minus the PVT
+    blocks, eval mode, no_grad); the oracle port only when the staged file is missing (`kind: "port"`).
+    Returns (images/s, seconds per step, cores, kind)."""
     import common
-    from oracle import texture_diffuser_ref as O
-    TD = common.package()
+    from oracle import ref_loader as R
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    enc, dec = TD.build_texture_diffuser(seed=0)
-    pe = {k: v.detach().float() for k, v in enc.state_dict().items()}
-    pd = {k: v.detach().float() for k, v in dec.state_dict().items()}
     image, depth = common.synthetic_inputs(images, size)
+    grids = common.pvt_token_grids((size, size))
+    if R.reference_available():
+        m = R.load_reference()
+        pe, pd = R.build_reference_hot_path(m, seed=0, img_size=size)
+        pe, pd = pe.eval(), pd.eval()
+        kind = "reference"
+
+        def one():
+            with R.on_cpu():
+                R.reference_hot_path(pe, pd, image, depth, grids)
+    else:
+        from oracle import texture_diffuser_ref as O
+        TD = common.package()
+        enc, dec = TD.build_texture_diffuser(seed=0)
+        pe = {k: v.detach().float() for k, v in enc.state_dict().items()}
+        pd = {k: v.detach().float() for k, v in dec.state_dict().items()}
+        kind = "port"
+
+        def one():
+            O.texture_prompts(image, depth, pe, pd)
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            O.texture_prompts(image, depth, pe, pd)
+            one()
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     dt = sum(times) / len(times)
-    return images / dt, dt, cores
+    return images / dt, dt, cores, kind
+
+
+def _gpu_time(fn, steps, warmup=2):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+def gpu_eager_reference(dev, args, common, ours):
+    """The bar of SURVEY.md 8(d) config 2 (iii) / BASELINE.md 4: the UNMODIFIED reference module (staged copy,
+    oracle/make_ref.py) in eager PyTorch on the SAME B200 -- fp32 and `torch.autocast(bfloat16)` -- on the same
+    batch: hot path (cod.py:1467-1505 minus the PVT blocks), the whole model in predict semantics (cod.py:179-180
+    without the PNG side effects), and eager `MessagePassing` (cod.py:1201-1205) at configs[3] size run
+    channel-chunked (its `unfold` is 49x the state: 49 GiB un-chunked).  `ours` = this library's numbers for the
+    same legs, so that every ratio is stated against stock PyTorch on the same GPU, not against a CPU."""
+    import torch.nn.functional as F
+    from oracle import ref_loader as R
+    if not R.reference_available():
+        return {"unavailable": "oracle/_ref/twig/model/cod.py not staged (run oracle/make_ref.py where /root/reference exists)"}
+    m = R.load_reference()
+    B, S = args.batch, args.size
+    out = {"what": "unmodified reference module, eager PyTorch %s on the same GPU, batch %d, %dx%d" % (torch.__version__, B, S, S),
+           "tf32": bool(torch.backends.cuda.matmul.allow_tf32), "cudnn_tf32": bool(torch.backends.cudnn.allow_tf32)}
+    image, depth = common.synthetic_inputs(B, S, seed=0)
+    image, depth = image.to(dev), depth.to(dev)
+    grids = common.pvt_token_grids((S, S))
+    pe, pd = R.build_reference_hot_path(m, seed=0, img_size=S)
+    pe, pd = pe.to(dev).eval(), pd.to(dev).eval()
+    with torch.no_grad():
+        ms32 = _gpu_time(lambda: R.reference_hot_path(pe, pd, image, depth, grids), 3, 1)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ms16 = _gpu_time(lambda: R.reference_hot_path(pe, pd, image, depth, grids), 5, 2)
+    out["hot_path"] = {"fp32_ms": ms32, "fp32_images_per_s": B / ms32 * 1e3, "bf16_autocast_ms": ms16,
+                       "bf16_autocast_images_per_s": B / ms16 * 1e3, "ours_bf16_ms": ours.get("hot_ms"),
+                       "speedup_vs_bf16_autocast": (ms16 / ours["hot_ms"]) if ours.get("hot_ms") else None}
+    del pe, pd
+    torch.cuda.empty_cache()
+    try:
+        net = m.cod(win_size=22, filter_ratio=0.9, using_sam=True, using_depth=True, finetune=True,
+                    binary_thresh=0.2, pretrain_sam=None, head=None).to(dev).eval()
+
+        def predict():
+            _, P1, P2 = net.hitnet(image, depth)
+            return F.interpolate(P1[-1] + P2, size=(S, S), mode="bilinear", align_corners=False).sigmoid()
+        with torch.no_grad():
+            f32 = _gpu_time(predict, 2, 1)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                f16 = _gpu_time(predict, 3, 1)
+        out["full_model_predict"] = {"fp32_ms": f32, "fp32_images_per_s": B / f32 * 1e3, "bf16_autocast_ms": f16,
+                                     "bf16_autocast_images_per_s": B / f16 * 1e3, "ours_bf16_ms": ours.get("full_ms"),
+                                     "speedup_vs_bf16_autocast": (f16 / ours["full_ms"]) if ours.get("full_ms") else None}
+        del net
+    except Exception as e:  # noqa: BLE001
+        out["full_model_predict"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    torch.cuda.empty_cache()
+    # eager MessagePassing core at configs[3] size, shared weights, T = 1, 16 channels per chunk (3.3 GB unfold)
+    try:
+        C, HW, CH = 256, 1024, 16
+        g = torch.Generator("cpu").manual_seed(0)
+        x = torch.randn(1, C, HW, HW, generator=g).to(dev)
+        wgt = torch.rand(1, 49, HW, HW, generator=g).to(dev)
+
+        def mp_step():
+            w_ = wgt.view(1, 1, 49, HW * HW)
+            nw = w_ / (torch.sum(w_, dim=2).unsqueeze(2) + 1e-5)                    # cod.py:1201
+            ys = []
+            for c0 in range(0, C, CH):
+                u = F.unfold(x[:, c0:c0 + CH], kernel_size=7, padding=3).view(1, CH, 49, HW * HW)   # cod.py:1204
+                ys.append((u * nw).sum(2).view(1, CH, HW, HW))                      # cod.py:1205
+            return torch.cat(ys, 1)
+        with torch.no_grad():
+            mp_ms = _gpu_time(mp_step, 2, 1)
+        out["message_passing_1024x256_T1"] = {"ms": mp_ms, "chunk_channels": CH, "ours_fp32_ms": ours.get("mp_ms"),
+                                              "speedup": (mp_ms / ours["mp_ms"]) if ours.get("mp_ms") else None}
+        del x, wgt
+    except Exception as e:  # noqa: BLE001
+        out["message_passing_1024x256_T1"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -564,16 +670,20 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 3))
-    rate, dt, cores = cpu_reference_rate(args.size, args.cpu_sample, steps, warmup)
-    sample = f"{args.cpu_sample} images of the batch-{args.batch} workload per step, fp32, torch CPU, {cpu_model()}"
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    n = args.cpu_sample if args.cpu_sample > 0 else 8
+    rate, dt, cores, kind = cpu_reference_rate(args.size, n, steps, warmup)
+    sample = (f"{n} images of the batch-{args.batch} workload per step ({steps} timed + {warmup} warm-up steps), fp32, "
+              f"eval/no_grad, torch {torch.__version__} CPU, {cores} threads, {cpu_model()}")
+    what = ("the UNMODIFIED reference module (oracle/_ref copy of twig/model/cod.py: prompt_encoder + 4 prompt_decoders + "
+            "injection, cod.py:1467-1505 minus the PVT blocks)" if kind == "reference" else "oracle port of the reference modules")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"COD inference hot path, batch {args.batch}/GPU, {args.size}x{args.size} RGB-D "
-                               "(BASELINE configs[1]); CPU arm = oracle port of the reference modules"},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                               f"(BASELINE configs[1]); CPU arm = {what}"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -741,11 +851,40 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        rate, dt, cores = cpu_reference_rate(S, args.cpu_sample, 3, 1)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_sample} images of the same workload per step, 3 steps, fp32 torch CPU, {cpu_model()}"}
+        n_cpu = min(args.cpu_sample, 8)
+        rate, dt, cores, kind = cpu_reference_rate(S, n_cpu, 2, 1)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{n_cpu} images of the same workload per step, 2 timed + 1 warm-up steps, fp32 torch CPU, {cpu_model()}"}
+
+    eager = None
+    if rank == 0 and not args.no_eager_reference:
+        ours = {"hot_ms": t_max / args.steps * 1e3,
+                "full_ms": (full_model or {}).get("ms_per_step"),
+                "mp_ms": ((diff or {}).get("sweep") or [{}])[0].get("ms")}
+        try:
+            eager = gpu_eager_reference(dev, args, common, ours)
+        except Exception as e:   # noqa: BLE001
+            eager = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     if rank == 0:
+        def pick(d, *keys):
+            return {k: d.get(k) for k in keys if isinstance(d, dict) and k in d} if isinstance(d, dict) else d
+        # the driver keeps the TAIL of this line: the compact `summary` object goes last, bulky per-sweep detail first
+        summary = {
+            "hot_path": {"images_per_s": value, "ms_per_step": t_max / args.steps * 1e3, "e2e_images_per_s": e2e},
+            "train_fwd_bwd": pick(train, "value", "ms_per_step", "batch_per_gpu", "precision", "allreduce_exposed_ms",
+                                  "allreduce_in_situ_ms", "grad_allreduce", "error"),
+            "train_fp32_exact": pick((train or {}).get("fp32_exact"), "value", "ms_per_step"),
+            "highres_768": pick(highres, "value", "ms_per_step", "batch_per_gpu", "error"),
+            "full_model_predict": pick(full_model, "value", "ms_per_step", "error"),
+            "full_model_predict_e2e": pick((full_model or {}).get("e2e"), "value", "h2d_bytes_per_step", "d2h_bytes_per_step", "error"),
+            "diffusion_W1": ({"fp32_ms_by_T": {str(r["T"]): round(r["ms"], 4) for r in diff.get("sweep", [])},
+                              "hbm_frac_T1": diff.get("hbm_frac_T1"),
+                              "bf16_storage_T1_ms": (diff.get("bf16_storage_T1") or {}).get("ms"),
+                              "bf16_storage_hbm_frac": (diff.get("bf16_storage_T1") or {}).get("hbm_frac"),
+                              "kernel": diff.get("kernel")} if isinstance(diff, dict) and "sweep" in diff else diff),
+            "gpu_eager_reference": eager,
+        }
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True,
@@ -756,8 +895,10 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "result": "stage-4 prompt tokens of the last block (B,144,512) fp32"},
             "gpu_launches": int(launches), "clocks": clocks.summary(),
-            "roofline": roof, "cpu_baseline": cpu, "train_fwd_bwd": train, "highres_768": highres, "backbone_forward_features": backbone, "full_model_predict": full_model, "structure_loss": loss_leg,
-            "diffusion_microbench": diff,
+            "roofline": roof, "cpu_baseline": cpu,
+            "diffusion_microbench": diff, "structure_loss": loss_leg, "backbone_forward_features": backbone,
+            "full_model_predict": full_model, "train_fwd_bwd": train, "highres_768": highres,
+            "summary": summary,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -9,9 +9,12 @@ matplotlib, mmseg ...).  Only three of those symbols are *used* by the hot path
 modules.  The reference also hard-codes `.cuda()` (cod.py:1259); on a CPU-only box that
 call is shimmed to the identity.  The reference source itself is never copied or edited.
 
-`/root/reference` exists only in the authoring container; this loader is used by
-`tests/golden/make_golden.py` to produce the committed fixtures and by the optional
-`tests/test_oracle_vs_reference.py` (skipped when the reference tree is absent).
+`/root/reference` exists only in the authoring container.  `oracle/make_ref.py` stages a
+byte-identical, git-ignored copy of the ONE file under `oracle/_ref/` (it ships to the GPU box like
+the built `.so`); this loader prefers that copy, so nothing reads `/root/reference` at run time.
+Users: `tests/golden/make_golden*.py` (fixtures), `tests/test_dropin_reference.py` (the reference's own
+`forward_features` with this repo's classes patched in), and the baseline legs of `bench.py`
+(`--impl reference` on the host cores, `gpu_eager_reference` on the same B200).
 """
 from __future__ import annotations
 
@@ -24,9 +27,36 @@ import types
 import torch
 import torch.nn as nn
 
-REFERENCE_ROOT = os.environ.get("DGTD_REFERENCE_ROOT", "/root/reference")
+import contextlib
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _resolve_root() -> str:
+    env = os.environ.get("DGTD_REFERENCE_ROOT")
+    if env:
+        return env
+    staged = os.path.join(_HERE, "_ref")
+    if os.path.isfile(os.path.join(staged, "twig", "model", "cod.py")):
+        return staged
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _resolve_root()
 _REF_FILE = os.path.join(REFERENCE_ROOT, "twig", "model", "cod.py")
 _CACHE = {}
+
+
+@contextlib.contextmanager
+def on_cpu():
+    """Run reference code on the host cores of a box that HAS a GPU: `prompt_encoder.fft` hard-codes
+    `.cuda()` for its mask (cod.py:1259); inside this context that call is the identity."""
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        yield
+    finally:
+        torch.Tensor.cuda = orig
 
 
 def reference_available() -> bool:
@@ -122,3 +152,35 @@ def load_reference():
             sys.modules[k] = v
     _CACHE["mod"] = mod
     return mod
+
+
+# ------------------------------------------------------------------------------------------------
+# The reference's hot path as the reference itself runs it (cod.py:1394-1396 construction,
+# :1399-1414 init, :1467-1505 minus the PVT blocks).  Used for fixtures and as the timed baseline.
+PVT_EMBED_DIMS = (64, 128, 320, 512)
+PVT_DEPTHS = (3, 4, 6, 3)
+
+
+def build_reference_hot_path(m, seed: int = 0, img_size: int = 384):
+    """`prompt_encoder(24, embed_dims, depths, True)` + 4 x `prompt_decoder` built and initialised exactly as
+    `PyramidVisionTransformerImpr.__init__` does (cod.py:1394-1414)."""
+    torch.manual_seed(seed)
+    pe = m.prompt_encoder(24, list(PVT_EMBED_DIMS), list(PVT_DEPTHS), True)
+    pd = nn.Sequential(*[m.prompt_decoder(24, e, d, True) for e, d in zip(PVT_EMBED_DIMS, PVT_DEPTHS)])
+    init = m.PyramidVisionTransformerImpr._init_weights
+    pe.apply(lambda mod: init(None, mod))
+    pd.apply(lambda mod: init(None, mod))
+    pe.message_passing.img_size = img_size      # the reference hard-codes 384 (cod.py:1252)
+    return pe, pd
+
+
+def reference_hot_path(pe, pd, image, depth, grids):
+    """embedding1, embedding3 and the 16 injected prompt tensors in token layout -- the statements of
+    `forward_features` (cod.py:1467-1505) with the PVT blocks left out."""
+    import torch.nn.functional as F
+    e1, e3 = pe(image, depth)
+    toks = []
+    for s in range(4):
+        ps = pd[s](e3)
+        toks.append([F.interpolate(p, size=grids[s], mode="bilinear").flatten(2).permute(0, 2, 1) for p in ps])
+    return e1, e3, toks

@@ -128,6 +128,73 @@ def test_message_passing_regress_generates_the_models_weights_on_chip(OP, n, h, 
     check(gotb.float().permute(0, 3, 1, 2), refb, 4e-3 * T + 2e-3)
 
 
+# 32 of the 256 channels (the operator is independent per channel): every residue mod 8 and every 64-channel
+# chunk occurs, so each lane / register slot / TMA channel box of the kernels is sampled; keeps the float64
+# oracle at seconds per crop
+CH_SUBSET = torch.tensor([8 * i + (i % 8) for i in range(32)])
+
+
+def _crop_reference(x_nhwc, wgt, T, y0, y1, x0, x1):
+    """float64 oracle of rows [y0,y1) x cols [x0,x1) of a big map: the oracle runs on the crop + 3T halo (clamped
+    to the map, so true borders keep the operator's zero padding) and only the crop proper is returned."""
+    H, W = x_nhwc.shape[1:3]
+    r = 3 * T
+    ya, yb, xa, xb = max(0, y0 - r), min(H, y1 + r), max(0, x0 - r), min(W, x1 + r)
+    xs = x_nhwc[:, ya:yb, xa:xb][..., CH_SUBSET].permute(0, 3, 1, 2).double().cpu()
+    ws = wgt[:, :, ya:yb, xa:xb].double().cpu()
+    ref = O.message_passing_core(xs, ws, 7, T)
+    return ref[:, :, y0 - ya:y1 - ya, x0 - xa:x1 - xa]
+
+
+CROPS_1024 = [(0, 160, 0, 160), (0, 160, 864, 1024), (864, 1024, 0, 160), (864, 1024, 864, 1024),     # corners
+              (0, 160, 430, 590), (500, 660, 864, 1024), (437, 597, 443, 603), (120, 280, 504, 664)]  # edges, interior
+
+
+@pytest.mark.parametrize("storage,T", [("fp32", 1), ("fp32", 4), ("bf16", 1), ("bf16", 4)])
+def test_message_passing_tiled_at_microbench_size(OP, storage, T):
+    """BASELINE configs[3] at FULL size (1024 x 1024 x 256; 8192 tiles, TMA boxes on every border): 8 crops of
+    160 x 160 (4 corners, 2 edges, 2 interior, none tile-aligned in the interior) against the float64 oracle on the
+    crop + 3T halo.  fp32 storage <= 1e-5; bf16 storage: one bf16 rounding per step (stated 4e-3 * T)."""
+    g = torch.Generator().manual_seed(77)
+    H = W = 1024
+    C = 256
+    x = torch.randn(1, H, W, C, generator=g)
+    wgt = torch.rand(1, 49, H, W, generator=g)
+    if storage == "bf16":
+        x = x.to(torch.bfloat16)
+    got = OP.message_passing_tiled(x.cuda(), wgt.cuda(), T)
+    assert got.dtype == x.dtype and torch.isfinite(got).all()
+    tol = 1e-5 if storage == "fp32" else 4e-3 * T
+    worst = 0.0
+    for (y0, y1, x0, x1) in CROPS_1024:
+        ref = _crop_reference(x.float(), wgt, T, y0, y1, x0, x1)
+        worst = max(worst, check(got[:, y0:y1, x0:x1][..., CH_SUBSET.cuda()].permute(0, 3, 1, 2), ref, tol))
+    print(f"mp_tiled 1024^2 x 256 {storage} T={T}: worst crop rel err {worst:.3e}")
+
+
+@pytest.mark.parametrize("storage,T", [("fp32", 1), ("bf16", 2)])
+def test_message_passing_regress_at_microbench_size(OP, storage, T):
+    """W2 (weights generated on chip) at 1024 x 1024 x 256: 3 crops of 96 x 96 against the float64 oracle."""
+    g = torch.Generator().manual_seed(78)
+    H = W = 1024
+    C = 256
+    x = torch.randn(1, H, W, C, generator=g)
+    guide = torch.randn(1, 3, H, W, generator=g)
+    reg_w = torch.randn(C * 49, 3, 1, 1, generator=g) * 0.8
+    reg_b = torch.randn(C * 49, generator=g)
+    if storage == "bf16":
+        x = x.to(torch.bfloat16)
+    got = OP.message_passing_regress(x.cuda(), guide.cuda(), reg_w.cuda(), reg_b.cuda(), T)
+    r = 3 * T
+    for (y0, y1, x0, x1) in [(0, 96, 0, 96), (928, 1024, 500, 596), (461, 557, 470, 566)]:
+        ya, yb, xa, xb = max(0, y0 - r), min(H, y1 + r), max(0, x0 - r), min(W, x1 + r)
+        rows = (CH_SUBSET[:, None] * 49 + torch.arange(49)[None, :]).reshape(-1)
+        wts = O.regress_weights(guide[:, :, ya:yb, xa:xb].double(), reg_w[rows].double(), reg_b[rows].double())
+        ref = O.message_passing_core(x[:, ya:yb, xa:xb][..., CH_SUBSET].permute(0, 3, 1, 2).double(), wts, 7, T)
+        ref = ref[:, :, y0 - ya:y1 - ya, x0 - xa:x1 - xa]
+        check(got[:, y0:y1, x0:x1][..., CH_SUBSET.cuda()].permute(0, 3, 1, 2), ref, 1e-5 if storage == "fp32" else 4e-3 * T)
+
+
 def test_message_passing_tiled_bf16_storage(OP):
     """bf16 storage / fp32 accumulate: exact on bf16-representable inputs up to the output rounding."""
     g = torch.Generator().manual_seed(22)

@@ -52,16 +52,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
+// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.  The bound is WALL time
+// (%globaltimer, ns) and generous (20 s): time-slicing, MPS, a debugger or a long preemption stretch a healthy
+// wait without advancing the protocol, and must not kill the context.  -DDGTD_NO_MBAR_TRAP removes the trap.
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+#ifdef DGTD_NO_MBAR_TRAP
+  while (!mbar_try_wait(bar, parity)) {}
+#else
+  const unsigned long long t0 = global_timer_ns();
+  unsigned spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
-      printf("dgtd: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+    if ((++spins & 0xfff) == 0 && global_timer_ns() - t0 > 20000000000ULL) {
+      printf("dgtd: mbarrier wait timed out after 20 s (block %d thread %d)\n", blockIdx.x, threadIdx.x);
       __trap();
     }
   }
+#endif
 }
 
 // ---- TMA ------------------------------------------------------------------------------------

@@ -6,8 +6,9 @@
 //   p *= 1 - lr * wd;  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;
 //   p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
 // HBM-bound: 16 bytes read + 12 bytes written per parameter, float4 accesses.  The per-parameter lr / weight decay
-// come from a block table (one entry per <= 4096-element slice of one parameter), so parameters need no padding
-// or alignment inside the flat buffers.
+// come from a block table (one entry per <= 4096-element slice of one parameter).  The flat layout
+// (twig/flat.py) starts every parameter on a 128-byte boundary -- the other kernels read parameters with float4 /
+// TMA accesses -- and the pad elements belong to no slice.
 #include "common.cuh"
 
 namespace dgtd {
@@ -22,9 +23,10 @@ struct AdamwSlice {   // 24 bytes
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, const AdamwSlice* __restrict__ table,
                                                     float b1, float b2, float eps, float inv_bc1, float inv_sqrt_bc2,
-                                                    float grad_scale) {
+                                                    float grad_scale, float lr_scale) {
   const AdamwSlice s = table[blockIdx.x];
-  const float decay = 1.0f - s.lr * s.wd, step = s.lr * inv_bc1;
+  const float lr = s.lr * lr_scale;   // lr_scale: the scheduler's factor (CosineAnnealingLR, config/sod.yml param_scheduler)
+  const float decay = 1.0f - lr * s.wd, step = lr * inv_bc1;
   auto upd = [&](float& pp, float gg, float& mm, float& vv) {
     gg *= grad_scale;
     pp *= decay;
@@ -66,14 +68,14 @@ extern "C" {
 int dgtd_adamw_slice_bytes(void) { return (int)sizeof(AdamwSlice); }
 
 int dgtd_adamw_step(float* p, const float* g, float* m, float* v, const void* table, int nslices, float beta1, float beta2,
-                    float eps, int step, float grad_scale, dgtd_stream_t stream) {
+                    float eps, int step, float grad_scale, float lr_scale, dgtd_stream_t stream) {
   DGTD_CHECK_ARG(p && g && m && v && table && nslices > 0 && step >= 1, "adamw_step: bad arguments");
   DGTD_CHECK_ARG(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                    reinterpret_cast<uintptr_t>(v)) & 15) == 0,
                  "adamw_step: flat buffers must be 16-byte aligned");
   const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
   adamw_kernel<<<nslices, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (const AdamwSlice*)table, beta1, beta2, eps,
-                                                          (float)(1.0 / bc1), (float)(1.0 / sqrt(bc2)), grad_scale);
+                                                          (float)(1.0 / bc1), (float)(1.0 / sqrt(bc2)), grad_scale, lr_scale);
   DGTD_LAUNCH_CHECK("adamw_step");
   return 0;
 }

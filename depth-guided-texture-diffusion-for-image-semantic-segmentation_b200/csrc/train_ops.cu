@@ -462,8 +462,12 @@ int dgtd_ln_rows_bwd(const float* g, const float* y, const float* w, float* dy, 
   // ws holds [blocks][2C]; dw and db are the two halves of the reduced vector
   sum_splits_kernel<<<cdiv(2 * C, 256), 256, 0, s>>>(ws, ws + (int64_t)blocks * 2 * C, 2 * C, blocks);
   DGTD_LAUNCH_CHECK("ln_rows_bwd.reduce");
-  cudaMemcpyAsync(dw, ws + (int64_t)blocks * 2 * C, C * sizeof(float), cudaMemcpyDeviceToDevice, s);
-  cudaMemcpyAsync(db, ws + (int64_t)blocks * 2 * C + C, C * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  cudaError_t e1 = cudaMemcpyAsync(dw, ws + (int64_t)blocks * 2 * C, C * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  cudaError_t e2 = cudaMemcpyAsync(db, ws + (int64_t)blocks * 2 * C + C, C * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    set_error("ln_rows_bwd: gradient copy failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    return -4;
+  }
   return 0;
 }
 int dgtd_ln_rows_bwd_ws_floats(int64_t rows, int C) {
@@ -502,8 +506,12 @@ int dgtd_dwconv7_wgrad(const float* x, const float* dy, float* ws, float* dwT, f
   }
   sum_splits_kernel<<<cdiv(n, 256), 256, 0, s>>>(ws, red, n, parts);
   DGTD_LAUNCH_CHECK("dwconv7_wgrad.reduce");
-  cudaMemcpyAsync(dwT, red, (size_t)49 * C * sizeof(float), cudaMemcpyDeviceToDevice, s);
-  cudaMemcpyAsync(db, red + (int64_t)49 * C, (size_t)C * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  cudaError_t e1 = cudaMemcpyAsync(dwT, red, (size_t)49 * C * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  cudaError_t e2 = cudaMemcpyAsync(db, red + (int64_t)49 * C, (size_t)C * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    set_error("dwconv7_wgrad: gradient copy failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    return -4;
+  }
   return 0;
 }
 

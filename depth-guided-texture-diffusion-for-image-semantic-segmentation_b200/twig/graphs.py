@@ -17,7 +17,23 @@ from typing import Callable, Optional
 import torch
 import torch.nn as nn
 
+from . import flat
 from .model import texture_diffuser as TD
+
+
+def _mark_captured(params) -> list:
+    """Pointers a captured graph reads parameters from; `_check_captured` raises when one moved (an optimizer that
+    re-homes `p.data`, `module.to()`, `load_state_dict(assign=True)`): the replay would read freed storage."""
+    for p in params:
+        p._dgtd_captured = True
+    return [p.data_ptr() for p in params]
+
+
+def _check_captured(params, ptrs, what: str) -> None:
+    for p, q in zip(params, ptrs):
+        if p.data_ptr() != q:
+            raise RuntimeError(f"{what}: a parameter's storage moved after capture (was an optimizer / .to() / "
+                               "load_state_dict(assign=True) applied afterwards?); re-capture the step")
 
 
 def default_loss(emb1, emb3, tokens) -> torch.Tensor:
@@ -39,20 +55,14 @@ class GraphedTrainStep:
         self.group = process_group
         self.image, self.depth = image.detach().clone(), depth.detach().clone()
         self.params = [p for p in list(enc.parameters()) + list(dec.parameters()) if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
+        self.offsets, n = flat.flat_offsets(self.params)
         if flat_grad is None:
             self.flat_grad = torch.zeros(n, device=image.device, dtype=torch.float32)
-            off = 0
-            for p in self.params:
-                p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
-                off += p.numel()
+            flat.bind_views(self.params, self.flat_grad, "grad")
         else:   # an optimizer (twig/optim.py::FusedAdamW) already owns the flat buffer and bound the views
-            assert flat_grad.numel() == n and flat_grad.dtype == torch.float32
+            assert flat_grad.dtype == torch.float32 and flat.views_match(self.params, flat_grad), \
+                "flat_grad does not follow the twig/flat.py layout of these parameters"
             self.flat_grad = flat_grad
-            off = 0
-            for p in self.params:
-                assert p.grad is not None and p.grad.data_ptr() == flat_grad.data_ptr() + 4 * off
-                off += p.numel()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):              # warm-up off the capture stream (allocator, lazy inits)
@@ -63,6 +73,7 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = self._fwd_bwd()
+        self._ptrs = _mark_captured(self.params)
 
     def _fwd_bwd(self) -> torch.Tensor:
         self.flat_grad.zero_()
@@ -76,6 +87,7 @@ class GraphedTrainStep:
             self.image.copy_(image, non_blocking=True)
         if depth is not None:
             self.depth.copy_(depth, non_blocking=True)
+        _check_captured(self.params, self._ptrs, "GraphedTrainStep")
         self.graph.replay()
         if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
                                       and torch.distributed.get_world_size() > 1):
@@ -112,6 +124,9 @@ class GraphedPredict:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.logits = self._forward()
+        self.params = list(model.parameters()) + list(model.buffers())
+        self._ptrs = _mark_captured(self.params)
+        self._versions = [p._version for p in self.params]
 
     @torch.no_grad()
     def _forward(self) -> torch.Tensor:
@@ -123,5 +138,13 @@ class GraphedPredict:
             self.image.copy_(image, non_blocking=True)
         if depth is not None:
             self.depth.copy_(depth, non_blocking=True)
+        _check_captured(self.params, self._ptrs, "GraphedPredict")
+        versions = [p._version for p in self.params]
+        if versions != self._versions:
+            # weights changed in place (load_state_dict / optimizer step): the captured kernels read re-packed /
+            # down-cast / BN-folded SHADOWS of the parameters (texture_diffuser._Packed).  One eager forward refreshes
+            # every shadow in place (same storage the graph reads), then the replay sees the new weights.
+            self._forward()
+            self._versions = versions
         self.graph.replay()
         return self.logits

@@ -64,8 +64,32 @@ class _Packed:
             return hit[1]
         with torch.no_grad():
             val = fn()
+            if hit is not None and _refresh_in_place(hit[1], val):
+                # same shapes as before: overwrite the old shadow instead of replacing it, so that a captured CUDA
+                # graph that reads the shadow's storage (twig/graphs.py::GraphedPredict) sees the new weights and
+                # never a freed block
+                val = hit[1]
         self._store[key] = (sig, val)
         return val
+
+
+def _refresh_in_place(old, new) -> bool:
+    if isinstance(old, torch.Tensor) and isinstance(new, torch.Tensor):
+        if old.shape != new.shape or old.dtype != new.dtype or old.device != new.device:
+            return False
+        if old.data_ptr() != new.data_ptr():
+            old.copy_(new)
+        return True
+    if isinstance(old, (tuple, list)) and isinstance(new, (tuple, list)) and len(old) == len(new):
+        ok = all(isinstance(a, torch.Tensor) and isinstance(b, torch.Tensor) and a.shape == b.shape and a.dtype == b.dtype
+                 and a.device == b.device for a, b in zip(old, new))
+        if not ok:
+            return False
+        for a, b in zip(old, new):
+            if a.data_ptr() != b.data_ptr():
+                a.copy_(b)
+        return True
+    return False
 
 
 def _packed(module: nn.Module) -> _Packed:
@@ -75,16 +99,28 @@ def _packed(module: nn.Module) -> _Packed:
     return pk
 
 
-_SCRATCH: Dict[torch.device, torch.Tensor] = {}
+_SCRATCH: Dict[tuple, torch.Tensor] = {}
+
+
+def scratch_buffer(name: str, device: torch.device, numel: int, dtype: torch.dtype) -> torch.Tensor:
+    """Scratch reused by consecutive launches of one call (producer and consumer are stream-ordered).
+
+    * eager: a grow-only buffer per (name, device, stream) -- two streams never share one, and growing only drops
+      the old block back to the stream-ordered caching allocator;
+    * under CUDA-graph capture: a fresh allocation from the capturing graph's private pool, never cached, so no
+      eager call can later replace or free memory a captured graph writes to."""
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(numel, device=device, dtype=dtype)
+    key = (name, device, torch.cuda.current_stream(device).cuda_stream, dtype)
+    buf = _SCRATCH.get(key)
+    if buf is None or buf.numel() < numel:
+        buf = _SCRATCH[key] = torch.empty(numel, device=device, dtype=dtype)
+    return buf
 
 
 def _scratch(device: torch.device, numel: int) -> torch.Tensor:
-    """Per-device fp32 scratch reused by every block (stream-ordered: producer and consumer of the
-    scratch are consecutive launches of the same call)."""
-    buf = _SCRATCH.get(device)
-    if buf is None or buf.numel() < numel:
-        buf = _SCRATCH[device] = torch.empty(numel, device=device, dtype=torch.float32)
-    return buf
+    """fp32 scratch of the ConvNeXt blocks."""
+    return scratch_buffer("block", device, numel, torch.float32)
 
 
 def _as(t: torch.Tensor, mode: int) -> torch.Tensor:

@@ -103,7 +103,7 @@ SIGNATURES = {
     "dgtd_ssim_loss_ws_floats": [_L],
     "dgtd_ssim_loss_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],
     "dgtd_adamw_slice_bytes": [],
-    "dgtd_adamw_step": [_P, _P, _P, _P, _P, _I, _F, _F, _F, _I, _F, _P],
+    "dgtd_adamw_step": [_P, _P, _P, _P, _P, _I, _F, _F, _F, _I, _F, _F, _P],
     "dgtd_sod_metrics_ws_bytes": [_I, _I, _I],
     "dgtd_sod_metrics_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
 }

@@ -51,15 +51,12 @@ def conv_affine(x: torch.Tensor, w: torch.Tensor, out_hw: Tuple[int, int], ks: i
     return out
 
 
-_COL = {}
 
 
 def _col_scratch(device: torch.device, numel: int) -> torch.Tensor:
     """bf16 im2col operand, reused by every conv of the decoder (stream-ordered producer / consumer pairs)."""
-    buf = _COL.get(device)
-    if buf is None or buf.numel() < numel:
-        buf = _COL[device] = torch.empty(numel, device=device, dtype=torch.bfloat16)
-    return buf
+    from ...model.texture_diffuser import scratch_buffer      # capture-safe, per-stream (see its docstring)
+    return scratch_buffer("hitnet_col", device, numel, torch.bfloat16)
 
 
 def conv_affine_tc(x: torch.Tensor, w: torch.Tensor, out_hw: Tuple[int, int], ks: int, stride: int, off: int,
@@ -86,7 +83,6 @@ def conv_affine_tc(x: torch.Tensor, w: torch.Tensor, out_hw: Tuple[int, int], ks
     return out
 
 
-_XB = {}
 
 
 def conv3_tc(x: torch.Tensor, w: torch.Tensor, shift: Optional[torch.Tensor] = None,
@@ -103,9 +99,8 @@ def conv3_tc(x: torch.Tensor, w: torch.Tensor, shift: Optional[torch.Tensor] = N
         out = torch.empty(B, h, wd, Cout, device=x.device, dtype=torch.float32)
     assert out.shape == (B, h, wd, Cout)
     n = B * h * wd * Cp
-    xb = _XB.get(x.device)
-    if xb is None or xb.numel() < n:
-        xb = _XB[x.device] = torch.empty(n, device=x.device, dtype=torch.bfloat16)
+    from ...model.texture_diffuser import scratch_buffer
+    xb = scratch_buffer("hitnet_xb", x.device, n, torch.bfloat16)
     call("dgtd_cast_pad_act_fwd", x.data_ptr(), _pitch(x), ptr(xb), ptr(prelu_in), B * h * wd, Cin, Cp, stream())
     call("dgtd_conv3x3_tc_fwd", ptr(xb), ptr(w), ptr(shift), out.data_ptr(), B, h, wd, Cp, Cout, _pitch(out), stream())
     return out

@@ -15,6 +15,7 @@ from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
 import torch
 
+from . import flat
 from .ops import capi
 from .ops.capi import call, ptr, stream
 
@@ -45,7 +46,12 @@ def paramwise_options(name: str, lr: float, weight_decay: float,
 
 
 class FusedAdamW:
-    """opt = FusedAdamW(named_params, lr, weight_decay=..., custom_keys=..., flat_grad=step.flat_grad); opt.step()."""
+    """opt = FusedAdamW(named_params, lr, weight_decay=..., custom_keys=...); opt.step(lr_scale=...).
+
+    ORDER MATTERS with captured steps: the constructor re-homes every `p.data` into `self.flat_param`, so it must run
+    BEFORE `GraphedTrainStep(..., flat_grad=opt.flat_grad)` / `GraphedPredict` capture -- a graph captured earlier
+    would keep reading the old, freed parameter storage.  Both Graphed* classes record the parameter pointers at
+    capture and raise if they changed; this constructor refuses parameters a live graph has captured."""
 
     def __init__(self, named_params: Iterable[Tuple[str, torch.nn.Parameter]], lr: float = 5e-4,
                  betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.1,
@@ -58,37 +64,34 @@ class FusedAdamW:
             raise RuntimeError("FusedAdamW runs on CUDA parameters only (no CPU fallback)")
         self.names = [n for n, _ in named]
         self.params = [p for _, p in named]
-        total = sum(p.numel() for p in self.params)
-        self.flat_param = torch.empty(total, device=dev, dtype=torch.float32)
+        for p in self.params:
+            if getattr(p, "_dgtd_captured", False):
+                raise RuntimeError("FusedAdamW: a CUDA graph has already captured these parameters; create the optimizer "
+                                   "first, then GraphedTrainStep(..., flat_grad=opt.flat_grad)")
+        offs, total = flat.flat_offsets(self.params)
+        self.offsets = offs
+        self.flat_param = torch.zeros(total, device=dev, dtype=torch.float32)
         self.exp_avg = torch.zeros(total, device=dev, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(total, device=dev, dtype=torch.float32)
         if flat_grad is None:
             flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
-            bind_grads = True
-        else:
-            assert flat_grad.numel() == total and flat_grad.dtype == torch.float32 and flat_grad.is_cuda
-            bind_grads = False
+            flat.bind_views(self.params, flat_grad, "grad")
+        else:   # the caller's flat gradient buffer must use the same layout (twig/flat.py)
+            assert flat_grad.dtype == torch.float32 and flat_grad.is_cuda
+            assert flat.views_match(self.params, flat_grad), ".grad views do not follow the twig/flat.py layout of flat_grad"
         self.flat_grad = flat_grad
         self.betas, self.eps, self.t = betas, eps, 0
         self.options: List[Tuple[float, float]] = []
         entries = []
-        off = 0
-        with torch.no_grad():
-            for name, p in zip(self.names, self.params):
-                n = p.numel()
-                assert p.dtype == torch.float32, "fp32 master parameters expected"
-                self.flat_param[off:off + n].copy_(p.detach().reshape(-1))
-                p.data = self.flat_param[off:off + n].view_as(p)
-                if bind_grads:
-                    p.grad = self.flat_grad[off:off + n].view_as(p)
-                else:   # the caller's flat gradient buffer must use the same order and offsets
-                    assert p.grad is not None and p.grad.data_ptr() == self.flat_grad.data_ptr() + 4 * off, \
-                        f"{name}: .grad is not the view at offset {off} of flat_grad"
-                plr, pwd = paramwise_options(name, lr, weight_decay, custom_keys)
-                self.options.append((plr, pwd))
-                for s in range(0, n, SLICE):
-                    entries.append(struct.pack("<qiffi", off + s, min(SLICE, n - s), plr, pwd, 0))
-                off += n
+        for p in self.params:
+            assert p.dtype == torch.float32, "fp32 master parameters expected"
+        flat.bind_views(self.params, self.flat_param, "data")
+        for name, p, off in zip(self.names, self.params, offs):
+            n = p.numel()
+            plr, pwd = paramwise_options(name, lr, weight_decay, custom_keys)
+            self.options.append((plr, pwd))
+            for s in range(0, n, SLICE):
+                entries.append(struct.pack("<qiffi", off + s, min(SLICE, n - s), plr, pwd, 0))
         assert capi.load().dgtd_adamw_slice_bytes() == struct.calcsize("<qiffi")
         self.nslices = len(entries)
         raw = torch.frombuffer(bytearray(b"".join(entries)), dtype=torch.uint8)
@@ -97,11 +100,13 @@ class FusedAdamW:
     def zero_grad(self) -> None:
         self.flat_grad.zero_()
 
-    def step(self, grad_scale: float = 1.0) -> None:
+    def step(self, grad_scale: float = 1.0, lr_scale: float = 1.0) -> None:
+        """`lr_scale` multiplies every parameter's lr for this step: the factor of the run's scheduler
+        (config/sod.yml `param_scheduler`: CosineAnnealingLR -> lr_t / lr_0), so a schedule needs no table rewrite."""
         self.t += 1
         call("dgtd_adamw_step", ptr(self.flat_param), ptr(self.flat_grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
              ptr(self.table), self.nslices, float(self.betas[0]), float(self.betas[1]), float(self.eps), self.t,
-             float(grad_scale), stream())
+             float(grad_scale), float(lr_scale), stream())
         # the kernel wrote the parameters behind autograd's back: bump the version counters so that cached
         # re-packed / down-cast shadows of the inference path (texture_diffuser._Packed) are refreshed
         torch.autograd.graph.increment_version(self.params)

@@ -386,10 +386,11 @@ int dgtd_sod_metrics_fwd(const float* pred, const float* gt, void* ws, double* o
  * twig/graphs.py).  table: nslices entries of dgtd_adamw_slice_bytes() bytes = {int64 off; int32 n (<= 4096);
  * float lr; float weight_decay; int32 pad} -- one per slice of one parameter, which is how the per-prefix lr
  * multipliers of paramwise_cfg.custom_keys are applied.  g is multiplied by grad_scale first (1 / world size after
- * a sum all-reduce).  step = 1-based step count for the bias corrections. */
+ * a sum all-reduce).  step = 1-based step count for the bias corrections.  lr_scale multiplies every slice's lr
+ * (the factor of the run's scheduler, e.g. CosineAnnealingLR of config/sod.yml param_scheduler; 1 = constant lr). */
 int dgtd_adamw_slice_bytes(void);
 int dgtd_adamw_step(float* p, const float* g, float* m, float* v, const void* table, int nslices, float beta1, float beta2,
-                    float eps, int step, float grad_scale, dgtd_stream_t stream);
+                    float eps, int step, float grad_scale, float lr_scale, dgtd_stream_t stream);
 
 #ifdef __cplusplus
 }

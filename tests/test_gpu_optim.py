@@ -69,3 +69,54 @@ def test_train_step_with_fused_adamw_changes_the_inference_result():
     assert float((after - before).abs().max()) > 0
     for p in list(enc.parameters()) + list(dec.parameters()):
         p.grad = None
+
+
+def test_flat_layout_is_aligned_and_lr_scale_follows_a_cosine_schedule():
+    """(1) every parameter re-homed into the flat buffer starts on a 128-byte boundary whatever the sizes
+    before it (a 1-element PReLU slope / 1-channel head bias must not shift later tensors off the float4 / TMA
+    alignment the kernels assume); (2) `step(lr_scale=...)` reproduces torch.optim.AdamW under CosineAnnealingLR
+    (config/sod.yml param_scheduler)."""
+    common.package()
+    from dgtd_b200.twig.optim import FusedAdamW
+    g = torch.Generator().manual_seed(1)
+    shapes = {"a.prelu": (1,), "b.weight": (24, 3, 3, 3), "c.bias": (1,), "d.weight": (129, 5), "e.bias": (3,)}
+    ours = {n: torch.nn.Parameter(torch.randn(s, generator=g).cuda()) for n, s in shapes.items()}
+    ref = {n: torch.nn.Parameter(p.detach().double().cpu().clone()) for n, p in ours.items()}
+    opt = FusedAdamW(ours.items(), lr=5e-4, weight_decay=0.1)
+    for p in ours.values():
+        assert p.data_ptr() % 128 == 0 and p.grad.data_ptr() % 128 == 0
+    topt = torch.optim.AdamW(list(ref.values()), lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.1)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(topt, T_max=6, eta_min=5e-6)
+    for step in range(6):
+        for n in shapes:
+            gr = torch.randn(shapes[n], generator=g)
+            ours[n].grad.copy_(gr.cuda())
+            ref[n].grad = gr.double()
+        opt.step(lr_scale=sched.get_last_lr()[0] / 5e-4)
+        topt.step()
+        sched.step()
+        for n in shapes:
+            a, b = ours[n].detach().double().cpu(), ref[n].detach()
+            assert float((a - b).abs().max()) <= 2e-6 * float(b.abs().max()), (step, n)
+
+
+def test_graph_capture_guards_against_re_homed_parameters():
+    """an optimizer built AFTER the graph capture would re-home p.data and leave the replay reading freed
+    storage: the constructor refuses, and a replay after any other storage move raises instead of computing garbage."""
+    TD = common.package()
+    from dgtd_b200.twig import graphs
+    from dgtd_b200.twig.optim import FusedAdamW
+    enc, dec = TD.build_texture_diffuser(seed=0)
+    enc, dec = enc.cuda().train(), dec.cuda().train()
+    image, depth = common.synthetic_inputs(1, 96, seed=3)
+    step = graphs.GraphedTrainStep(enc, dec, image.cuda(), depth.cuda(), precision="fp32", warmup=1)
+    step()
+    named = [("enc." + n, p) for n, p in enc.named_parameters()] + [("dec." + n, p) for n, p in dec.named_parameters()]
+    with pytest.raises(RuntimeError, match="already captured"):
+        FusedAdamW(named, flat_grad=step.flat_grad)
+    p = enc.encoder1.weight
+    p.data = p.data.clone()                         # any storage move
+    with pytest.raises(RuntimeError, match="storage moved"):
+        step()
+    for q in list(enc.parameters()) + list(dec.parameters()):
+        q.grad = None

@@ -21,12 +21,24 @@ from . import flat
 from .model import texture_diffuser as TD
 
 
-def _mark_captured(params) -> list:
+import weakref
+
+_LIVE_GRAPHS: "weakref.WeakSet" = weakref.WeakSet()     # Graphed* objects whose captured graphs are still alive
+
+
+def _mark_captured(owner, params) -> list:
     """Pointers a captured graph reads parameters from; `_check_captured` raises when one moved (an optimizer that
     re-homes `p.data`, `module.to()`, `load_state_dict(assign=True)`): the replay would read freed storage."""
-    for p in params:
-        p._dgtd_captured = True
+    owner._param_ids = {id(p) for p in params}
+    _LIVE_GRAPHS.add(owner)
     return [p.data_ptr() for p in params]
+
+
+def captured_by_live_graph(params) -> bool:
+    """True when a still-alive GraphedTrainStep / GraphedPredict captured any of `params` (twig/optim.py refuses to
+    re-home those)."""
+    ids = {id(p) for p in params}
+    return any(ids & g._param_ids for g in list(_LIVE_GRAPHS))
 
 
 def _check_captured(params, ptrs, what: str) -> None:
@@ -73,7 +85,7 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = self._fwd_bwd()
-        self._ptrs = _mark_captured(self.params)
+        self._ptrs = _mark_captured(self, self.params)
 
     def _fwd_bwd(self) -> torch.Tensor:
         self.flat_grad.zero_()
@@ -125,7 +137,7 @@ class GraphedPredict:
         with torch.cuda.graph(self.graph):
             self.logits = self._forward()
         self.params = list(model.parameters()) + list(model.buffers())
-        self._ptrs = _mark_captured(self.params)
+        self._ptrs = _mark_captured(self, self.params)
         self._versions = [p._version for p in self.params]
 
     @torch.no_grad()

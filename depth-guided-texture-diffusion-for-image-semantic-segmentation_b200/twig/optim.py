@@ -64,10 +64,10 @@ class FusedAdamW:
             raise RuntimeError("FusedAdamW runs on CUDA parameters only (no CPU fallback)")
         self.names = [n for n, _ in named]
         self.params = [p for _, p in named]
-        for p in self.params:
-            if getattr(p, "_dgtd_captured", False):
-                raise RuntimeError("FusedAdamW: a CUDA graph has already captured these parameters; create the optimizer "
-                                   "first, then GraphedTrainStep(..., flat_grad=opt.flat_grad)")
+        from . import graphs
+        if graphs.captured_by_live_graph(self.params):
+            raise RuntimeError("FusedAdamW: a CUDA graph has already captured these parameters; create the optimizer "
+                               "first, then GraphedTrainStep(..., flat_grad=opt.flat_grad)")
         offs, total = flat.flat_offsets(self.params)
         self.offsets = offs
         self.flat_param = torch.zeros(total, device=dev, dtype=torch.float32)

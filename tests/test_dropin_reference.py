@@ -50,11 +50,15 @@ def test_patched_reference_keeps_the_reference_state_dict():
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not R.reference_available(), reason="reference file not staged (oracle/make_ref.py)")
-def test_reference_forward_features_runs_on_the_repo_classes():
+def test_reference_forward_features_runs_on_the_repo_classes(monkeypatch):
     m = R.load_reference()
     TD = common.package()
     g = np.load(os.path.join(common.GOLDEN, "pvt_128.npz"))
     S, B = int(g["S"]), int(g["B"])
+    # the reference's own eager convolutions (patch embeds, spatial-reduction convs) would otherwise run as TF32 in
+    # cuDNN (torch default `cudnn.allow_tf32 = True`: 1.8e-4 on stage 1, measured) -- the fixture is a float64 run
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    monkeypatch.setattr(torch.backends.cuda.matmul, "allow_tf32", False)
     net = _patched_backbone(m, TD).eval()
     common.fill_params_(net, seed=0)
     net = net.cuda()

@@ -33,6 +33,8 @@ SIGNATURES = {
     "dgtd_diffusion_front_fwd": [_P] * 11 + [_I] * 6 + [_P],
     "dgtd_message_passing_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     "dgtd_message_passing_tiled_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P],
+    "dgtd_message_passing_tiled_simt_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P],
+    "dgtd_message_passing_tc_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _I, _P],
     "dgtd_pack_regressor": [_P, _P, _P, _I, _P],
     "dgtd_message_passing_regress_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _I, _P],
     "dgtd_message_passing_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],

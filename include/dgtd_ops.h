@@ -92,6 +92,17 @@ int dgtd_message_passing_fwd(const float* x, const float* weight, float* out, fl
 int dgtd_message_passing_tiled_fwd(const void* x, const float* weight, void* out, void* tmp,
                                    int n, int h, int w, int c, int T, float eps, int dtype,
                                    dgtd_stream_t stream);
+/* The same operator forced onto the CUDA-core (SIMT) kernel, whatever the shape (A/B reference for the tensor path). */
+int dgtd_message_passing_tiled_simt_fwd(const void* x, const float* weight, void* out, void* tmp,
+                                        int n, int h, int w, int c, int T, float eps, int dtype,
+                                        dgtd_stream_t stream);
+/* The same operator (cod.py:1201-1205, shared weights) on the TENSOR pipe: per 8x16-pixel tile the step is the
+ * banded GEMM Y[128 px, c] = A[128, 336 halo px] . X[336, c] on tcgen05.mma; A holds the 49 normalised weights of
+ * each pixel in bf16, X is the NHWC map read through TMA as an MN-major operand.  bf16 storage, c a multiple
+ * of 256, flags must be 0.  dgtd_message_passing_tiled_fwd dispatches here when the shape qualifies. */
+int dgtd_message_passing_tc_fwd(const void* x, const float* weight, void* out, void* tmp,
+                                int n, int h, int w, int c, int T, float eps, int dtype, int flags,
+                                dgtd_stream_t stream);
 /* Same operator with the MODEL's per-channel weights generated on chip (mode W2):
  * W[c,k,p] = sigmoid(Wr[c*49+k,:] . guide[:,p] + br[c*49+k]) (ShapePropWeightRegressor, cod.py:1051-1060,
  * 1296), normalised over the 49 taps (+eps, cod.py:1201) and applied as the 7x7 zero-padded stencil.

@@ -154,7 +154,7 @@ CROPS_1024 = [(0, 160, 0, 160), (0, 160, 864, 1024), (864, 1024, 0, 160), (864, 
 def test_message_passing_tiled_at_microbench_size(OP, storage, T):
     """BASELINE configs[3] at FULL size (1024 x 1024 x 256; 8192 tiles, TMA boxes on every border): 8 crops of
     160 x 160 (4 corners, 2 edges, 2 interior, none tile-aligned in the interior) against the float64 oracle on the
-    crop + 3T halo.  fp32 storage <= 1e-5; bf16 storage: one bf16 rounding per step (stated 4e-3 * T)."""
+    crop + 3T halo.  fp32 storage <= 1e-5; bf16 storage: one bf16 rounding per step (stated 6e-3 * T: tensor-pipe kernel, weights operand in bf16)."""
     g = torch.Generator().manual_seed(77)
     H = W = 1024
     C = 256
@@ -164,7 +164,7 @@ def test_message_passing_tiled_at_microbench_size(OP, storage, T):
         x = x.to(torch.bfloat16)
     got = OP.message_passing_tiled(x.cuda(), wgt.cuda(), T)
     assert got.dtype == x.dtype and torch.isfinite(got).all()
-    tol = 1e-5 if storage == "fp32" else 4e-3 * T
+    tol = 1e-5 if storage == "fp32" else 6e-3 * T
     worst = 0.0
     for (y0, y1, x0, x1) in CROPS_1024:
         ref = _crop_reference(x.float(), wgt, T, y0, y1, x0, x1)
@@ -193,6 +193,44 @@ def test_message_passing_regress_at_microbench_size(OP, storage, T):
         ref = O.message_passing_core(x[:, ya:yb, xa:xb][..., CH_SUBSET].permute(0, 3, 1, 2).double(), wts, 7, T)
         ref = ref[:, :, y0 - ya:y1 - ya, x0 - xa:x1 - xa]
         check(got[:, y0:y1, x0:x1][..., CH_SUBSET.cuda()].permute(0, 3, 1, 2), ref, 1e-5 if storage == "fp32" else 4e-3 * T)
+
+
+@pytest.mark.parametrize("n,h,w,c,T", [(1, 40, 70, 256, 1), (2, 17, 33, 256, 3), (1, 64, 64, 512, 2), (1, 8, 16, 256, 1),
+                                       (1, 5, 3, 256, 2), (3, 23, 16, 256, 1), (2, 200, 264, 256, 2)])
+def test_message_passing_tensor_core_banded_gemm(OP, n, h, w, c, T):
+    """mp_tc.cu: the step as Y[128 px, C] = A[128, 336] . X[336, C] on tcgen05 (bf16 storage).  Ragged maps (tiles
+    clipped by TMA on both axes), maps smaller than one tile, two channel passes (C = 512), several images, T > 1.
+    The last case has 850 tiles (> 148 CTAs: every CTA walks several tiles, the A ring is rewritten in flight).
+    Stated tolerance 6e-3 * T of max|ref|: one bf16 rounding of the stored result per step (2^-9 of the element)
+    plus the bf16 rounding of the normalised weights in the A operand (zero-mean, ~1e-3 of max|ref| at 4.5 sigma)."""
+    impl = "tc"
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(n, c, h, w, generator=g).to(torch.bfloat16)
+    wgt = torch.rand(n, 49, h, w, generator=g)
+    ref = O.message_passing_core(x.double(), wgt.double(), 7, T)
+    xc = x.permute(0, 2, 3, 1).contiguous().cuda()
+    got = OP.message_passing_tiled(xc, wgt.cuda(), T, impl=impl)
+    assert got.dtype == torch.bfloat16
+    err = check(got.float().permute(0, 3, 1, 2), ref, 6e-3 * T)
+    simt = OP.message_passing_tiled(xc, wgt.cuda(), T, impl="simt") if c % 128 == 0 else None
+    if simt is not None:      # the CUDA-core kernel of the same operator (fp32 weights): two independently bf16-rounded results
+        d = float((got.float() - simt.float()).abs().max() / ref.abs().max())
+        print(f"tc[{impl}] vs oracle {err:.2e}; vs SIMT kernel {d:.2e}")
+        assert d <= 1e-2 * T
+
+
+def test_message_passing_tensor_core_constant_map(OP):
+    """Interior pixels of a constant map stay constant (weights sum to sum/(sum+eps)); borders lose exactly the
+    weight of the taps that fall outside (zero padding, no renormalisation: cod.py:1204)."""
+    h, w, c = 32, 48, 256
+    x = torch.full((1, h, w, c), 1.5, dtype=torch.bfloat16).cuda()
+    g = torch.Generator().manual_seed(24)
+    wgt = torch.rand(1, 49, h, w, generator=g)
+    got = OP.message_passing_tiled(x, wgt.cuda(), 1, impl="tc").float()
+    assert float((got[:, 3:-3, 3:-3] - 1.5).abs().max()) <= 1.5 * 2 ** -8
+    wn = wgt / (wgt.sum(1, keepdim=True) + 1e-5)
+    inside = wn[:, [ky * 7 + kx for ky in range(3, 7) for kx in range(3, 7)]].sum(1)     # taps in-bounds at the (0,0) corner
+    assert abs(float(got[0, 0, 0, 0]) - 1.5 * float(inside[0, 0, 0])) <= 1.5 * 2 ** -7
 
 
 def test_message_passing_tiled_bf16_storage(OP):

@@ -112,52 +112,57 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def diffusion_microbench(OP, dev, peaks, C=256, S=1024, steps=(1, 2, 4, 8)):
-    """MessagePassing core (cod.py:1190-1205), shared weights, fp32 NHWC; one kernel per step.
-    Algorithmic bytes are T-independent when steps are fused; this kernel runs one pass per step,
-    so both the per-step GB/s (what the kernel achieves) and the T-step roofline fraction are given."""
+def diffusion_microbench(OP, dev, peaks, C=256, S=1024, steps=(1, 2, 4, 8, 16)):
+    """MessagePassing core (cod.py:1190-1205), shared weights, NHWC, 1024^2 x 256 (BASELINE configs[3]), T sweep, both
+    storage dtypes.  One launch per step (at C = 256 the per-step tensor / FMA time is at or
+    above the per-step HBM time, so fusing steps only adds halo recomputation).  Reported per T: time, the GB/s the
+    kernel achieves per step, and the fraction of the T-fused roofline of SURVEY.md 8(d) (algorithmic bytes
+    T-independent)."""
     g = torch.Generator("cpu").manual_seed(0)
     x = torch.randn(1, S, S, C, generator=g).to(dev)
     wgt = torch.rand(1, 49, S, S, generator=g).to(dev)
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     fma_roof = 148 * 128 * 2 * 1.965e9
-    step_bytes = (2 * C + 49) * S * S * 4
-    out = {"shape": [1, C, S, S], "k": 7, "dtype": "f32", "layout": "NHWC", "weights": "shared (wc=1)",
-           "alg_bytes_per_step": step_bytes, "hbm_peak_gbs": hbm, "sweep": []}
-    for T in steps:
+
+    def timed(xx, T, reps=3):
         for _ in range(2):
-            OP.message_passing_tiled(x, wgt, T)
+            OP.message_passing_tiled(xx, wgt, T)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
-        reps = 3
         a.record()
         for _ in range(reps):
-            OP.message_passing_tiled(x, wgt, T)
+            OP.message_passing_tiled(xx, wgt, T)
         b.record()
         torch.cuda.synchronize()
-        ms = a.elapsed_time(b) / reps
+        return a.elapsed_time(b) / reps
+
+    step_bytes = (2 * C + 49) * S * S * 4
+    out = {"shape": [1, C, S, S], "k": 7, "layout": "NHWC", "weights": "shared (wc=1)", "hbm_peak_gbs": hbm,
+           "alg_bytes_per_step_f32": step_bytes, "sweep": []}
+    for T in steps:
+        ms = timed(x, T)
         flops = 2.0 * 49 * C * S * S * T
         bound_ms = max(step_bytes / (hbm * 1e9), flops / fma_roof) * 1e3     # fused-T roofline (SURVEY 8d)
         out["sweep"].append({"T": T, "ms": ms, "gbs_per_step": step_bytes * T / (ms * 1e-3) / 1e9,
-                             "tflops": flops / (ms * 1e-3) / 1e12, "roofline_ms": bound_ms,
-                             "frac_of_roofline": bound_ms / ms})
+                             "tflops": flops / (ms * 1e-3) / 1e12, "frac_of_fused_roofline": bound_ms / ms})
     out["hbm_frac_T1"] = out["sweep"][0]["gbs_per_step"] / hbm
-    # bf16 storage / fp32 accumulate (configs[3] second dtype), T = 1
+    out["kernel_f32"] = "mp_tiled_kernel (CUDA cores, fp32 weights broadcast from shared memory)"
+    # bf16 storage / fp32 accumulate (configs[3] second dtype): banded GEMM on tcgen05 (mp_tc.cu)
     xb = x.to(torch.bfloat16)
     del x
-    for _ in range(2):
-        OP.message_passing_tiled(xb, wgt, 1)
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    a.record()
-    for _ in range(3):
-        OP.message_passing_tiled(xb, wgt, 1)
-    b.record()
-    torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / 3
     bb = (2 * C * 2 + 49 * 4) * S * S
-    out["bf16_storage_T1"] = {"ms": ms, "alg_bytes": bb, "gbs": bb / (ms * 1e-3) / 1e9, "hbm_frac": bb / (ms * 1e-3) / 1e9 / hbm,
-                              "tflops": 2.0 * 49 * C * S * S / (ms * 1e-3) / 1e12}
+    exec_flops = 2.0 * 336 * C * S * S
+    out["alg_bytes_per_step_bf16"] = bb
+    out["bf16_storage"] = []
+    for T in (1, 4, 16):
+        ms = timed(xb, T)
+        out["bf16_storage"].append({"T": T, "ms": ms, "gbs_per_step": bb * T / (ms * 1e-3) / 1e9,
+                                    "hbm_frac_per_step": bb * T / (ms * 1e-3) / 1e9 / hbm,
+                                    "executed_mma_tflops": exec_flops * T / (ms * 1e-3) / 1e12})
+    b1 = out["bf16_storage"][0]
+    out["bf16_storage_T1"] = {"ms": b1["ms"], "alg_bytes": bb, "gbs": b1["gbs_per_step"], "hbm_frac": b1["hbm_frac_per_step"]}
+    out["kernel"] = ("bf16 storage: mp_tc_kernel = banded GEMM Y[128 px,C] = A[128,336].X[336,C] on tcgen05 (TMA halo boxes as "
+                     "MN-major operand, weights operand rebuilt per tile); fp32 storage: mp_tiled_kernel (CUDA cores)")
     del wgt
     out["w2_fused_regressor"] = diffusion_microbench_w2(OP, dev, xb, hbm, fma_roof, C, S)
     out["cpu_port"] = diffusion_microbench_cpu()

@@ -36,18 +36,36 @@ namespace mptc {
 constexpr int TH = 8, TW = 16;                 // output tile = 128 pixels = the M of one MMA
 constexpr int PW = 24, PH = 14;                // halo window (22 -> 24 columns), K = 336
 constexpr int NCHUNK = 7, CK = 48;             // chunk = 2 halo rows = 48 K rows = 3 K steps
-constexpr int A_CHUNK = 128 * 128;             // 128 pixel rows x 128 B (96 B used), SWIZZLE_128B K-major
 constexpr int XBLK = CK * 128;                 // 64-channel block of a chunk: 48 K rows x 128 B
 constexpr int NB = 256;                        // channels per pass (N of the MMA)
 constexpr int X_STAGE = (NB / 64) * XBLK;      // 24 KB
-constexpr int XSTAGES = 3;
-constexpr int STG = 4 * 2 * 4096;              // 4 epilogue warps x 2 staging tiles (32 px x 128 B)
-constexpr int OFF_X = NCHUNK * A_CHUNK;
-constexpr int OFF_STG = OFF_X + XSTAGES * X_STAGE;
-constexpr int OFF_BAR = OFF_STG + STG;
-constexpr int NBARS = 2 * XSTAGES + 2 * NCHUNK + 4;
-constexpr int SMEM = OFF_BAR + NBARS * 8 + 16 + 1024;   // + alignment slack
+constexpr int STG = 4 * 4096;                  // 4 epilogue warps x one staging tile (32 px x 128 B)
 constexpr int THREADS = 384;
+
+// Layout of the A (weights) operand in shared memory.  The kernel is bound by how many bytes of X it keeps in flight
+// (r2 profile: 72 KB per SM at ~2.8 us of loaded TMA latency = 3.8 TB/s of L2->SM traffic, tensor pipe 24 % busy),
+// so every KB not spent on A is a KB of X prefetch:
+//   SW128: rows of 128 B (96 used), SWIZZLE_128B K-major, 16 KB per chunk -> 4 X stages
+//   SW32 : one 4 KB block of 32-byte rows per K step, SWIZZLE_32B K-major, 12 KB per chunk -> 5 X stages
+template <int SW>
+struct Cfg {
+  static constexpr int A_CHUNK = SW == 128 ? 128 * 128 : 3 * 128 * 32;
+  static constexpr int XSTAGES = SW == 128 ? 4 : 5;
+  static constexpr int OFF_X = NCHUNK * A_CHUNK;
+  static constexpr int OFF_STG = OFF_X + XSTAGES * X_STAGE;
+  static constexpr int OFF_BAR = OFF_STG + STG;
+  static constexpr int NBARS = 2 * XSTAGES + 2 * NCHUNK + 4;
+  static constexpr int SMEM = OFF_BAR + NBARS * 8 + 16 + 1024;   // + alignment slack
+  // byte offset of element (row m, chunk-local column kl) inside a chunk
+  static __device__ __forceinline__ uint32_t a_off(uint32_t m, uint32_t kl) {
+    if (SW == 128) return m * 128 + ((((kl >> 3)) ^ (m & 7)) << 4) + ((kl & 7) << 1);
+    return (kl >> 4) * 4096 + m * 32 + (((((kl >> 3) & 1)) ^ ((m >> 2) & 1)) << 4) + ((kl & 7) << 1);
+  }
+  // descriptor of K step k of chunk j, relative to the descriptor of the ring's first byte
+  static __device__ __forceinline__ uint64_t a_desc_off(int j, int k) {
+    return (uint64_t)((j * A_CHUNK + (SW == 128 ? 32 * k : 4096 * k)) >> 4);
+  }
+};
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
@@ -68,8 +86,11 @@ struct Params {
   float eps;
 };
 
+template <int SW>
 __global__ void __launch_bounds__(THREADS, 1)
 mp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmOut, const Params p) {
+  using C = Cfg<SW>;
+  constexpr int A_CHUNK = C::A_CHUNK, XSTAGES = C::XSTAGES, OFF_X = C::OFF_X, OFF_STG = C::OFF_STG, OFF_BAR = C::OFF_BAR;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -117,64 +138,75 @@ mp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer: X halo rows, 2 at a time =====================
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        int t = tile;
-        const int tx = t % p.tiles_x; t /= p.tiles_x;
-        const int ty = t % p.tiles_y;
-        const int img = t / p.tiles_y;
-        const int x0 = tx * TW - 3, y0 = ty * TH - 3;
-        for (int nb = 0; nb < nblk; ++nb) {
-          for (int j = 0; j < NCHUNK; ++j) {
-            bw::mbar_wait(&x_empty[stage], phase ^ 1);
+    // ===================== TMA producer: X halo rows, 2 at a time =====================
+    // The whole warp walks the loop (warp-uniform control flow: no divergence bookkeeping around the uniform-datapath
+    // TMA instructions); one elected lane issues.
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t x_base = bw::smem_u32(sX);
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int t = tile;
+      const int tx = t % p.tiles_x; t /= p.tiles_x;
+      const int ty = t % p.tiles_y;
+      const int img = t / p.tiles_y;
+      const int x0 = tx * TW - 3, y0 = ty * TH - 3;
+      for (int nb = 0; nb < nblk; ++nb) {
+#pragma unroll 1
+        for (int j = 0; j < NCHUNK; ++j) {
+          bw::mbar_wait(&x_empty[stage], phase ^ 1);
+          if (bw::elect_one()) {
             bw::mbar_arrive_expect_tx(&x_full[stage], X_STAGE);
             uint8_t* dst = sX + stage * X_STAGE;
 #pragma unroll
             for (int b = 0; b < NB / 64; ++b)
               bw::tma_load_4d(&tmX, &x_full[stage], dst + b * XBLK, nb * NB + 64 * b, x0, y0 + 2 * j, img);
-            if (++stage == XSTAGES) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == XSTAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
+    (void)x_base;
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t IDESC = idesc();
-      int stage = 0, iter = 0;
-      uint32_t phase = 0, tphase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, tphase ^= 1) {
-        for (int nb = 0; nb < nblk; ++nb, ++iter) {
-          const int as = iter & 1;
-          bw::mbar_wait(&t_empty[as], ((iter >> 1) & 1) ^ 1);
+    // ===================== MMA issuer (whole warp in the loop, one elected lane issues) =====================
+    // 21 MMAs of 128 clocks per tile: the loop around them must stay well under 384 clocks per chunk, so the
+    // descriptors are precomputed and the chunk loop is unrolled (r2 profile: the first version spent 2/3 of the
+    // issuing warp's time on loop overhead and ran the tensor pipe at 24 %).
+    constexpr uint32_t IDESC = idesc();
+    const uint64_t da0 = bw::umma_smem_desc_kmajor(bw::smem_u32(sA), SW);
+    const uint64_t db0 = bw::umma_smem_desc_mnmajor_sw128(bw::smem_u32(sX), XBLK, 1024);
+    int stage = 0, iter = 0;
+    uint32_t phase = 0, tphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, tphase ^= 1) {
+      for (int nb = 0; nb < nblk; ++nb, ++iter) {
+        const int as = iter & 1;
+        bw::mbar_wait(&t_empty[as], ((iter >> 1) & 1) ^ 1);
+        const uint32_t d_tmem = tmem_base + as * NB;
+        const bool first = nb == 0, last = nb == nblk - 1;
+#pragma unroll 1
+        for (int j = 0; j < NCHUNK; ++j) {
+          bw::mbar_wait(&x_full[stage], phase);
+          if (first) bw::mbar_wait(&a_full[j], tphase);
           bw::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + as * NB;
-          for (int j = 0; j < NCHUNK; ++j) {
-            bw::mbar_wait(&x_full[stage], phase);
-            if (nb == 0) bw::mbar_wait(&a_full[j], tphase);
-            bw::tc_fence_after();
-            const uint64_t da = bw::umma_smem_desc_kmajor(bw::smem_u32(sA + j * A_CHUNK), 128);
-            const uint64_t db = bw::umma_smem_desc_mnmajor_sw128(bw::smem_u32(sX + stage * X_STAGE), XBLK, 1024);
+          if (bw::elect_one()) {
+            const uint64_t db = db0 + (uint64_t)(stage * (X_STAGE >> 4));
 #pragma unroll
             for (int k = 0; k < CK / 16; ++k)
-              bw::umma_bf16(d_tmem, da + 2u * k, db + 128u * k, IDESC, (j | k) != 0);
+              bw::umma_bf16(d_tmem, da0 + C::a_desc_off(j, k), db + 128u * k, IDESC, (j | k) != 0);
             bw::umma_commit(&x_empty[stage]);
-            if (nb == nblk - 1) bw::umma_commit(&a_empty[j]);
-            if (++stage == XSTAGES) { stage = 0; phase ^= 1; }
+            if (last) bw::umma_commit(&a_empty[j]);
+            if (j == NCHUNK - 1) bw::umma_commit(&t_full[as]);
           }
-          bw::umma_commit(&t_full[as]);
+          __syncwarp();
+          if (++stage == XSTAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp >= 4 && warp < 8) {
     // ===================== epilogue: TMEM -> bf16 -> staging -> TMA store =====================
     const int quad = warp & 3;
-    uint8_t* stg = sStg + quad * 8192;
+    uint8_t* tl = sStg + quad * 4096;
     const uint32_t swz = (uint32_t)(lane & 7);
-    uint32_t sbuf = 0;
     int iter = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       int t = tile;
@@ -196,8 +228,7 @@ mp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             bw::tc_fence_before();
             bw::mbar_arrive(&t_empty[as]);
           }
-          uint8_t* tl = stg + (sbuf & 1) * 4096;
-          if (lane == 0) bw::tma_store_wait_read<1>();   // the store that last read this staging tile is done
+          if (lane == 0) bw::tma_store_wait_read<0>();   // the store that last read the staging tile is done
           __syncwarp();
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf)
@@ -218,16 +249,26 @@ mp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             tma_store_4d(&tmOut, tl, nb * NB + c * 64, tx * TW, ty * TH + 2 * quad, img);
             bw::tma_store_commit();
           }
-          ++sbuf;
         }
       }
     }
     if (lane == 0) bw::tma_store_wait_all<0>();
   } else if (warp >= 8) {
     // ===================== A builders: one thread per output pixel =====================
+    // This role sets the pace of the kernel (r2 profile: the MMA warp spent 1/3 of its time waiting for chunk 0 of
+    // the next tile while a builder thread needed ~1500 instructions per tile), so everything that does not change
+    // from tile to tile is hoisted: the 14 byte offsets of a pixel's taps inside a chunk (7 per halo-row parity),
+    // 32-bit plane offsets for the 49 weight loads, fences only after chunks the thread actually wrote.
     const int m = threadIdx.x - 256;
     const int py = m >> 4, px = m & 15;
-    const int64_t plane = (int64_t)p.h * p.w;
+    const int plane = p.h * p.w;                      // host guarantees 49 * h * w < 2^31
+    uint32_t off_e[7], off_o[7];                      // taps kx = 0..6 in an even / odd halo row of a chunk
+#pragma unroll
+    for (int kx = 0; kx < 7; ++kx) {
+      off_e[kx] = C::a_off((uint32_t)m, (uint32_t)(px + kx));
+      off_o[kx] = C::a_off((uint32_t)m, (uint32_t)(24 + px + kx));
+    }
+    const uint32_t sA_u32 = bw::smem_u32(sA);
     float wr[49];
     auto load_raw = [&](int tile) {
       int t = tile;
@@ -236,25 +277,28 @@ mp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       const int img = t / p.tiles_y;
       const int gy = ty * TH + py, gx = tx * TW + px;
       const bool ok = gy < p.h && gx < p.w;
-      const float* wp = p.weight + (int64_t)img * 49 * plane + (int64_t)gy * p.w + gx;
+      const float* wp = p.weight + ((int64_t)img * 49 * plane + (int64_t)gy * p.w + gx);
+      if (ok) {
 #pragma unroll
-      for (int k = 0; k < 49; ++k) wr[k] = ok ? __ldg(wp + k * plane) : 0.f;
+        for (int k = 0; k < 49; ++k) wr[k] = __ldg(wp + k * plane);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 49; ++k) wr[k] = 0.f;
+      }
     };
     uint32_t tcount = 0;
     int tile = blockIdx.x;
     if (tile < p.num_tiles) load_raw(tile);
-    uint8_t* rowbase = sA + m * 128;
-    const uint32_t rsw = (uint32_t)(m & 7);
     for (; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
-      float s = 0.f;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-      for (int k = 0; k < 49; ++k) s += wr[k];
-      const float inv = 1.0f / (s + p.eps);
-      unsigned short wh[49];
+      for (int k = 0; k < 48; k += 4) { s0 += wr[k]; s1 += wr[k + 1]; s2 += wr[k + 2]; s3 += wr[k + 3]; }
+      const float inv = 1.0f / (((s0 + s1) + (s2 + s3)) + wr[48] + p.eps);
+      uint32_t wp2[25];   // normalised weights as bf16 pairs (tap 2i in the low half)
 #pragma unroll
-      for (int k = 0; k < 49; ++k) {
-        const float v = wr[k] * inv;
-        wh[k] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+      for (int k = 0; k < 25; ++k) {
+        const __nv_bfloat162 b = __floats2bfloat162_rn(wr[2 * k] * inv, k < 24 ? wr[2 * k + 1] * inv : 0.f);
+        wp2[k] = *reinterpret_cast<const uint32_t*>(&b);
       }
       if (tile + (int)gridDim.x < p.num_tiles) load_raw(tile + gridDim.x);   // prefetch the next tile's weights
       // Chunks are acquired strictly in order, EVERY chunk by EVERY builder thread (also the chunks a pixel has no
@@ -263,31 +307,38 @@ mp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       // twice inside one phase of a_full[c] (a thread running a tile ahead would otherwise complete the phase early).
       const uint32_t eparity = (tcount & 1) ^ 1;
       int cur = 0;
+      bool wrote = false;
       bw::mbar_wait(&a_empty[0], eparity);
 #pragma unroll
       for (int ky = 0; ky < 7; ++ky) {
-        const int iy = py + ky, j = iy >> 1, r = iy & 1;
+        const int j = (py + ky) >> 1;
         while (cur < j) {                       // done with chunk `cur`: publish it, acquire the next
-          bw::fence_proxy_async_smem();
+          if (wrote) bw::fence_proxy_async_smem();
+          wrote = false;
           bw::mbar_arrive(&a_full[cur]);
           ++cur;
           bw::mbar_wait(&a_empty[cur], eparity);
         }
-        uint8_t* row = rowbase + j * A_CHUNK;
-        const int k0 = r * 24 + px;
+        const uint32_t cbase = sA_u32 + (uint32_t)(j * A_CHUNK);
+        // halo row parity r = (py + ky) & 1: for even ky it is py & 1, for odd ky the other one
+        const bool odd_row = ((py + ky) & 1) != 0;
 #pragma unroll
         for (int kx = 0; kx < 7; ++kx) {
-          const uint32_t kl = (uint32_t)(k0 + kx);
-          *reinterpret_cast<unsigned short*>(row + (((kl >> 3) ^ rsw) << 4) + ((kl & 7) << 1)) = wh[ky * 7 + kx];
+          const int t = ky * 7 + kx;
+          const uint32_t v = (t & 1) ? (wp2[t >> 1] >> 16) : wp2[t >> 1];
+          const uint32_t addr = cbase + (odd_row ? off_o[kx] : off_e[kx]);
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
         }
+        wrote = true;
       }
       while (cur < NCHUNK - 1) {
-        bw::fence_proxy_async_smem();
+        if (wrote) bw::fence_proxy_async_smem();
+        wrote = false;
         bw::mbar_arrive(&a_full[cur]);
         ++cur;
         bw::mbar_wait(&a_empty[cur], eparity);
       }
-      bw::fence_proxy_async_smem();
+      if (wrote) bw::fence_proxy_async_smem();
       bw::mbar_arrive(&a_full[NCHUNK - 1]);
     }
   }
@@ -299,10 +350,26 @@ mp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 }  // namespace mptc
 
 // One diffusion step on the tensor pipe; 0 on success, 1 when the shape is not handled here.
-int mp_tc_step_bf16(const void* x, const float* weight, void* out, int n, int h, int w, int c, float eps,
+template <int SW>
+static int mp_tc_launch(const CUtensorMap& tmX, const CUtensorMap& tmOut, const mptc::Params& p, int grid, cudaStream_t s) {
+  using namespace mptc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e1 = cudaFuncSetAttribute(mp_tc_kernel<SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<SW>::SMEM);
+    if (e1 != cudaSuccess) {
+      set_error("message_passing_tc: cannot opt in to %d B smem: %s", Cfg<SW>::SMEM, cudaGetErrorString(e1));
+      return -2;
+    }
+    configured = true;
+  }
+  mp_tc_kernel<SW><<<grid, THREADS, Cfg<SW>::SMEM, s>>>(tmX, tmOut, p);
+  return 0;
+}
+
+int mp_tc_step_bf16(const void* x, const float* weight, void* out, int n, int h, int w, int c, float eps, int variant,
                     cudaStream_t s) {
   using namespace mptc;
-  if (c % NB != 0) return 1;
+  if (c % NB != 0 || (int64_t)h * w * 49 >= (int64_t)1 << 31) return 1;
   CUtensorMap tmX, tmOut;
   const uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n};
   const uint64_t strides[3] = {(uint64_t)c * 2, (uint64_t)w * c * 2, (uint64_t)h * w * c * 2};
@@ -311,15 +378,6 @@ int mp_tc_step_bf16(const void* x, const float* weight, void* out, int n, int h,
   if (rc) return rc;
   rc = make_tmap(&tmOut, out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, strides, box_out, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e1 = cudaFuncSetAttribute(mp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    if (e1 != cudaSuccess) {
-      set_error("message_passing_tc: cannot opt in to %d B smem: %s", SMEM, cudaGetErrorString(e1));
-      return -2;
-    }
-    configured = true;
-  }
   Params p;
   p.weight = weight;
   p.n = n; p.h = h; p.w = w; p.C = c;
@@ -328,8 +386,7 @@ int mp_tc_step_bf16(const void* x, const float* weight, void* out, int n, int h,
   p.num_tiles = n * p.tiles_x * p.tiles_y;
   p.eps = eps;
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  mp_tc_kernel<<<grid, THREADS, SMEM, s>>>(tmX, tmOut, p);
-  return 0;
+  return variant == 1 ? mp_tc_launch<128>(tmX, tmOut, p, grid, s) : mp_tc_launch<32>(tmX, tmOut, p, grid, s);
 }
 
 }  // namespace dgtd

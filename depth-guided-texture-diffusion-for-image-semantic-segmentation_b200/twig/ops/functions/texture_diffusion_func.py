@@ -253,14 +253,15 @@ def resize_bilinear_nchw_autograd(x, size):
 
 def message_passing_tiled(x: torch.Tensor, weight: torch.Tensor, steps: int, eps: float = 1e-5, impl: str = "auto"):
     """Large-map variant: x (n,h,w,c) channels-last storage (fp32|bf16), weight (n,49,h,w) fp32.
-    impl: "auto" (tensor-pipe banded GEMM when the shape qualifies, else the SIMT kernel), "simt", "tc"."""
+    impl: "auto" (tensor-pipe banded GEMM when the shape qualifies, else the SIMT kernel), "simt", "tc",
+    "tc_sw128" (weights operand in SWIZZLE_128B rows instead of the compact SWIZZLE_32B blocks)."""
     check_cuda(x, weight)
     n, h, w, c = x.shape
     out = torch.empty_like(x)
     tmp = torch.empty_like(x) if steps > 1 else None
-    if impl == "tc":
+    if impl in ("tc", "tc_sw128"):
         call("dgtd_message_passing_tc_fwd", ptr(x), ptr(weight), ptr(out), ptr(tmp), n, h, w, c, steps,
-             float(eps), capi.dtype_code(x.dtype), 0, stream())
+             float(eps), capi.dtype_code(x.dtype), 1 if impl == "tc_sw128" else 0, stream())
         return out
     assert impl in ("auto", "simt")
     call("dgtd_message_passing_tiled_fwd" if impl == "auto" else "dgtd_message_passing_tiled_simt_fwd", ptr(x),

@@ -99,7 +99,8 @@ int dgtd_message_passing_tiled_simt_fwd(const void* x, const float* weight, void
 /* The same operator (cod.py:1201-1205, shared weights) on the TENSOR pipe: per 8x16-pixel tile the step is the
  * banded GEMM Y[128 px, c] = A[128, 336 halo px] . X[336, c] on tcgen05.mma; A holds the 49 normalised weights of
  * each pixel in bf16, X is the NHWC map read through TMA as an MN-major operand.  bf16 storage, c a multiple
- * of 256, flags must be 0.  dgtd_message_passing_tiled_fwd dispatches here when the shape qualifies. */
+ * of 256.  flags: 0 = weights operand in the compact SWIZZLE_32B layout (5 X stages in flight), 1 = SWIZZLE_128B rows
+ * (4 stages; A/B variant of the same kernel).  dgtd_message_passing_tiled_fwd dispatches here when the shape qualifies. */
 int dgtd_message_passing_tc_fwd(const void* x, const float* weight, void* out, void* tmp,
                                 int n, int h, int w, int c, int T, float eps, int dtype, int flags,
                                 dgtd_stream_t stream);

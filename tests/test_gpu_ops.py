@@ -197,13 +197,14 @@ def test_message_passing_regress_at_microbench_size(OP, storage, T):
 
 @pytest.mark.parametrize("n,h,w,c,T", [(1, 40, 70, 256, 1), (2, 17, 33, 256, 3), (1, 64, 64, 512, 2), (1, 8, 16, 256, 1),
                                        (1, 5, 3, 256, 2), (3, 23, 16, 256, 1), (2, 200, 264, 256, 2)])
-def test_message_passing_tensor_core_banded_gemm(OP, n, h, w, c, T):
+@pytest.mark.parametrize("impl", ["tc", "tc_sw128"])
+def test_message_passing_tensor_core_banded_gemm(OP, n, h, w, c, T, impl):
     """mp_tc.cu: the step as Y[128 px, C] = A[128, 336] . X[336, C] on tcgen05 (bf16 storage).  Ragged maps (tiles
     clipped by TMA on both axes), maps smaller than one tile, two channel passes (C = 512), several images, T > 1.
     The last case has 850 tiles (> 148 CTAs: every CTA walks several tiles, the A ring is rewritten in flight).
     Stated tolerance 6e-3 * T of max|ref|: one bf16 rounding of the stored result per step (2^-9 of the element)
-    plus the bf16 rounding of the normalised weights in the A operand (zero-mean, ~1e-3 of max|ref| at 4.5 sigma)."""
-    impl = "tc"
+    plus the bf16 rounding of the normalised weights in the A operand (zero-mean, ~1e-3 of max|ref| at 4.5 sigma).
+    impl "tc" = compact SWIZZLE_32B weights operand (shipped), "tc_sw128" = SWIZZLE_128B rows (A/B variant)."""
     g = torch.Generator().manual_seed(23)
     x = torch.randn(n, c, h, w, generator=g).to(torch.bfloat16)
     wgt = torch.rand(n, 49, h, w, generator=g)

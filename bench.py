@@ -486,30 +486,49 @@ def train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding, s
             step()
             opt.step()
         launch = "CUDA graph replay of fwd+bwd + one fused AdamW launch"
-        reduce = "one NCCL all-reduce of the flat gradient buffer after the replay" if world > 1 else "none (1 GPU)"
+        reduce = (step.bucketer.describe() + " inside the captured step (overlaps backward)") if world > 1 else "none (1 GPU)"
+
+    def timed_loop(fn, n):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return sharding.max_over_ranks(a.elapsed_time(b) / 1e3, dev)
 
     for _ in range(warmup):
         one()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(steps):
-        one()
-    b.record()
-    torch.cuda.synchronize()
-    t = sharding.max_over_ranks(a.elapsed_time(b) / 1e3, dev)
-    allreduce_ms = None
-    if world > 1 and not args.train_eager:      # exposed time of the gradient reduction (it follows the replay)
-        c, d = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize(); dist.barrier()
-        c.record()
-        for _ in range(steps):
-            dist.all_reduce(step.flat_grad)
-        d.record()
-        torch.cuda.synchronize()
-        allreduce_ms = sharding.max_over_ranks(c.elapsed_time(d) / 1e3, dev) / steps * 1e3
+    t = timed_loop(one, steps)
+    allreduce_ms = in_situ_ms = after_ms = None
+    if world > 1 and not args.train_eager:
+        # exposed time of the gradient reduction, IN SITU: the same captured step with the reduction left out
+        # (reduce="none": gradients stay local), timed the same way; and the round-1 scheme (one all-reduce of the whole
+        # flat buffer after the replay) for comparison
+        step.close()
+        local = graphs.GraphedTrainStep(enc, dec, image, depth, precision=precision, flat_grad=opt.flat_grad, reduce="none")
+
+        def one_local():
+            local()
+            opt.step()
+        for _ in range(warmup):
+            one_local()
+        t_local = timed_loop(one_local, steps)
+        in_situ_ms = (t - t_local) / steps * 1e3
+        del local
+        after = graphs.GraphedTrainStep(enc, dec, image, depth, precision=precision, flat_grad=opt.flat_grad, reduce="after")
+
+        def one_after():
+            after()
+            opt.step()
+        for _ in range(warmup):
+            one_after()
+        after_ms = (timed_loop(one_after, steps) - t_local) / steps * 1e3
+        del after
+        allreduce_ms = timed_loop(lambda: dist.all_reduce(opt.flat_grad), steps) / steps * 1e3
     e, f = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e.record()
@@ -530,7 +549,8 @@ def train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding, s
                          f"{n_grad} parameters, 28 B/parameter",
             "optimizer_ms": opt_ms, "optimizer_gbs": n_grad * 28 / (opt_ms * 1e-3) / 1e9,
             "grad_allreduce": f"{reduce}, {n_grad} fp32 grads" if world > 1 else reduce,
-            "allreduce_exposed_ms": allreduce_ms}
+            "allreduce_in_situ_ms": in_situ_ms, "allreduce_after_replay_exposed_ms": after_ms,
+            "allreduce_standalone_ms": allreduce_ms, "allreduce_exposed_ms": in_situ_ms}
 
 
 def cpu_model() -> str:

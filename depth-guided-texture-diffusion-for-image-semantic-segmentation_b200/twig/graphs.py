@@ -6,9 +6,12 @@ kernels at 16 images).  The shapes of a training run are static, so the step is 
 replayed: every kernel of libdgtd_ops.so takes its stream from the caller and allocates nothing, so the
 capture needs no special casing.
 
-Gradients live in ONE flat fp32 buffer (`.grad` of every parameter is a view into it): with data
-parallel training the whole gradient is reduced by a single NCCL all-reduce after the replay
-(354.7 MB for the hot path; cod.py:238 `MMDistributedDataParallel` does the same reduction in buckets).
+Gradients live in ONE flat fp32 buffer (`.grad` of every parameter is a view into it).  With data parallel
+training the buffer is reduced in ~25 MiB buckets whose NCCL all-reduces are launched from gradient hooks INSIDE the
+captured step (twig/buckets.py), i.e. as a forked branch of the graph that overlaps the rest of backward -- the
+mechanism of the reference's `MMDistributedDataParallel` (cod.py:8,238) without its bucket copies.
+`reduce="after"` keeps the round-1 behaviour (one all-reduce of the whole buffer after the replay), `reduce="none"`
+leaves the gradients local (used to measure the exposed reduction time).
 """
 from __future__ import annotations
 
@@ -18,6 +21,7 @@ import torch
 import torch.nn as nn
 
 from . import flat
+from .buckets import GradBucketer
 from .model import texture_diffuser as TD
 
 
@@ -61,10 +65,16 @@ class GraphedTrainStep:
 
     def __init__(self, enc: nn.Module, dec: nn.Module, image: torch.Tensor, depth: torch.Tensor,
                  loss_fn: Callable = default_loss, precision: Optional[str] = None, warmup: int = 3,
-                 process_group=None, flat_grad: Optional[torch.Tensor] = None):
+                 process_group=None, flat_grad: Optional[torch.Tensor] = None, reduce: str = "bucketed",
+                 bucket_bytes: int = 25 << 20):
         assert image.is_cuda and depth.is_cuda, "GraphedTrainStep needs CUDA tensors"
+        assert reduce in ("bucketed", "after", "none")
         self.enc, self.dec, self.loss_fn, self.precision = enc, dec, loss_fn, precision
         self.group = process_group
+        import torch.distributed as dist
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.reduce = reduce if self.world > 1 else "none"
+        self.bucketer = None
         self.image, self.depth = image.detach().clone(), depth.detach().clone()
         self.params = [p for p in list(enc.parameters()) + list(dec.parameters()) if p.requires_grad]
         self.offsets, n = flat.flat_offsets(self.params)
@@ -75,24 +85,39 @@ class GraphedTrainStep:
             assert flat_grad.dtype == torch.float32 and flat.views_match(self.params, flat_grad), \
                 "flat_grad does not follow the twig/flat.py layout of these parameters"
             self.flat_grad = flat_grad
+        if self.reduce == "bucketed":
+            self.bucketer = GradBucketer(self.params, self.flat_grad, process_group, bucket_bytes)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):              # warm-up off the capture stream (allocator, lazy inits)
-            for _ in range(max(1, warmup)):
+        with torch.cuda.stream(side):              # warm-up off the capture stream (allocator, lazy inits, NCCL)
+            for i in range(max(2, warmup)):
                 self._fwd_bwd()
+                if i == 0 and self.bucketer is not None:
+                    self.bucketer.calibrate()      # which parameters receive gradients at all (adaptor.* do not)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.loss = self._fwd_bwd()
         self._ptrs = _mark_captured(self, self.params)
 
     def _fwd_bwd(self) -> torch.Tensor:
         self.flat_grad.zero_()
+        if self.bucketer is not None:
+            self.bucketer.begin()
         out = TD.texture_prompts_train(self.enc, self.dec, self.image, self.depth, precision=self.precision)
         loss = self.loss_fn(*out)
-        loss.backward()                            # accumulates in place into the flat buffer's views
+        loss.backward()                            # accumulates in place into the flat buffer's views; the hooks of
+        if self.bucketer is not None:              # twig/buckets.py launch each bucket's all-reduce as it completes
+            self.bucketer.finish()
         return loss.detach()
+
+    def close(self) -> None:
+        """Remove the gradient hooks (the captured graph keeps working; eager backward of the same parameters outside
+        this object no longer triggers reductions)."""
+        if self.bucketer is not None:
+            self.bucketer.enabled = False
+            self.bucketer.remove()
 
     def __call__(self, image: Optional[torch.Tensor] = None, depth: Optional[torch.Tensor] = None) -> torch.Tensor:
         if image is not None:
@@ -101,11 +126,9 @@ class GraphedTrainStep:
             self.depth.copy_(depth, non_blocking=True)
         _check_captured(self.params, self._ptrs, "GraphedTrainStep")
         self.graph.replay()
-        if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
-                                      and torch.distributed.get_world_size() > 1):
+        if self.reduce == "after":
             import torch.distributed as dist
-            dist.all_reduce(self.flat_grad, group=self.group)
-            self.flat_grad.div_(dist.get_world_size(self.group))
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG, group=self.group)
         return self.loss
 
 

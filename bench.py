@@ -434,7 +434,8 @@ def diffusion_microbench_w2(OP, dev, xb, hbm, fma_roof, C, S):
     return res
 
 
-def train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding, steps=5, warmup=2, precision="bf16"):
+def train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding, steps=5, warmup=2, precision="bf16",
+                measure_reduce=True):
     """Forward + backward of the hot path (block-level autograd Functions; `precision` selects the exact
     fp32 CUDA-core path or the bf16 tcgen05 path) on `train-batch` images per GPU.  Default: the step is
     captured in a CUDA graph and replayed (twig/graphs.py); with N > 1 the flat gradient buffer is
@@ -504,7 +505,7 @@ def train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding, s
         one()
     t = timed_loop(one, steps)
     allreduce_ms = in_situ_ms = after_ms = None
-    if world > 1 and not args.train_eager:
+    if world > 1 and not args.train_eager and measure_reduce:
         # exposed time of the gradient reduction, IN SITU: the same captured step with the reduction left out
         # (reduce="none": gradients stay local), timed the same way; and the round-1 scheme (one all-reduce of the whole
         # flat buffer after the replay) for comparison
@@ -833,7 +834,7 @@ def run_ours(args):
         try:
             train = train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding, precision="bf16")
             train["fp32_exact"] = train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding, steps=2,
-                                              precision="fp32")
+                                              precision="fp32", measure_reduce=False)
         except Exception as e:   # noqa: BLE001
             train = dict(train or {}, error=f"{type(e).__name__}: {e}"[:300])
 

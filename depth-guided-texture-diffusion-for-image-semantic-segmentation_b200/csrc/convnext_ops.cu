@@ -356,6 +356,8 @@ int ln_rows_any(const float* y, const float* ln_w, const float* ln_b, void* out,
                 float eps, cudaStream_t s);
 int dwconv7_ln_tma(const float* x, const float* wT, const float* dw_b, const float* ln_w, const float* ln_b,
                    float* ws, void* out, int out_dtype, int B, int h, int w, int C, float eps, cudaStream_t s);
+int dwconv7_stats_tma(const float* x, const float* wT, const float* dw_b, __nv_bfloat16* y, float2* stats, int B, int h,
+                      int w, int C, float eps, cudaStream_t s);
 }
 using namespace dgtd;
 
@@ -462,6 +464,21 @@ int dgtd_dwconv7_ln_tma_fwd(const float* x, const float* dw_wT, const float* dw_
   if (rc) return rc;
   DGTD_LAUNCH_CHECK("dwconv7_ln_tma.ln");
   return 0;
+}
+
+int dgtd_dwconv7_stats_tma_fwd(const float* x, const float* dw_wT, const float* dw_b, void* y, float* stats, int B, int h,
+                               int w, int C, float eps, dgtd_stream_t stream) {
+  DGTD_CHECK_ARG(x && dw_wT && dw_b && y && stats, "dwconv7_stats_tma: null pointer");
+  DGTD_CHECK_ARG(B > 0 && h > 0 && w > 0 && C >= 128 && C % 128 == 0 && C <= 1024,
+                 "dwconv7_stats_tma: bad shape B=%d h=%d w=%d C=%d (C must be a multiple of 128)", B, h, w, C);
+  DGTD_CHECK_ARG((reinterpret_cast<uintptr_t>(stats) & 7) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+                 "dwconv7_stats_tma: y must be 16-byte, stats 8-byte aligned");
+  int rc = dwconv7_stats_tma(x, dw_wT, dw_b, (__nv_bfloat16*)y, (float2*)stats, B, h, w, C, eps, (cudaStream_t)stream);
+  if (rc > 0) {
+    set_error("dwconv7_stats_tma: shape not supported by the TMA variant");
+    return -1;
+  }
+  return rc;
 }
 
 int dgtd_ln_rows_fwd(const float* y, const float* ln_w, const float* ln_b, void* out, int out_dtype, int64_t rows,

@@ -14,10 +14,10 @@
 
 namespace dgtd {
 
-template <int SY, int SX, bool ADD>
+template <int SY, int SX, bool ADD, typename OT = float>
 __global__ void __launch_bounds__(SY * SX * 32, 2)
 dwconv7_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ wT,
-                   const float* __restrict__ bias, const float* __restrict__ add, float* __restrict__ y, int h,
+                   const float* __restrict__ bias, const float* __restrict__ add, OT* __restrict__ y, int h,
                    int w, int C, int tiles_x, int tiles_y) {
   constexpr int TH = 4 * SY, TW = 8 * SX, PH = TH + 6, PW = TW + 6, NCH = 4;
   constexpr int TILE_FLOATS = PH * PW * 32;
@@ -112,7 +112,7 @@ dwconv7_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restr
     }
     {
       const int oy0 = y0 + 4 * sy, ox0 = x0 + 8 * sx;
-      float* yp = y + (((int64_t)b * h + oy0) * w + ox0) * C + c;
+      OT* yp = y + (((int64_t)b * h + oy0) * w + ox0) * C + c;
       const int rs = w * C;   // one image row; a sub-tile spans < 2^31 elements
       if (oy0 + 4 <= h && ox0 + 8 <= w) {   // interior sub-tile (warp-uniform): no per-store predicates
 #pragma unroll
@@ -121,8 +121,8 @@ dwconv7_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restr
           for (int j = 0; j < 8; ++j) {
             float v0, v1;
             up2(acc[q][j], v0, v1);
-            yp[(2 * q) * rs + j * C] = v0;
-            yp[(2 * q + 1) * rs + j * C] = v1;
+            store1(yp + (2 * q) * rs + j * C, v0);
+            store1(yp + (2 * q + 1) * rs + j * C, v1);
           }
       } else {
 #pragma unroll
@@ -132,8 +132,8 @@ dwconv7_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restr
             float v0, v1;
             up2(acc[q][j], v0, v1);
             if (ox0 + j < w) {
-              if (oy0 + 2 * q < h) yp[(2 * q) * rs + j * C] = v0;
-              if (oy0 + 2 * q + 1 < h) yp[(2 * q + 1) * rs + j * C] = v1;
+              if (oy0 + 2 * q < h) store1(yp + (2 * q) * rs + j * C, v0);
+              if (oy0 + 2 * q + 1 < h) store1(yp + (2 * q + 1) * rs + j * C, v1);
             }
           }
       }
@@ -268,6 +268,68 @@ ln_rows_kernel(const float* __restrict__ y, const float* __restrict__ ln_w, cons
     store4(o + c0, (v[j].x - mean) * rstd * g.x + be.x, (v[j].y - mean) * rstd * g.y + be.y,
            (v[j].z - mean) * rstd * g.z + be.z, (v[j].w - mean) * rstd * g.w + be.w);
   }
+}
+
+// (mean, rstd) of every row of a bf16 matrix (rows x C), statistics in fp32 from the stored (rounded) values -- the
+// values the LayerNorm-folded GEMM multiplies, so the centring in its epilogue is exact for them.  One warp per row.
+template <int VPL>
+__global__ void __launch_bounds__(256)
+row_stats_bf16_kernel(const __nv_bfloat16* __restrict__ y, float2* __restrict__ stats, int64_t rows, int C, float eps) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const __nv_bfloat16* p = y + row * C;
+  float4 v[VPL];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    v[j] = load4(p + (j * 32 + lane) * 4);
+    s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / C + eps);
+  if (lane == 0) stats[row] = make_float2(mean, rstd);
+}
+
+int row_stats_bf16(const __nv_bfloat16* y, float2* stats, int64_t rows, int C, float eps, cudaStream_t s) {
+  const int blocks = cdiv(rows, 8);
+  switch (C / 128) {
+    case 1: row_stats_bf16_kernel<1><<<blocks, 256, 0, s>>>(y, stats, rows, C, eps); break;
+    case 2: row_stats_bf16_kernel<2><<<blocks, 256, 0, s>>>(y, stats, rows, C, eps); break;
+    case 4: row_stats_bf16_kernel<4><<<blocks, 256, 0, s>>>(y, stats, rows, C, eps); break;
+    case 8: row_stats_bf16_kernel<8><<<blocks, 256, 0, s>>>(y, stats, rows, C, eps); break;
+    default:
+      set_error("row_stats: C=%d must be 128*{1,2,4,8}", C);
+      return -1;
+  }
+  return 0;
+}
+
+template <int SY, int SX>
+static int dw_launch_bf16(const CUtensorMap& tm, const float* wT, const float* bias, __nv_bfloat16* y, int B, int h, int w,
+                          int C, cudaStream_t s) {
+  constexpr int PH = 4 * SY + 6, PW = 8 * SX + 6;
+  constexpr int SMEM = 2 * PH * PW * 128 + 128;
+  auto kern = dwconv7_tma_kernel<SY, SX, false, __nv_bfloat16>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) {
+      set_error("dwconv7_tma(bf16): cannot opt in to %d B smem: %s", SMEM, cudaGetErrorString(e));
+      return -2;
+    }
+    configured = true;
+  }
+  const int tiles_x = cdiv(w, 8 * SX), tiles_y = cdiv(h, 4 * SY);
+  const int64_t blocks = (int64_t)B * tiles_x * tiles_y * (C / 128);
+  kern<<<(unsigned)blocks, SY * SX * 32, SMEM, s>>>(tm, wT, bias, nullptr, y, h, w, C, tiles_x, tiles_y);
+  return 0;
 }
 
 template <int SY, int SX>
@@ -420,6 +482,38 @@ int dwconv7_wgrad_tma(const float* x, const float* dy, float* part, int max_part
   }
   count_launch();
   *parts = P;
+  return 0;
+}
+
+// bf16-mode front of a ConvNeXt block with the LayerNorm folded into pwconv1: y = dwconv(x) stored ONCE as bf16
+// (no fp32 scratch), then (mean, rstd) per pixel from the stored values.  Returns 1 when the shape is not handled.
+int dwconv7_stats_tma(const float* x, const float* wT, const float* dw_b, __nv_bfloat16* y, float2* stats, int B, int h,
+                      int w, int C, float eps, cudaStream_t s) {
+  if (C % 128 || C > 1024 || (reinterpret_cast<uintptr_t>(x) & 15)) return 1;
+  int SY, SX;
+  dw_tile_shape(h, w, &SY, &SX);
+  CUtensorMap tm;
+  int rc = dw_make_tmap(&tm, x, B, h, w, C, SY, SX);
+  if (rc) return rc;
+  if (SY == 2 && SX == 2) rc = dw_launch_bf16<2, 2>(tm, wT, dw_b, y, B, h, w, C, s);
+  else if (SY == 2 && SX == 3) rc = dw_launch_bf16<2, 3>(tm, wT, dw_b, y, B, h, w, C, s);
+  else if (SY == 3 && SX == 2) rc = dw_launch_bf16<3, 2>(tm, wT, dw_b, y, B, h, w, C, s);
+  else rc = dw_launch_bf16<3, 3>(tm, wT, dw_b, y, B, h, w, C, s);
+  if (rc) return rc;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("dwconv7_stats_tma: launch failed: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  count_launch();
+  rc = row_stats_bf16(y, stats, (int64_t)B * h * w, C, eps, s);
+  if (rc) return rc;
+  e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("row_stats: launch failed: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  count_launch();
   return 0;
 }
 

@@ -79,6 +79,11 @@ struct TcParams {
   int split_rows = 0;     // M rounded up to the 256-row pair tile
   int mn_major = 0;       // 1: A is (K x M) and B is (K x N) row-major (operands read "transposed":
                           //    the reduction runs over the ROWS of two activation matrices, no copy)
+  // LayerNorm folded into the GEMM (cod.py:1108-1109: pwconv1(LN(y))): A holds the UN-normalised rows y, B holds
+  // W' = W1 * ln_weight, and the epilogue applies  rstd_m * (acc - mean_m * col_s[n]) + bias[n]  with
+  // col_s[n] = sum_k W'[n,k] (of the bf16-rounded W') and bias = W1 . ln_bias + b1.
+  const float2* row_stats = nullptr;   // [M] (mean, rstd) of each row of A
+  const float* col_s = nullptr;        // [N]
   // implicit 3x3 / stride 1 / pad 1 convolution (tc_gemm_kernel<..., CONV3 = true>): the A operand of k-block
   // (tap, 64-channel chunk) is one 4-D TMA box {64 ch, 16 px, 8 rows, 1 image} of the NHWC input shifted by the
   // tap (zero fill outside the image = padding); M tiles are 8 x 16 pixel patches.
@@ -99,6 +104,8 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
   const bool row_ok = row < p.M;
   float ks = 1.f;
   if (RESIDUAL && p.keep && row_ok) ks = p.keep[row / p.rows_per_sample];
+  float2 rs = make_float2(0.f, 1.f);
+  if (p.row_stats && row_ok) rs = p.row_stats[row];
   const uint32_t t0 = tmem_tile + ((uint32_t)(quad * 32) << 16) + half * HALF_COLS;
   uint32_t v[2][32];
   if (has_work) bw::tmem_ld_32x32(t0, v[0]);
@@ -121,6 +128,13 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
         float f[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(vv[j + e]);
+        if (p.row_stats) {
+          const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.col_s + col0 + j));
+          const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.col_s + col0 + j + 4));
+          const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = rs.y * fmaf(-rs.x, sv[e], f[e]);
+        }
         if (p.bias) {
           float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
           float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j + 4));
@@ -173,6 +187,8 @@ __device__ __forceinline__ void tc_epilogue_tile_tma(const TcParams& p, const CU
   const int row = row0 + lane;
   float ks = 1.f;
   if (RESIDUAL && p.keep && row < p.M) ks = p.keep[row / p.rows_per_sample];
+  float2 rs = make_float2(0.f, 1.f);
+  if (p.row_stats && row < p.M) rs = p.row_stats[row];
   const uint32_t t0 = tmem_tile + ((uint32_t)(quad * 32) << 16) + half * HALF_COLS;
   const int colbase = n_blk * BN + half * HALF_COLS;
   const uint32_t swz = (uint32_t)(lane & 7);
@@ -208,7 +224,21 @@ __device__ __forceinline__ void tc_epilogue_tile_tma(const TcParams& p, const CU
       float f[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(vv[j + e]);
-      if (p.bias && col0 + j < p.N) {
+      if (p.row_stats && col0 + j < p.N) {
+        // LayerNorm fold: rstd * (acc - mean * s) + c as two packed FMAs per pair of columns -- the same issue slots
+        // as the plain bias add it replaces
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.col_s + col0 + j));
+        const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.col_s + col0 + j + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j + 4));
+        const uint64_t nm = pk2(-rs.x, -rs.x), rr = pk2(rs.y, rs.y);
+        uint64_t x0 = fma2(nm, pk2(s0.x, s0.y), pk2(f[0], f[1])), x1 = fma2(nm, pk2(s0.z, s0.w), pk2(f[2], f[3]));
+        uint64_t x2 = fma2(nm, pk2(s1.x, s1.y), pk2(f[4], f[5])), x3 = fma2(nm, pk2(s1.z, s1.w), pk2(f[6], f[7]));
+        up2(fma2(rr, x0, pk2(b0.x, b0.y)), f[0], f[1]);
+        up2(fma2(rr, x1, pk2(b0.z, b0.w)), f[2], f[3]);
+        up2(fma2(rr, x2, pk2(b1.x, b1.y)), f[4], f[5]);
+        up2(fma2(rr, x3, pk2(b1.z, b1.w)), f[6], f[7]);
+      } else if (p.bias && col0 + j < p.N) {
         float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
         float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j + 4));
         f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;

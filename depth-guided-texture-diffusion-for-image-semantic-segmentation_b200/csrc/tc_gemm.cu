@@ -300,9 +300,11 @@ int tc_conv3(const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, 
 }
 
 int tc_linear(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B, int64_t ldb, const float* bias,
-              void* out, int M, int N, int K, int64_t ldo, int dtype_out, int act, cudaStream_t s) {
+              void* out, int M, int N, int K, int64_t ldo, int dtype_out, int act, cudaStream_t s,
+              const float2* row_stats = nullptr, const float* col_s = nullptr) {
   TcParams p{};
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.ldo = ldo; p.rows_per_sample = 1;
+  p.row_stats = row_stats; p.col_s = col_s;
   {
     int rc2 = tc_gemm2_launch(A, lda, B, ldb, p, act, dtype_out, false, s);
     if (rc2 <= 0) return rc2;
@@ -371,6 +373,21 @@ int dgtd_linear_fwd(const void* a, const void* w, const float* bias, void* out, 
   }
 #undef DGTD_SIMT_LIN
   DGTD_LAUNCH_CHECK("linear(fp32)");
+  return 0;
+}
+
+int dgtd_linear_lnfold_fwd(const void* a, const void* w, const float* bias, const float* col_s, const float* row_stats,
+                           void* out, int M, int N, int K, int ldo, int dtype_out, int act, dgtd_stream_t stream) {
+  DGTD_CHECK_ARG(a && w && bias && col_s && row_stats && out, "linear_lnfold: null pointer");
+  DGTD_CHECK_ARG(M > 0 && N > 0 && K > 0 && ldo >= N, "linear_lnfold: bad shape M=%d N=%d K=%d ldo=%d", M, N, K, ldo);
+  DGTD_CHECK_ARG(act >= 0 && act <= 2, "linear_lnfold: bad activation %d", act);
+  DGTD_CHECK_ARG(K % 8 == 0 && N % 8 == 0 && ldo % 8 == 0, "linear_lnfold: K, N, ldo must be multiples of 8");
+  DGTD_CHECK_ARG((reinterpret_cast<uintptr_t>(row_stats) & 7) == 0 && (reinterpret_cast<uintptr_t>(col_s) & 15) == 0,
+                 "linear_lnfold: row_stats must be 8-byte, col_s 16-byte aligned");
+  int rc = tc_linear((const __nv_bfloat16*)a, K, (const __nv_bfloat16*)w, K, bias, out, M, N, K, ldo, dtype_out, act,
+                     (cudaStream_t)stream, (const float2*)row_stats, col_s);
+  if (rc) return rc;
+  DGTD_LAUNCH_CHECK("linear_lnfold(tcgen05)");
   return 0;
 }
 

@@ -12,6 +12,8 @@ forward runs under ``torch.autocast``.
 """
 from __future__ import annotations
 
+import os
+
 import math
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -29,6 +31,11 @@ __all__ = [
     "build_texture_diffuser", "pvt_token_grids", "texture_prompts", "texture_prompts_train", "PVT_EMBED_DIMS",
     "PVT_DEPTHS",
 ]
+
+# bf16 inference: fold each block's LayerNorm into pwconv1 (no normalised copy, no fp32 conv scratch).  The folded form
+# centres in fp32 AFTER the bf16 rounding of the un-normalised conv output, i.e. it loses accuracy when a pixel's
+# channel mean dwarfs its channel spread (|mean| >> std); DGTD_LN_FOLD=0 keeps the two-pass form.
+LN_FOLD = os.environ.get("DGTD_LN_FOLD", "1") != "0"
 
 PVT_EMBED_DIMS = (64, 128, 320, 512)  # pvt_v2_b2, cod.py:1785
 PVT_DEPTHS = (3, 4, 6, 3)             # cod.py:1786
@@ -210,6 +217,24 @@ class convnext_Block(nn.Module):
         dw_w = pk.get("dw", [self.dwconv.weight], lambda: self.dwconv.weight.detach().reshape(C, 49).float().contiguous())
         w1 = pk.get(f"w1.{mode}", [self.pwconv1.weight], lambda: _as(self.pwconv1.weight, mode))
         w2 = pk.get(f"w2.{mode}", [self.pwconv2.weight], lambda: _as(self.pwconv2.weight, mode))
+        keep = self.drop_path.keep_scale(B, x.device) if isinstance(self.drop_path, DropPath) else None
+        gamma = self.gamma.detach() if self.gamma is not None else None
+        if mode == BF16 and LN_FOLD and C % 128 == 0 and B * h * w >= 2048:
+            # LayerNorm folded into pwconv1: the conv output is stored once (bf16), per-pixel (mean, rstd) come from the
+            # stored values, and pwconv1's epilogue applies rstd * (y W'^T - mean * rowsum(W')) + (W1 ln_b + b1)
+            dw_wT = pk.get("dwT", [self.dwconv.weight],
+                           lambda: self.dwconv.weight.detach().reshape(C, 49).t().float().contiguous())
+
+            def fold():
+                w1f = self.pwconv1.weight.detach().float()
+                wq = (w1f * self.norm.weight.detach().float()[None, :]).to(torch.bfloat16).contiguous()
+                return (wq, wq.float().sum(1).contiguous(),
+                        (w1f @ self.norm.bias.detach().float() + self.pwconv1.bias.detach().float()).contiguous())
+            wq, col_s, cbias = pk.get("w1.lnfold", [self.pwconv1.weight, self.pwconv1.bias, self.norm.weight, self.norm.bias], fold)
+            y, stats = OP.dwconv7_stats_tma(x, dw_wT, self.dwconv.bias.detach(), self.norm.eps)
+            hid = OP.linear_lnfold(y.view(-1, C), wq, cbias, col_s, stats, act=ACT_GELU)
+            OP.linear_residual_(hid, w2, self.pwconv2.bias.detach(), gamma, keep, h * w, x)
+            return x
         if C % 128 == 0 and B * h * w >= 2048:   # TMA-staged conv + row LayerNorm (large maps)
             dw_wT = pk.get("dwT", [self.dwconv.weight],
                            lambda: self.dwconv.weight.detach().reshape(C, 49).t().float().contiguous())
@@ -220,8 +245,6 @@ class convnext_Block(nn.Module):
             a = OP.dwconv7_ln(x, dw_w, self.dwconv.bias.detach(), self.norm.weight.detach(),
                               self.norm.bias.detach(), mode, self.norm.eps)
         hid = OP.linear(a.view(-1, C), w1, self.pwconv1.bias.detach(), act=ACT_GELU)
-        keep = self.drop_path.keep_scale(B, x.device) if isinstance(self.drop_path, DropPath) else None
-        gamma = self.gamma.detach() if self.gamma is not None else None
         OP.linear_residual_(hid, w2, self.pwconv2.bias.detach(), gamma, keep, h * w, x)
         return x
 

@@ -364,6 +364,32 @@ def dwconv7_ln_tma(x: torch.Tensor, dw_wT, dw_b, ln_w, ln_b, out_dtype: int, ws:
     return out
 
 
+def dwconv7_stats_tma(x: torch.Tensor, dw_wT, dw_b, eps: float = 1e-6):
+    """bf16-mode block front with the LayerNorm folded into pwconv1: returns (y bf16 (B,h,w,C) = depthwise 7x7 of x,
+    stats (B*h*w, 2) fp32 = (mean, rstd) per pixel of the stored values)."""
+    check_cuda(x, dw_wT, dw_b)
+    B, h, w, C = x.shape
+    y = torch.empty(B, h, w, C, device=x.device, dtype=torch.bfloat16)
+    stats = torch.empty(B * h * w, 2, device=x.device, dtype=torch.float32)
+    call("dgtd_dwconv7_stats_tma_fwd", ptr(x), ptr(dw_wT), ptr(dw_b), ptr(y), ptr(stats), B, h, w, C, float(eps), stream())
+    return y, stats
+
+
+def linear_lnfold(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, col_s: torch.Tensor, row_stats: torch.Tensor,
+                  act: int = ACT_NONE, out_dtype: int = BF16) -> torch.Tensor:
+    """act(LN(a) @ W1^T + b1) with the LayerNorm applied in the GEMM epilogue (see dgtd_linear_lnfold_fwd)."""
+    check_cuda(a, w, bias, col_s, row_stats)
+    K = a.shape[-1]
+    M = a.numel() // K
+    N = w.shape[0]
+    assert w.shape[1] == K and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and row_stats.shape == (M, 2)
+    out = torch.empty(tuple(a.shape[:-1]) + (N,), device=a.device, dtype=_tdtype(out_dtype))
+    with _timed(2.0 * M * N * K, True, (M, N, K)):
+        call("dgtd_linear_lnfold_fwd", ptr(a), ptr(w), ptr(bias), ptr(col_s), ptr(row_stats), ptr(out), M, N, K, N,
+             out_dtype, act, stream())
+    return out
+
+
 def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int = ACT_NONE,
            out_dtype: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M,N] = act(a[M,K] @ w[N,K]^T + bias).  a and w share a dtype (fp32 exact / bf16 tcgen05)."""

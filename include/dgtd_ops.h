@@ -164,6 +164,17 @@ int dgtd_dwconv7_ln_fwd(const float* x, const float* dw_w, const float* dw_b, co
 int dgtd_dwconv7_ln_tma_fwd(const float* x, const float* dw_wT, const float* dw_b, const float* ln_w,
                             const float* ln_b, float* ws, void* out, int out_dtype, int B, int h, int w,
                             int C, float eps, dgtd_stream_t stream);
+/* bf16-mode front of a block with the LayerNorm FOLDED into pwconv1 (cod.py:1106-1109): y = depthwise 7x7 of x,
+ * stored once as bf16 (B,h,w,C) -- no fp32 scratch, no normalised copy -- and stats[pixel] = (mean, rstd) over C of
+ * the stored values (eps inside the sqrt).  C multiple of 128. */
+int dgtd_dwconv7_stats_tma_fwd(const float* x, const float* dw_wT, const float* dw_b, void* y, float* stats, int B,
+                               int h, int w, int C, float eps, dgtd_stream_t stream);
+/* out[M,N] = act(rstd_m * (a[M,K] . w[N,K]^T - mean_m * col_s[N]) + bias[N]) on tcgen05, a / w bf16:
+ * == act(LN(a) . W1^T + b1) when w = W1 * ln_weight (rounded to bf16), col_s[n] = sum_k w[n,k] (of the rounded values),
+ * bias = W1 . ln_bias + b1, row_stats[m] = (mean, rstd) of row m of a (float2).  pwconv1 with its LayerNorm folded
+ * in (cod.py:1108-1110): the normalised activation never exists in memory. */
+int dgtd_linear_lnfold_fwd(const void* a, const void* w, const float* bias, const float* col_s, const float* row_stats,
+                           void* out, int M, int N, int K, int ldo, int dtype_out, int act, dgtd_stream_t stream);
 /* out[M,N] = act(a[M,K] . w[N,K]^T + bias): pwconv1+GELU (:1109-1110), downsample conv
  * (:1134), head 1x1 convs (:1160,1174).  a/w dtype = dtype_in (fp32: CUDA-core exact path,
  * bf16: tcgen05), out dtype = dtype_out, ldo = row stride of out in elements. */

@@ -153,3 +153,54 @@ def test_wgrad_tc_mn_reads_untransposed_operands(Mo, No, Kr, lda, ldb, tr):
     assert err <= 2e-3, err
     got2 = TF.wgrad_tc_mn(a, b, transpose_out=tr)
     assert torch.equal(got, got2)
+
+
+@pytest.mark.parametrize("M,C,mean", [(600, 256, 0.0), (2304, 128, 0.7), (4096, 512, 2.0)])
+def test_layernorm_folded_into_pwconv1(M, C, mean):
+    """cod.py:1108-1110 as ONE GEMM: act(rstd * (y W'^T - mean * rowsum(W')) + (W1 ln_b + b1)) against float64
+    GELU(LN(y) W1^T + b1) on the same bf16-rounded y; also against the two-pass form (LayerNorm kernel -> bf16 ->
+    GEMM).  Rows with a channel mean up to 2 sigma: the folded form rounds y BEFORE centring, so its error grows with
+    |mean| / sigma -- bounded here at 2x the two-pass error + 1e-2."""
+    common.package()
+    from dgtd_b200.twig.ops.functions import texture_diffusion_func as OP
+    from dgtd_b200.twig.ops import capi
+    g = torch.Generator().manual_seed(C + M)
+    y = (torch.randn(M, C, generator=g) * 1.3 + mean + 0.3 * torch.randn(M, 1, generator=g)).to(torch.bfloat16)
+    ln_w = 1.0 + 0.2 * torch.randn(C, generator=g)
+    ln_b = 0.2 * torch.randn(C, generator=g)
+    w1 = torch.randn(4 * C, C, generator=g) / C ** 0.5
+    b1 = 0.1 * torch.randn(4 * C, generator=g)
+    y64 = y.double()
+    mu, var = y64.mean(1, keepdim=True), y64.var(1, unbiased=False, keepdim=True)
+    a64 = (y64 - mu) / torch.sqrt(var + 1e-6) * ln_w.double() + ln_b.double()
+    ref = torch.nn.functional.gelu(a64 @ w1.double().t() + b1.double())
+    # folded
+    wq = (w1 * ln_w[None, :]).to(torch.bfloat16)
+    col_s = wq.float().sum(1)
+    cbias = w1 @ ln_b + b1
+    stats = torch.stack([mu.float().squeeze(1), (1.0 / torch.sqrt(var + 1e-6)).float().squeeze(1)], 1).contiguous()
+    got = OP.linear_lnfold(y.cuda(), wq.cuda(), cbias.cuda(), col_s.cuda(), stats.cuda(), act=capi.ACT_GELU)
+    e_fold = common.rel_err(got, ref)
+    # two-pass: normalised activation rounded to bf16, plain GEMM
+    two = OP.linear(a64.float().to(torch.bfloat16).cuda(), w1.to(torch.bfloat16).cuda(), b1.cuda(), act=capi.ACT_GELU)
+    e_two = common.rel_err(two, ref)
+    print(f"M={M} C={C} mean={mean}: folded {e_fold:.2e}, two-pass {e_two:.2e}")
+    assert e_fold <= 2.0 * e_two + 1e-2
+
+
+def test_dwconv7_stats_matches_conv_and_row_moments():
+    """dgtd_dwconv7_stats_tma_fwd: y = depthwise 7x7 (bf16 store), stats = (mean, rstd) of the STORED row."""
+    common.package()
+    from dgtd_b200.twig.ops.functions import texture_diffusion_func as OP
+    g = torch.Generator().manual_seed(5)
+    B, h, w, C = 2, 24, 40, 256
+    x = torch.randn(B, h, w, C, generator=g)
+    wt = torch.randn(C, 1, 7, 7, generator=g) * 0.2
+    bias = torch.randn(C, generator=g) * 0.1
+    ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), wt.double(), bias.double(), padding=3, groups=C)
+    y, stats = OP.dwconv7_stats_tma(x.cuda(), wt.reshape(C, 49).t().contiguous().cuda(), bias.cuda(), 1e-6)
+    assert y.dtype == torch.bfloat16
+    assert common.rel_err(y.float().permute(0, 3, 1, 2), ref) <= 5e-3
+    yf = y.double().cpu().view(-1, C)
+    mu, var = yf.mean(1), yf.var(1, unbiased=False)
+    assert common.rel_err(stats[:, 0], mu) <= 1e-5 and common.rel_err(stats[:, 1], 1.0 / torch.sqrt(var + 1e-6)) <= 1e-5

@@ -33,5 +33,5 @@ summ = capi.profile_summary()
 capi.enable_profile(False)
 tot = sum(v[1] for v in summ.values())
 print(f"sum of entry points: {tot:.1f} ms/step (B={B}, fwd+bwd {prec})")
-for k, v in sorted(summ.items(), key=lambda kv: -kv[1][1])[:16]:
+for k, v in sorted(summ.items(), key=lambda kv: -kv[1][1])[:28]:
     print(f"| `{k}` | {v[0]} | {v[1]:.2f} | {100 * v[1] / tot:.1f}% |")

@@ -74,6 +74,8 @@ SIGNATURES = {
     "dgtd_resize_nhwc_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "dgtd_transpose_op": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "dgtd_colsum_bf16": [_P, _P, _P, _I, _I, _P],
+    "dgtd_eltwise_colsum_ws_floats": [_I, _I],
+    "dgtd_eltwise_colsum": [_P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _P],
     "dgtd_wgrad_tc": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "dgtd_wgrad_tc_ws_floats": [_I, _I, _I],
     "dgtd_wgrad_tc_mn": [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _P],

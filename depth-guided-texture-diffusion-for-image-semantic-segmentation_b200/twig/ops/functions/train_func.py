@@ -105,6 +105,17 @@ def transpose_op(src, mode, aux=None, want_dst=False, want_T=True, keep=None, ga
     return dst, dstT
 
 
+def eltwise_colsum(src, mode, aux=None, keep=None, rows_per_sample=1):
+    """bf16 dst = (mode 0: keep * fp32 src | mode 2: src * gelu'(aux)) AND its fp32 column sums in one pass."""
+    M, N = src.shape
+    dst = torch.empty(M, N, device=src.device, dtype=torch.bfloat16)
+    ws = _empty((capi.load().dgtd_eltwise_colsum_ws_floats(M, N),), src)
+    out = torch.empty(N, device=src.device, dtype=torch.float32)
+    call("dgtd_eltwise_colsum", ptr(src), ptr(aux), ptr(dst), ptr(keep), rows_per_sample, ptr(ws), ptr(out), M, N, mode,
+         stream())
+    return dst, out
+
+
 def wgrad_tc(aT, bT, transpose_out=False):
     """(Mo x No) = aT[Mo,Kr] @ bT[No,Kr]^T on tcgen05 (split-K over Kr); fp32 result (optionally transposed)."""
     Mo, Kr = aT.shape
@@ -182,8 +193,7 @@ class ConvNextBlockBf16Fn(Function):
         B, h, w, C = x.shape
         rows, C4, M = h * w, 4 * C, B * h * w
         g2 = g.view(M, C)
-        s = colsum(g2, C, keep, rows)
-        gk, _ = transpose_op(g2, 0, want_dst=True, want_T=False, keep=keep, rows_per_sample=rows)   # bf16 keep*g
+        gk, s = eltwise_colsum(g2, 0, keep=keep, rows_per_sample=rows)   # bf16 keep*g and its column sums, one pass
         G = wgrad_tc_mn(gk, hid)                                       # (C, 4C) = (keep g)^T hid
         dW2, db2 = torch.empty_like(w2), _empty((C,), g)
         dgamma = _empty((C,), g) if gamma is not None else None
@@ -191,10 +201,9 @@ class ConvNextBlockBf16Fn(Function):
              ptr(dgamma), C, C4, stream())
         w2g = w2 if gamma is None else w2 * gamma[:, None]
         dh = OP.linear(gk, w2g.t().to(torch.bfloat16).contiguous(), None)   # bf16 (M, 4C) = (keep g) @ (gamma W2)
-        dhpre, _ = transpose_op(dh, 2, aux=hpre, want_dst=True, want_T=False)
+        dhpre, db1 = eltwise_colsum(dh, 2, aux=hpre)                   # dH * gelu'(pre) and db1, one pass
         del dh, gk
         dW1 = wgrad_tc_mn(dhpre, a)                                    # (4C, C)
-        db1 = colsum_bf16(dhpre)
         da = OP.linear(dhpre, w1b.t().contiguous(), None, out_dtype=F32)   # fp32 (M, C)
         del dhpre
         dy, dln_w, dln_b = ln_rows_bwd(da, y, ln_w, ctx.eps)

@@ -274,6 +274,13 @@ int dgtd_resize_nhwc_bwd(const float* g, float* dx, int B, int h, int w, int C, 
 int dgtd_transpose_op(const void* src, const void* aux, void* dst, void* dstT, const float* keep, const float* gamma,
                       int rows_per_sample, int M, int N, int mode, dgtd_stream_t stream);
 int dgtd_colsum_bf16(const void* x, float* ws, float* out, int M, int N, dgtd_stream_t stream);
+/* The element-wise pass of modes 0 / 2 above fused with the column sums of its result (taken before the bf16
+ * rounding): dst (M x N bf16) = v, colsum[n] = sum_m v[m,n] -- the bias gradient of pwconv1 (mode 2) and the
+ * layer-scale / pwconv2 bias sum (mode 0) without a second pass over the matrix.  Fixed-order (deterministic).
+ * ws: dgtd_eltwise_colsum_ws_floats(M, N) floats. */
+int dgtd_eltwise_colsum_ws_floats(int M, int N);
+int dgtd_eltwise_colsum(const void* src, const void* aux, void* dst, const float* keep, int rows_per_sample, float* ws,
+                        float* colsum, int M, int N, int mode, dgtd_stream_t stream);
 /* out (Mo x No fp32, or its transpose) = aT[Mo,Kr] . bT[No,Kr]^T: weight gradient on tcgen05 with
  * split-K over the long row axis Kr + fixed-order reduction.  ws: dgtd_wgrad_tc_ws_floats floats. */
 int dgtd_wgrad_tc(const void* aT, const void* bT, float* out, float* ws, int Mo, int No, int Kr, int transpose_out,

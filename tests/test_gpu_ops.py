@@ -220,6 +220,24 @@ def test_message_passing_tensor_core_banded_gemm(OP, n, h, w, c, T, impl):
         assert d <= 1e-2 * T
 
 
+@pytest.mark.parametrize("n,h,w,c,T", [(1, 40, 72, 256, 1), (2, 17, 36, 256, 3), (1, 64, 64, 512, 2), (1, 8, 16, 256, 1),
+                                       (1, 5, 4, 256, 2), (2, 200, 264, 256, 2)])
+def test_message_passing_tensor_core_fp32_storage(OP, n, h, w, c, T):
+    """mp_tc_f32.cu: fp32 storage on the tensor pipe as three bf16 products (A_hi X_hi + A_hi X_lo + A_lo X_hi,
+    16 significant bits per operand): <= 1e-5 of max|ref| against the float64 oracle -- the bar of the CUDA-core
+    kernel.  Ragged heights, maps smaller than a tile, two channel blocks, several images, 850 tiles, T > 1."""
+    g = torch.Generator().manual_seed(29)
+    x = torch.randn(n, c, h, w, generator=g)
+    wgt = torch.rand(n, 49, h, w, generator=g)
+    ref = O.message_passing_core(x.double(), wgt.double(), 7, T)
+    xc = x.permute(0, 2, 3, 1).contiguous().cuda()
+    got = OP.message_passing_tiled(xc, wgt.cuda(), T, impl="tc")
+    assert got.dtype == torch.float32
+    err = check(got.permute(0, 3, 1, 2), ref, 1e-5)
+    simt = OP.message_passing_tiled(xc, wgt.cuda(), T, impl="simt")
+    print(f"tc[fp32] vs oracle {err:.2e}; SIMT kernel vs oracle {common.rel_err(simt.permute(0, 3, 1, 2), ref):.2e}")
+
+
 def test_message_passing_tensor_core_constant_map(OP):
     """Interior pixels of a constant map stay constant (weights sum to sum/(sum+eps)); borders lose exactly the
     weight of the taps that fall outside (zero padding, no renormalisation: cod.py:1204)."""

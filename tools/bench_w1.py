@@ -22,5 +22,8 @@ for impl in sys.argv[1:] or ["tc", "tc_sw128", "simt"]:
         ms = t(lambda: OP.message_passing_tiled(xb, wgt, T, impl=impl))
         nbytes = (2 * C * 2 + 49 * 4) * S * S
         print(f"bf16 {impl} T={T}: {ms:.4f} ms  per-step {ms / T:.4f} ms  {nbytes * T / ms / 1e6:.0f} GB/s  hbm_frac {nbytes * T / ms / 1e6 / 6549:.3f}")
-ms = t(lambda: OP.message_passing_tiled(x, wgt, 1))
-print(f"fp32 auto T=1: {ms:.4f} ms")
+for impl in ("tc", "simt"):
+    for T in (1, 4):
+        ms = t(lambda: OP.message_passing_tiled(x, wgt, T, impl=impl))
+        nbytes = (2 * C * 4 + 49 * 4) * S * S
+        print(f"fp32 {impl} T={T}: {ms:.4f} ms  per-step {ms / T:.4f} ms  {nbytes * T / ms / 1e6:.0f} GB/s  hbm_frac {nbytes * T / ms / 1e6 / 6549:.3f}")

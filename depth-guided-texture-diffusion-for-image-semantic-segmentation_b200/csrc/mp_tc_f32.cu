@@ -36,7 +36,8 @@ constexpr int A_HALF = 3 * 128 * 32;           // one plane (hi or lo) of a chun
 constexpr int A_STAGE = 2 * A_HALF, NA = 3;
 constexpr int XBLK = CK * 128;                 // 64-channel block of a chunk: 48 K rows x 128 B
 constexpr int X_HALF = (NB / 64) * XBLK;       // one plane of a chunk, 24 KB
-constexpr int X_STAGE = 2 * X_HALF, NX = 2;
+constexpr int X_STAGE = 2 * X_HALF, NX = 2;    // (staging X per K step -- 6 stages of 16 KB -- was measured: 0.89 ms
+                                               // against 0.74 ms, three times the fences and barrier round trips)
 constexpr int W_BYTES = 49 * TH * TW * 4, W_SLOT = 25600;
 constexpr int STG = 4 * 4096;
 constexpr int OFF_X = NA * A_STAGE;
@@ -82,8 +83,15 @@ __device__ __forceinline__ Item decode_item(const Params& p, int item) {   // it
   return it;
 }
 
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
-mp_tc_f32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, const Params p) {
+mp_tc_f32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut,
+                 const __grid_constant__ CUtensorMap tmX, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -109,6 +117,7 @@ mp_tc_f32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   if (warp == 0 && lane == 0) {
     bw::prefetch_tmap(&tmW);
     bw::prefetch_tmap(&tmOut);
+    bw::prefetch_tmap(&tmX);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < NX; ++i) {
@@ -142,6 +151,21 @@ mp_tc_f32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         bw::mbar_arrive_expect_tx(w_full, W_BYTES);
         bw::tma_load_4d(&tmW, w_full, sW, it.tx * TW, it.ty * TH, 0, it.img);
       }
+      __syncwarp();
+    }
+  } else if (warp == 3) {
+    // ===================== L2 prefetcher: the converters' register pipeline holds 48 KB per SM in flight, which at
+    // the ~1.8 us of a loaded DRAM round trip caps the kernel at 4 TB/s of L2->SM traffic (r2 measurement, 0.75 ms).
+    // One TMA L2-prefetch of the {256 ch, 24 px, 2 rows} box per chunk, PF chunks ahead of the conversion, turns the
+    // converters' loads into L2 hits without a register or a byte of shared memory. =====================
+    constexpr int PF = 3;
+    const int total_chunks = num_items * NCHUNK;
+    for (int c = -PF; c < total_chunks - PF; ++c) {
+      if (c >= 0) bw::mbar_wait(&x_empty[(uint32_t)c % NX], (((uint32_t)c / NX) & 1) ^ 1);   // pace with the consumption
+      const int t = c + PF;
+      const Item it = decode_item(p, t / NCHUNK);
+      if (bw::elect_one())
+        tma_prefetch_l2_4d(&tmX, it.nb * NB, it.tx * TW - 3, it.ty * TH - 3 + 2 * (t % NCHUNK), it.img);
       __syncwarp();
     }
   } else if (warp == 1) {
@@ -290,58 +314,75 @@ mp_tc_f32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     }
   } else if (warp >= 16) {
     // ===================== X converters: fp32 halo rows -> (hi, lo) bf16 planes, MN-major SWIZZLE_128B ===========
+    // r2 profile of the first version: 410 instructions per chunk per warp (64-bit address arithmetic, item decoding
+    // and bounds checks per 16-byte piece) made this role issue-bound at 3x the MMA time.  Everything that does not
+    // depend on the chunk is hoisted: a thread's six pieces are rows rg, rg+8, rg+16 of halo row 0 and of halo row 1,
+    // their shared-memory slots are 1 KB apart, the item is decoded once per seven chunks.
     const int cid = threadIdx.x - 512;
     const int pc = cid & 63, rg = cid >> 6;                 // 16-byte piece (4 channels) of a pixel, row group 0..7
-    const uint32_t dst_col = (uint32_t)(pc >> 4) * XBLK + (uint32_t)(pc & 1) * 8;
-    const uint32_t chunk16 = (uint32_t)(pc & 15) >> 1;
     const int total_chunks = num_items * NCHUNK;
+    const int rowstride = p.w * p.C;                        // floats per image row (host: < 2^31)
+    const int o0 = rg * p.C, o1 = (rg + 8) * p.C, o2 = (rg + 16) * p.C;
+    // slot of piece i: row rg + 8i of the 48-row stage (1 KB apart); (rg + 8i) & 7 == rg, so the swizzle term is fixed
+    const uint32_t dst0 = bw::smem_u32(sX) + (uint32_t)(pc >> 4) * XBLK + (uint32_t)(pc & 1) * 8 + (uint32_t)rg * 128 +
+                          (((((uint32_t)(pc & 15)) >> 1) ^ (uint32_t)rg) << 4);
+    // state of the chunk that is fetched NEXT
+    int item_n = 0, j_n = 0, gy_n = 0;
+    const float* p_n = p.x;
+    bool col0 = false, col1 = false, col2 = false, live = total_chunks > 0;
+    auto start_item = [&]() {
+      const Item it = decode_item(p, item_n);
+      const int gx0 = it.tx * TW - 3;
+      gy_n = it.ty * TH - 3;
+      col0 = (unsigned)(gx0 + rg) < (unsigned)p.w;
+      col1 = (unsigned)(gx0 + rg + 8) < (unsigned)p.w;
+      col2 = (unsigned)(gx0 + rg + 16) < (unsigned)p.w;
+      p_n = p.x + ((int64_t)it.img * p.h + gy_n) * rowstride + (int64_t)gx0 * p.C + it.nb * NB + pc * 4;
+    };
+    auto advance = [&]() {
+      if (++j_n == NCHUNK) {
+        j_n = 0;
+        live = ++item_n < num_items;
+        if (live) start_item();
+      } else {
+        p_n += 2 * rowstride;
+        gy_n += 2;
+      }
+    };
+    auto fetch = [&](int i) {   // piece i of the next chunk (i < 3: halo row 0, else halo row 1)
+      const bool rowok = (unsigned)(gy_n + (i >= 3 ? 1 : 0)) < (unsigned)p.h;
+      const bool colok = (i % 3 == 0) ? col0 : (i % 3 == 1) ? col1 : col2;
+      const float* q = p_n + (i >= 3 ? rowstride : 0) + ((i % 3 == 0) ? o0 : (i % 3 == 1) ? o1 : o2);
+      return (live && rowok && colok) ? __ldg(reinterpret_cast<const float4*>(q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
     float4 v[6];
-    // chunk counter c -> (base pointer of this thread's piece, first halo row / column); rolling register pipeline:
-    // piece i of chunk c+1 is requested right after piece i of chunk c has been split and stored
-    struct Src { const float* base; int gy0, gx0; bool live; };
-    auto locate = [&](int c) {
-      Src q;
-      q.live = c < total_chunks;
-      const Item it = decode_item(p, q.live ? c / NCHUNK : 0);
-      const int j = c % NCHUNK;
-      q.gy0 = it.ty * TH - 3 + 2 * j;
-      q.gx0 = it.tx * TW - 3;
-      q.base = p.x + (int64_t)it.img * p.h * p.w * p.C + it.nb * NB + pc * 4;
-      return q;
-    };
-    auto fetch = [&](const Src& q, int i) {
-      const int r = rg + 8 * i;
-      const int gy = q.gy0 + (r >= PW ? 1 : 0), gx = q.gx0 + (r >= PW ? r - PW : r);
-      const bool ok = q.live && gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
-      return ok ? __ldg(reinterpret_cast<const float4*>(q.base + ((int64_t)gy * p.w + gx) * p.C)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-    if (total_chunks > 0) {
-      const Src q0 = locate(0);
+    if (live) {
+      start_item();
 #pragma unroll
-      for (int i = 0; i < 6; ++i) v[i] = fetch(q0, i);
+      for (int i = 0; i < 6; ++i) v[i] = fetch(i);
+      advance();
     }
     for (int c = 0; c < total_chunks; ++c) {
       const uint32_t xs = (uint32_t)c % NX;
-      const Src nxt = locate(c + 1);
       bw::mbar_wait(&x_empty[xs], (((uint32_t)c / NX) & 1) ^ 1);
-      const uint32_t sbase = bw::smem_u32(sX) + xs * X_STAGE + dst_col;
+      const uint32_t sbase = dst0 + xs * X_STAGE;
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
-        const uint32_t r = (uint32_t)(rg + 8 * i);
         const float4 cur = v[i];
         const __nv_bfloat162 h01 = __floats2bfloat162_rn(cur.x, cur.y), h23 = __floats2bfloat162_rn(cur.z, cur.w);
-        const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-        const __nv_bfloat162 l01 = __floats2bfloat162_rn(cur.x - f01.x, cur.y - f01.y);
-        const __nv_bfloat162 l23 = __floats2bfloat162_rn(cur.z - f23.x, cur.w - f23.y);
-        const uint32_t addr = sbase + r * 128 + ((chunk16 ^ (r & 7)) << 4);
-        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(*reinterpret_cast<const uint32_t*>(&h01)),
-                     "r"(*reinterpret_cast<const uint32_t*>(&h23))
-                     : "memory");
+        const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&h01), u23 = *reinterpret_cast<const uint32_t*>(&h23);
+        // bf16 -> fp32 is a 16-bit shift: low half << 16, high half masked
+        const float l0 = cur.x - __uint_as_float(u01 << 16), l1 = cur.y - __uint_as_float(u01 & 0xffff0000u);
+        const float l2 = cur.z - __uint_as_float(u23 << 16), l3 = cur.w - __uint_as_float(u23 & 0xffff0000u);
+        const __nv_bfloat162 l01 = __floats2bfloat162_rn(l0, l1), l23 = __floats2bfloat162_rn(l2, l3);
+        const uint32_t addr = sbase + (uint32_t)i * 1024;
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(u01), "r"(u23) : "memory");
         asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr + X_HALF), "r"(*reinterpret_cast<const uint32_t*>(&l01)),
                      "r"(*reinterpret_cast<const uint32_t*>(&l23))
                      : "memory");
-        v[i] = fetch(nxt, i);   // the next chunk's piece flies while the rest of this chunk is split and stored
+        v[i] = fetch(i);   // the next chunk's piece flies while the rest of this chunk is split and stored
       }
+      advance();
       bw::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) bw::mbar_arrive(&x_full[xs]);
@@ -357,8 +398,15 @@ mp_tc_f32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
 // One fp32-storage diffusion step on the tensor pipe; 0 on success, 1 when the shape is not handled here.
 int mp_tc_step_f32(const void* x, const float* weight, void* out, int n, int h, int w, int c, float eps, cudaStream_t s) {
   using namespace mptc32;
-  if (c % NB != 0 || w % 4 != 0 || (int64_t)h * w * 49 >= (int64_t)1 << 31) return 1;   // TMA strides: multiples of 16 B
-  CUtensorMap tmW, tmOut;
+  if (c % NB != 0 || w % 4 != 0 || (int64_t)h * w * 49 >= (int64_t)1 << 31 || (int64_t)w * c >= (int64_t)1 << 29) return 1;   // TMA strides: multiples of 16 B
+  CUtensorMap tmW, tmOut, tmX;
+  {
+    const uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    const uint64_t strides[3] = {(uint64_t)c * 4, (uint64_t)w * c * 4, (uint64_t)h * w * c * 4};
+    const uint32_t box[4] = {NB, PW, 2, 1};
+    int rc = make_tmap(&tmX, x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+  }
   {
     const uint64_t dims[4] = {(uint64_t)w, (uint64_t)h, 49, (uint64_t)n};
     const uint64_t strides[3] = {(uint64_t)w * 4, (uint64_t)h * w * 4, (uint64_t)49 * h * w * 4};
@@ -391,7 +439,7 @@ int mp_tc_step_f32(const void* x, const float* weight, void* out, int n, int h, 
   p.nblk = c / NB;
   p.eps = eps;
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  mp_tc_f32_kernel<<<grid, THREADS, SMEM, s>>>(tmW, tmOut, p);
+  mp_tc_f32_kernel<<<grid, THREADS, SMEM, s>>>(tmW, tmOut, tmX, p);
   return 0;
 }
 

@@ -542,7 +542,9 @@ def train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding, s
             one_after()
         after_ms = (timed_loop(one_after, steps) - t_local) / steps * 1e3
         del after
-        allreduce_ms = timed_loop(lambda: dist.all_reduce(opt.flat_grad), steps) / steps * 1e3
+        for _ in range(3):                                   # NCCL sets its channels up lazily per op / size
+            dist.all_reduce(opt.flat_grad, op=dist.ReduceOp.AVG)
+        allreduce_ms = timed_loop(lambda: dist.all_reduce(opt.flat_grad, op=dist.ReduceOp.AVG), steps) / steps * 1e3
     e, f = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e.record()

@@ -160,6 +160,82 @@ ln_rows_bwd_kernel(const float* __restrict__ g, const float* __restrict__ y, con
   }
 }
 
+// Register-resident form for C = 128 * VPL (every trunk width): a lane owns the 4 * VPL channels (j * 32 + lane) * 4 + e of
+// every row its warp visits; the row's y and g are read ONCE (16-byte loads) and stay in registers through the three
+// passes (statistics, projections, result), and the dw / db partial sums stay in registers across all rows of the warp
+// -- the generic kernel above re-read y four times and paid two shared-memory read-modify-writes per element
+// (r2 profile: 2.7 ms of the 33 ms training step at ~4x its HBM floor of 12 bytes per element).
+template <int VPL>
+__global__ void __launch_bounds__(256)
+ln_rows_bwd_v_kernel(const float* __restrict__ g, const float* __restrict__ y, const float* __restrict__ w,
+                     float* __restrict__ dy, float* __restrict__ part, int64_t rows, float eps) {
+  constexpr int C = 128 * VPL;
+  extern __shared__ float sm[];   // [8 warps][2][C]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float4 wv[VPL], adw[VPL], adb[VPL];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    wv[j] = *reinterpret_cast<const float4*>(w + (j * 32 + lane) * 4);
+    adw[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    adb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int64_t row = (int64_t)blockIdx.x * 8 + wid; row < rows; row += (int64_t)gridDim.x * 8) {
+    const float* yp = y + row * C;
+    const float* gp = g + row * C;
+    float4 yv[VPL], gv[VPL];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      yv[j] = *reinterpret_cast<const float4*>(yp + (j * 32 + lane) * 4);
+      gv[j] = *reinterpret_cast<const float4*>(gp + (j * 32 + lane) * 4);
+      s += (yv[j].x + yv[j].y) + (yv[j].z + yv[j].w);
+    }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      yv[j].x -= mean; yv[j].y -= mean; yv[j].z -= mean; yv[j].w -= mean;
+      q += (yv[j].x * yv[j].x + yv[j].y * yv[j].y) + (yv[j].z * yv[j].z + yv[j].w * yv[j].w);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / C + eps);
+    float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {   // yv <- xhat
+      yv[j].x *= rstd; yv[j].y *= rstd; yv[j].z *= rstd; yv[j].w *= rstd;
+      const float gx0 = gv[j].x * wv[j].x, gx1 = gv[j].y * wv[j].y, gx2 = gv[j].z * wv[j].z, gx3 = gv[j].w * wv[j].w;
+      a1 += (gx0 + gx1) + (gx2 + gx3);
+      a2 += (gx0 * yv[j].x + gx1 * yv[j].y) + (gx2 * yv[j].z + gx3 * yv[j].w);
+    }
+    const float m1 = warp_sum(a1) / C, m2 = warp_sum(a2) / C;
+    float* dp = dy + row * C;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      float4 o;
+      o.x = rstd * (gv[j].x * wv[j].x - m1 - yv[j].x * m2);
+      o.y = rstd * (gv[j].y * wv[j].y - m1 - yv[j].y * m2);
+      o.z = rstd * (gv[j].z * wv[j].z - m1 - yv[j].z * m2);
+      o.w = rstd * (gv[j].w * wv[j].w - m1 - yv[j].w * m2);
+      *reinterpret_cast<float4*>(dp + (j * 32 + lane) * 4) = o;
+      adw[j].x = fmaf(gv[j].x, yv[j].x, adw[j].x); adw[j].y = fmaf(gv[j].y, yv[j].y, adw[j].y);
+      adw[j].z = fmaf(gv[j].z, yv[j].z, adw[j].z); adw[j].w = fmaf(gv[j].w, yv[j].w, adw[j].w);
+      adb[j].x += gv[j].x; adb[j].y += gv[j].y; adb[j].z += gv[j].z; adb[j].w += gv[j].w;
+    }
+  }
+  float* mydw = sm + (wid * 2) * C;
+  float* mydb = mydw + C;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    *reinterpret_cast<float4*>(mydw + (j * 32 + lane) * 4) = adw[j];
+    *reinterpret_cast<float4*>(mydb + (j * 32 + lane) * 4) = adb[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += 256) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sm[i * 2 * C + c];
+    part[(int64_t)blockIdx.x * 2 * C + c] = t;
+  }
+}
+
 // ---- depthwise 7x7: plain forward (optionally + add) and weight gradient -------------------------
 // thread = channel, CTA = (image, 8-row band, 128-channel group), sliding 7-row window
 __global__ void __launch_bounds__(128)
@@ -358,10 +434,18 @@ __global__ void resize_nhwc_bwd_kernel(const float* __restrict__ g, float* __res
   store4(o, acc.x, acc.y, acc.z, acc.w);
 }
 
-static int pick_splits(int M) {
-  int s = M / 4096;
+// Split-K factor of the CUDA-core weight-gradient GEMM (reduction over the M rows).  Round 1 used M / 4096 whatever the
+// output size, which left the thin gradients of the head / fusion / stem convs (N x K = 24 x 128 ... 128 x 48: ONE
+// 128 x 128 output tile) on 36 CTAs streaming 4096 rows each: 2.7 ms of the 33 ms training step at 2 TFLOP/s.  Now the
+// splits fill the machine (~2 CTAs per SM in total) as long as a split keeps >= 256 rows.
+static int pick_splits(int M, int N, int K) {
+  const int tiles = cdiv(N, 128) * cdiv(K, 128);
+  int s = cdiv(2 * 148, tiles);
+  const int by_rows = M / 256;
+  if (s > by_rows) s = by_rows;
+  if (s < M / 4096) s = M / 4096;
+  if (s > 512) s = 512;
   if (s < 1) s = 1;
-  if (s > 64) s = 64;
   return s;
 }
 
@@ -391,7 +475,7 @@ int dgtd_linear_wgrad(const float* g, const float* a, float* dw, float* ws, cons
                       int off, dgtd_stream_t stream) {
   DGTD_CHECK_ARG(g && a && dw && ws && M > 0 && N > 0 && K > 0 && N % 4 == 0 && K % 4 == 0, "linear_wgrad: bad args");
   cudaStream_t s = (cudaStream_t)stream;
-  const int S = pick_splits(M);
+  const int S = pick_splits(M, N, K);
   const int zrows = cdiv(M, S);
   SplitRowLoader al{g, N, M, N, zrows, keep, nullptr, rows_per_sample > 0 ? rows_per_sample : 1};
   EpiSplitStore ep{ws, K, (int64_t)N * K};
@@ -408,7 +492,7 @@ int dgtd_linear_wgrad(const float* g, const float* a, float* dw, float* ws, cons
   DGTD_LAUNCH_CHECK("linear_wgrad.reduce");
   return 0;
 }
-int dgtd_linear_wgrad_ws_floats(int M, int N, int K) { return pick_splits(M) * N * K; }
+int dgtd_linear_wgrad_ws_floats(int M, int N, int K) { return pick_splits(M, N, K) * N * K; }
 
 // out[N] = sum_m keep[m/rows] x[m,n];  ws: cdiv(M,1024)*N floats
 int dgtd_colsum(const float* x, const float* keep, int rows_per_sample, float* ws, float* out, int M, int N,
@@ -457,7 +541,22 @@ int dgtd_ln_rows_bwd(const float* g, const float* y, const float* w, float* dy, 
     cudaError_t e = cudaFuncSetAttribute(ln_rows_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     DGTD_CHECK_ARG(e == cudaSuccess, "ln_rows_bwd: cannot opt in to %zu B smem", smem);
   }
-  ln_rows_bwd_kernel<<<blocks, 256, smem, s>>>(g, y, w, dy, ws, rows, C, eps);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dy) |
+                         reinterpret_cast<uintptr_t>(w)) & 15) == 0;
+#define DGTD_LNB(V)                                                                                             \
+  {                                                                                                             \
+    if (smem > 48 * 1024) {                                                                                     \
+      cudaError_t e = cudaFuncSetAttribute(ln_rows_bwd_v_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      DGTD_CHECK_ARG(e == cudaSuccess, "ln_rows_bwd: cannot opt in to %zu B smem", smem);                       \
+    }                                                                                                           \
+    ln_rows_bwd_v_kernel<V><<<blocks, 256, smem, s>>>(g, y, w, dy, ws, rows, eps);                              \
+  }
+  if (aligned && C == 128) DGTD_LNB(1)
+  else if (aligned && C == 256) DGTD_LNB(2)
+  else if (aligned && C == 512) DGTD_LNB(4)
+  else if (aligned && C == 1024) DGTD_LNB(8)
+  else ln_rows_bwd_kernel<<<blocks, 256, smem, s>>>(g, y, w, dy, ws, rows, C, eps);
+#undef DGTD_LNB
   DGTD_LAUNCH_CHECK("ln_rows_bwd");
   // ws holds [blocks][2C]; dw and db are the two halves of the reduced vector
   sum_splits_kernel<<<cdiv(2 * C, 256), 256, 0, s>>>(ws, ws + (int64_t)blocks * 2 * C, 2 * C, blocks);

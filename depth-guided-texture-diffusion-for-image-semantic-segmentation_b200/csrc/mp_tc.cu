@@ -300,7 +300,9 @@ mp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         const __nv_bfloat162 b = __floats2bfloat162_rn(wr[2 * k] * inv, k < 24 ? wr[2 * k + 1] * inv : 0.f);
         wp2[k] = *reinterpret_cast<const uint32_t*>(&b);
       }
-      if (tile + (int)gridDim.x < p.num_tiles) load_raw(tile + gridDim.x);   // prefetch the next tile's weights
+      // prefetch the next tile's weights (measured: issuing these loads only after the last publish of the tile, to keep
+      // them out of the way of the membar inside fence.proxy.async, costs 0.249 -> 0.319 ms: the loads are then exposed)
+      if (tile + (int)gridDim.x < p.num_tiles) load_raw(tile + gridDim.x);
       // Chunks are acquired strictly in order, EVERY chunk by EVERY builder thread (also the chunks a pixel has no
       // taps in): a thread may only arrive on a_full[c] for this tile after a_empty[c] says the previous tile's MMAs
       // are done with chunk c, which in turn needed all 128 arrivals of the previous tile -- so no thread can arrive

@@ -380,12 +380,16 @@ mp_tc_f32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr + X_HALF), "r"(*reinterpret_cast<const uint32_t*>(&l01)),
                      "r"(*reinterpret_cast<const uint32_t*>(&l23))
                      : "memory");
-        v[i] = fetch(i);   // the next chunk's piece flies while the rest of this chunk is split and stored
       }
-      advance();
       bw::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) bw::mbar_arrive(&x_full[xs]);
+      // the next chunk's loads are issued AFTER the fence: fence.proxy.async contains a MEMBAR.ALL.CTA that waits for
+      // every outstanding global load of the thread, so loads requested before it were not a prefetch at all (r2 profile:
+      // the converters' long-scoreboard stalls sat on the fence).  They now fly while this thread waits for x_empty.
+#pragma unroll
+      for (int i = 0; i < 6; ++i) v[i] = fetch(i);
+      advance();
     }
   }
   bw::tc_fence_before();

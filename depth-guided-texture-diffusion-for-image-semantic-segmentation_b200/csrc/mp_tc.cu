@@ -259,8 +259,12 @@ mp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     // the next tile while a builder thread needed ~1500 instructions per tile), so everything that does not change
     // from tile to tile is hoisted: the 14 byte offsets of a pixel's taps inside a chunk (7 per halo-row parity),
     // 32-bit plane offsets for the 49 weight loads, fences only after chunks the thread actually wrote.
-    const int m = threadIdx.x - 256;
-    const int py = m >> 4, px = m & 15;
+    // Builder warp w owns tile rows w and w + 4 (lanes 0-15 / 16-31): rows of the SAME parity cross chunk boundaries at
+    // the same tap row ky, so the publish / acquire steps inside the ky loop are warp-uniform.  With rows 2w and 2w + 1
+    // in one warp every ky iteration diverged and the warp executed both paths (r2 profile: 1340 instructions per tile,
+    // the MMA warp waiting on a_full 44 % of the time).
+    const int py = (warp - 8) + 4 * (lane >> 4), px = lane & 15;
+    const int m = py * 16 + px;
     const int plane = p.h * p.w;                      // host guarantees 49 * h * w < 2^31
     uint32_t off_e[7], off_o[7];                      // taps kx = 0..6 in an even / odd halo row of a chunk
 #pragma unroll

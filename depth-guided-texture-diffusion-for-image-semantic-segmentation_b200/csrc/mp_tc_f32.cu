@@ -238,9 +238,11 @@ mp_tc_f32_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     if (lane == 0) bw::tma_store_wait_all<0>();
   } else if (warp >= 8 && warp < 16) {
     // ===================== A builders: thread = (pixel, plane); warps 8-11 build A_hi, warps 12-15 A_lo ==========
-    const int tb = threadIdx.x - 256;
-    const int m = tb & 127, plane = tb >> 7;
-    const int py = m >> 4, px = m & 15;
+    // warp (8 + w) / (12 + w) builds plane hi / lo of tile rows w and w + 4 (same parity: the chunk transitions inside
+    // the ky loop are warp-uniform, see mp_tc.cu)
+    const int plane = (warp - 8) >> 2;
+    const int py = ((warp - 8) & 3) + 4 * (lane >> 4), px = lane & 15;
+    const int m = py * 16 + px;
     uint32_t off_e[7], off_o[7];
 #pragma unroll
     for (int kx = 0; kx < 7; ++kx) {

@@ -126,12 +126,11 @@ eltwise_op_kernel(const ST* __restrict__ src, const __nv_bfloat16* __restrict__ 
 // full passes over the (M x 4C) / (M x C) matrices (r2 profile: 3.4 ms of a 33 ms step).  CTA = RB rows x (TPR * 8)
 // columns, thread = 8 columns x every RL-th row; fixed-order reduction over the row lanes in shared memory, one
 // partial row per CTA row-block, summed by sum_parts_kernel (deterministic, no atomics).
-constexpr int EC_RB = 64;
 template <typename ST, int MODE>
 __global__ void __launch_bounds__(256)
 eltwise_colsum_kernel(const ST* __restrict__ src, const __nv_bfloat16* __restrict__ aux, __nv_bfloat16* __restrict__ dst,
                       const float* __restrict__ keep, int rows_per_sample, float* __restrict__ part, int M, int N,
-                      int tpr) {
+                      int tpr, int EC_RB) {
   __shared__ float red[256 * 8];
   const int tcol = threadIdx.x % tpr, rlane = threadIdx.x / tpr, rl = 256 / tpr;
   const int n = (blockIdx.x * tpr + tcol) * 8;
@@ -297,9 +296,20 @@ int dgtd_transpose_op(const void* src, const void* aux, void* dst, void* dstT, c
   return 0;
 }
 
+// rows per CTA trip: as many as leave ~4 CTAs per SM (592 in total), between one 4-row trip per row lane and 64 rows
+// (with a fixed 64 the 9216 x 2048 matrices of stage 2 ran on 144 CTAs, one 8-warp CTA per SM)
+static int ec_rows(int M, int N, int tpr) {
+  const int gx = cdiv(N / 8, tpr), rl = 256 / tpr;
+  int rb = cdiv((int64_t)M * gx, 592);
+  const int unit = 4 * rl;
+  rb = cdiv(rb, unit) * unit;
+  if (rb < unit) rb = unit;
+  if (rb > 64) rb = 64 / unit * unit > 0 ? 64 / unit * unit : unit;
+  return rb;
+}
 static int ec_row_ctas(int M, int N, int tpr) {
   const int gx = cdiv(N / 8, tpr);
-  int gy = cdiv(M, EC_RB);
+  int gy = cdiv(M, ec_rows(M, N, tpr));
   const int cap = 592 / gx > 1 ? 592 / gx : 1;       // ~4 CTAs per SM in total
   return gy < cap ? gy : cap;
 }
@@ -322,10 +332,11 @@ int dgtd_eltwise_colsum(const void* src, const void* aux, void* dst, const float
   const dim3 grid(cdiv(N / 8, tpr), ec_row_ctas(M, N, tpr));
   if (mode == 0)
     eltwise_colsum_kernel<float, 0><<<grid, 256, 0, s>>>((const float*)src, nullptr, (__nv_bfloat16*)dst, keep, rps, ws, M,
-                                                         N, tpr);
+                                                         N, tpr, ec_rows(M, N, tpr));
   else
     eltwise_colsum_kernel<__nv_bfloat16, 2><<<grid, 256, 0, s>>>((const __nv_bfloat16*)src, (const __nv_bfloat16*)aux,
-                                                                 (__nv_bfloat16*)dst, nullptr, 1, ws, M, N, tpr);
+                                                                 (__nv_bfloat16*)dst, nullptr, 1, ws, M, N, tpr,
+                                                                 ec_rows(M, N, tpr));
   DGTD_LAUNCH_CHECK("eltwise_colsum");
   colsum_parts_kernel<<<cdiv(N, 32), 256, 0, s>>>(ws, colsum, N, (int)grid.y);
   DGTD_LAUNCH_CHECK("eltwise_colsum.reduce");

@@ -47,14 +47,20 @@ constexpr int THREADS = 384;
 // so every KB not spent on A is a KB of X prefetch:
 //   SW128: rows of 128 B (96 used), SWIZZLE_128B K-major, 16 KB per chunk -> 4 X stages
 //   SW32 : one 4 KB block of 32-byte rows per K step, SWIZZLE_32B K-major, 12 KB per chunk -> 5 X stages
-template <int SW>
+//   RAWTMA: the 49 raw weights of the tile's pixels arrive as ONE TMA box {16 px, 8 rows, 49 taps} (25 KB, warp 3) instead
+//   of 49 global loads per builder thread.  fence.proxy.async compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC and the
+//   membar waits for every outstanding global load of the thread: with register prefetch the first publish of every
+//   tile stalled for a DRAM round trip (r2 profile: builder ~7900 cycles per tile against 2688 cycles of MMAs).
+constexpr int W_BYTES = 49 * TH * TW * 4, W_SLOT = 25600;
+template <int SW, bool RAWTMA = false>
 struct Cfg {
   static constexpr int A_CHUNK = SW == 128 ? 128 * 128 : 3 * 128 * 32;
-  static constexpr int XSTAGES = SW == 128 ? 4 : 5;
+  static constexpr int XSTAGES = (SW == 128 || RAWTMA) ? 4 : 5;
   static constexpr int OFF_X = NCHUNK * A_CHUNK;
   static constexpr int OFF_STG = OFF_X + XSTAGES * X_STAGE;
-  static constexpr int OFF_BAR = OFF_STG + STG;
-  static constexpr int NBARS = 2 * XSTAGES + 2 * NCHUNK + 4;
+  static constexpr int OFF_W = OFF_STG + STG;
+  static constexpr int OFF_BAR = OFF_W + (RAWTMA ? W_SLOT : 0);
+  static constexpr int NBARS = 2 * XSTAGES + 2 * NCHUNK + 4 + 2;
   static constexpr int SMEM = OFF_BAR + NBARS * 8 + 16 + 1024;   // + alignment slack
   // byte offset of element (row m, chunk-local column kl) inside a chunk
   static __device__ __forceinline__ uint32_t a_off(uint32_t m, uint32_t kl) {
@@ -86,10 +92,11 @@ struct Params {
   float eps;
 };
 
-template <int SW>
+template <int SW, bool RAWTMA>
 __global__ void __launch_bounds__(THREADS, 1)
-mp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmOut, const Params p) {
-  using C = Cfg<SW>;
+mp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmOut,
+             const __grid_constant__ CUtensorMap tmW, const Params p) {
+  using C = Cfg<SW, RAWTMA>;
   constexpr int A_CHUNK = C::A_CHUNK, XSTAGES = C::XSTAGES, OFF_X = C::OFF_X, OFF_STG = C::OFF_STG, OFF_BAR = C::OFF_BAR;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -103,7 +110,10 @@ mp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   uint64_t* a_empty = a_full + NCHUNK;
   uint64_t* t_full = a_empty + NCHUNK;
   uint64_t* t_empty = t_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  uint64_t* w_full = t_empty + 2;
+  uint64_t* w_empty = w_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + 1);
+  float* sW = reinterpret_cast<float*>(smem + C::OFF_W);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = p.C / NB;
@@ -128,6 +138,8 @@ mp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       bw::mbar_init(&t_full[i], 1);
       bw::mbar_init(&t_empty[i], 128);  // every epilogue thread
     }
+    bw::mbar_init(w_full, 1);
+    bw::mbar_init(w_empty, 128);        // every builder thread, once it has read its 49 raw weights
     bw::fence_mbar_init();
   }
   if (warp == 2) bw::tmem_alloc(tmem_slot, 512);
@@ -167,6 +179,23 @@ mp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       }
     }
     (void)x_base;
+  } else if (warp == 3) {
+    if (RAWTMA) {
+      // ===================== raw weights of the next tile: one TMA box per tile =====================
+      uint32_t tcount = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+        int t = tile;
+        const int tx = t % p.tiles_x; t /= p.tiles_x;
+        const int ty = t % p.tiles_y;
+        const int img = t / p.tiles_y;
+        bw::mbar_wait(w_empty, (tcount & 1) ^ 1);
+        if (bw::elect_one()) {
+          bw::mbar_arrive_expect_tx(w_full, W_BYTES);
+          bw::tma_load_4d(&tmW, w_full, sW, tx * TW, ty * TH, 0, img);
+        }
+        __syncwarp();
+      }
+    }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp in the loop, one elected lane issues) =====================
     // 21 MMAs of 128 clocks per tile: the loop around them must stay well under 384 clocks per chunk, so the
@@ -292,8 +321,15 @@ mp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     };
     uint32_t tcount = 0;
     int tile = blockIdx.x;
-    if (tile < p.num_tiles) load_raw(tile);
+    if (!RAWTMA && tile < p.num_tiles) load_raw(tile);
     for (; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+      if (RAWTMA) {   // this tile's raw weights: shared memory [49][8][16], filled by TMA (zero outside the map)
+        bw::mbar_wait(w_full, tcount & 1);
+        const float* wsrc = sW + py * TW + px;
+#pragma unroll
+        for (int k = 0; k < 49; ++k) wr[k] = wsrc[k * (TH * TW)];
+        bw::mbar_arrive(w_empty);   // consumed: warp 3 may fetch the next tile's box
+      }
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
       for (int k = 0; k < 48; k += 4) { s0 += wr[k]; s1 += wr[k + 1]; s2 += wr[k + 2]; s3 += wr[k + 3]; }
@@ -306,7 +342,7 @@ mp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       }
       // prefetch the next tile's weights (measured: issuing these loads only after the last publish of the tile, to keep
       // them out of the way of the membar inside fence.proxy.async, costs 0.249 -> 0.319 ms: the loads are then exposed)
-      if (tile + (int)gridDim.x < p.num_tiles) load_raw(tile + gridDim.x);
+      if (!RAWTMA && tile + (int)gridDim.x < p.num_tiles) load_raw(tile + gridDim.x);
       // Chunks are acquired strictly in order, EVERY chunk by EVERY builder thread (also the chunks a pixel has no
       // taps in): a thread may only arrive on a_full[c] for this tile after a_empty[c] says the previous tile's MMAs
       // are done with chunk c, which in turn needed all 128 arrivals of the previous tile -- so no thread can arrive
@@ -356,19 +392,21 @@ mp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 }  // namespace mptc
 
 // One diffusion step on the tensor pipe; 0 on success, 1 when the shape is not handled here.
-template <int SW>
-static int mp_tc_launch(const CUtensorMap& tmX, const CUtensorMap& tmOut, const mptc::Params& p, int grid, cudaStream_t s) {
+template <int SW, bool RAWTMA>
+static int mp_tc_launch(const CUtensorMap& tmX, const CUtensorMap& tmOut, const CUtensorMap& tmW, const mptc::Params& p,
+                        int grid, cudaStream_t s) {
   using namespace mptc;
+  using Cf = Cfg<SW, RAWTMA>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e1 = cudaFuncSetAttribute(mp_tc_kernel<SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<SW>::SMEM);
+    cudaError_t e1 = cudaFuncSetAttribute(mp_tc_kernel<SW, RAWTMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::SMEM);
     if (e1 != cudaSuccess) {
-      set_error("message_passing_tc: cannot opt in to %d B smem: %s", Cfg<SW>::SMEM, cudaGetErrorString(e1));
+      set_error("message_passing_tc: cannot opt in to %d B smem: %s", Cf::SMEM, cudaGetErrorString(e1));
       return -2;
     }
     configured = true;
   }
-  mp_tc_kernel<SW><<<grid, THREADS, Cfg<SW>::SMEM, s>>>(tmX, tmOut, p);
+  mp_tc_kernel<SW, RAWTMA><<<grid, THREADS, Cf::SMEM, s>>>(tmX, tmOut, tmW, p);
   return 0;
 }
 
@@ -392,7 +430,17 @@ int mp_tc_step_bf16(const void* x, const float* weight, void* out, int n, int h,
   p.num_tiles = n * p.tiles_x * p.tiles_y;
   p.eps = eps;
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  return variant == 1 ? mp_tc_launch<128>(tmX, tmOut, p, grid, s) : mp_tc_launch<32>(tmX, tmOut, p, grid, s);
+  CUtensorMap tmW = tmX;   // placeholder when the raw weights are read with plain loads
+  const bool rawtma = variant == 0 && w % 4 == 0;   // TMA needs 16-byte multiples for the weight planes' row pitch
+  if (rawtma) {
+    const uint64_t wdims[4] = {(uint64_t)w, (uint64_t)h, 49, (uint64_t)n};
+    const uint64_t wstr[3] = {(uint64_t)w * 4, (uint64_t)h * w * 4, (uint64_t)49 * h * w * 4};
+    const uint32_t wbox[4] = {TW, TH, 49, 1};
+    rc = make_tmap(&tmW, weight, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, wdims, wstr, wbox, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+  }
+  if (variant == 1) return mp_tc_launch<128, false>(tmX, tmOut, tmW, p, grid, s);
+  return rawtma ? mp_tc_launch<32, true>(tmX, tmOut, tmW, p, grid, s) : mp_tc_launch<32, false>(tmX, tmOut, tmW, p, grid, s);
 }
 
 }  // namespace dgtd

@@ -15,6 +15,7 @@ Parameters that never receive a gradient (`prompt_encoder.adaptor.*`) would keep
 `find_unused_parameters=True` for the same reason)."""
 from __future__ import annotations
 
+import weakref
 from typing import List, Optional, Sequence
 
 import torch
@@ -59,17 +60,26 @@ class GradBucketer:
 
     # ---------------------------------------------------------------------------------------------
     def _make_hook(self, i: int):
+        ref = weakref.ref(self)      # the hook lives on the parameter: it must neither keep the bucketer (and its flat
+                                     # buffer) alive nor fire once the owner is gone
         def hook(_param):
-            if not self.enabled:
+            me = ref()
+            if me is None or not me.enabled:
                 return
-            self._fired[i] = True
-            if self._used is None:                    # calibration pass: only record who fires
+            me._fired[i] = True
+            if me._used is None:                      # calibration pass: only record who fires
                 return
-            bk = self.buckets[self._bucket_of[i]]
+            bk = me.buckets[me._bucket_of[i]]
             bk["pending"] += 1
             if bk["pending"] == bk["need"]:
-                self._launch(self._bucket_of[i])
+                me._launch(me._bucket_of[i])
         return hook
+
+    def __del__(self):
+        try:
+            self.remove()
+        except Exception:
+            pass
 
     def _launch(self, b: int) -> None:
         bk = self.buckets[b]

@@ -114,10 +114,16 @@ class GraphedTrainStep:
 
     def close(self) -> None:
         """Remove the gradient hooks (the captured graph keeps working; eager backward of the same parameters outside
-        this object no longer triggers reductions)."""
+        this object no longer triggers reductions).  Also called when the object is garbage-collected."""
         if self.bucketer is not None:
             self.bucketer.enabled = False
             self.bucketer.remove()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def __call__(self, image: Optional[torch.Tensor] = None, depth: Optional[torch.Tensor] = None) -> torch.Tensor:
         if image is not None:

@@ -129,7 +129,7 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&f)[8]) {
 
 // CTA = 64 channels (8 threads x 8 channels) x 32 groups of 4 pixels; the 9 x 64 taps of the CTA's channel group
 // sit in shared memory and are re-read per kernel row (24 registers instead of 72).
-template <typename T>
+template <typename T, bool GELU = true>
 __global__ void __launch_bounds__(256)
 dwconv3_gelu_kernel(const T* __restrict__ x, const float* __restrict__ wT, const float* __restrict__ bias,
                     T* __restrict__ out, int h, int w, int C) {
@@ -258,8 +258,10 @@ dwconv3_gelu_kernel(const T* __restrict__ x, const float* __restrict__ wT, const
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       up2(acc[p][e], r[2 * e], r[2 * e + 1]);
-      if (sizeof(T) == 2) gelu_fast2(r[2 * e], r[2 * e + 1]);
-      else { r[2 * e] = gelu_erf(r[2 * e]); r[2 * e + 1] = gelu_erf(r[2 * e + 1]); }
+      if (GELU) {
+        if (sizeof(T) == 2) gelu_fast2(r[2 * e], r[2 * e + 1]);
+        else { r[2 * e] = gelu_erf(r[2 * e]); r[2 * e + 1] = gelu_erf(r[2 * e + 1]); }
+      }
     }
     st8(out + (((int64_t)b * h + oy) * w + ox0 + p) * C + c, r);
   }
@@ -563,6 +565,23 @@ int dgtd_dwconv3_gelu_fwd(const void* x, const float* wT, const float* bias, voi
     dwconv3_gelu_kernel<<<blocks, 256, 0, s>>>((const float*)x, wT, bias, (float*)out, h, w, C);
   else DGTD_CHECK_ARG(false, "dwconv3_gelu: bad dtype %d", dtype);
   DGTD_LAUNCH_CHECK("dwconv3_gelu");
+  return 0;
+}
+
+// the depthwise 3x3 alone (`DWConv.forward`, cod.py:1520-1531, called on its own by a maintainer)
+int dgtd_dwconv3_fwd(const void* x, const float* wT, const float* bias, void* out, int dtype, int B, int h, int w, int C,
+                     dgtd_stream_t stream) {
+  DGTD_CHECK_ARG(x && wT && bias && out && B > 0 && h > 0 && w > 0 && C % 8 == 0, "dwconv3: bad args (C % 8)");
+  const int64_t total = (int64_t)B * cdiv(h, 8) * cdiv(w, 16);
+  DGTD_CHECK_ARG(total <= 65535, "dwconv3: too many pixels for one launch");
+  dim3 blocks(cdiv(C, 64), (unsigned)total);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == DGTD_BF16)
+    dwconv3_gelu_kernel<__nv_bfloat16, false><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)x, wT, bias, (__nv_bfloat16*)out, h, w, C);
+  else if (dtype == DGTD_F32)
+    dwconv3_gelu_kernel<float, false><<<blocks, 256, 0, s>>>((const float*)x, wT, bias, (float*)out, h, w, C);
+  else DGTD_CHECK_ARG(false, "dwconv3: bad dtype %d", dtype);
+  DGTD_LAUNCH_CHECK("dwconv3");
   return 0;
 }
 

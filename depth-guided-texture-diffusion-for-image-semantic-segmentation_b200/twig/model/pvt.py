@@ -58,7 +58,11 @@ class DWConv(nn.Module):
                                  lambda: self.dwconv.weight.detach().reshape(-1, 9).t().float().contiguous())
 
     def forward(self, x, H, W):
-        raise NotImplementedError("the depthwise conv only exists fused with the GELU that follows it (Mlp.forward)")
+        """(B, N, C) tokens -> depthwise 3x3 on the (H, W) grid -> (B, N, C), as cod.py:1526-1531 (inside `Mlp.forward`
+        the same kernel runs fused with the GELU that follows)."""
+        B, N, C = x.shape
+        y = PF.dwconv3(x.contiguous().float().view(B, H, W, C), self._packed_taps(), _f(self.dwconv.bias))
+        return y.view(B, N, C)
 
 
 class Mlp(nn.Module):

@@ -180,6 +180,11 @@ class LayerNorm(nn.Module):
         self.normalized_shape = (normalized_shape,)
 
     def forward(self, x):
+        if _wants_grad(self, x):   # stand-alone differentiable call (weight / bias / input gradients)
+            if self.data_format == "channels_first":
+                y = TF.LayerNormRowsFn.apply(TF.LayoutFn.apply(x, True), self.weight, self.bias, self.eps)
+                return TF.LayoutFn.apply(y, False)
+            return TF.LayerNormRowsFn.apply(x, self.weight, self.bias, self.eps)
         return OP.layer_norm(x.contiguous().float(), self.weight.detach(), self.bias.detach(), self.eps,
                              self.data_format == "channels_first")
 

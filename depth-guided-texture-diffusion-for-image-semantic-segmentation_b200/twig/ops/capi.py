@@ -83,6 +83,7 @@ SIGNATURES = {
     "dgtd_ln_tokens_fwd": [_P, _P, _I, _P, _P, _P, _P, _I, _L, _I, _F, _P],
     "dgtd_patchify_tokens_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "dgtd_dwconv3_gelu_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "dgtd_dwconv3_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "dgtd_attention_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "dgtd_boundary_weight_fwd": [_P, _P, _I, _I, _I, _P],
     "dgtd_structure_loss_ws_floats": [_I, _L],

@@ -48,6 +48,15 @@ def dwconv3_gelu(x: torch.Tensor, wT: torch.Tensor, bias: torch.Tensor) -> torch
     return out
 
 
+def dwconv3(x: torch.Tensor, wT: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """x (B,h,w,C) tokens (fp32 | bf16), wT (9,C) fp32: depthwise 3x3 pad 1 + bias (no activation)."""
+    check_cuda(x, wT, bias)
+    B, h, w, C = x.shape
+    out = torch.empty_like(x)
+    call("dgtd_dwconv3_fwd", ptr(x), ptr(wT), ptr(bias), ptr(out), capi.dtype_code(x.dtype), B, h, w, C, stream())
+    return out
+
+
 def attention(q: torch.Tensor, kv: torch.Tensor, B: int, N: int, Nk: int, heads: int) -> torch.Tensor:
     """q (B*N, heads*64), kv (B*Nk, 2*heads*64) -> softmax(q k^T / 8) v as (B*N, heads*64)."""
     check_cuda(q, kv)

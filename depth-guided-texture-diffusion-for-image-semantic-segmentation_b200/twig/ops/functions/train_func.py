@@ -485,6 +485,26 @@ class ResizeNHWCFn(Function):
         return dx, None
 
 
+class LayerNormRowsFn(Function):
+    """LayerNorm over the last dim of an fp32 (..., C) tensor with input / weight / bias gradients (the stand-alone
+    differentiable form of the custom `LayerNorm`, cod.py:1025-1049)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        x, w, b = _f32(x), _f32(w), _f32(b)
+        check_cuda(x, w, b)
+        ctx.eps = eps
+        ctx.save_for_backward(x, w)
+        return ln_rows(x, w, b, eps)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        dx, dw, db = ln_rows_bwd(_f32(g), x, w, ctx.eps)
+        return dx, dw, db, None
+
+
 class LayoutFn(Function):
     """NCHW <-> NHWC copies (pure data movement) with the transposed copy as backward."""
 

@@ -331,6 +331,9 @@ int dgtd_patchify_tokens_fwd(const void* x, void* out, int dtype, int B, int h, 
 /* Mlp.dwconv + act (cod.py:852-854): depthwise 3x3 pad 1 + bias + GELU(erf) on (B,h,w,C) tokens; wT (9,C) */
 int dgtd_dwconv3_gelu_fwd(const void* x, const float* wT, const float* bias, void* out, int dtype, int B, int h, int w,
                           int C, dgtd_stream_t stream);
+/* The depthwise 3x3 without the activation: DWConv.forward (cod.py:1520-1531) called on its own. */
+int dgtd_dwconv3_fwd(const void* x, const float* wT, const float* bias, void* out, int dtype, int B, int h, int w, int C,
+                     dgtd_stream_t stream);
 /* Attention core (cod.py:911-915), head_dim 64: q (B*N, heads*64), kv (B*Nk, 2*heads*64) [k | v], out like q;
  * softmax(scale * q k^T) v in fp32 with an online softmax over key tiles. */
 int dgtd_attention_fwd(const void* q, const void* kv, void* out, int dtype, int B, int N, int Nk, int heads,

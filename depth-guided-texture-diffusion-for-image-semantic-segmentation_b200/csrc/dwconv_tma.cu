@@ -14,6 +14,9 @@
 
 namespace dgtd {
 
+int sm_count();   // tc_gemm.cu
+static inline int sm_count_dw() { return sm_count(); }
+
 template <int SY, int SX, bool ADD, typename OT = float>
 __global__ void __launch_bounds__(SY * SX * 32, 2)
 dwconv7_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ wT,
@@ -142,6 +145,156 @@ dwconv7_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restr
   }
 }
 
+
+// Persistent form of the kernel above (round 2).  The one-shot kernel ran the FMA pipe at 44 %: its grid is a fixed
+// number of (tile, 128-channel group) CTAs -- 768 at stage 2 on 296 CTA slots = 2.6 waves, the last one 60 % full -- and
+// every CTA pays its own barrier setup, first-tile TMA latency and, per 32-channel chunk, 49 global weight loads in front
+// of the first FMA.  Here 2 CTAs per SM walk (tile, 32-channel chunk) ITEMS round-robin (3072 at stage 2: 10.4 per
+// CTA, a quantisation loss of 5 % instead of 13 %), the next item's halo tile AND its 49 x 32 weights arrive by TMA while
+// the current item computes (the weights box lands in a single 6 KB buffer that is free again as soon as every warp has
+// copied its taps into registers), and nothing but the bias is read with a plain global load -- issued after the
+// proxy fence of the iteration, whose membar would otherwise wait for it.
+template <int SY, int SX, bool ADD, typename OT>
+__global__ void __launch_bounds__(SY * SX * 32, 2)
+dwconv7_tma_persist_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                           const float* __restrict__ bias, const float* __restrict__ add, OT* __restrict__ y, int h,
+                           int w, int C, int tiles_x, int tiles_y, int num_items) {
+  constexpr int TH = 4 * SY, TW = 8 * SX, PH = TH + 6, PW = TW + 6;
+  constexpr int TILE_FLOATS = PH * PW * 32;
+  constexpr uint32_t TILE_BYTES = TILE_FLOATS * 4, W_BYTES = 49 * 32 * 4;
+  extern __shared__ __align__(128) float xs[];   // [2][TILE_FLOATS] halo tiles, then [49][32] weights
+  float* wbuf = xs + 2 * TILE_FLOATS;
+  __shared__ uint64_t bar[3];                    // tile buffer 0 / 1, weights
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sy = warp / SX, sx = warp - sy * SX;
+  const int nch = C >> 5;
+  auto issue_tile = [&](int item, int buf) {
+    const int chunk = item % nch;
+    int t = item / nch;
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y;
+    const int b = t / tiles_y;
+    bw::mbar_arrive_expect_tx(&bar[buf], TILE_BYTES);
+    bw::tma_load_4d(&tmX, &bar[buf], xs + buf * TILE_FLOATS, chunk * 32, tx * TW - 3, ty * TH - 3, b);
+  };
+  auto issue_weights = [&](int item) {
+    bw::mbar_arrive_expect_tx(&bar[2], W_BYTES);
+    bw::tma_load_2d(&tmW, &bar[2], wbuf, (item % nch) * 32, 0);
+  };
+  if (threadIdx.x == 0) {
+    bw::prefetch_tmap(&tmX);
+    bw::prefetch_tmap(&tmW);
+    bw::mbar_init(&bar[0], 1);
+    bw::mbar_init(&bar[1], 1);
+    bw::mbar_init(&bar[2], 1);
+    bw::fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && (int)blockIdx.x < num_items) {
+    issue_tile(blockIdx.x, 0);
+    issue_weights(blockIdx.x);
+  }
+  int it = 0;
+#pragma unroll 1
+  for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+    const int next = item + gridDim.x;
+    if (threadIdx.x == 0 && next < num_items) {   // buffer (it+1)&1 was released by the barrier that ended the last item
+      bw::fence_proxy_async_smem();
+      issue_tile(next, (it + 1) & 1);
+    }
+    const int chunk = item % nch;
+    int t = item / nch;
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y;
+    const int b = t / tiles_y;
+    const int x0 = tx * TW, y0 = ty * TH;
+    const int c = chunk * 32 + lane;
+    // taps duplicated into both halves of a 64-bit register (see the one-shot kernel)
+    bw::mbar_wait(&bar[2], it & 1);
+    uint64_t w2[49];
+#pragma unroll
+    for (int k = 0; k < 49; ++k) {
+      const float tv = wbuf[k * 32 + lane];
+      w2[k] = pk2(tv, tv);
+    }
+    __syncthreads();                              // every warp holds its taps: the weights buffer is free
+    if (threadIdx.x == 0 && next < num_items) {
+      bw::fence_proxy_async_smem();
+      issue_weights(next);
+    }
+    const float bc = bias ? __ldg(bias + c) : 0.f;
+    uint64_t acc[2][8];
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[q][j] = pk2(bc, bc);
+
+    bw::mbar_wait(&bar[it & 1], (it >> 1) & 1);
+    const float* base = xs + (it & 1) * TILE_FLOATS + ((4 * sy) * PW + 8 * sx) * 32 + lane;
+#pragma unroll
+    for (int iy = 0; iy < 9; ++iy) {
+      uint64_t pr[14];
+#pragma unroll
+      for (int j = 0; j < 14; ++j) {
+        const volatile float* p0 = base + (iy * PW + j) * 32;
+        pr[j] = pk2(p0[0], p0[PW * 32]);
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int ky = iy - 2 * q;
+        if (ky < 0 || ky >= 7) continue;
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[q][j] = fma2(w2[ky * 7 + kx], pr[j + kx], acc[q][j]);
+      }
+    }
+    if (ADD) {
+      float av[4][8];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int oy = y0 + 4 * sy + a, ox = x0 + 8 * sx + j;
+          av[a][j] = (oy < h && ox < w) ? __ldg(add + (((int64_t)b * h + oy) * w + ox) * C + c) : 0.f;
+        }
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[q][j] = add2(acc[q][j], pk2(av[2 * q][j], av[2 * q + 1][j]));
+    }
+    {
+      const int oy0 = y0 + 4 * sy, ox0 = x0 + 8 * sx;
+      OT* yp = y + (((int64_t)b * h + oy0) * w + ox0) * C + c;
+      const int rs = w * C;
+      if (oy0 + 4 <= h && ox0 + 8 <= w) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float v0, v1;
+            up2(acc[q][j], v0, v1);
+            store1(yp + (2 * q) * rs + j * C, v0);
+            store1(yp + (2 * q + 1) * rs + j * C, v1);
+          }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float v0, v1;
+            up2(acc[q][j], v0, v1);
+            if (ox0 + j < w) {
+              if (oy0 + 2 * q < h) store1(yp + (2 * q) * rs + j * C, v0);
+              if (oy0 + 2 * q + 1 < h) store1(yp + (2 * q + 1) * rs + j * C, v1);
+            }
+          }
+      }
+    }
+    __syncthreads();   // every warp is done with tile buffer it&1 before it is refilled
+  }
+}
 
 // Weight/bias gradient of the depthwise 7x7 (training backward of cod.py:1106):
 //   dW[ky,kx,c] = sum_{b,oy,ox} dy[b,oy,ox,c] * x[b,oy+ky-3,ox+kx-3,c],   db[c] = sum dy
@@ -311,9 +464,46 @@ int row_stats_bf16(const __nv_bfloat16* y, float2* stats, int64_t rows, int C, f
   return 0;
 }
 
+// persistent launch (both output types, with / without the residual operand); 0 ok, < 0 error
+template <int SY, int SX, bool ADD, typename OT>
+static int dw_launch_persist(const CUtensorMap& tm, const float* wT, const float* bias, const float* add, OT* y, int B, int h,
+                             int w, int C, cudaStream_t s) {
+  constexpr int PH = 4 * SY + 6, PW = 8 * SX + 6;
+  constexpr int SMEM = 2 * PH * PW * 128 + 49 * 32 * 4 + 128;
+  auto kern = dwconv7_tma_persist_kernel<SY, SX, ADD, OT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) {
+      set_error("dwconv7_tma(persistent): cannot opt in to %d B smem: %s", SMEM, cudaGetErrorString(e));
+      return -2;
+    }
+    configured = true;
+  }
+  CUtensorMap tmW;
+  {
+    const uint64_t dims[2] = {(uint64_t)C, 49}, strides[1] = {(uint64_t)C * 4};
+    const uint32_t box[2] = {32, 49};
+    int rc = make_tmap(&tmW, wT, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+  }
+  const int tiles_x = cdiv(w, 8 * SX), tiles_y = cdiv(h, 4 * SY);
+  const int64_t items = (int64_t)B * tiles_x * tiles_y * (C / 32);
+  if (items > 0x7fffffff) {
+    set_error("dwconv7_tma(persistent): too many items");
+    return -1;
+  }
+  const int slots = 2 * sm_count_dw();
+  const int grid = items < slots ? (int)items : slots;
+  kern<<<grid, SY * SX * 32, SMEM, s>>>(tm, tmW, bias, add, y, h, w, C, tiles_x, tiles_y, (int)items);
+  return 0;
+}
+
 template <int SY, int SX>
 static int dw_launch_bf16(const CUtensorMap& tm, const float* wT, const float* bias, __nv_bfloat16* y, int B, int h, int w,
                           int C, cudaStream_t s) {
+  if ((reinterpret_cast<uintptr_t>(wT) & 15) == 0)
+    return dw_launch_persist<SY, SX, false, __nv_bfloat16>(tm, wT, bias, nullptr, y, B, h, w, C, s);
   constexpr int PH = 4 * SY + 6, PW = 8 * SX + 6;
   constexpr int SMEM = 2 * PH * PW * 128 + 128;
   auto kern = dwconv7_tma_kernel<SY, SX, false, __nv_bfloat16>;
@@ -335,6 +525,10 @@ static int dw_launch_bf16(const CUtensorMap& tm, const float* wT, const float* b
 template <int SY, int SX>
 static int dw_launch(const CUtensorMap& tm, const float* wT, const float* bias, const float* add, float* y, int B,
                      int h, int w, int C, cudaStream_t s) {
+  if ((reinterpret_cast<uintptr_t>(wT) & 15) == 0) {
+    if (add) return dw_launch_persist<SY, SX, true, float>(tm, wT, bias, add, y, B, h, w, C, s);
+    return dw_launch_persist<SY, SX, false, float>(tm, wT, bias, nullptr, y, B, h, w, C, s);
+  }
   constexpr int PH = 4 * SY + 6, PW = 8 * SX + 6;
   constexpr int SMEM = 2 * PH * PW * 128 + 128;
   static bool configured = false;

@@ -65,10 +65,38 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #ifdef DGTD_NO_MBAR_TRAP
   while (!mbar_try_wait(bar, parity)) {}
 #else
+  // the timer is read once per 4096 failed polls (an inner loop without it: written the obvious way, with the read
+  // behind `(++spins & 0xfff) == 0`, ptxas speculates the CS2R into every iteration -- 13 instructions per poll, which
+  // at 30 M polls per launch of mp_tc_f32_kernel was 40 % of ALL issued instructions, r2 profile)
   const unsigned long long t0 = global_timer_ns();
-  unsigned spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0xfff) == 0 && global_timer_ns() - t0 > 20000000000ULL) {
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 4096; ++i)
+      if (mbar_try_wait(bar, parity)) return;
+    if (global_timer_ns() - t0 > 20000000000ULL) {
+      printf("dgtd: mbarrier wait timed out after 20 s (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+#endif
+}
+
+// Wait of a role that has slack: between polls the warp sleeps, so it does not compete for issue slots with the warps
+// on the critical path (r2 trace of mp_tc_f32_kernel: with ~12 of 32 warps polling, an instruction of the MMA-issuing
+// warp took 10-15 clocks to be selected).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned ns) {
+  if (mbar_try_wait(bar, parity)) return;
+#ifdef DGTD_NO_MBAR_TRAP
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+#else
+  const unsigned long long t0 = global_timer_ns();
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 4096; ++i) {
+      __nanosleep(ns);
+      if (mbar_try_wait(bar, parity)) return;
+    }
+    if (global_timer_ns() - t0 > 20000000000ULL) {
       printf("dgtd: mbarrier wait timed out after 20 s (block %d thread %d)\n", blockIdx.x, threadIdx.x);
       __trap();
     }

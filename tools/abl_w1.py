@@ -1,4 +1,7 @@
-"""Ablation timing of the fp32 W1 kernel (DGTD_ABL bit mask; results are NOT valid outputs)."""
+"""Ablation timing of the fp32 W1 kernel (DGTD_ABL bit mask; results are NOT valid outputs).
+
+The DGTD_ABL switches lived in csrc/mp_tc_f32.cu only while the experiment ran (r2, removed again: they cost 0.05 ms);
+the results are recorded in profiles/r2_ncu_w1_diffusion.md.  Kept as the record of how the numbers were taken."""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))

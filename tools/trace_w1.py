@@ -1,4 +1,7 @@
-"""Per-role timeline of one CTA of the fp32 W1 kernel (debug build with the TR() probes)."""
+"""Per-role timeline of one CTA of the fp32 W1 kernel (debug build with the TR() probes).
+
+The TR() probes (clock64 + event id into a global buffer, block 3 only, DGTD_TRACE_PTR) lived in csrc/mp_tc_f32.cu only
+while the experiment ran (r2); results in profiles/r2_ncu_w1_diffusion.md.  Kept as the record of how the numbers were taken."""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))

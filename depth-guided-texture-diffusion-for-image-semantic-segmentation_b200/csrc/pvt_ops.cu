@@ -259,7 +259,7 @@ dwconv3_gelu_kernel(const T* __restrict__ x, const float* __restrict__ wT, const
     for (int e = 0; e < 4; ++e) {
       up2(acc[p][e], r[2 * e], r[2 * e + 1]);
       if (GELU) {
-        if (sizeof(T) == 2) gelu_fast2(r[2 * e], r[2 * e + 1]);
+        if (sizeof(T) == 2) DGTD_GELU2(r[2 * e], r[2 * e + 1]);   // tanh form, tc_common.cuh
         else { r[2 * e] = gelu_erf(r[2 * e]); r[2 * e + 1] = gelu_erf(r[2 * e + 1]); }
       }
     }

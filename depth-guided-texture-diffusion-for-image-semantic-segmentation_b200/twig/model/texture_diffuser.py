@@ -36,6 +36,7 @@ __all__ = [
 # centres in fp32 AFTER the bf16 rounding of the un-normalised conv output, i.e. it loses accuracy when a pixel's
 # channel mean dwarfs its channel spread (|mean| >> std); DGTD_LN_FOLD=0 keeps the two-pass form.
 LN_FOLD = os.environ.get("DGTD_LN_FOLD", "1") != "0"
+MLP_FUSED = os.environ.get("DGTD_MLP_FUSED", "1") != "0"   # A/B switch of the fused stage-0 MLP kernel
 
 PVT_EMBED_DIMS = (64, 128, 320, 512)  # pvt_v2_b2, cod.py:1785
 PVT_DEPTHS = (3, 4, 6, 3)             # cod.py:1786
@@ -237,6 +238,10 @@ class convnext_Block(nn.Module):
                         (w1f @ self.norm.bias.detach().float() + self.pwconv1.bias.detach().float()).contiguous())
             wq, col_s, cbias = pk.get("w1.lnfold", [self.pwconv1.weight, self.pwconv1.bias, self.norm.weight, self.norm.bias], fold)
             y, stats = OP.dwconv7_stats_tma(x, dw_wT, self.dwconv.bias.detach(), self.norm.eps)
+            if MLP_FUSED and keep is None and C in OP.MLP_FUSED_C and (B * h * w) % 128 == 0:
+                # stage 0: both pointwise GEMMs in one kernel, the 4C hidden tensor never reaches HBM
+                OP.convnext_mlp_fused_(y.view(-1, C), stats, wq, col_s, cbias, w2, self.pwconv2.bias.detach(), gamma, x)
+                return x
             hid = OP.linear_lnfold(y.view(-1, C), wq, cbias, col_s, stats, act=ACT_GELU)
             OP.linear_residual_(hid, w2, self.pwconv2.bias.detach(), gamma, keep, h * w, x)
             return x

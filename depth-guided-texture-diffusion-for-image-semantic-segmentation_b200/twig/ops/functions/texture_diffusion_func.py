@@ -424,6 +424,28 @@ def linear_residual_(a: torch.Tensor, w: torch.Tensor, bias, gamma, keep: Option
     return out
 
 
+MLP_FUSED_C = (128,)   # channel counts dgtd_convnext_mlp_fused_fwd is built for
+
+
+def convnext_mlp_fused_(y: torch.Tensor, row_stats: torch.Tensor, w1: torch.Tensor, col_s: torch.Tensor,
+                        cbias: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, gamma: Optional[torch.Tensor],
+                        residual: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = residual + gamma * (GELU(LN(y) @ W1^T + b1) @ W2^T + b2) in one kernel (hidden tensor on chip); in place on
+    `residual` when `out` is None.  y (M, C) bf16 conv output, row_stats (M, 2), w1 (4C, C) bf16 = W1 * ln_weight,
+    w2 (C, 4C) bf16."""
+    check_cuda(y, row_stats, w1, col_s, cbias, w2, b2, gamma, residual)
+    C = y.shape[-1]
+    M = y.numel() // C
+    assert y.dtype == torch.bfloat16 and w1.dtype == torch.bfloat16 and w2.dtype == torch.bfloat16
+    assert w1.shape == (4 * C, C) and w2.shape == (C, 4 * C) and row_stats.shape == (M, 2)
+    assert residual.dtype == torch.float32 and residual.numel() == M * C
+    out = residual if out is None else out
+    with _timed(4.0 * M * C * 4 * C, True, (M, 4 * C, C)):
+        call("dgtd_convnext_mlp_fused_fwd", ptr(y), ptr(row_stats), ptr(w1), ptr(col_s), ptr(cbias), ptr(w2), ptr(b2),
+             ptr(gamma), ptr(residual), ptr(out), M, C, stream())
+    return out
+
+
 # ------------------------------------------------------------------------------------------ a9
 def fusion_head(levels: List[torch.Tensor], hw: List[Tuple[int, int]], wf, bf, B: int, want_nhwc=True,
                 want_nchw=False, pad_to: int = 0):

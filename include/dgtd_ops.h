@@ -175,6 +175,14 @@ int dgtd_dwconv7_stats_tma_fwd(const float* x, const float* dw_wT, const float* 
  * in (cod.py:1108-1110): the normalised activation never exists in memory. */
 int dgtd_linear_lnfold_fwd(const void* a, const void* w, const float* bias, const float* col_s, const float* row_stats,
                            void* out, int M, int N, int K, int ldo, int dtype_out, int act, dgtd_stream_t stream);
+/* out = residual + gamma * (GELU(LN(y) . W1^T + b1) . W2^T + b2) in ONE kernel, the (M, 4C) hidden tensor staying in
+ * shared memory / TMEM: pwconv1 -> act -> pwconv2 -> layer scale -> residual of convnext_Block (cod.py:1108-1116) in bf16
+ * inference mode, LayerNorm folded as in dgtd_linear_lnfold_fwd (w1 = W1 * ln_weight in bf16 (4C, C), col_s, cbias (4C),
+ * row_stats (M, 2) from dgtd_dwconv7_stats_tma_fwd); w2 bf16 (C, 4C); residual / out fp32 (M, C), out may alias residual.
+ * Built for C = 128 (stage 0) and M a multiple of 128; any other shape returns an error (callers use the two GEMMs). */
+int dgtd_convnext_mlp_fused_fwd(const void* y, const float* row_stats, const void* w1, const float* col_s,
+                                const float* cbias, const void* w2, const float* b2, const float* gamma,
+                                const float* residual, float* out, int64_t M, int C, dgtd_stream_t stream);
 /* out[M,N] = act(a[M,K] . w[N,K]^T + bias): pwconv1+GELU (:1109-1110), downsample conv
  * (:1134), head 1x1 convs (:1160,1174).  a/w dtype = dtype_in (fp32: CUDA-core exact path,
  * bf16: tcgen05), out dtype = dtype_out, ldo = row stride of out in elements. */

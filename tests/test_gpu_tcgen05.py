@@ -188,6 +188,48 @@ def test_layernorm_folded_into_pwconv1(M, C, mean):
     assert e_fold <= 2.0 * e_two + 1e-2
 
 
+@pytest.mark.parametrize("M", [128, 1280, 148 * 128 * 2 + 384])
+def test_convnext_mlp_fused_matches_the_two_gemms(M):
+    """dgtd_convnext_mlp_fused_fwd (stage 0, C = 128): x + gamma * (GELU(LN(y) W1^T + b1) W2^T + b2) with the hidden tensor on
+    chip, against (a) the two un-fused tcgen05 GEMMs (same bf16 rounding points: must agree to accumulation order) and
+    (b) the float64 formula on the same bf16-rounded y.  One tile, a partial wave, and more tiles than SMs x 2 (both TMEM
+    accumulators and every ring wrap)."""
+    common.package()
+    from dgtd_b200.twig.ops.functions import texture_diffusion_func as OP
+    from dgtd_b200.twig.ops import capi
+    C = 128
+    g = torch.Generator().manual_seed(M)
+    y = (torch.randn(M, C, generator=g) * 1.3 + 0.4 + 0.3 * torch.randn(M, 1, generator=g)).to(torch.bfloat16)
+    ln_w, ln_b = 1.0 + 0.2 * torch.randn(C, generator=g), 0.2 * torch.randn(C, generator=g)
+    w1, b1 = torch.randn(4 * C, C, generator=g) / C ** 0.5, 0.1 * torch.randn(4 * C, generator=g)
+    w2, b2 = torch.randn(C, 4 * C, generator=g) / (4 * C) ** 0.5, 0.1 * torch.randn(C, generator=g)
+    gamma = 0.5 + torch.rand(C, generator=g)
+    x = torch.randn(M, C, generator=g)
+    y64 = y.double()
+    mu, var = y64.mean(1, keepdim=True), y64.var(1, unbiased=False, keepdim=True)
+    a64 = (y64 - mu) / torch.sqrt(var + 1e-6) * ln_w.double() + ln_b.double()
+    hid64 = torch.nn.functional.gelu(a64 @ w1.double().t() + b1.double())
+    ref = x.double() + gamma.double() * (hid64 @ w2.double().t() + b2.double())
+    wq = (w1 * ln_w[None, :]).to(torch.bfloat16).cuda()
+    col_s, cbias = wq.float().sum(1), (w1 @ ln_b + b1).cuda()
+    stats = torch.stack([mu.float().squeeze(1), (1.0 / torch.sqrt(var + 1e-6)).float().squeeze(1)], 1).contiguous().cuda()
+    w2q = w2.to(torch.bfloat16).cuda()
+    hid = OP.linear_lnfold(y.cuda(), wq, cbias, col_s, stats, act=capi.ACT_GELU)
+    two = OP.linear_residual_(hid, w2q, b2.cuda(), gamma.cuda(), None, M, x.cuda().clone())
+    got = OP.convnext_mlp_fused_(y.cuda(), stats, wq, col_s, cbias, w2q, b2.cuda(), gamma.cuda(), x.cuda().clone())
+    torch.cuda.synchronize()
+    delta = common.rel_err(got - x.cuda(), (two - x.cuda()).double().cpu())      # the update, not the residual stream
+    e_f, e_t = common.rel_err(got - x.cuda(), ref - x.double()), common.rel_err(two - x.cuda(), ref - x.double())
+    print(f"M={M}: fused vs two-GEMM {delta:.2e}; vs float64: fused {e_f:.2e}, two-GEMM {e_t:.2e}")
+    assert delta <= 1e-5 and e_f <= 1.05 * e_t + 1e-4
+    # in place on the residual stream, and gamma = None
+    xin = x.cuda().clone()
+    out = OP.convnext_mlp_fused_(y.cuda(), stats, wq, col_s, cbias, w2q, b2.cuda(), None, xin)
+    assert out.data_ptr() == xin.data_ptr()
+    two1 = OP.linear_residual_(hid, w2q, b2.cuda(), None, None, M, x.cuda().clone())
+    assert common.rel_err(out, two1.double().cpu()) <= 1e-5
+
+
 def test_dwconv7_stats_matches_conv_and_row_moments():
     """dgtd_dwconv7_stats_tma_fwd: y = depthwise 7x7 (bf16 store), stats = (mean, rstd) of the STORED row."""
     common.package()

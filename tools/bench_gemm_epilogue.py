@@ -25,4 +25,6 @@ for st, (hw, C) in enumerate([(96, 128), (48, 256), (24, 512), (12, 1024)]):
     r["gelu"] = t(lambda: OP.linear(a, w, bias, OP.ACT_GELU, OP.BF16))
     r["lnfold+gelu"] = t(lambda: OP.linear_lnfold(a, w, bias, col_s, rs, OP.ACT_GELU, OP.BF16))
     r["pwconv2"] = t(lambda: OP.linear_residual_(h, w2, b2, g, None, hw * hw, res))
+    if C in OP.MLP_FUSED_C:
+        r["fused mlp"] = t(lambda: OP.convnext_mlp_fused_(a, rs, w, col_s, bias, w2, b2, g, res))
     print(f"stage {st} M={M} K={K} N={N}: " + "  ".join(f"{k} {v:.1f} us ({fl / v / 1e6:.0f} TF/s)" for k, v in r.items()), flush=True)

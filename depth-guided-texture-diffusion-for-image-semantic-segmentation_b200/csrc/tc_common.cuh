@@ -198,15 +198,19 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
 // full 128-byte lines instead of 32 scattered 16-byte accesses per instruction.
 // Invariant: before a staging tile is overwritten (by a TMA load or by the lanes) the store that
 // last read it -- two commits ago -- has finished reading: cp.async.bulk.wait_group.read 1.
-template <int BN, int ACT, typename OT, bool RESIDUAL, class Release>
+// PARTS = epilogue warps per TMEM lane quadrant (2: two staging tiles per warp, used alternately; 4: ONE tile per warp
+// -- the 16-warp form of the bf16 GELU epilogue, which is bound by issue latency, not by slots: see mlp_fused.cu).
+template <int BN, int ACT, typename OT, bool RESIDUAL, int PARTS = 2, class Release>
 __device__ __forceinline__ void tc_epilogue_tile_tma(const TcParams& p, const CUtensorMap* tmOut,
                                                      const CUtensorMap* tmRes, uint32_t tmem_tile, int quad,
                                                      int half, int lane, int row0, int n_blk, uint8_t* stg,
                                                      uint64_t* rbar, uint32_t& sbuf, Release release) {
-  constexpr int HALF_COLS = BN / 2;
+  constexpr int HALF_COLS = BN / PARTS;
   constexpr int NCH = HALF_COLS / 32;
   constexpr bool BF16_OUT = sizeof(OT) == 2;
+  constexpr bool ONE_BUF = PARTS == 4;
   static_assert(!(RESIDUAL && BF16_OUT), "residual epilogue writes fp32");
+  static_assert(!ONE_BUF || (BF16_OUT && NCH == 2 && !RESIDUAL), "the 16-warp epilogue is the bf16 one at BN = 256");
   const int row = row0 + lane;
   float ks = 1.f;
   if (RESIDUAL && p.keep && row < p.M) ks = p.keep[row / p.rows_per_sample];
@@ -224,7 +228,7 @@ __device__ __forceinline__ void tc_epilogue_tile_tma(const TcParams& p, const CU
   }
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
-    const uint32_t b = sbuf & 1;
+    const uint32_t b = ONE_BUF ? 0u : (sbuf & 1);
     uint8_t* tile = stg + b * 4096;
     const bool first_of_tile = !BF16_OUT || (c & 1) == 0;
     const bool last_of_tile = !BF16_OUT || (c & 1) == 1;
@@ -237,7 +241,10 @@ __device__ __forceinline__ void tc_epilogue_tile_tma(const TcParams& p, const CU
     if (RESIDUAL) {
       bw::mbar_wait(&rbar[b], (sbuf >> 1) & 1);
     } else if (first_of_tile) {
-      if (lane == 0) bw::tma_store_wait_read<1>();
+      if (lane == 0) {
+        if (ONE_BUF) bw::tma_store_wait_read<0>();
+        else bw::tma_store_wait_read<1>();
+      }
       __syncwarp();
     }
     const uint32_t(&vv)[32] = v[c & 1];

@@ -80,8 +80,8 @@ struct Tc2Cfg {
   static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + STG_BYTES + 512 + 1024;
 };
 
-template <int BN, int ACT, typename OT, bool RESIDUAL>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+template <int BN, int ACT, typename OT, bool RESIDUAL, int NEPI = 8>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEPI, 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                 const TcParams p) {
@@ -121,7 +121,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       bw::mbar_init(&tfull[i], 1);
-      bw::mbar_init(&tempty[i], 512);  // 8 epilogue warps x 2 CTAs
+      bw::mbar_init(&tempty[i], 2 * NEPI * 32);  // epilogue threads of both CTAs
     }
     for (int i = 0; i < 16; ++i) bw::mbar_init(&rbars[i], 1);
     bw::fence_mbar_init();
@@ -196,9 +196,9 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs, own 128 TMEM lanes) =====================
-    const int quad = warp & 3, half = (warp - 4) >> 2;
-    uint8_t* stg = sStg + (warp - 4) * 8192;
-    uint64_t* rbar = rbars + (warp - 4) * 2;
+    const int quad = warp & 3, half = (warp - 4) >> 2;   // half = column part (2 or 4 per quadrant)
+    uint8_t* stg = sStg + (warp - 4) * (NEPI == 8 ? 8192 : 4096);
+    uint64_t* rbar = rbars + ((warp - 4) & 7) * 2;
     uint32_t sbuf = 0;
     int iter = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++iter) {
@@ -209,7 +209,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       bw::mbar_wait(&tfull[as], aphase);
       bw::tc_fence_after();
       const uint32_t rel = bw2::map_to_rank(&tempty[as], 0);
-      tc_epilogue_tile_tma<BN, ACT, OT, RESIDUAL>(p, &tmOut, &tmRes, tmem_base + as * BN, quad, half, lane,
+      tc_epilogue_tile_tma<BN, ACT, OT, RESIDUAL, NEPI / 4>(p, &tmOut, &tmRes, tmem_base + as * BN, quad, half, lane,
                                                   z * p.split_rows + m_blk * 256 + (int)rank * BM + quad * 32, n_blk, stg, rbar,
                                                   sbuf, [rel] { bw2::mbar_arrive_cluster(rel); });
     }
@@ -225,11 +225,11 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-template <int BN, int ACT, typename OT, bool RESIDUAL>
+template <int BN, int ACT, typename OT, bool RESIDUAL, int NEPI = 8>
 static int tc2_launch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B, int64_t ldb, TcParams p,
                       cudaStream_t s) {
   using Cfg = Tc2Cfg<BN>;
-  auto kern = tc_gemm2_kernel<BN, ACT, OT, RESIDUAL>;
+  auto kern = tc_gemm2_kernel<BN, ACT, OT, RESIDUAL, NEPI>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -283,7 +283,7 @@ static int tc2_launch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* 
   int tiles = p.tiles_m * p.tiles_n * p.splits;
   int pairs = sm_count() / 2;
   int clusters = tiles < pairs ? tiles : pairs;
-  kern<<<2 * clusters, 384, Cfg::SMEM_BYTES, s>>>(tmA, tmB, tmOut, tmRes, p);
+  kern<<<2 * clusters, 128 + 32 * NEPI, Cfg::SMEM_BYTES, s>>>(tmA, tmB, tmOut, tmRes, p);
   return 0;
 }
 
@@ -292,7 +292,8 @@ static int tc2_dispatch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16
                         const TcParams& p, int act, int dtype_out, bool residual, cudaStream_t s) {
   if (residual) return tc2_launch<BN, DGTD_ACT_NONE, float, true>(A, lda, B, ldb, p, s);
   if (dtype_out == DGTD_BF16) {
-    if (act == DGTD_ACT_GELU) return tc2_launch<BN, DGTD_ACT_GELU, __nv_bfloat16, false>(A, lda, B, ldb, p, s);
+    if (act == DGTD_ACT_GELU)   // pwconv1: the GELU epilogue is issue-latency bound -> 16 epilogue warps at BN = 256
+      return tc2_launch<BN, DGTD_ACT_GELU, __nv_bfloat16, false, BN == 256 ? 16 : 8>(A, lda, B, ldb, p, s);
     if (act == DGTD_ACT_RELU) return tc2_launch<BN, DGTD_ACT_RELU, __nv_bfloat16, false>(A, lda, B, ldb, p, s);
     return tc2_launch<BN, DGTD_ACT_NONE, __nv_bfloat16, false>(A, lda, B, ldb, p, s);
   }

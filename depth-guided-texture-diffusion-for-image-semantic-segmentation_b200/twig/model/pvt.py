@@ -3,7 +3,9 @@
 Same class names, constructor signatures, attribute names (identical ``state_dict`` keys) and return
 values as the reference; every forward runs on libdgtd_ops.so.  Tokens are (B, N, C) = NHWC, the residual
 stream is fp32, GEMM operands bf16 (tcgen05) or fp32 (exact mode), selected like the hot path
-(``set_precision`` / ``torch.autocast``).  Inference only (no autograd graph) in this round.
+(``set_precision`` / ``torch.autocast``).  With gradients enabled and parameters that require them the same
+forwards build an autograd graph through ``ops/functions/pvt_train_func.py`` (one Function per Block / patch embed,
+backward on the same library); otherwise the fused inference kernels run.
 
 ``PyramidVisionTransformerImpr.forward_features`` is the fused pipeline: the hot path produces the prompt
 tokens directly in token layout, `x + prompt[i]` (cod.py:1472) is fused into the block's first LayerNorm.
@@ -19,9 +21,11 @@ import torch.nn as nn
 
 from ..ops.capi import BF16, F32
 from ..ops.functions import pvt_func as PF
+from ..ops.functions import pvt_train_func as PT
 from ..ops.functions import texture_diffusion_func as OP
+from ..ops.functions import train_func as TF
 from . import texture_diffuser as TD
-from .texture_diffuser import DropPath, _as, _mode, _packed, prompt_decoder, prompt_encoder
+from .texture_diffuser import DropPath, _as, _mode, _packed, _wants_grad, prompt_decoder, prompt_encoder
 
 __all__ = ["DWConv", "Mlp", "Attention", "Block", "OverlapPatchEmbed", "PyramidVisionTransformerImpr", "pvt_v2_b2"]
 
@@ -171,13 +175,30 @@ class Block(nn.Module):
 
     def _forward_tokens(self, x: torch.Tensor, prompt: Optional[torch.Tensor], H: int, W: int, mode: int) -> torch.Tensor:
         """x (B,N,C) fp32 residual stream (updated in place when no prompt is added), prompt (B,N,C) | None."""
-        assert not self.training, "the PVT blocks are inference-only in this round"
         a, x = PF.ln_tokens(x, _f(self.norm1.weight), _f(self.norm1.bias), self.norm1.eps, mode, add=prompt, want_sum=True)
         x = self.attn._branch(a, H, W, mode, x)
         a, _ = PF.ln_tokens(x, _f(self.norm2.weight), _f(self.norm2.bias), self.norm2.eps, mode)
         return self.mlp._branch(a, H, W, mode, x)
 
+    def _forward_train(self, x: torch.Tensor, prompt: Optional[torch.Tensor], H: int, W: int, mode: int) -> torch.Tensor:
+        """Same block with an autograd graph (DropPath masks drawn per branch like timm's, cod.py:959-960)."""
+        at, mlp = self.attn, self.mlp
+        assert x.shape[-1] // at.num_heads == 64 and qk_scale_ok(at), "attention kernel is built for head_dim 64"
+        dp = isinstance(self.drop_path, DropPath)
+        keep1 = self.drop_path.keep_scale(x.shape[0], x.device) if dp else None
+        keep2 = self.drop_path.keep_scale(x.shape[0], x.device) if dp else None
+        sr = at.sr_ratio
+        cfg = (H, W, at.num_heads, sr, mode, self.norm1.eps, at.norm.eps if sr > 1 else 0.0)
+        return PT.PvtBlockFn.apply(
+            x, prompt, keep1, keep2, cfg, self.norm1.weight, self.norm1.bias, at.q.weight, at.q.bias, at.kv.weight,
+            at.kv.bias, at.sr.weight if sr > 1 else None, at.sr.bias if sr > 1 else None,
+            at.norm.weight if sr > 1 else None, at.norm.bias if sr > 1 else None, at.proj.weight, at.proj.bias,
+            self.norm2.weight, self.norm2.bias, mlp.fc1.weight, mlp.fc1.bias, mlp.dwconv.dwconv.weight,
+            mlp.dwconv.dwconv.bias, mlp.fc2.weight, mlp.fc2.bias)
+
     def forward(self, x, H, W):
+        if _wants_grad(self, x):
+            return self._forward_train(x, None, H, W, _mode(self))
         return self._forward_tokens(x.detach().float().contiguous().clone(), None, H, W, _mode(self))
 
 
@@ -229,7 +250,17 @@ class OverlapPatchEmbed(nn.Module):
         t, _ = PF.ln_tokens(y.view(B, oh * ow, Cout), _f(self.norm.weight), _f(self.norm.bias), self.norm.eps, F32)
         return t, oh, ow
 
+    def _forward_train(self, x: torch.Tensor, mode: int = F32) -> Tuple[torch.Tensor, int, int]:
+        """x (B,H,W,Cin) fp32 NHWC -> tokens with an autograd graph (conv + LayerNorm as one Function)."""
+        k, s = self.patch_size[0], self.stride
+        t = PT.PatchEmbedFn.apply(x, self.proj.weight, self.proj.bias, self.norm.weight, self.norm.bias,
+                                  (k, s, mode, self.norm.eps))
+        H, W = x.shape[1], x.shape[2]
+        return t, (H + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
+
     def forward(self, x):
+        if _wants_grad(self, x):
+            return self._forward_train(TF.LayoutFn.apply(x, True), _mode(self))
         return self._forward_nhwc(OP.nchw_to_nhwc(x.detach().float().contiguous()), _mode(self))
 
 
@@ -291,12 +322,37 @@ class PyramidVisionTransformerImpr(nn.Module):
             outs.append(cur)
         return emb1, outs
 
-    @torch.no_grad()
+    def _forward_features_train(self, x, depth):
+        """cod.py:1455-1509 with an autograd graph: hot path through `texture_prompts_train`, blocks and patch embeds
+        through PvtBlockFn / PatchEmbedFn; stage maps stay NHWC fp32."""
+        self.batch += 1
+        if isinstance(depth, (list, tuple)):
+            depth = torch.stack([d.reshape(1, *d.shape[-2:]) for d in depth], 0)
+        mode = _mode(self)
+        image = x.float().contiguous()
+        emb1, _, tokens = TD.texture_prompts_train(self.prompt_encoder, self.prompt_decoder, image, depth,
+                                                   precision="bf16" if mode == BF16 else "fp32")
+        B = image.shape[0]
+        outs: List[torch.Tensor] = []
+        cur = TF.LayoutFn.apply(image, True) if image.requires_grad else OP.nchw_to_nhwc(image.detach())
+        for s in range(4):
+            t, H, W = getattr(self, f"patch_embed{s + 1}")._forward_train(cur, mode)
+            for i, blk in enumerate(getattr(self, f"block{s + 1}")):
+                t = blk._forward_train(t, tokens[s][i].reshape(t.shape), H, W, mode)
+            norm = getattr(self, f"norm{s + 1}")
+            cur = TF.LayerNormRowsFn.apply(t, norm.weight, norm.bias, norm.eps).view(B, H, W, -1)
+            outs.append(cur)
+        return emb1, outs
+
     def forward_features(self, x, depth):
         """cod.py:1455-1509 -> (embedding1, [(B, C_s, H_s, W_s) fp32]).  `depth` may be the reference's list of
-        (1,H,W) maps or a (B,1,H,W) tensor."""
-        emb1, outs = self._forward_features_nhwc(x, depth)
-        return emb1, [OP.nhwc_to_nchw(o) for o in outs]
+        (1,H,W) maps or a (B,1,H,W) tensor.  Builds an autograd graph when gradients are wanted."""
+        if _wants_grad(self, x):
+            emb1, outs = self._forward_features_train(x, depth)
+            return emb1, [TF.LayoutFn.apply(o, False) for o in outs]
+        with torch.no_grad():
+            emb1, outs = self._forward_features_nhwc(x, depth)
+            return emb1, [OP.nhwc_to_nchw(o) for o in outs]
 
     def forward(self, x, depth):
         return self.forward_features(x, depth)

@@ -86,6 +86,9 @@ SIGNATURES = {
     "dgtd_dwconv3_gelu_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "dgtd_dwconv3_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "dgtd_attention_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "dgtd_attention_bwd_ws_floats": [_I, _I, _I],
+    "dgtd_attention_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "dgtd_dwconv3_gelu_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "dgtd_boundary_weight_fwd": [_P, _P, _I, _I, _I, _P],
     "dgtd_structure_loss_ws_floats": [_I, _L],
     "dgtd_structure_loss_fwd": [_P, _P, _P, _P, _P, _P, _I, _L, _P],

@@ -346,6 +346,18 @@ int dgtd_dwconv3_fwd(const void* x, const float* wT, const float* bias, void* ou
  * softmax(scale * q k^T) v in fp32 with an online softmax over key tiles. */
 int dgtd_attention_fwd(const void* q, const void* kv, void* out, int dtype, int B, int N, int Nk, int heads,
                        float scale, dgtd_stream_t stream);
+/* Backward of the attention core (training of the PVT blocks, cod.py:911-915 under autograd): q / kv / out as in
+ * dgtd_attention_fwd (dtype fp32 | bf16), dout (B*N, heads*64) fp32 -> dq (B*N, heads*64) and dkv (B*Nk, 2*heads*64)
+ * [dk | dv], both fp32 (dkv is zeroed here; dk / dv accumulate through fp32 atomics, so their last bits depend on the
+ * schedule).  ws: dgtd_attention_bwd_ws_floats floats (per-row log-sum-exp and dO.O). */
+int dgtd_attention_bwd_ws_floats(int B, int N, int heads);
+int dgtd_attention_bwd(const void* q, const void* kv, const void* out, const float* dout, float* dq, float* dkv, float* ws,
+                       int dtype, int B, int N, int Nk, int heads, float scale, dgtd_stream_t stream);
+/* Backward of Mlp.dwconv + act (cod.py:852-854): x / wT / bias as in dgtd_dwconv3_gelu_fwd, g = dL/d(out) fp32 ->
+ * du = g * gelu'(conv3(x) + bias) fp32 (B,h,w,C), dwT (9,C) and dbias (C) (zeroed here, fp32 atomics).  The input
+ * gradient is dgtd_dwconv3_fwd(du) with the taps rotated by 180 degrees and a zero bias. */
+int dgtd_dwconv3_gelu_bwd(const void* x, const float* wT, const float* bias, const float* g, float* du, float* dwT,
+                          float* dbias, int dtype, int B, int h, int w, int C, dgtd_stream_t stream);
 
 /* ---- structure loss (cod.cal_loss, cod.py:75-84) ------------------------------------------
  * weit = 1 + 5 |avgpool31x31(gt) - gt| (zero padding, divisor 961); depends on the label only. */

@@ -7,8 +7,10 @@ argument shares between all CABs); every forward runs on libdgtd_ops.so (csrc/hi
 implicit GEMMs (the mask-parity path); bf16 mode (`set_precision` / autocast, like the hot path) = tcgen05: the 3x3
 convs as implicit GEMMs (one shifted 4-D TMA box per tap, nothing materialised), the 1x1 / 8x8-stride-4 convs
 through a bf16 im2col operand; BatchNorm scale folded into the weights, fp32 accumulation and fp32 outputs.
-Inference semantics only in this round: BatchNorm uses its running statistics (folded into the conv epilogue),
-there is no autograd graph through the decoder, and `train()` mode raises.
+Two paths, like the hot path: with gradients disabled and eval() the fused inference kernels (BatchNorm's running
+statistics folded into the conv epilogue, concatenations produced in place); with gradients wanted or in train() the
+autograd Functions of ops/functions/hitnet_train_func.py (train-mode BatchNorm with batch statistics and running
+updates, every parameter of `cod.forward(mode='loss')` receives its gradient).
 
 The reference's `torch.cat` operands are produced in place: a conv / resize writes straight into its channel
 slice of the concatenated tensor (pixel pitch argument of the kernels), nothing is copied twice.
@@ -21,10 +23,11 @@ import torch
 import torch.nn as nn
 
 from ..ops.functions import hitnet_func as HF
+from ..ops.functions import hitnet_train_func as HT
 from ..ops.functions import texture_diffusion_func as OP
 from ..ops.capi import BF16
 from .pvt import pvt_v2_b2
-from .texture_diffuser import _mode, _packed
+from .texture_diffuser import _mode, _packed, _wants_grad
 
 __all__ = ["BasicConv2d", "ChannelAttention", "SpatialAttention", "CALayer", "CAB", "SAM", "Hitnet", "cod"]
 
@@ -53,10 +56,8 @@ def _tap_major_padded_bf16(w: torch.Tensor, scale: Optional[torch.Tensor] = None
 
 
 def _no_training(m: nn.Module) -> None:
-    if m.training:
-        raise NotImplementedError(
-            f"{type(m).__name__}: only eval() semantics are built for the Hitnet decoder in this round "
-            "(BatchNorm batch statistics and the decoder backward are not implemented; there is no fallback)")
+    """The fused inference kernels fold BatchNorm's RUNNING statistics; train() goes through `_forward_train`."""
+    assert not m.training, f"{type(m).__name__}: the fused inference path was entered in train() mode"
 
 
 class BasicConv2d(nn.Module):
@@ -81,7 +82,7 @@ class BasicConv2d(nn.Module):
         return _tap_major(self.conv.weight), scale, shift
 
     def _forward_nhwc(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        _no_training(self)
+        _no_training(self.bn)
         assert self.conv.dilation == (1, 1)
         w, scale, shift = self._params()
         k, s, p = self.conv.kernel_size[0], self.conv.stride[0], self.conv.padding[0]
@@ -97,7 +98,27 @@ class BasicConv2d(nn.Module):
             return HF.conv_affine_tc(x, wb, (oh, ow), k, s, -p, shift=shift, out=out)
         return HF.conv_affine(x, w, (oh, ow), k, s, -p, scale=scale, shift=shift, out=out)
 
+    def _forward_train(self, x: torch.Tensor) -> torch.Tensor:
+        """NHWC fp32 in / out under autograd; train(): batch statistics + running update like nn.BatchNorm2d
+        (cod.py:362), eval(): the running statistics."""
+        assert self.conv.dilation == (1, 1)
+        bn = self.bn
+        batch_stats = bn.training or bn.running_mean is None
+        mom = bn.momentum
+        if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+            if mom is None:
+                mom = 1.0 / float(bn.num_batches_tracked)
+        update = bn.training and bn.track_running_stats
+        k, s, p = self.conv.kernel_size[0], self.conv.stride[0], self.conv.padding[0]
+        return HT.ConvBnFn.apply(x, self.conv.weight, bn.weight, bn.bias, bn.running_mean if update or not batch_stats else None,
+                                 bn.running_var if update or not batch_stats else None,
+                                 (k, s, p, _mode(self), bn.eps, 0.0 if mom is None else mom, batch_stats))
+
     def forward(self, x):
+        if self.bn.training or _wants_grad(self, x):
+            from ..ops.functions import train_func as TF
+            return TF.LayoutFn.apply(self._forward_train(TF.LayoutFn.apply(x, True)), False)
         return OP.nhwc_to_nchw(self._forward_nhwc(OP.nchw_to_nhwc(x.detach().float().contiguous())))
 
 
@@ -190,7 +211,18 @@ class CAB(nn.Module):
             r = HF.conv_affine(r, w2, hw, k, 1, -(k // 2))
         return HF.gated_sum(r, ga=self.CA._gate(r), b=x, out=out)
 
+    def _forward_train(self, x: torch.Tensor) -> torch.Tensor:
+        c0, act, c2 = self.body[0], self.body[1], self.body[2]
+        assert isinstance(act, nn.PReLU) and act.weight.numel() == 1, "the reference's act is nn.PReLU() (cod.py:686)"
+        assert c0.bias is None and c2.bias is None and c0.kernel_size == (3, 3), "CAB(bias=True / kernel != 3) is not built"
+        du = self.CA.conv_du
+        assert du[0].bias is None and du[2].bias is None, "CALayer(bias=True) is not built"
+        return HT.CabFn.apply(x, c0.weight, act.weight, c2.weight, du[0].weight, du[2].weight, _mode(self))
+
     def forward(self, x):
+        if _wants_grad(self, x):
+            from ..ops.functions import train_func as TF
+            return TF.LayoutFn.apply(self._forward_train(TF.LayoutFn.apply(x, True)), False)
         return OP.nhwc_to_nchw(self._forward_nhwc(OP.nchw_to_nhwc(x.detach().float().contiguous())))
 
 
@@ -215,7 +247,14 @@ class SAM(nn.Module):
         return HF.gated_sum(x_h, ga=HF.channel_gate(ph, hw_h, f0, f2), sa=HF.channel_gate(ph, hw_h, g0, g2),
                             b=x_l, gb=HF.channel_gate(pl, hw_l, f0, f2), sb=HF.channel_gate(pl, hw_l, g0, g2))
 
+    def _forward_train(self, x_h: torch.Tensor, x_l: torch.Tensor) -> torch.Tensor:
+        return HT.SamFn.apply(x_h, x_l, self.fc[0].weight, self.fc[2].weight, self.fc_wight[0].weight,
+                              self.fc_wight[2].weight)
+
     def forward(self, x_h, x_l):
+        if _wants_grad(self, x_h, x_l):
+            from ..ops.functions import train_func as TF
+            return TF.LayoutFn.apply(self._forward_train(TF.LayoutFn.apply(x_h, True), TF.LayoutFn.apply(x_l, True)), False)
         n = lambda t: OP.nchw_to_nhwc(t.detach().float().contiguous())  # noqa: E731
         return OP.nhwc_to_nchw(self._forward_nhwc(n(x_h), n(x_l)))
 
@@ -269,7 +308,7 @@ class Hitnet(nn.Module):
         Returns (stage predictions [(B,1,8h,8w)] (empty when not wanted), SAM prediction (B,1,8h,8w) (None when not
         wanted), (out_CFM(cfm_last), out_SAM(sam)) on the stride-8 grid (B,1,h,w): the x8 up-sample of their sum is
         the predict logit map, bilinear interpolation being linear)."""
-        _no_training(self)
+        assert not self._decoder_training(), "decode() folds the running statistics; train() goes through decode_train()"
         x1, x2, x3, x4 = feats
         B, ch = x1.shape[0], self.channel
         dev = x1.device
@@ -318,12 +357,57 @@ class Hitnet(nn.Module):
         p2_8 = OP.resize_nchw(p2, (8 * h2, 8 * w2)) if want_stage_preds else None   # :806
         return preds, p2_8, (pr, p2)
 
-    @torch.no_grad()
+    def decode_train(self, feats: Sequence[torch.Tensor], iterations: int = 4) -> Tuple[List[torch.Tensor], torch.Tensor]:
+        """cod.py:752-806 on the four NHWC backbone maps under autograd (train-mode BatchNorm when the module is in
+        train()): ([stage predictions (B,1,8h,8w)], SAM prediction).  The `torch.cat`s are ATen copies here (their
+        backward is a slice); everything else runs on libdgtd_ops.so."""
+        x1, x2, x3, x4 = feats
+        h2, w2 = x2.shape[1], x2.shape[2]
+        h3, w3 = x3.shape[1], x3.shape[2]
+        h4, w4 = x4.shape[1], x4.shape[2]
+        assert (4 * h4, 4 * w4) == (h2, w2) and (2 * h3, 2 * w3) == (h2, w2), "backbone grids must be 8/16/32 strides"
+        up = lambda t, hw: HT.ResizeLdFn.apply(t, hw, True)                     # noqa: E731
+        pair = lambda seq, t: seq[1]._forward_train(seq[0]._forward_train(t))   # noqa: E731
+        cim = pair(self.decoder_level1, x1)                                     # :760
+        x2_t = self.Translayer2_1._forward_train(x2)                            # :763
+        x3_t = self.Translayer3_1._forward_train(x3)                            # :764
+        x4_t = self.Translayer4_1._forward_train(x4)                            # :765
+        preds: List[torch.Tensor] = []
+        cfm = None
+        for it in range(iterations):
+            if cfm is not None:
+                x4_t = self.compress_out._forward_train(torch.cat((up(x4_t, (4 * h4, 4 * w4)), cfm), -1))   # :778-779
+            x4_f = pair(self.decoder_level4, x4_t)                              # :786
+            x3_f = pair(self.decoder_level3, torch.cat((x3_t, up(x4_f, (h3, w3))), -1))      # :785-786
+            if it > 0:
+                x2_t = self.compress_out2._forward_train(torch.cat((x2_t, cfm), -1))         # :789-790
+            x2_f = pair(self.decoder_level2, torch.cat((x2_t, up(x3_f, (h2, w2))), -1))      # :791-792
+            cfm = self.conv4._forward_train(x2_f)                               # :793
+            pr = HT.Head1Fn.apply(cfm, self.out_CFM.weight, self.out_CFM.bias)  # :794
+            preds.append(OP.resize_bilinear_nchw_autograd(pr, (8 * h2, 8 * w2)))             # :796
+        t2 = self.Translayer2_0._forward_train(cim)                             # :800
+        t2 = up(t2, (t2.shape[1] // 2, t2.shape[2] // 2))                       # :801
+        sam = self.SAM._forward_train(cfm, t2)                                  # :802
+        p2 = HT.Head1Fn.apply(sam, self.out_SAM.weight, self.out_SAM.bias)      # :805
+        return preds, OP.resize_bilinear_nchw_autograd(p2, (8 * h2, 8 * w2))    # :806
+
+    def _decoder_training(self) -> bool:
+        return any(m.training for m in self.modules() if isinstance(m, nn.BatchNorm2d))
+
     def forward(self, x, pred_normal):
-        """cod.py:743-807 -> (embedding1, [4 stage predictions], prediction2_8)."""
-        emb1, feats = self.backbone._forward_features_nhwc(x, pred_normal)
-        preds, p2_8, _ = self.decode(feats)
-        return emb1, preds, p2_8
+        """cod.py:743-807 -> (embedding1, [4 stage predictions], prediction2_8).  Builds an autograd graph when
+        gradients are wanted; train() uses BatchNorm batch statistics (with or without gradients)."""
+        if _wants_grad(self, x):
+            emb1, feats = self.backbone._forward_features_train(x, pred_normal)
+            preds, p2_8 = self.decode_train(feats)
+            return emb1, preds, p2_8
+        with torch.no_grad():
+            emb1, feats = self.backbone._forward_features_nhwc(x, pred_normal)
+            if self._decoder_training():
+                preds, p2_8 = self.decode_train(feats)
+            else:
+                preds, p2_8, _ = self.decode(feats)
+            return emb1, preds, p2_8
 
     @torch.no_grad()
     def predict_logits(self, x, depth, size: Optional[Sequence[int]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -331,6 +415,12 @@ class Hitnet(nn.Module):
         predictions: the two 1-channel heads are summed on the stride-8 grid and up-sampled once when `size` is the
         x8 grid (bilinear interpolation is linear)."""
         emb1, feats = self.backbone._forward_features_nhwc(x, depth)
+        if self._decoder_training():      # train() under no_grad: batch statistics, like the reference would
+            preds, p2_8 = self.decode_train(feats)
+            out = _add_planes(preds[-1], p2_8)
+            if size is not None and tuple(int(v) for v in size) != tuple(out.shape[-2:]):
+                out = OP.resize_nchw(out, (int(size[0]), int(size[1])))
+            return emb1, out
         _, p2_8, (pr, p2) = self.decode(feats, want_stage_preds=False)
         H8, W8 = 8 * pr.shape[-2], 8 * pr.shape[-1]
         size = (H8, W8) if size is None else (int(size[0]), int(size[1]))
@@ -355,7 +445,7 @@ class cod(nn.Module):
 
     `forward(raw, input, label, depth, mode)`: 'predict' -> (sigmoid(output), label) like cod.py:217 without the
     PNG side effects; 'tensor' -> output logits; 'loss' -> {'loss': loss_p1 + loss_P2 + loss_3} of cod.py:135-146
-    (forward value only: no autograd graph through the decoder in this round)."""
+    with an autograd graph to every parameter when gradients are enabled (the training step of cod.py:118-146)."""
 
     def __init__(self, win_size=None, filter_ratio=None, using_depth=None, using_sam=None, finetune=None,
                  binary_thresh=None, pretrain_sam=None, head=None):
@@ -364,7 +454,6 @@ class cod(nn.Module):
         self.batch = 0
         self.binary_thresh = binary_thresh
 
-    @torch.no_grad()
     def forward(self, raw, input, label, depth, mode='loss'):
         if isinstance(input, (tuple, list)):
             input = torch.stack(input, dim=0)
@@ -373,11 +462,12 @@ class cod(nn.Module):
         if isinstance(depth, (tuple, list)):
             depth = torch.stack(depth, dim=0)
         if mode in ('predict', 'tensor'):
-            size = label.shape[-2:] if label is not None else None
-            _, output = self.hitnet.predict_logits(input, depth, size)
-            if mode == 'tensor':
-                return output
-            return _sigmoid(output), label
+            with torch.no_grad():
+                size = label.shape[-2:] if label is not None else None
+                _, output = self.hitnet.predict_logits(input, depth, size)
+                if mode == 'tensor':
+                    return output
+                return _sigmoid(output), label
         if mode == 'loss':
             from .losses import total_loss
             emb1, P1, P2 = self.hitnet(input, depth)

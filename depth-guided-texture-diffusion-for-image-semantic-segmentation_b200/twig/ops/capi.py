@@ -111,6 +111,18 @@ SIGNATURES = {
     "dgtd_cast_pad_act_fwd": [_P, _I, _P, _P, _L, _I, _I, _P],
     "dgtd_conv3x3_tc_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "dgtd_im2col_act_fwd": [_P, _I, _P, _P] + [_I] * 9 + [_P],
+    "dgtd_col_stats_ws_bytes": [_L, _I],
+    "dgtd_bn_train_fwd": [_P, _I, _P, _P, _P, _P, _F, _F, _P, _I, _P, _P, _P, _L, _I, _P],
+    "dgtd_bn_apply_fwd": [_P, _I, _P, _P, _P, _P, _P, _I, _L, _I, _P],
+    "dgtd_bn_train_bwd": [_P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _P, _I, _L, _I, _P],
+    "dgtd_prelu_fwd": [_P, _P, _P, _L, _P],
+    "dgtd_prelu_bwd_ws_bytes": [_L],
+    "dgtd_prelu_bwd": [_P, _P, _P, _P, _P, _P, _L, _P],
+    "dgtd_channel_dot_fwd": [_P, _I, _P, _I, _P, _I, _I, _I, _P],
+    "dgtd_gate_bwd": [_P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "dgtd_gated_bwd": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "dgtd_head1_bwd": [_P, _P, _I, _P, _P, _I, _P, _P, _P, _L, _I, _P],
+    "dgtd_resize_nhwc_ld_bwd": [_P, _I, _P, _I] + [_I] * 7 + [_P],
     "dgtd_ssim_loss_ws_floats": [_L],
     "dgtd_ssim_loss_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],
     "dgtd_adamw_slice_bytes": [],
@@ -118,7 +130,8 @@ SIGNATURES = {
     "dgtd_sod_metrics_ws_bytes": [_I, _I, _I],
     "dgtd_sod_metrics_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
 }
-_RESTYPES = {"dgtd_last_error": c_char_p, "dgtd_launch_count": c_int64, "dgtd_sod_metrics_ws_bytes": c_int64}
+_RESTYPES = {"dgtd_last_error": c_char_p, "dgtd_launch_count": c_int64, "dgtd_sod_metrics_ws_bytes": c_int64,
+             "dgtd_col_stats_ws_bytes": c_int64, "dgtd_prelu_bwd_ws_bytes": c_int64}
 
 _lib: Optional[ctypes.CDLL] = None
 

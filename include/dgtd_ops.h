@@ -422,6 +422,52 @@ int dgtd_conv3x3_tc_fwd(const void* x, const void* w, const float* bias, float* 
 /* `output.sigmoid()` of the predict mode (cod.py:212,217) */
 int dgtd_sigmoid_fwd(const float* x, float* out, int64_t n, dgtd_stream_t stream);
 
+/* ---- training of the Hitnet decoder (SURVEY.md 8f-2 under autograd; csrc/hitnet_train.cu) ------------------------
+ * All reductions in a fixed order (per-CTA partials in double + one finalising pass; no atomics).  NHWC fp32 maps,
+ * `ld*` = pixel pitch.  ws: scratch of dgtd_col_stats_ws_bytes(M, C) bytes (8-byte aligned).
+ * Train-mode nn.BatchNorm2d of BasicConv2d (cod.py:362,366-367): mean / rstd of the batch (biased variance) are
+ * written for the backward, out = (y - mean) rstd gamma + beta; run_mean / run_var (nullable together) get the
+ * momentum update with the unbiased variance. */
+int64_t dgtd_col_stats_ws_bytes(int64_t M, int C);
+int dgtd_bn_train_fwd(const float* y, int ldy, const float* gamma, const float* beta, float* run_mean, float* run_var,
+                      float momentum, float eps, float* out, int ldo, float* mean, float* rstd, void* ws, int64_t M,
+                      int C, dgtd_stream_t stream);
+/* the apply step alone with given statistics (eval-mode BatchNorm inside an autograd graph) */
+int dgtd_bn_apply_fwd(const float* y, int ldy, const float* mean, const float* rstd, const float* gamma,
+                      const float* beta, float* out, int ldo, int64_t M, int C, dgtd_stream_t stream);
+/* dgamma = sum dy xhat, dbeta = sum dy; batch_stats 1: dx = gamma rstd (dy - dbeta / M - xhat dgamma / M),
+ * 0 (fixed statistics): dx = gamma rstd dy.  y = the conv output the forward normalised. */
+int dgtd_bn_train_bwd(const float* dy, int lddy, const float* y, int ldy, const float* mean, const float* rstd,
+                      const float* gamma, float* dx, int lddx, float* dgamma, float* dbeta, void* ws, int batch_stats,
+                      int64_t M, int C, dgtd_stream_t stream);
+/* nn.PReLU() with ONE slope (the `act` every CAB shares, cod.py:686,440): v = u >= 0 ? u : slope u over n values
+ * (n % 4 == 0); backward du = g (u >= 0 ? 1 : slope), dslope[0] = sum g u [u < 0]; ws: dgtd_prelu_bwd_ws_bytes(n). */
+int dgtd_prelu_fwd(const float* u, const float* slope, float* v, int64_t n, dgtd_stream_t stream);
+int64_t dgtd_prelu_bwd_ws_bytes(int64_t n);
+int dgtd_prelu_bwd(const float* u, const float* g, const float* slope, float* du, float* dslope, void* ws, int64_t n,
+                   dgtd_stream_t stream);
+/* partial[b][chunk][c] = sum over the chunk's pixels of a * b (same chunking as dgtd_channel_sums_fwd): the channel
+ * dots sum_p g x that the gates' backward starts from. */
+int dgtd_channel_dot_fwd(const float* a, int lda, const float* b, int ldb, float* partial, int B, int hw, int C,
+                         dgtd_stream_t stream);
+/* Backward of out = x * gc[c] * gs, gc = sigmoid(W2 relu(W1 m)) (CALayer cod.py:427-429 / SAM.fc :482), gs =
+ * sigmoid(v2 relu(V1 m)) (SAM.fc_wight :480; Cs = 0: no scalar gate), m = mean(x): part = channel sums of x, dpart =
+ * channel dots of (g, x).  Writes dmean (B,C) (to be spread as dmean / hw over the pixels) and the weight gradients
+ * dw1 (Cr,C), dw2 (C,Cr), dv1 (Cs,C), dv2 (Cs); accumulate 1 adds to them (SAM runs both inputs through the same
+ * weights). */
+int dgtd_gate_bwd(const float* part, int nch, int hw, const float* dpart, int nchd, const float* w1, const float* w2,
+                  const float* v1, const float* v2, float* dmean, float* dw1, float* dw2, float* dv1, float* dv2,
+                  int accumulate, int B, int C, int Cr, int Cs, dgtd_stream_t stream);
+/* out = g * gate[b,c] * scal[b] + dmean[b,c] / hw  (scal, dmean nullable): gradient w.r.t. the gated operand */
+int dgtd_gated_bwd(const float* g, int ldg, const float* gate, const float* scal, const float* dmean, float* out, int ldo,
+                   int B, int hw, int C, dgtd_stream_t stream);
+/* backward of dgtd_head1_fwd: dx[row,c] = g[row] w[c] (dx nullable), dw[c] = sum g[row] x[row,c], db[0] = sum g */
+int dgtd_head1_bwd(const float* g, const float* x, int ldx, const float* w, float* dx, int lddx, float* dw, float* db,
+                   void* ws, int64_t rows, int C, dgtd_stream_t stream);
+/* adjoint of dgtd_resize_nhwc_ld_fwd (gather form): g (B,oh,ow,C) -> dx (B,h,w,C) */
+int dgtd_resize_nhwc_ld_bwd(const float* g, int ldg, float* dx, int lddx, int B, int h, int w, int C, int oh, int ow,
+                            int align_corners, dgtd_stream_t stream);
+
 /* ---- evaluation metrics (twig/metric/{MAE,Smeasure,Fmeasure,Emeasure}.py:18-36 + pysodmetrics
  * 1.3.1) -- the four evaluators of config/cod.yml:123-128 / sod.yml:85-89.
  * pred, gt (B,1,H,W) fp32 in [0,1] as the `predict` mode returns them (cod.py:217).  Quantises both like the

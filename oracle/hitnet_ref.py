@@ -5,7 +5,9 @@ TEST INFRASTRUCTURE ONLY: imported by tests/, tests/golden/make_golden_hitnet.py
 legs; never by the product path.  Plain functional torch on a state dict with the reference's keys
 (`Hitnet`, cod.py:685-807); pinned against the unmodified reference class by
 tests/golden/make_golden_hitnet.py (fixture tests/golden/hitnet_*.npz).  Inference semantics
-(BatchNorm uses its running statistics).
+(BatchNorm uses its running statistics) by default; `train=True` = train-mode BatchNorm (batch
+statistics, biased variance; the running buffers are not touched here), pinned against the
+unmodified class in train() by the same script (fixture hitnet_train_128.npz: loss + gradients).
 
 Reference lines followed:
   BasicConv2d   cod.py:355-368   conv (no bias) -> BatchNorm2d; the ReLU member is never applied
@@ -58,8 +60,13 @@ def resize_bilinear(x: torch.Tensor, oh: int, ow: int, align_corners: bool) -> t
     return rows[:, :, :, x0] * (1 - fx) + rows[:, :, :, x1] * fx
 
 
-def basic_conv(x: torch.Tensor, p: Params, stride: int = 1, padding: int = 0) -> torch.Tensor:
+def basic_conv(x: torch.Tensor, p: Params, stride: int = 1, padding: int = 0, train: bool = False) -> torch.Tensor:
     y = F.conv2d(x, p["conv.weight"], None, stride=stride, padding=padding)
+    if train:       # nn.BatchNorm2d in train(): statistics of this batch over (B, H, W), biased variance
+        mean = y.mean(dim=(0, 2, 3), keepdim=True)
+        var = ((y - mean) ** 2).mean(dim=(0, 2, 3), keepdim=True)
+        xhat = (y - mean) / torch.sqrt(var + BN_EPS)
+        return xhat * p["bn.weight"][None, :, None, None] + p["bn.bias"][None, :, None, None]
     scale = p["bn.weight"] / torch.sqrt(p["bn.running_var"] + BN_EPS)
     shift = p["bn.bias"] - p["bn.running_mean"] * scale
     return y * scale[None, :, None, None] + shift[None, :, None, None]
@@ -98,41 +105,43 @@ def conv1x1_bias(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Ten
     return F.conv2d(x, w, b)
 
 
-def decode(feats: Sequence[torch.Tensor], p: Params, iterations: int = 4) -> Tuple[List[torch.Tensor], torch.Tensor]:
+def decode(feats: Sequence[torch.Tensor], p: Params, iterations: int = 4, train: bool = False
+           ) -> Tuple[List[torch.Tensor], torch.Tensor]:
     """cod.py:752-805 on the four backbone maps -> ([4 stage predictions], SAM prediction), each (B,1,8h,8w)
     with (h, w) the stride-8 grid."""
     x1, x2, x3, x4 = feats
     cim = cab_pair(x1, sub(p, "decoder_level1"))
-    x2_t = basic_conv(x2, sub(p, "Translayer2_1"))
-    x3_t = basic_conv(x3, sub(p, "Translayer3_1"))
-    x4_t = basic_conv(x4, sub(p, "Translayer4_1"))
+    x2_t = basic_conv(x2, sub(p, "Translayer2_1"), train=train)
+    x3_t = basic_conv(x3, sub(p, "Translayer3_1"), train=train)
+    x4_t = basic_conv(x4, sub(p, "Translayer4_1"), train=train)
     preds: List[torch.Tensor] = []
     cfm = None
     for it in range(iterations):
         if cfm is not None:
             up = resize_bilinear(x4_t, 4 * x4_t.shape[2], 4 * x4_t.shape[3], True)
-            x4_t = basic_conv(torch.cat((up, cfm), 1), sub(p, "compress_out"), stride=4, padding=2)
+            x4_t = basic_conv(torch.cat((up, cfm), 1), sub(p, "compress_out"), stride=4, padding=2, train=train)
         x4_f = cab_pair(x4_t, sub(p, "decoder_level4"))
         up = resize_bilinear(x4_f, 2 * x4_f.shape[2], 2 * x4_f.shape[3], True)
         x3_f = cab_pair(torch.cat((x3_t, up), 1), sub(p, "decoder_level3"))
         if it > 0:
-            x2_t = basic_conv(torch.cat((x2_t, cfm), 1), sub(p, "compress_out2"))
+            x2_t = basic_conv(torch.cat((x2_t, cfm), 1), sub(p, "compress_out2"), train=train)
         up = resize_bilinear(x3_f, 2 * x3_f.shape[2], 2 * x3_f.shape[3], True)
         x2_f = cab_pair(torch.cat((x2_t, up), 1), sub(p, "decoder_level2"))
-        cfm = basic_conv(x2_f, sub(p, "conv4"), padding=1)
+        cfm = basic_conv(x2_f, sub(p, "conv4"), padding=1, train=train)
         pr = conv1x1_bias(cfm, p["out_CFM.weight"], p["out_CFM.bias"])
         preds.append(resize_bilinear(pr, 8 * pr.shape[2], 8 * pr.shape[3], False))
-    t2 = basic_conv(cim, sub(p, "Translayer2_0"))
+    t2 = basic_conv(cim, sub(p, "Translayer2_0"), train=train)
     t2 = resize_bilinear(t2, t2.shape[2] // 2, t2.shape[3] // 2, True)
     s = sam(cfm, t2, sub(p, "SAM"))
     pr = conv1x1_bias(s, p["out_SAM.weight"], p["out_SAM.bias"])
     return preds, resize_bilinear(pr, 8 * pr.shape[2], 8 * pr.shape[3], False)
 
 
-def hitnet_forward(image: torch.Tensor, depth: torch.Tensor, p: Params):
-    """`Hitnet.forward(x, pred_normal)` (cod.py:743-807) -> (embedding1, [P1 x4], P2)."""
+def hitnet_forward(image: torch.Tensor, depth: torch.Tensor, p: Params, train: bool = False):
+    """`Hitnet.forward(x, pred_normal)` (cod.py:743-807) -> (embedding1, [P1 x4], P2).  `train`: the decoder's
+    BatchNorms use batch statistics (the backbone has no BatchNorm; its DropPath is the identity here)."""
     emb1, feats = PVT.forward_features(image, depth, sub(p, "backbone"))
-    preds, p2 = decode(feats, p)
+    preds, p2 = decode(feats, p, train=train)
     return emb1, preds, p2
 
 

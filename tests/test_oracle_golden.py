@@ -160,3 +160,44 @@ def test_ssim_constant_oracle_matches_reference_golden():
     g = np.load(os.path.join(common.GOLDEN, "loss_small.npz"))
     v = L.ssim_constant(torch.from_numpy(g["ssim_emb"]), torch.from_numpy(g["ssim_img"]))
     assert abs(float(v) - float(g["ssim_value"])) < 1e-13
+
+
+def test_hitnet_train_oracle_matches_reference_golden():
+    """SURVEY.md 8f-2 in training: oracle/hitnet_ref.py with train=True (batch-statistics BatchNorm) + oracle/loss_ref.py
+    on the mirror module's state dict == the loss and the gradients (norm + 8 samples of each of the 845 tensors) the
+    UNMODIFIED reference `Hitnet` produced in train() (tests/golden/make_golden_hitnet_train.py), float64."""
+    import os
+    import numpy as np
+    from oracle import hitnet_ref as H
+    from oracle import loss_ref as L
+    common.package()
+    from dgtd_b200.twig.model import hitnet
+    fx = np.load(os.path.join(common.GOLDEN, "hitnet_train_128.npz"))
+    S, B = int(fx["S"]), int(fx["B"])
+    net = hitnet.Hitnet()
+    common.hitnet_fixture_params_(net, seed=0)
+    common.perturb_regressor_(net.backbone.prompt_encoder)
+    sd = {k: v.detach().double().requires_grad_("running" not in k) for k, v in net.state_dict().items()
+          if v.dtype.is_floating_point}
+    image, depth = common.synthetic_inputs(B, S, seed=7)
+    _, label = common.loss_inputs(B, S, S, seed=11)
+    _, P1, P2 = H.hitnet_forward(image.double(), depth.double(), sd, train=True)
+    loss = L.deep_supervision_loss(P1, P2, label.double())
+    assert abs(float(loss.detach()) - float(fx["loss"])) <= 1e-10 * abs(float(fx["loss"]))
+    names = [k for k, v in sd.items() if v.requires_grad]
+    grads = dict(zip(names, torch.autograd.grad(loss, [sd[k] for k in names], allow_unused=True)))
+    slopes = [k for k in names if k.endswith("body.1.weight")]
+    grads[slopes[0]] = sum(grads[k] for k in slopes)             # ONE shared nn.PReLU() (cod.py:686)
+    n = 0
+    for k in fx.files:
+        if not k.startswith("g/"):
+            continue
+        flat = grads[k[2:]].flatten()
+        step = max(1, flat.numel() // 8)
+        have = torch.cat([flat.norm().reshape(1), flat[::step][:8]])
+        want = torch.from_numpy(fx[k])
+        assert float((have - want).abs().max() / want.abs().max()) <= 1e-8, k
+        n += 1
+    assert n == 845
+    for k in [str(s) for s in fx["unused"]]:
+        assert grads[k] is None or float(grads[k].abs().max()) < 1e-13, k

@@ -569,6 +569,77 @@ def train_bench(TD, enc, dec, dev, world, rank, local, args, common, sharding, s
             "allreduce_standalone_ms": allreduce_ms, "allreduce_exposed_ms": in_situ_ms}
 
 
+def full_model_train_bench(dev, world, rank, args, common, sharding, steps=5, warmup=2, precision="bf16"):
+    """BASELINE configs[2] on the WHOLE model: `cod.forward(mode='loss')` (cod.py:118-146: pvt_v2_b2 backbone with the
+    texture prompts, Hitnet decoder with train-mode BatchNorm, deep supervision) + backward + the fused AdamW of
+    config/sod.yml:56-76 over all 114 M parameters, `train-batch` images per GPU; the step is one CUDA-graph replay
+    (twig/graphs.py::GraphedModelTrainStep), gradients reduced in buckets over NCCL inside it when N > 1."""
+    import torch.distributed as dist
+    from dgtd_b200.twig import graphs
+    from dgtd_b200.twig.model import hitnet
+    from dgtd_b200.twig.optim import SOD_CUSTOM_KEYS, FusedAdamW
+    B, S = args.train_batch, args.size
+    torch.manual_seed(0)
+    net = hitnet.cod(win_size=22, filter_ratio=0.9, using_sam=True, using_depth=True, finetune=True, binary_thresh=0.2)
+    common.hitnet_fixture_params_(net.hitnet, seed=0)
+    net = net.to(dev).train()
+    image, depth = common.synthetic_inputs(B, S, seed=200 + rank)
+    _, label = common.loss_inputs(B, S, S, seed=300 + rank)
+    image, depth, label = image.to(dev), depth.to(dev), label.to(dev)
+    named = [(n, p) for n, p in net.named_parameters() if p.requires_grad]
+    n_grad = sum(p.numel() for _, p in named)
+    opt = FusedAdamW(named, lr=5e-4, weight_decay=0.1, custom_keys=SOD_CUSTOM_KEYS)
+    n0 = capi_launches()
+    step = graphs.GraphedModelTrainStep(net, image, depth, label, precision=precision, flat_grad=opt.flat_grad)
+    launches_per_step = (capi_launches() - n0) // 4         # 3 warm-up passes + the capture
+
+    def one():
+        step()
+        opt.step()
+
+    def timed_loop(fn, n):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return sharding.max_over_ranks(a.elapsed_time(b) / 1e3, dev)
+
+    for _ in range(warmup):
+        one()
+    t = timed_loop(one, steps)
+    loss = float(step.loss)
+    grad_less = [n for n, p in named if p.grad is None or float(p.grad.abs().max()) == 0.0]
+    exposed = None
+    if world > 1:
+        step.close()
+        local = graphs.GraphedModelTrainStep(net, image, depth, label, precision=precision, flat_grad=opt.flat_grad,
+                                             reduce="none")
+
+        def one_local():
+            local()
+            opt.step()
+        for _ in range(warmup):
+            one_local()
+        exposed = (t - timed_loop(one_local, steps)) / steps * 1e3
+    return {"value": world * B * steps / t, "unit": UNIT, "batch_per_gpu": B, "steps": steps, "ms_per_step": t / steps * 1e3,
+            "precision": precision, "parameters": n_grad, "launches_per_step": int(launches_per_step),
+            "loss_after": loss, "loss_finite": bool(loss == loss and abs(loss) < 1e30), "grad_less_parameters": len(grad_less),
+            "what": "cod.forward(mode='loss') + backward + fused AdamW, all parameters, train-mode BatchNorm (per-GPU "
+                    "statistics), DropPath on; one CUDA-graph replay per step",
+            "grad_allreduce": (step.bucketer.describe() if step.bucketer is not None else "none (1 GPU)"),
+            "allreduce_exposed_ms": exposed}
+
+
+def capi_launches() -> int:
+    from dgtd_b200.twig.ops import capi
+    return capi.launch_count()
+
+
 def cpu_model() -> str:
     try:
         for line in open("/proc/cpuinfo"):
@@ -853,6 +924,14 @@ def run_ours(args):
         except Exception as e:   # noqa: BLE001
             train = dict(train or {}, error=f"{type(e).__name__}: {e}"[:300])
 
+    full_train = None
+    if not args.no_train and not args.no_backbone:
+        try:
+            full_train = full_model_train_bench(dev, world, rank, args, common, sharding)
+        except Exception as e:   # noqa: BLE001
+            full_train = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
+
     # ---- high-resolution inference (BASELINE configs[4]: B = 8 at 768^2, sharded by image) --------
     highres = None
     if not args.no_highres:
@@ -916,6 +995,9 @@ def run_ours(args):
             "train_fwd_bwd": pick(train, "value", "ms_per_step", "batch_per_gpu", "precision", "allreduce_exposed_ms",
                                   "allreduce_in_situ_ms", "grad_allreduce", "error"),
             "train_fp32_exact": pick((train or {}).get("fp32_exact"), "value", "ms_per_step"),
+            "full_model_train": pick(full_train, "value", "ms_per_step", "batch_per_gpu", "precision", "parameters",
+                                     "launches_per_step", "loss_finite", "grad_less_parameters", "allreduce_exposed_ms",
+                                     "error"),
             "highres_768": pick(highres, "value", "ms_per_step", "batch_per_gpu", "error"),
             "full_model_predict": pick(full_model, "value", "ms_per_step", "error"),
             "full_model_predict_e2e": pick((full_model or {}).get("e2e"), "value", "h2d_bytes_per_step", "d2h_bytes_per_step", "error"),
@@ -939,7 +1021,8 @@ def run_ours(args):
             "gpu_launches": int(launches), "clocks": clocks.summary(),
             "roofline": roof, "cpu_baseline": cpu,
             "diffusion_microbench": diff, "structure_loss": loss_leg, "backbone_forward_features": backbone,
-            "full_model_predict": full_model, "train_fwd_bwd": train, "highres_768": highres,
+            "full_model_predict": full_model, "train_fwd_bwd": train, "full_model_train": full_train,
+            "highres_768": highres,
             "summary": summary,
         }
         print(json.dumps(line), flush=True)

@@ -67,19 +67,24 @@ class GraphedTrainStep:
                  loss_fn: Callable = default_loss, precision: Optional[str] = None, warmup: int = 3,
                  process_group=None, flat_grad: Optional[torch.Tensor] = None, reduce: str = "bucketed",
                  bucket_bytes: int = 25 << 20):
-        assert image.is_cuda and depth.is_cuda, "GraphedTrainStep needs CUDA tensors"
-        assert reduce in ("bucketed", "after", "none")
         self.enc, self.dec, self.loss_fn, self.precision = enc, dec, loss_fn, precision
+        self.image, self.depth = image.detach().clone(), depth.detach().clone()
+        self._capture([p for p in list(enc.parameters()) + list(dec.parameters()) if p.requires_grad], warmup,
+                      process_group, flat_grad, reduce, bucket_bytes)
+
+    def _capture(self, params, warmup, process_group, flat_grad, reduce, bucket_bytes) -> None:
+        """Flat gradient buffer, bucketed reduction, warm-up on a side stream, capture of `self._fwd_bwd`."""
+        assert self.image.is_cuda and self.depth.is_cuda, "a captured training step needs CUDA tensors"
+        assert reduce in ("bucketed", "after", "none")
         self.group = process_group
         import torch.distributed as dist
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.reduce = reduce if self.world > 1 else "none"
         self.bucketer = None
-        self.image, self.depth = image.detach().clone(), depth.detach().clone()
-        self.params = [p for p in list(enc.parameters()) + list(dec.parameters()) if p.requires_grad]
+        self.params = params
         self.offsets, n = flat.flat_offsets(self.params)
         if flat_grad is None:
-            self.flat_grad = torch.zeros(n, device=image.device, dtype=torch.float32)
+            self.flat_grad = torch.zeros(n, device=self.image.device, dtype=torch.float32)
             flat.bind_views(self.params, self.flat_grad, "grad")
         else:   # an optimizer (twig/optim.py::FusedAdamW) already owns the flat buffer and bound the views
             assert flat_grad.dtype == torch.float32 and flat.views_match(self.params, flat_grad), \
@@ -136,6 +141,47 @@ class GraphedTrainStep:
             import torch.distributed as dist
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG, group=self.group)
         return self.loss
+
+
+class GraphedModelTrainStep(GraphedTrainStep):
+    """The training step of the WHOLE model captured once and replayed: `cod.forward(raw, input, label, depth,
+    mode='loss')` (cod.py:118-146: backbone with the texture prompts, Hitnet decoder with train-mode BatchNorm, deep
+    supervision + SSIM constant) followed by backward into the flat gradient buffer.
+
+        opt  = FusedAdamW(model.named_parameters(), ...)            # first: it re-homes the parameters
+        step = GraphedModelTrainStep(model, image, depth, label, flat_grad=opt.flat_grad)
+        loss = step(next_image, next_depth, next_label); opt.step()
+
+    ~2900 launches per step at 384^2; the BatchNorm running statistics and `num_batches_tracked` are updated by kernels
+    inside the graph, DropPath draws from torch's graph-safe CUDA generator.  Bucketed NCCL reduction as in the base class
+    (per-GPU BatchNorm statistics, like the reference's plain nn.BatchNorm2d under DDP)."""
+
+    def __init__(self, model: nn.Module, image: torch.Tensor, depth: torch.Tensor, label: torch.Tensor,
+                 precision: Optional[str] = None, warmup: int = 3, process_group=None,
+                 flat_grad: Optional[torch.Tensor] = None, reduce: str = "bucketed", bucket_bytes: int = 25 << 20):
+        self.model, self.precision = model, precision
+        if precision is not None:
+            TD.set_precision(model, precision)
+        self.image, self.depth = image.detach().clone(), depth.detach().clone()
+        self.label = label.detach().clone().float()
+        self._capture([p for p in model.parameters() if p.requires_grad], warmup, process_group, flat_grad, reduce,
+                      bucket_bytes)
+
+    def _fwd_bwd(self) -> torch.Tensor:
+        self.flat_grad.zero_()
+        if self.bucketer is not None:
+            self.bucketer.begin()
+        loss = self.model(None, self.image, self.label, self.depth, mode="loss")["loss"]
+        loss.backward()
+        if self.bucketer is not None:
+            self.bucketer.finish()
+        return loss.detach()
+
+    def __call__(self, image: Optional[torch.Tensor] = None, depth: Optional[torch.Tensor] = None,
+                 label: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if label is not None:
+            self.label.copy_(label, non_blocking=True)
+        return super().__call__(image, depth)
 
 
 class GraphedPredict:

@@ -363,3 +363,37 @@ def test_train_mode_without_grad_uses_batch_statistics(net):
         _, eP1, eP2 = H.hitnet_forward(image.double(), depth.double(), sd, train=False)
     assert rel(P2e, eP2) <= 1e-4
     set_precision(net, None)
+
+
+def test_graphed_full_model_step_replays_the_eager_step(net):
+    """twig/graphs.py::GraphedModelTrainStep: the captured `cod.forward(mode='loss')` + backward leaves the eager
+    step's gradients in the flat buffer (same kernels, same order: bit-identical), replays follow new inputs, and the
+    BatchNorm buffers advance inside the graph."""
+    from dgtd_b200.twig import graphs
+    from dgtd_b200.twig.model.texture_diffuser import set_precision
+    _, image, depth, label = _case()
+    state = {k: v.clone() for k, v in net.state_dict().items()}
+    set_precision(net, "fp32")
+    _train_mode(net)
+    loss, eager = _step(net, image, depth, label)
+    eager = {k: v.clone() for k, v in eager.items() if v is not None}
+    for p in net.parameters():
+        p.grad = None
+    step = graphs.GraphedModelTrainStep(net, image.cuda(), depth.cuda(), label.cuda(), precision="fp32", warmup=2)
+    tracked = int(net.hitnet.conv4.bn.num_batches_tracked)
+    got_loss = step()
+    assert int(net.hitnet.conv4.bn.num_batches_tracked) == tracked + 4
+    assert float(got_loss) == float(loss)
+    named = dict(net.hitnet.named_parameters())
+    for k, r in eager.items():
+        assert torch.equal(named[k].grad, r), k
+    image2, depth2 = common.synthetic_inputs(image.shape[0], image.shape[-1], seed=8)
+    loss2 = float(step(image2.cuda(), depth2.cuda(), label.cuda()))
+    assert loss2 != float(loss) and loss2 == loss2
+    step.close()
+    del step
+    for p in net.parameters():
+        p.grad = None
+    net.load_state_dict(state)
+    set_precision(net, None)
+    net.eval()

@@ -225,7 +225,9 @@ def _step(net, image, depth, label):
         p.grad = None
     out = net(None, image.cuda(), label.cuda(), depth.cuda(), mode="loss")
     out["loss"].backward()
-    return out["loss"], {k: p.grad for k, p in net.hitnet.named_parameters()}
+    # detached: a live loss keeps the autograd graph (and its AccumulateGrad nodes, bound to this stream) alive, which
+    # would invalidate a later CUDA-graph capture of the same parameters
+    return out["loss"].detach(), {k: p.grad for k, p in net.hitnet.named_parameters()}
 
 
 def _train_mode(net):

@@ -238,14 +238,13 @@ __global__ void __launch_bounds__(256) channel_dot_kernel(const float* __restric
 // ---- backward of the gates ---------------------------------------------------------------------------------------
 // out = x * gc[c] * gs with gc = sigmoid(W2 relu(W1 m)), gs = sigmoid(v2 relu(V1 m)) (gs = 1 without V), m = mean(x).
 // Given D[c] = sum_p g x (the channel dots): d gc = D gs, d gs = sum_c D gc; back through both MLPs to d m and the
-// weight gradients.  ONE CTA walks the images in order, each thread owns fixed elements of the weight gradients.
+// weight gradients.  One CTA per image writes d m and the image's share of the weight gradients (ws[b][dw1 | dw2 | dv1 |
+// dv2]); gate_bwd_reduce_kernel sums the shares over the images in order.
 __global__ void __launch_bounds__(256) gate_bwd_kernel(const float* __restrict__ part, int nch, float inv_hw,
                                                        const float* __restrict__ dpart, int nchd,
                                                        const float* __restrict__ w1, const float* __restrict__ w2,
                                                        const float* __restrict__ v1, const float* __restrict__ v2,
-                                                       float* __restrict__ dmean, float* __restrict__ dw1,
-                                                       float* __restrict__ dw2, float* __restrict__ dv1,
-                                                       float* __restrict__ dv2, int accumulate, int B, int C, int Cr,
+                                                       float* __restrict__ dmean, float* __restrict__ ws, int C, int Cr,
                                                        int Cs) {
   extern __shared__ float sm[];
   float* m = sm;              // [C]
@@ -258,82 +257,96 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const float* __restrict__
   float* dhs = hs + Cs;       // [Cs]
   float* sc = dhs + Cs;       // [2]: gs, dzs
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int b = 0; b < B; ++b) {
-    const bool first = (b == 0) && !accumulate;
-    for (int c = tid; c < C; c += nt) {
-      float s = 0.f, d = 0.f;
-      for (int k = 0; k < nch; ++k) s += part[((int64_t)b * nch + k) * C + c];
-      for (int k = 0; k < nchd; ++k) d += dpart[((int64_t)b * nchd + k) * C + c];
-      m[c] = s * inv_hw;
-      D[c] = d;
-    }
-    __syncthreads();
-    for (int j = tid; j < Cr + Cs; j += nt) {
-      const float* w = j < Cr ? w1 + (int64_t)j * C : v1 + (int64_t)(j - Cr) * C;
-      float s = 0.f;
-      for (int c = 0; c < C; ++c) s = fmaf(w[c], m[c], s);
-      if (j < Cr) h[j] = fmaxf(s, 0.f);
-      else hs[j - Cr] = fmaxf(s, 0.f);
-    }
-    __syncthreads();
-    for (int o = tid; o < C; o += nt) {
-      float s = 0.f;
-      for (int j = 0; j < Cr; ++j) s = fmaf(w2[(int64_t)o * Cr + j], h[j], s);
-      gate[o] = sigmoidf_acc(s);
-    }
-    if (tid == 0) {
-      float gs = 1.f;
-      if (Cs > 0) {
-        float s = 0.f;
-        for (int j = 0; j < Cs; ++j) s = fmaf(v2[j], hs[j], s);
-        gs = sigmoidf_acc(s);
-      }
-      sc[0] = gs;
-    }
-    __syncthreads();
-    for (int o = tid; o < C; o += nt) dz[o] = D[o] * sc[0] * gate[o] * (1.f - gate[o]);
-    if (tid == 32 && Cs > 0) {
-      float s = 0.f;
-      for (int c = 0; c < C; ++c) s = fmaf(D[c], gate[c], s);
-      sc[1] = s * sc[0] * (1.f - sc[0]);
-    }
-    __syncthreads();
-    for (int j = tid; j < Cr + Cs; j += nt) {
-      if (j < Cr) {
-        float s = 0.f;
-        for (int o = 0; o < C; ++o) s = fmaf(w2[(int64_t)o * Cr + j], dz[o], s);
-        dh[j] = h[j] > 0.f ? s : 0.f;
-      } else {
-        const int k = j - Cr;
-        dhs[k] = hs[k] > 0.f ? v2[k] * sc[1] : 0.f;
-      }
-    }
-    __syncthreads();
-    for (int e = tid; e < C * Cr; e += nt) {       // dW2[o][j] += dz[o] h[j];  dW1[j][c] += dh[j] m[c]
-      const int o = e / Cr, j = e - o * Cr;
-      const float v = dz[o] * h[j];
-      dw2[e] = first ? v : dw2[e] + v;
-      const int jj = e / C, c = e - jj * C;
-      const float u = dh[jj] * m[c];
-      dw1[e] = first ? u : dw1[e] + u;
-    }
-    for (int e = tid; e < Cs * C; e += nt) {
-      const int j = e / C, c = e - j * C;
-      const float u = dhs[j] * m[c];
-      dv1[e] = first ? u : dv1[e] + u;
-    }
-    for (int j = tid; j < Cs; j += nt) {
-      const float u = sc[1] * hs[j];
-      dv2[j] = first ? u : dv2[j] + u;
-    }
-    for (int c = tid; c < C; c += nt) {
-      float s = 0.f;
-      for (int j = 0; j < Cr; ++j) s = fmaf(w1[(int64_t)j * C + c], dh[j], s);
-      for (int j = 0; j < Cs; ++j) s = fmaf(v1[(int64_t)j * C + c], dhs[j], s);
-      dmean[(int64_t)b * C + c] = s;
-    }
-    __syncthreads();
+  const int b = blockIdx.x;
+  const int nW = 2 * C * Cr + Cs * C + Cs;
+  float* pw1 = ws + (int64_t)b * nW;
+  float* pw2 = pw1 + C * Cr;
+  float* pv1 = pw2 + C * Cr;
+  float* pv2 = pv1 + Cs * C;
+  for (int c = tid; c < C; c += nt) {
+    float s = 0.f, d = 0.f;
+    for (int k = 0; k < nch; ++k) s += part[((int64_t)b * nch + k) * C + c];
+    for (int k = 0; k < nchd; ++k) d += dpart[((int64_t)b * nchd + k) * C + c];
+    m[c] = s * inv_hw;
+    D[c] = d;
   }
+  __syncthreads();
+  for (int j = tid; j < Cr + Cs; j += nt) {
+    const float* w = j < Cr ? w1 + (int64_t)j * C : v1 + (int64_t)(j - Cr) * C;
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s = fmaf(w[c], m[c], s);
+    if (j < Cr) h[j] = fmaxf(s, 0.f);
+    else hs[j - Cr] = fmaxf(s, 0.f);
+  }
+  __syncthreads();
+  for (int o = tid; o < C; o += nt) {
+    float s = 0.f;
+    for (int j = 0; j < Cr; ++j) s = fmaf(w2[(int64_t)o * Cr + j], h[j], s);
+    gate[o] = sigmoidf_acc(s);
+  }
+  if (tid == 0) {
+    float gs = 1.f;
+    if (Cs > 0) {
+      float s = 0.f;
+      for (int j = 0; j < Cs; ++j) s = fmaf(v2[j], hs[j], s);
+      gs = sigmoidf_acc(s);
+    }
+    sc[0] = gs;
+  }
+  __syncthreads();
+  for (int o = tid; o < C; o += nt) dz[o] = D[o] * sc[0] * gate[o] * (1.f - gate[o]);
+  if (tid == 32 && Cs > 0) {
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s = fmaf(D[c], gate[c], s);
+    sc[1] = s * sc[0] * (1.f - sc[0]);
+  }
+  __syncthreads();
+  for (int j = tid; j < Cr + Cs; j += nt) {
+    if (j < Cr) {
+      float s = 0.f;
+      for (int o = 0; o < C; ++o) s = fmaf(w2[(int64_t)o * Cr + j], dz[o], s);
+      dh[j] = h[j] > 0.f ? s : 0.f;
+    } else {
+      const int k = j - Cr;
+      dhs[k] = hs[k] > 0.f ? v2[k] * sc[1] : 0.f;
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < C * Cr; e += nt) {       // dW2[o][j] = dz[o] h[j];  dW1[j][c] = dh[j] m[c]
+    const int o = e / Cr, j = e - o * Cr;
+    pw2[e] = dz[o] * h[j];
+    const int jj = e / C, c = e - jj * C;
+    pw1[e] = dh[jj] * m[c];
+  }
+  for (int e = tid; e < Cs * C; e += nt) {
+    const int j = e / C, c = e - j * C;
+    pv1[e] = dhs[j] * m[c];
+  }
+  for (int j = tid; j < Cs; j += nt) pv2[j] = sc[1] * hs[j];
+  for (int c = tid; c < C; c += nt) {
+    float s = 0.f;
+    for (int j = 0; j < Cr; ++j) s = fmaf(w1[(int64_t)j * C + c], dh[j], s);
+    for (int j = 0; j < Cs; ++j) s = fmaf(v1[(int64_t)j * C + c], dhs[j], s);
+    dmean[(int64_t)b * C + c] = s;
+  }
+}
+
+// dw1 | dw2 | dv1 | dv2 (+)= sum over the images, in order
+__global__ void __launch_bounds__(256) gate_bwd_reduce_kernel(const float* __restrict__ ws, int B, int C, int Cr, int Cs,
+                                                              float* __restrict__ dw1, float* __restrict__ dw2,
+                                                              float* __restrict__ dv1, float* __restrict__ dv2,
+                                                              int accumulate) {
+  const int nW = 2 * C * Cr + Cs * C + Cs;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nW) return;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += ws[(int64_t)b * nW + e];
+  float* dst;
+  if (e < C * Cr) dst = dw1 + e;
+  else if (e < 2 * C * Cr) dst = dw2 + (e - C * Cr);
+  else if (e < 2 * C * Cr + Cs * C) dst = dv1 + (e - 2 * C * Cr);
+  else dst = dv2 + (e - 2 * C * Cr - Cs * C);
+  *dst = accumulate ? *dst + s : s;
 }
 
 // out = g * gate[b,c] * scal[b] + dmean[b,c] * inv_hw
@@ -540,17 +553,22 @@ int dgtd_channel_dot_fwd(const float* a, int lda, const float* b, int ldb, float
   return 0;
 }
 
+int64_t dgtd_gate_bwd_ws_floats(int B, int C, int Cr, int Cs) { return (int64_t)B * (2 * C * Cr + Cs * C + Cs); }
+
 int dgtd_gate_bwd(const float* part, int nch, int hw, const float* dpart, int nchd, const float* w1, const float* w2,
                   const float* v1, const float* v2, float* dmean, float* dw1, float* dw2, float* dv1, float* dv2,
-                  int accumulate, int B, int C, int Cr, int Cs, dgtd_stream_t stream) {
-  DGTD_CHECK_ARG(part && dpart && w1 && w2 && dmean && dw1 && dw2, "gate_bwd: null pointer");
+                  float* ws, int accumulate, int B, int C, int Cr, int Cs, dgtd_stream_t stream) {
+  DGTD_CHECK_ARG(part && dpart && w1 && w2 && dmean && dw1 && dw2 && ws, "gate_bwd: null pointer");
   DGTD_CHECK_ARG((Cs == 0) || (v1 && v2 && dv1 && dv2), "gate_bwd: scalar gate needs v1, v2, dv1, dv2");
   DGTD_CHECK_ARG(B > 0 && C > 0 && Cr > 0 && Cs >= 0 && nch > 0 && nchd > 0 && hw > 0 && 4 * C + 2 * Cr + 2 * Cs + 2 <= 8192,
                  "gate_bwd: bad shape");
   const size_t smem = (size_t)(4 * C + 2 * Cr + 2 * Cs + 2) * sizeof(float);
-  gate_bwd_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(part, nch, 1.0f / hw, dpart, nchd, w1, w2, v1, v2, dmean, dw1, dw2,
-                                                         dv1, dv2, accumulate, B, C, Cr, Cs);
+  cudaStream_t st = (cudaStream_t)stream;
+  gate_bwd_kernel<<<B, 256, smem, st>>>(part, nch, 1.0f / hw, dpart, nchd, w1, w2, v1, v2, dmean, ws, C, Cr, Cs);
   DGTD_LAUNCH_CHECK("gate_bwd");
+  const int nW = 2 * C * Cr + Cs * C + Cs;
+  gate_bwd_reduce_kernel<<<cdiv(nW, 256), 256, 0, st>>>(ws, B, C, Cr, Cs, dw1, dw2, dv1, dv2, accumulate);
+  DGTD_LAUNCH_CHECK("gate_bwd.reduce");
   return 0;
 }
 

@@ -501,6 +501,10 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* _
 
 }  // namespace dgtd
 
+namespace dgtd {
+int dwconv3_gelu_tma(const void* x, const float* wT, const float* bias, void* out, int B, int h, int w, int C,
+                     cudaStream_t s);   // dwconv3_tma.cu
+}
 using namespace dgtd;
 
 extern "C" {
@@ -560,9 +564,15 @@ int dgtd_dwconv3_gelu_fwd(const void* x, const float* wT, const float* bias, voi
   DGTD_CHECK_ARG(total <= 65535, "dwconv3_gelu: too many pixels for one launch");
   dim3 blocks(cdiv(C, 64), (unsigned)total);
   cudaStream_t s = (cudaStream_t)stream;
-  if (dtype == DGTD_BF16)
+  if (dtype == DGTD_BF16) {
+    const int rc = dwconv3_gelu_tma(x, wT, bias, out, B, h, w, C, s);   // persistent TMA-staged kernel (dwconv3_tma.cu)
+    if (rc < 0) return rc;
+    if (rc == 0) {
+      DGTD_LAUNCH_CHECK("dwconv3_gelu(tma)");
+      return 0;
+    }
     dwconv3_gelu_kernel<<<blocks, 256, 0, s>>>((const __nv_bfloat16*)x, wT, bias, (__nv_bfloat16*)out, h, w, C);
-  else if (dtype == DGTD_F32)
+  } else if (dtype == DGTD_F32)
     dwconv3_gelu_kernel<<<blocks, 256, 0, s>>>((const float*)x, wT, bias, (float*)out, h, w, C);
   else DGTD_CHECK_ARG(false, "dwconv3_gelu: bad dtype %d", dtype);
   DGTD_LAUNCH_CHECK("dwconv3_gelu");

@@ -316,6 +316,11 @@ dwconv3_gelu_bwd_kernel(const T* __restrict__ x, const float* __restrict__ wT, c
 }  // namespace
 }  // namespace dgtd
 
+namespace dgtd {
+int64_t dwconv3_gelu_bwd_tma_ws_floats();   // dwconv3_tma.cu
+int dwconv3_gelu_bwd_tma(const void* x, const float* wT, const float* bias, const float* g, float* du, float* dwT,
+                         float* dbias, float* ws, int B, int h, int w, int C, cudaStream_t s);
+}
 using namespace dgtd;
 
 extern "C" {
@@ -356,12 +361,23 @@ int dgtd_attention_bwd(const void* q, const void* kv, const void* out, const flo
   return 0;
 }
 
+int64_t dgtd_dwconv3_gelu_bwd_ws_floats(void) { return dwconv3_gelu_bwd_tma_ws_floats(); }
+
 int dgtd_dwconv3_gelu_bwd(const void* x, const float* wT, const float* bias, const float* g, float* du, float* dwT,
-                          float* dbias, int dtype, int B, int h, int w, int C, dgtd_stream_t stream) {
+                          float* dbias, float* ws, int dtype, int B, int h, int w, int C, dgtd_stream_t stream) {
   DGTD_CHECK_ARG(x && wT && bias && g && du && dwT && dbias && B > 0 && h > 0 && w > 0 && C > 0 && C % 4 == 0,
                  "dwconv3_gelu_bwd: bad args (C % 4)");
   DGTD_CHECK_ARG(dtype == DGTD_F32 || dtype == DGTD_BF16, "dwconv3_gelu_bwd: bad dtype %d", dtype);
   cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == DGTD_BF16) {   // persistent TMA-staged kernel, per-CTA partial tap gradients summed in order (no atomics)
+    const int rc = dwconv3_gelu_bwd_tma(x, wT, bias, g, du, dwT, dbias, ws, B, h, w, C, s);
+    if (rc < 0) return rc;
+    if (rc == 0) {
+      DGTD_LAUNCH_CHECK("dwconv3_gelu_bwd(tma)");
+      count_launch();
+      return 0;
+    }
+  }
   cudaError_t e1 = cudaMemsetAsync(dwT, 0, (size_t)9 * C * sizeof(float), s);
   cudaError_t e2 = cudaMemsetAsync(dbias, 0, (size_t)C * sizeof(float), s);
   DGTD_CHECK_ARG(e1 == cudaSuccess && e2 == cudaSuccess, "dwconv3_gelu_bwd: memset failed");

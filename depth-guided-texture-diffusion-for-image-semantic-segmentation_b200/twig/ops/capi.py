@@ -88,7 +88,8 @@ SIGNATURES = {
     "dgtd_attention_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "dgtd_attention_bwd_ws_floats": [_I, _I, _I],
     "dgtd_attention_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
-    "dgtd_dwconv3_gelu_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "dgtd_dwconv3_gelu_bwd_ws_floats": [],
+    "dgtd_dwconv3_gelu_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "dgtd_boundary_weight_fwd": [_P, _P, _I, _I, _I, _P],
     "dgtd_structure_loss_ws_floats": [_I, _L],
     "dgtd_structure_loss_fwd": [_P, _P, _P, _P, _P, _P, _I, _L, _P],
@@ -119,7 +120,8 @@ SIGNATURES = {
     "dgtd_prelu_bwd_ws_bytes": [_L],
     "dgtd_prelu_bwd": [_P, _P, _P, _P, _P, _P, _L, _P],
     "dgtd_channel_dot_fwd": [_P, _I, _P, _I, _P, _I, _I, _I, _P],
-    "dgtd_gate_bwd": [_P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "dgtd_gate_bwd_ws_floats": [_I, _I, _I, _I],
+    "dgtd_gate_bwd": [_P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "dgtd_gated_bwd": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "dgtd_head1_bwd": [_P, _P, _I, _P, _P, _I, _P, _P, _P, _L, _I, _P],
     "dgtd_resize_nhwc_ld_bwd": [_P, _I, _P, _I] + [_I] * 7 + [_P],
@@ -131,7 +133,7 @@ SIGNATURES = {
     "dgtd_sod_metrics_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
 }
 _RESTYPES = {"dgtd_last_error": c_char_p, "dgtd_launch_count": c_int64, "dgtd_sod_metrics_ws_bytes": c_int64,
-             "dgtd_col_stats_ws_bytes": c_int64, "dgtd_prelu_bwd_ws_bytes": c_int64}
+             "dgtd_col_stats_ws_bytes": c_int64, "dgtd_dwconv3_gelu_bwd_ws_floats": c_int64, "dgtd_gate_bwd_ws_floats": c_int64, "dgtd_prelu_bwd_ws_bytes": c_int64}
 
 _lib: Optional[ctypes.CDLL] = None
 

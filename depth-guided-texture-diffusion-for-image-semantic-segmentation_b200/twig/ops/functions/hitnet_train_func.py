@@ -182,8 +182,9 @@ def gate_bwd(part, hw, dpart, w1, w2, v1=None, v2=None, grads=None):
         dv2 = torch.empty_like(v2) if Cs else None
     else:
         dw1, dw2, dv1, dv2 = grads
+    ws = torch.empty(capi.load().dgtd_gate_bwd_ws_floats(B, C, Cr, Cs), device=part.device, dtype=torch.float32)
     call("dgtd_gate_bwd", ptr(part), nch, hw, ptr(dpart), dpart.shape[1], ptr(w1), ptr(w2), ptr(v1), ptr(v2), ptr(dmean),
-         ptr(dw1), ptr(dw2), ptr(dv1), ptr(dv2), int(grads is not None), B, C, Cr, Cs, stream())
+         ptr(dw1), ptr(dw2), ptr(dv1), ptr(dv2), ptr(ws), int(grads is not None), B, C, Cr, Cs, stream())
     return dmean, dw1, dw2, dv1, dv2
 
 

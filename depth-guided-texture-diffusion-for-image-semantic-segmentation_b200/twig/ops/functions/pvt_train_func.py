@@ -51,7 +51,10 @@ def dwconv3_gelu_bwd(x, wT, bias, g):
     du = torch.empty(x.shape, device=x.device, dtype=torch.float32)
     dwT = torch.empty(9, C, device=x.device, dtype=torch.float32)
     db = torch.empty(C, device=x.device, dtype=torch.float32)
-    call("dgtd_dwconv3_gelu_bwd", ptr(x), ptr(wT), ptr(bias), ptr(g), ptr(du), ptr(dwT), ptr(db),
+    ws = None
+    if x.dtype == torch.bfloat16:
+        ws = torch.empty(capi.load().dgtd_dwconv3_gelu_bwd_ws_floats(), device=x.device, dtype=torch.float32)
+    call("dgtd_dwconv3_gelu_bwd", ptr(x), ptr(wT), ptr(bias), ptr(g), ptr(du), ptr(dwT), ptr(db), ptr(ws),
          capi.dtype_code(x.dtype), B, h, w, C, stream())
     dx = PF.dwconv3(du, wT.flip(0).contiguous(), torch.zeros_like(bias))      # rotated taps = input gradient
     return dx, dwT, db

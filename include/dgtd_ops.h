@@ -354,10 +354,13 @@ int dgtd_attention_bwd_ws_floats(int B, int N, int heads);
 int dgtd_attention_bwd(const void* q, const void* kv, const void* out, const float* dout, float* dq, float* dkv, float* ws,
                        int dtype, int B, int N, int Nk, int heads, float scale, dgtd_stream_t stream);
 /* Backward of Mlp.dwconv + act (cod.py:852-854): x / wT / bias as in dgtd_dwconv3_gelu_fwd, g = dL/d(out) fp32 ->
- * du = g * gelu'(conv3(x) + bias) fp32 (B,h,w,C), dwT (9,C) and dbias (C) (zeroed here, fp32 atomics).  The input
- * gradient is dgtd_dwconv3_fwd(du) with the taps rotated by 180 degrees and a zero bias. */
+ * du = g * gelu'(conv3(x) + bias) fp32 (B,h,w,C), dwT (9,C) and dbias (C).  bf16 x with C % 64 == 0: persistent
+ * TMA-staged kernel (csrc/dwconv3_tma.cu), per-CTA partial gradients in ws (dgtd_dwconv3_gelu_bwd_ws_floats() floats)
+ * summed in a fixed order; otherwise (fp32 x, ws NULL) the pixel-strip kernel with fp32 atomics.  The input gradient is
+ * dgtd_dwconv3_fwd(du) with the taps rotated by 180 degrees and a zero bias. */
+int64_t dgtd_dwconv3_gelu_bwd_ws_floats(void);
 int dgtd_dwconv3_gelu_bwd(const void* x, const float* wT, const float* bias, const float* g, float* du, float* dwT,
-                          float* dbias, int dtype, int B, int h, int w, int C, dgtd_stream_t stream);
+                          float* dbias, float* ws, int dtype, int B, int h, int w, int C, dgtd_stream_t stream);
 
 /* ---- structure loss (cod.cal_loss, cod.py:75-84) ------------------------------------------
  * weit = 1 + 5 |avgpool31x31(gt) - gt| (zero padding, divisor 961); depends on the label only. */
@@ -454,10 +457,11 @@ int dgtd_channel_dot_fwd(const float* a, int lda, const float* b, int ldb, float
  * sigmoid(v2 relu(V1 m)) (SAM.fc_wight :480; Cs = 0: no scalar gate), m = mean(x): part = channel sums of x, dpart =
  * channel dots of (g, x).  Writes dmean (B,C) (to be spread as dmean / hw over the pixels) and the weight gradients
  * dw1 (Cr,C), dw2 (C,Cr), dv1 (Cs,C), dv2 (Cs); accumulate 1 adds to them (SAM runs both inputs through the same
- * weights). */
+ * weights).  One CTA per image + a fixed-order sum over the images; ws: dgtd_gate_bwd_ws_floats(B, C, Cr, Cs) floats. */
+int64_t dgtd_gate_bwd_ws_floats(int B, int C, int Cr, int Cs);
 int dgtd_gate_bwd(const float* part, int nch, int hw, const float* dpart, int nchd, const float* w1, const float* w2,
                   const float* v1, const float* v2, float* dmean, float* dw1, float* dw2, float* dv1, float* dv2,
-                  int accumulate, int B, int C, int Cr, int Cs, dgtd_stream_t stream);
+                  float* ws, int accumulate, int B, int C, int Cr, int Cs, dgtd_stream_t stream);
 /* out = g * gate[b,c] * scal[b] + dmean[b,c] / hw  (scal, dmean nullable): gradient w.r.t. the gated operand */
 int dgtd_gated_bwd(const float* g, int ldg, const float* gate, const float* scal, const float* dmean, float* out, int ldo,
                    int B, int hw, int C, dgtd_stream_t stream);

@@ -145,6 +145,22 @@ def test_sweep_dwconv3_gelu(B, h, w, c8):
     assert rel(gotb.float().cpu(), refb) <= 8e-3
 
 
+@pytest.mark.parametrize("B,h,w,C", [(3, 20, 37, 128), (2, 24, 24, 320), (1, 96, 96, 512), (5, 12, 12, 2048)])
+def test_dwconv3_gelu_tma_tiles(B, h, w, C):
+    """bf16 storage, C % 64 == 0: the persistent TMA-staged kernel (csrc/dwconv3_tma.cu) over several tiles per CTA,
+    partial tiles in both directions, and the four stage shapes' channel counts."""
+    common.package()
+    from dgtd_b200.twig.ops.functions import pvt_func as PF
+    g = torch.Generator().manual_seed(B + h + w + C)
+    x = torch.randn(B, h, w, C, generator=g).to(torch.bfloat16)
+    wt = torch.randn(C, 1, 3, 3, generator=g) * 0.4
+    bias = torch.randn(C, generator=g)
+    ref = torch.nn.functional.gelu(torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt, bias, padding=1,
+                                                              groups=C)).permute(0, 2, 3, 1)
+    got = PF.dwconv3_gelu(x.cuda(), wt.reshape(C, 9).t().contiguous().cuda(), bias.cuda())
+    assert rel(got.float().cpu(), ref) <= 8e-3
+
+
 @settings(**_SET)
 @given(B=st.integers(1, 2), N=st.integers(1, 130), Nk=st.integers(1, 150), heads=st.integers(1, 3))
 def test_sweep_attention_fp32_and_bf16(B, N, Nk, heads):

@@ -42,11 +42,13 @@ def test_attention_backward_kernel(B, N, Nk, heads, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_dwconv3_gelu_backward_kernel(dtype):
+@pytest.mark.parametrize("B,h,w,C", [(2, 9, 13, 328), (3, 20, 37, 128), (1, 24, 24, 320), (2, 5, 3, 64)])
+def test_dwconv3_gelu_backward_kernel(dtype, B, h, w, C):
+    """328 channels: ragged strip (234 pixels) and channel tail of the pixel-strip kernel; C % 64 == 0 in bf16: the
+    persistent TMA-staged kernel over several tiles per CTA (partial tiles in both directions, 1-5 channel groups)."""
     common.package()
     from dgtd_b200.twig.ops.functions import pvt_train_func as PT
     g = torch.Generator().manual_seed(6)
-    B, h, w, C = 2, 9, 13, 328         # ragged strip (234 pixels), channel tail (328 = 256 + 72)
     x = torch.randn(B, h, w, C, generator=g).to(dtype)
     wt = torch.randn(C, 1, 3, 3, generator=g) * 0.3
     b = torch.randn(C, generator=g) * 0.1

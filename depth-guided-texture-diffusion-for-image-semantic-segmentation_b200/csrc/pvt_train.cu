@@ -317,6 +317,17 @@ dwconv3_gelu_bwd_kernel(const T* __restrict__ x, const float* __restrict__ wT, c
 }  // namespace dgtd
 
 namespace dgtd {
+int64_t attention_bwd_tc_ws_floats(int B, int N, int Nk, int heads);   // attn_bwd_tc.cu
+int attention_bwd_tc(const void* q, const void* kv, const void* o, const float* dout, float* dq, float* dkv, float* ws, int B,
+                     int N, int Nk, int heads, float scale, cudaStream_t s);
+static bool attention_bwd_tc_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("DGTD_ATTN_BWD_TC");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
 int64_t dwconv3_gelu_bwd_tma_ws_floats();   // dwconv3_tma.cu
 int dwconv3_gelu_bwd_tma(const void* x, const float* wT, const float* bias, const float* g, float* du, float* dwT,
                          float* dbias, float* ws, int B, int h, int w, int C, cudaStream_t s);
@@ -325,7 +336,7 @@ using namespace dgtd;
 
 extern "C" {
 
-int dgtd_attention_bwd_ws_floats(int B, int N, int heads) { return 2 * B * N * heads; }
+int64_t dgtd_attention_bwd_ws_floats(int B, int N, int Nk, int heads) { return attention_bwd_tc_ws_floats(B, N, Nk, heads); }
 
 int dgtd_attention_bwd(const void* q, const void* kv, const void* out, const float* dout, float* dq, float* dkv, float* ws,
                        int dtype, int B, int N, int Nk, int heads, float scale, dgtd_stream_t stream) {
@@ -335,6 +346,12 @@ int dgtd_attention_bwd(const void* q, const void* kv, const void* out, const flo
   DGTD_CHECK_ARG(dtype == DGTD_F32 || dtype == DGTD_BF16, "attention_bwd: bad dtype %d", dtype);
   const int C = heads * AB_D;
   cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == DGTD_BF16 && attention_bwd_tc_enabled()) {   // mma.sync path, no atomics (attn_bwd_tc.cu)
+    const int rc = attention_bwd_tc(q, kv, out, dout, dq, dkv, ws, B, N, Nk, heads, scale, s);
+    if (rc) return rc;
+    DGTD_LAUNCH_CHECK("attention_bwd(tc)");
+    return 0;
+  }
   float* lse = ws;
   float* dsum = ws + (int64_t)B * N * heads;
   cudaError_t e = cudaMemsetAsync(dkv, 0, (size_t)B * Nk * 2 * C * sizeof(float), s);

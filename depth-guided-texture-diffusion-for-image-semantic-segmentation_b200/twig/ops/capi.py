@@ -86,7 +86,7 @@ SIGNATURES = {
     "dgtd_dwconv3_gelu_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "dgtd_dwconv3_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "dgtd_attention_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
-    "dgtd_attention_bwd_ws_floats": [_I, _I, _I],
+    "dgtd_attention_bwd_ws_floats": [_I, _I, _I, _I],
     "dgtd_attention_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "dgtd_dwconv3_gelu_bwd_ws_floats": [],
     "dgtd_dwconv3_gelu_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
@@ -133,7 +133,7 @@ SIGNATURES = {
     "dgtd_sod_metrics_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
 }
 _RESTYPES = {"dgtd_last_error": c_char_p, "dgtd_launch_count": c_int64, "dgtd_sod_metrics_ws_bytes": c_int64,
-             "dgtd_col_stats_ws_bytes": c_int64, "dgtd_dwconv3_gelu_bwd_ws_floats": c_int64, "dgtd_gate_bwd_ws_floats": c_int64, "dgtd_prelu_bwd_ws_bytes": c_int64}
+             "dgtd_col_stats_ws_bytes": c_int64, "dgtd_attention_bwd_ws_floats": c_int64, "dgtd_dwconv3_gelu_bwd_ws_floats": c_int64, "dgtd_gate_bwd_ws_floats": c_int64, "dgtd_prelu_bwd_ws_bytes": c_int64}
 
 _lib: Optional[ctypes.CDLL] = None
 

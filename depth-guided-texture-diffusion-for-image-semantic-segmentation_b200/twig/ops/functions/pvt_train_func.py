@@ -39,7 +39,7 @@ def attention_bwd(q, kv, o, do, B, N, Nk, heads):
     """(dq, dkv) fp32 of softmax(q k^T / 8) v; q / kv / o in the forward's dtype, do fp32."""
     dq = torch.empty(q.shape, device=q.device, dtype=torch.float32)
     dkv = torch.empty(kv.shape, device=q.device, dtype=torch.float32)
-    ws = torch.empty(capi.load().dgtd_attention_bwd_ws_floats(B, N, heads), device=q.device, dtype=torch.float32)
+    ws = torch.empty(capi.load().dgtd_attention_bwd_ws_floats(B, N, Nk, heads), device=q.device, dtype=torch.float32)
     call("dgtd_attention_bwd", ptr(q), ptr(kv), ptr(o), ptr(do), ptr(dq), ptr(dkv), ptr(ws), capi.dtype_code(q.dtype),
          B, N, Nk, heads, 64 ** -0.5, stream())
     return dq, dkv

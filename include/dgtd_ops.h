@@ -348,9 +348,11 @@ int dgtd_attention_fwd(const void* q, const void* kv, void* out, int dtype, int 
                        float scale, dgtd_stream_t stream);
 /* Backward of the attention core (training of the PVT blocks, cod.py:911-915 under autograd): q / kv / out as in
  * dgtd_attention_fwd (dtype fp32 | bf16), dout (B*N, heads*64) fp32 -> dq (B*N, heads*64) and dkv (B*Nk, 2*heads*64)
- * [dk | dv], both fp32 (dkv is zeroed here; dk / dv accumulate through fp32 atomics, so their last bits depend on the
- * schedule).  ws: dgtd_attention_bwd_ws_floats floats (per-row log-sum-exp and dO.O). */
-int dgtd_attention_bwd_ws_floats(int B, int N, int heads);
+ * [dk | dv], both fp32.  bf16 inputs: warp-level tensor-core kernels (csrc/attn_bwd_tc.cu: dQ with rows = queries, dK / dV
+ * with rows = keys over query splits whose partials are summed in order -- bit-stable).  fp32 inputs: CUDA-core kernels,
+ * dkv is zeroed here and dk / dv accumulate through fp32 atomics (last bits depend on the schedule).
+ * ws: dgtd_attention_bwd_ws_floats floats (per-row log-sum-exp and dO.O, plus the split partials). */
+int64_t dgtd_attention_bwd_ws_floats(int B, int N, int Nk, int heads);
 int dgtd_attention_bwd(const void* q, const void* kv, const void* out, const float* dout, float* dq, float* dkv, float* ws,
                        int dtype, int B, int N, int Nk, int heads, float scale, dgtd_stream_t stream);
 /* Backward of Mlp.dwconv + act (cod.py:852-854): x / wT / bias as in dgtd_dwconv3_gelu_fwd, g = dL/d(out) fp32 ->

@@ -17,7 +17,7 @@ def rel(a, b):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("B,N,Nk,heads", [(2, 100, 70, 2), (1, 576, 144, 5), (2, 16, 16, 8), (1, 300, 200, 1)])
+@pytest.mark.parametrize("B,N,Nk,heads", [(2, 100, 70, 2), (1, 576, 144, 5), (2, 16, 16, 8), (1, 300, 200, 1), (1, 2304, 144, 2)])
 def test_attention_backward_kernel(B, N, Nk, heads, dtype):
     """Ragged query / key counts (N % 64 != 0, Nk % 64 != 0, several key tiles); bf16 inputs with fp32 math."""
     common.package()

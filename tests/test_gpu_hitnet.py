@@ -154,13 +154,32 @@ def test_decode_against_the_oracle_on_random_features(net):
         assert a.shape == b.shape and rel(a.cpu(), b) <= 1e-4, rel(a.cpu(), b)
 
 
-def test_train_mode_raises_instead_of_falling_back(net):
-    net.train()
+def test_train_mode_uses_batch_statistics_like_nn_batchnorm(net):
+    """BasicConv2d in train() (cod.py:362): batch statistics + running update, checked against nn.Conv2d + nn.BatchNorm2d
+    in float64 on the same weights (the whole decoder in train(): tests/test_gpu_hitnet_train.py)."""
+    from dgtd_b200.twig.model.texture_diffuser import set_precision
+    set_precision(net, "fp32")
+    x = torch.randn(3, 96, 6, 5, generator=torch.Generator().manual_seed(2))
+    m = net.conv4
+    state = {k: v.clone() for k, v in m.state_dict().items()}
+    ref_conv = torch.nn.Conv2d(96, 32, 3, padding=1, bias=False).double()
+    ref_bn = torch.nn.BatchNorm2d(32).double().train()
+    ref_conv.load_state_dict({"weight": state["conv.weight"].double().cpu()})
+    ref_bn.load_state_dict({k[3:]: v.double().cpu() if v.dtype.is_floating_point else v.cpu() for k, v in state.items()
+                            if k.startswith("bn.")})
+    want = ref_bn(ref_conv(x.double()))
+    m.train()
     try:
-        with pytest.raises(NotImplementedError):
-            net.conv4(torch.randn(1, 96, 4, 4, device="cuda"))
+        with torch.no_grad():
+            got = m(x.cuda())
+        assert rel(got.cpu(), want.detach()) <= 1e-5
+        assert rel(m.bn.running_mean.cpu(), ref_bn.running_mean) <= 1e-5
+        assert rel(m.bn.running_var.cpu(), ref_bn.running_var) <= 1e-5
+        assert int(m.bn.num_batches_tracked) == int(ref_bn.num_batches_tracked)
     finally:
+        m.load_state_dict(state)
         net.eval()
+        set_precision(net, None)
 
 
 def test_cod_modes():

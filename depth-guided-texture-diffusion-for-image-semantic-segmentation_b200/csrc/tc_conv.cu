@@ -478,7 +478,19 @@ static int conv_halo_launch(const void* x, int B, int h, int wd, int ldx, const 
     uint64_t dims[4] = {(uint64_t)ldx, (uint64_t)wd, (uint64_t)h, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)ldx * 2, (uint64_t)wd * ldx * 2, (uint64_t)h * wd * ldx * 2};
     uint32_t box[4] = {32, HALO_PW, HALO_PH, 1};
-    int rc = make_tmap(&tmX, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    // 64-byte channel slices of pixel rows that interleave all groups (ldx * 2 bytes per pixel): how far L2 widens each
+    // request decides how much of the neighbouring groups' slices is dragged in (and evicted again before their CTAs
+    // arrive).  DGTD_HALO_L2PROMO = 0 / 64 / 128 / 256 for A/B runs.
+    static int promo_sel = -1;
+    if (promo_sel < 0) {
+      const char* e = getenv("DGTD_HALO_L2PROMO");
+      promo_sel = e ? atoi(e) : 256;
+    }
+    const CUtensorMapL2promotion promo = promo_sel == 0     ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                         : promo_sel == 64  ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                         : promo_sel == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                            : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    int rc = make_tmap_promo(&tmX, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B, promo);
     if (rc) return rc;
   }
   {

@@ -132,6 +132,62 @@ ln_patchify_kernel(const float* __restrict__ x, const float* __restrict__ ln_w,
   }
 }
 
+// The same operator for C = 128 * V4 with 16-byte accesses: a warp owns R consecutive pixels in PATCH-MAJOR order
+// (pixel index = ((b * h2 + y2) * w2 + x2) * 4 + 2 * (y & 1) + (x & 1), which is also its output row), so that its
+// R * V4 = 4 loads per lane are in flight together and its stores cover R * C contiguous outputs.
+template <typename OT, int V4, int R>
+__global__ void __launch_bounds__(256)
+ln_patchify_v4_kernel(const float* __restrict__ x, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                      OT* __restrict__ out, int B, int h, int w, int C, float eps) {
+  const int h2 = h >> 1, w2 = w >> 1;
+  const int64_t total = (int64_t)B * h2 * w2 * 4;
+  const int64_t pix0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * R;
+  if (pix0 >= total) return;
+  const int lane = threadIdx.x & 31;
+  float4 v[R][V4];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int64_t pix = pix0 + r;
+    const int r4 = (int)(pix & 3);
+    int64_t t = pix >> 2;
+    const int x2 = (int)(t % w2);
+    t /= w2;
+    const int y2 = (int)(t % h2), b = (int)(t / h2);
+    const float* p = x + (((int64_t)b * h + 2 * y2 + (r4 >> 1)) * w + 2 * x2 + (r4 & 1)) * C;
+#pragma unroll
+    for (int j = 0; j < V4; ++j)
+      v[r][j] = pix < total ? __ldg(reinterpret_cast<const float4*>(p + (j * 32 + lane) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float4 g[V4], be[V4];
+#pragma unroll
+  for (int j = 0; j < V4; ++j) {
+    g[j] = __ldg(reinterpret_cast<const float4*>(ln_w + (j * 32 + lane) * 4));
+    be[j] = __ldg(reinterpret_cast<const float4*>(ln_b + (j * 32 + lane) * 4));
+  }
+  const float inv_c = 1.0f / C;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < V4; ++j) s += (v[r][j].x + v[r][j].y) + (v[r][j].z + v[r][j].w);
+    const float mean = warp_sum(s) * inv_c;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < V4; ++j) {
+      const float a = v[r][j].x - mean, bb = v[r][j].y - mean, c = v[r][j].z - mean, d = v[r][j].w - mean;
+      q += (a * a + bb * bb) + (c * c + d * d);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) * inv_c + eps);
+    if (pix0 + r < total) {
+      OT* o = out + (pix0 + r) * C;
+#pragma unroll
+      for (int j = 0; j < V4; ++j)
+        store4(o + (j * 32 + lane) * 4, (v[r][j].x - mean) * rstd * g[j].x + be[j].x, (v[r][j].y - mean) * rstd * g[j].y + be[j].y,
+               (v[r][j].z - mean) * rstd * g[j].z + be[j].z, (v[r][j].w - mean) * rstd * g[j].w + be[j].w);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------ a8 dwconv + LN
 // CTA = TH x 8 output pixels x all C channels.  thread = channel (coalesced NHWC), 49 taps in
 // registers, TH x 8 accumulators, every input row loaded once and reused by up to TH output
@@ -385,6 +441,16 @@ template <typename OT>
 static int ln_patchify_dispatch(const float* x, const float* ln_w, const float* ln_b, OT* out, int B,
                                 int h, int w, int C, float eps, cudaStream_t s) {
   int64_t pix = (int64_t)B * (h / 2) * 2 * (w / 2) * 2;
+  if (C % 128 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(ln_w) & 15) == 0 && (reinterpret_cast<uintptr_t>(ln_b) & 15) == 0) {
+    switch (C / 128) {   // pixels per block = 8 warps x R
+      case 1: ln_patchify_v4_kernel<OT, 1, 4><<<cdiv(pix, 32), 256, 0, s>>>(x, ln_w, ln_b, out, B, h, w, C, eps); return 0;
+      case 2: ln_patchify_v4_kernel<OT, 2, 2><<<cdiv(pix, 16), 256, 0, s>>>(x, ln_w, ln_b, out, B, h, w, C, eps); return 0;
+      case 4: ln_patchify_v4_kernel<OT, 4, 1><<<cdiv(pix, 8), 256, 0, s>>>(x, ln_w, ln_b, out, B, h, w, C, eps); return 0;
+      case 8: ln_patchify_v4_kernel<OT, 8, 1><<<cdiv(pix, 8), 256, 0, s>>>(x, ln_w, ln_b, out, B, h, w, C, eps); return 0;
+      default: break;
+    }
+  }
   int blocks = cdiv(pix, 8);
   switch (C / 32) {
     case 1: ln_patchify_kernel<OT, 1><<<blocks, 256, 0, s>>>(x, ln_w, ln_b, out, B, h, w, C, eps); break;

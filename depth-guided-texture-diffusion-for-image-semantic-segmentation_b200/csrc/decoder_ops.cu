@@ -7,7 +7,8 @@
 namespace dgtd {
 int tc_conv_nhwc(const void* x, const void* w, const float* bias, void* out, int B, int h, int wd, int Cin,
                  int ldx, int oh, int ow, int Cout, int ldo, int ks, int stride, int off, int act,
-                 int dtype_out, int groups, int w_group_rows, int64_t out_group_stride, cudaStream_t s);
+                 int dtype_out, int groups, int64_t x_group_stride, int w_group_rows, int64_t out_group_stride,
+                 cudaStream_t s);
 }
 using namespace dgtd;
 
@@ -16,20 +17,23 @@ extern "C" {
 int dgtd_conv_nhwc_grouped_fwd(const void* x, const void* w, const float* bias, void* out, int B, int h,
                                int wd, int Cin, int ldx, int oh, int ow, int Cout, int ldo, int ks,
                                int stride, int off, int act, int dtype_in, int dtype_out, int groups,
-                               int x_group_stride, int w_group_rows, int64_t out_group_stride,
+                               int64_t x_group_stride, int w_group_rows, int64_t out_group_stride,
                                dgtd_stream_t stream) {
   DGTD_CHECK_ARG(x && w && out, "conv_nhwc: null pointer");
   DGTD_CHECK_ARG(B > 0 && h > 0 && wd > 0 && oh > 0 && ow > 0 && Cin > 0 && Cout > 0 && ks > 0 && stride > 0 &&
                      groups > 0,
                  "conv_nhwc: bad shape");
-  DGTD_CHECK_ARG(ldx >= Cin && ldo >= Cout, "conv_nhwc: leading dims too small");
+  const bool out_split = groups == 1 && out_group_stride > 0;   // 32-channel output chunks scattered group-major
+  DGTD_CHECK_ARG(ldx >= Cin && (ldo >= Cout || (out_split && ldo >= 32)), "conv_nhwc: leading dims too small");
+  DGTD_CHECK_ARG(!out_split || dtype_in == DGTD_BF16, "conv_nhwc: the chunk-scattered output is a bf16 (tcgen05) mode");
   DGTD_CHECK_ARG(act == DGTD_ACT_NONE || act == DGTD_ACT_RELU, "conv_nhwc: activation must be none or relu");
   DGTD_CHECK_ARG(groups == 1 || w_group_rows >= Cout, "conv_nhwc: w_group_rows < Cout");
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype_in == DGTD_BF16) {
-    DGTD_CHECK_ARG(groups == 1 || x_group_stride == 32, "conv_nhwc(bf16): x_group_stride must be 32");
+    DGTD_CHECK_ARG(groups == 1 || (x_group_stride >= 32 && x_group_stride % 8 == 0),
+                   "conv_nhwc(bf16): x_group_stride must be 32 (interleaved slices) or a multiple of 8 >= 32 (group-major)");
     int rc = tc_conv_nhwc(x, w, bias, out, B, h, wd, Cin, ldx, oh, ow, Cout, ldo, ks, stride, off, act, dtype_out,
-                          groups, groups == 1 ? Cout : w_group_rows, out_group_stride, s);
+                          groups, x_group_stride, groups == 1 ? Cout : w_group_rows, out_group_stride, s);
     if (rc) return rc;
     DGTD_LAUNCH_CHECK("conv_nhwc(tcgen05)");
     return 0;

@@ -21,6 +21,8 @@ struct ConvParams {
   int TW, TH, tiles_x, tiles_y, tiles_n, groups;
   int w_group_rows;
   int64_t out_group_stride;
+  int x5d;        // group-major input: tmX is 5-D {32 ch, W, H, B, group}, a group's pixels are dense 64-byte rows
+  int out_split;  // groups == 1, bf16: 32-channel chunk c of the output goes to out + c * out_group_stride (pixel pitch ldo)
   const float* bias;  // [groups * w_group_rows] nullable
   void* out;
 };
@@ -97,7 +99,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           const int dy = t / p.ks, dx = t - dy * p.ks;
           bw::mbar_wait(&empty[stage], phase ^ 1);
           bw::mbar_arrive_expect_tx(&full[stage], a_bytes + Cfg::B_BYTES);
-          bw::tma_load_4d(&tmX, &full[stage], sA + stage * Cfg::A_BYTES, g * Cfg::CP, ix0 + dx, iy0 + dy, b);
+          if (p.x5d) bw::tma_load_5d(&tmX, &full[stage], sA + stage * Cfg::A_BYTES, 0, ix0 + dx, iy0 + dy, b, g);
+          else bw::tma_load_4d(&tmX, &full[stage], sA + stage * Cfg::A_BYTES, g * Cfg::CP, ix0 + dx, iy0 + dy, b);
           bw::tma_load_2d(&tmW, &full[stage], sB + stage * Cfg::B_BYTES, t * Cfg::CP,
                           g * p.w_group_rows + nb * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -308,8 +311,12 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         for (; wk.tt < per_cta; walk_next(wk)) {
           bw::mbar_wait(&empty[stage], phase ^ 1);
           bw::mbar_arrive_expect_tx(&full[stage], HALO_BYTES);
-          bw::tma_load_4d(&tmX, &full[stage], sA + stage * HALO_STAGE, wk.g * 32, wk.tx * HALO_TW - 1,
-                          wk.ty * HALO_TH - 1, wk.b);
+          if (p.x5d)
+            bw::tma_load_5d(&tmX, &full[stage], sA + stage * HALO_STAGE, 0, wk.tx * HALO_TW - 1, wk.ty * HALO_TH - 1,
+                            wk.b, wk.g);
+          else
+            bw::tma_load_4d(&tmX, &full[stage], sA + stage * HALO_STAGE, wk.g * 32, wk.tx * HALO_TW - 1,
+                            wk.ty * HALO_TH - 1, wk.b);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -408,7 +415,8 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           bw::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            bw::tma_store_5d(&tmO, buf, col0, tx * HALO_TW, ty * HALO_TH + ew * 4, b, g);
+            if (p.out_split) bw::tma_store_5d(&tmO, buf, 0, tx * HALO_TW, ty * HALO_TH + ew * 4, b, col0 >> 5);
+            else bw::tma_store_5d(&tmO, buf, col0, tx * HALO_TW, ty * HALO_TH + ew * 4, b, g);
             bw::tma_store_commit();
           }
           ++sbuf;
@@ -460,7 +468,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 }
 
 template <int BN, int ACT, typename OT>
-static int conv_halo_launch(const void* x, int B, int h, int wd, int ldx, const __nv_bfloat16* w, int Wrows,
+static int conv_halo_launch(const void* x, int B, int h, int wd, int ldx, int64_t xgs, const __nv_bfloat16* w, int Wrows,
                             ConvParams p, cudaStream_t s) {
   using Cfg = HaloCfg<BN>;
   auto kern = tc_conv_halo_kernel<BN, ACT, OT>;
@@ -490,7 +498,15 @@ static int conv_halo_launch(const void* x, int B, int h, int wd, int ldx, const 
                                          : promo_sel == 64  ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                                          : promo_sel == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
                                                             : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
-    int rc = make_tmap_promo(&tmX, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B, promo);
+    int rc;
+    if (p.x5d) {   // group-major: every group is a dense (B, h, w, 32) tensor, xgs elements apart
+      uint64_t dims5[5] = {32, (uint64_t)wd, (uint64_t)h, (uint64_t)B, (uint64_t)p.groups};
+      uint64_t str5[4] = {(uint64_t)ldx * 2, (uint64_t)wd * ldx * 2, (uint64_t)h * wd * ldx * 2, (uint64_t)xgs * 2};
+      uint32_t box5[5] = {32, HALO_PW, HALO_PH, 1, 1};
+      rc = make_tmap_promo(&tmX, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, dims5, str5, box5, CU_TENSOR_MAP_SWIZZLE_64B, promo);
+    } else {
+      rc = make_tmap_promo(&tmX, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B, promo);
+    }
     if (rc) return rc;
   }
   {
@@ -501,9 +517,10 @@ static int conv_halo_launch(const void* x, int B, int h, int wd, int ldx, const 
   }
   CUtensorMap tmO = tmW;
   if (sizeof(OT) == 2) {
-    uint64_t dims[5] = {(uint64_t)p.Cout, (uint64_t)p.ow, (uint64_t)p.oh, (uint64_t)p.B, (uint64_t)p.groups};
+    uint64_t dims[5] = {(uint64_t)(p.out_split ? 32 : p.Cout), (uint64_t)p.ow, (uint64_t)p.oh, (uint64_t)p.B,
+                        (uint64_t)(p.out_split ? p.Cout / 32 : p.groups)};
     uint64_t str[4] = {(uint64_t)p.ldo * 2, (uint64_t)p.ow * p.ldo * 2, (uint64_t)p.oh * p.ow * p.ldo * 2,
-                       (uint64_t)(p.groups > 1 ? p.out_group_stride : (int64_t)p.B * p.oh * p.ow * p.ldo) * 2};
+                       (uint64_t)(p.groups > 1 || p.out_split ? p.out_group_stride : (int64_t)p.B * p.oh * p.ow * p.ldo) * 2};
     uint32_t box[5] = {32, HALO_TW, 4, 1, 1};
     int rc = make_tmap(&tmO, p.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
@@ -522,11 +539,11 @@ static int conv_halo_launch(const void* x, int B, int h, int wd, int ldx, const 
 }
 
 template <int ACT, typename OT>
-static int conv_halo_dispatch_bn(const void* x, int B, int h, int wd, int ldx, const __nv_bfloat16* w, int Wrows,
+static int conv_halo_dispatch_bn(const void* x, int B, int h, int wd, int ldx, int64_t xgs, const __nv_bfloat16* w, int Wrows,
                                  const ConvParams& p, cudaStream_t s) {
-  if (p.Cout <= 32) return conv_halo_launch<32, ACT, OT>(x, B, h, wd, ldx, w, Wrows, p, s);
-  if (p.Cout <= 64) return conv_halo_launch<64, ACT, OT>(x, B, h, wd, ldx, w, Wrows, p, s);
-  return conv_halo_launch<128, ACT, OT>(x, B, h, wd, ldx, w, Wrows, p, s);
+  if (p.Cout <= 32) return conv_halo_launch<32, ACT, OT>(x, B, h, wd, ldx, xgs, w, Wrows, p, s);
+  if (p.Cout <= 64) return conv_halo_launch<64, ACT, OT>(x, B, h, wd, ldx, xgs, w, Wrows, p, s);
+  return conv_halo_launch<128, ACT, OT>(x, B, h, wd, ldx, xgs, w, Wrows, p, s);
 }
 
 static void pick_tile(int ow, int oh, int stride, int& TW, int& TH) {
@@ -577,7 +594,8 @@ static int conv_dispatch_bn(const CUtensorMap& tmX, const __nv_bfloat16* w, int 
 // x: NHWC bf16, 32-channel slices per group (ldx >= 32*groups... or the caller's channel offset)
 int tc_conv_nhwc(const void* x, const void* w, const float* bias, void* out, int B, int h, int wd, int Cin,
                  int ldx, int oh, int ow, int Cout, int ldo, int ks, int stride, int off, int act,
-                 int dtype_out, int groups, int w_group_rows, int64_t out_group_stride, cudaStream_t s) {
+                 int dtype_out, int groups, int64_t x_group_stride, int w_group_rows, int64_t out_group_stride,
+                 cudaStream_t s) {
   if (Cin != 32) {
     set_error("conv_nhwc(bf16): Cin must be padded to 32 channels per group (got %d)", Cin);
     return -1;
@@ -594,15 +612,28 @@ int tc_conv_nhwc(const void* x, const void* w, const float* bias, void* out, int
   p.B = B; p.oh = oh; p.ow = ow; p.Cout = Cout; p.ldo = ldo; p.ks = ks; p.stride = stride; p.off = off;
   p.groups = groups; p.w_group_rows = w_group_rows; p.out_group_stride = out_group_stride;
   p.bias = bias; p.out = out;
+  // group-major operands (round 2): x_group_stride != 32 = every group a dense (B, h, w, ldx) tensor; groups == 1 with
+  // an out_group_stride = the 32-channel chunks of the output scattered to dense (B, oh, ow, ldo) tensors
+  p.x5d = groups > 1 && x_group_stride != 32;
+  p.out_split = groups == 1 && out_group_stride > 0;
+  if (p.x5d && (x_group_stride % 8 || ldx < 32)) {
+    set_error("conv_nhwc(bf16): x_group_stride must be a multiple of 8 elements");
+    return -1;
+  }
+  const bool halo_ok = ks == 3 && stride == 1 && off == -1 && oh == h && ow == wd && !getenv("DGTD_CONV_NO_HALO");
+  if (p.out_split && !(halo_ok && dtype_out == DGTD_BF16 && Cout % 32 == 0)) {
+    set_error("conv_nhwc(bf16): the chunk-scattered output needs the 3x3 stride-1 conv, bf16 output and Cout %% 32 == 0");
+    return -1;
+  }
   if (ks == 3 && stride == 1 && off == -1 && oh == h && ow == wd && !getenv("DGTD_CONV_NO_HALO")) {
     const int Wrows = groups * w_group_rows;
     const __nv_bfloat16* wp = (const __nv_bfloat16*)w;
     if (dtype_out == DGTD_BF16) {
-      if (act == DGTD_ACT_RELU) return conv_halo_dispatch_bn<DGTD_ACT_RELU, __nv_bfloat16>(x, B, h, wd, ldx, wp, Wrows, p, s);
-      return conv_halo_dispatch_bn<DGTD_ACT_NONE, __nv_bfloat16>(x, B, h, wd, ldx, wp, Wrows, p, s);
+      if (act == DGTD_ACT_RELU) return conv_halo_dispatch_bn<DGTD_ACT_RELU, __nv_bfloat16>(x, B, h, wd, ldx, x_group_stride, wp, Wrows, p, s);
+      return conv_halo_dispatch_bn<DGTD_ACT_NONE, __nv_bfloat16>(x, B, h, wd, ldx, x_group_stride, wp, Wrows, p, s);
     }
-    if (act == DGTD_ACT_RELU) return conv_halo_dispatch_bn<DGTD_ACT_RELU, float>(x, B, h, wd, ldx, wp, Wrows, p, s);
-    return conv_halo_dispatch_bn<DGTD_ACT_NONE, float>(x, B, h, wd, ldx, wp, Wrows, p, s);
+    if (act == DGTD_ACT_RELU) return conv_halo_dispatch_bn<DGTD_ACT_RELU, float>(x, B, h, wd, ldx, x_group_stride, wp, Wrows, p, s);
+    return conv_halo_dispatch_bn<DGTD_ACT_NONE, float>(x, B, h, wd, ldx, x_group_stride, wp, Wrows, p, s);
   }
   pick_tile(ow, oh, stride, p.TW, p.TH);
   p.tiles_x = cdiv(ow, p.TW);
@@ -610,16 +641,17 @@ int tc_conv_nhwc(const void* x, const void* w, const float* bias, void* out, int
   CUtensorMap tmX;
   {
     // dims innermost first: channels (all groups), W, H, B
-    uint64_t dims[4] = {(uint64_t)ldx, (uint64_t)wd, (uint64_t)h, (uint64_t)B};
-    uint64_t str[3] = {(uint64_t)ldx * 2, (uint64_t)wd * ldx * 2, (uint64_t)h * wd * ldx * 2};
-    uint32_t box[4] = {32, (uint32_t)(p.TW * stride), (uint32_t)(p.TH * stride), 1};
+    const int rank = p.x5d ? 5 : 4;
+    uint64_t dims[5] = {(uint64_t)(p.x5d ? 32 : ldx), (uint64_t)wd, (uint64_t)h, (uint64_t)B, (uint64_t)groups};
+    uint64_t str[4] = {(uint64_t)ldx * 2, (uint64_t)wd * ldx * 2, (uint64_t)h * wd * ldx * 2, (uint64_t)x_group_stride * 2};
+    uint32_t box[5] = {32, (uint32_t)(p.TW * stride), (uint32_t)(p.TH * stride), 1, 1};
     PFN_tmapEncodeTiled enc = get_tmap_encoder();
     if (!enc) return -3;
-    cuuint64_t gd[4], gs[3];
-    cuuint32_t bx[4], es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-    for (int i = 0; i < 4; ++i) { gd[i] = dims[i]; bx[i] = box[i]; }
-    for (int i = 0; i < 3; ++i) gs[i] = str[i];
-    CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gd, gs, bx, es,
+    cuuint64_t gd[5], gs[4];
+    cuuint32_t bx[5], es[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1, 1};
+    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; }
+    for (int i = 0; i < rank - 1; ++i) gs[i] = str[i];
+    CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(x), gd, gs, bx, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {

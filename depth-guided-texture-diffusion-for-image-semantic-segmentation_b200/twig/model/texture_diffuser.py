@@ -476,6 +476,10 @@ def _decoder_front(decoders: Sequence[ShapePropDecoder], emb: torch.Tensor) -> t
     return h2
 
 
+# hidden maps of the bf16 decoder bank: group-major (default) or interleaved channel slices (DGTD_DEC_GROUP_MAJOR=0, A/B)
+_GROUP_MAJOR = os.environ.get("DGTD_DEC_GROUP_MAJOR", "1") != "0"
+
+
 def _decoder_front_bf16(decoders: Sequence[ShapePropDecoder], emb_pad: torch.Tensor) -> torch.Tensor:
     """tcgen05 path: emb_pad NHWC (B,h,w,32) bf16 (24 latent channels + zero pad) ->
     (B,h,w,32*D) bf16; decoder d owns channels [32d, 32d+24), the pad channels stay zero."""
@@ -492,17 +496,26 @@ def _decoder_front_bf16(decoders: Sequence[ShapePropDecoder], emb_pad: torch.Ten
                 lambda: torch.cat([_pad_taps_bf16(_pack_conv3(d.decoder[2].weight), L, 32) for d in decoders], 0).contiguous())
     b2 = pk.get(key + ".b2", [d.decoder[2].bias for d in decoders],
                 lambda: torch.cat([_pad_rows(d.decoder[2].bias, 32) for d in decoders]).contiguous())
-    h1 = torch.empty(B, h, w, 32 * D, device=emb_pad.device, dtype=torch.bfloat16)
-    OP.conv_nhwc_grouped(emb_pad, w1, b1, 32, (h, w), 3, 1, -1, ACT_RELU, h1, 32 * D, 32 * D, 1, 0, 32 * D, 0)
+    if not _GROUP_MAJOR:   # interleaved slices: decoder d owns channels [32d, 32d+32) of every pixel row
+        h1 = torch.empty(B, h, w, 32 * D, device=emb_pad.device, dtype=torch.bfloat16)
+        OP.conv_nhwc_grouped(emb_pad, w1, b1, 32, (h, w), 3, 1, -1, ACT_RELU, h1, 32 * D, 32 * D, 1, 0, 32 * D, 0)
+        h2 = torch.empty_like(h1)
+        OP.conv_nhwc_grouped(h1, w2, b2, 32, (h, w), 3, 1, -1, ACT_RELU, h2, 32, 32 * D, D, 32, 32, 32)
+        return h2
+    # group-major: every decoder's hidden map is its own dense (B,h,w,32) tensor, so each halo box is made of whole
+    # 64-byte pixel rows that no other group's CTA shares (the interleaved form read 2.5x its input from DRAM)
+    gs = B * h * w * 32
+    h1 = torch.empty(D, B, h, w, 32, device=emb_pad.device, dtype=torch.bfloat16)
+    OP.conv_nhwc_grouped(emb_pad, w1, b1, 32, (h, w), 3, 1, -1, ACT_RELU, h1, 32 * D, 32, 1, 0, 32 * D, gs)
     h2 = torch.empty_like(h1)
-    OP.conv_nhwc_grouped(h1, w2, b2, 32, (h, w), 3, 1, -1, ACT_RELU, h2, 32, 32 * D, D, 32, 32, 32)
+    OP.conv_nhwc_grouped(h1[0], w2, b2, 32, (h, w), 3, 1, -1, ACT_RELU, h2, 32, 32, D, gs, 32, gs)
     return h2
 
 
 def _decode_tokens_bf16(decoders: Sequence[ShapePropDecoder], h2: torch.Tensor, index0: int,
                         src_hw: Tuple[int, int], grid: Tuple[int, int]) -> List[torch.Tensor]:
     """All decoders of one PVT stage in ONE grouped tcgen05 launch, output (D_s, B, H_s*W_s, E_s) bf16."""
-    B = h2.shape[0]
+    B = h2.shape[-4]
     D = len(decoders)
     E = decoders[0].decoder[4].out_channels
     L = decoders[0].decoder[4].in_channels
@@ -522,9 +535,13 @@ def _decode_tokens_bf16(decoders: Sequence[ShapePropDecoder], h2: torch.Tensor, 
     b3 = pk.get(key + ".b", [d.decoder[4].bias for d in decoders],
                 lambda: torch.cat([d.decoder[4].bias.detach().float() for d in decoders]).contiguous())
     out = torch.empty(D, B, grid[0] * grid[1], E, device=h2.device, dtype=torch.bfloat16)
-    src = h2[..., index0 * 32:]
-    OP.conv_nhwc_grouped(src, w3, b3, 32, grid, ks, stride, off, ACT_NONE, out, E, E, D, 32, E,
-                         B * grid[0] * grid[1] * E)
+    if h2.dim() == 5:      # group-major hidden maps (D_all, B, h, w, 32)
+        OP.conv_nhwc_grouped(h2[index0], w3, b3, 32, grid, ks, stride, off, ACT_NONE, out, E, E, D, h2.stride(0), E,
+                             B * grid[0] * grid[1] * E)
+    else:
+        src = h2[..., index0 * 32:]
+        OP.conv_nhwc_grouped(src, w3, b3, 32, grid, ks, stride, off, ACT_NONE, out, E, E, D, 32, E,
+                             B * grid[0] * grid[1] * E)
     return [out[i] for i in range(D)]
 
 

@@ -55,7 +55,7 @@ SIGNATURES = {
     "dgtd_fusion_head_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "dgtd_fusion_sum_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "dgtd_conv_nhwc_fwd": [_P, _P, _P, _P] + [_I] * 15 + [_P],
-    "dgtd_conv_nhwc_grouped_fwd": [_P, _P, _P, _P] + [_I] * 18 + [_L, _P],
+    "dgtd_conv_nhwc_grouped_fwd": [_P, _P, _P, _P] + [_I] * 16 + [_L, _I, _L, _P],
     "dgtd_resize_nhwc_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "dgtd_linear_dgrad": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "dgtd_linear_wgrad": [_P, _P, _P, _P, _P] + [_I] * 13 + [_P],

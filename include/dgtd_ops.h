@@ -222,11 +222,16 @@ int dgtd_conv_nhwc_fwd(const void* x, const void* w, const float* bias, void* ou
 /* Grouped form (the 16 decoders of the path in one launch): group g reads input channels
  * [g*x_group_stride, +Cin) of x, weight rows [g*w_group_rows, +Cout), bias + g*w_group_rows and
  * writes out + g*out_group_stride (elements).  bf16 (tcgen05) needs Cin == 32 (zero-padded
- * latent channels) and tap-major weights (Cout rows, ks*ks*32). */
+ * latent channels) and tap-major weights (Cout rows, ks*ks*32).
+ * Group-major operands (bf16): x_group_stride == 32 means the groups' 32-channel slices interleave in
+ * every pixel row of x (pitch ldx); any larger multiple of 8 means group g is its own dense tensor
+ * (B,h,w,ldx) at x + g*x_group_stride.  With groups == 1 and out_group_stride > 0 (3x3 stride-1 conv,
+ * bf16 output, Cout % 32 == 0) the 32-channel chunk c of the output is written to the dense tensor
+ * (B,oh,ow,ldo) at out + c*out_group_stride -- the layout the next grouped conv reads as group-major. */
 int dgtd_conv_nhwc_grouped_fwd(const void* x, const void* w, const float* bias, void* out, int B,
                                int h, int wd, int Cin, int ldx, int oh, int ow, int Cout, int ldo,
                                int ks, int stride, int off, int act, int dtype_in, int dtype_out,
-                               int groups, int x_group_stride, int w_group_rows,
+                               int groups, int64_t x_group_stride, int w_group_rows,
                                int64_t out_group_stride, dgtd_stream_t stream);
 /* generic bilinear resize NHWC (B,h,w,C) -> (B,oh,ow,C) == tokens (B,oh*ow,C) */
 int dgtd_resize_nhwc_fwd(const void* x, void* out, int B, int h, int w, int C, int oh, int ow,

@@ -190,6 +190,238 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Resident-weights form of the per-tap kernel (the injection-folded 4x4 stride-r convs, round 2).  The kernel
+// above re-loads the BN x 32 weight tile of every tap for every output tile: as many L2 -> SM bytes as the
+// activations, and the three launches of a step ran at 10.5 TB/s of L2 traffic (85 % of the LTS cap) with the
+// tensor pipe at 28 %.  Here a CTA owns ONE (group, n-block) key, loads its taps x BN x 32 weights once and
+// walks that key's output tiles; only the activation tiles stream.
+template <int BN>
+struct ConvRwCfg {
+  static constexpr int BM = 128, CP = 32, MAX_TAPS = 16;
+  static constexpr int A_BYTES = BM * CP * 2;
+  static constexpr int W_BYTES = MAX_TAPS * BN * CP * 2;
+  static constexpr int STAGES = 8;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int STG_BYTES = 4 * 2048;   // per epilogue warp: one 32-row x 64-byte staging tile
+  static constexpr int SMEM_BYTES = STAGES * A_BYTES + W_BYTES + STG_BYTES + 256 + 1024;
+};
+
+template <int BN, int ACT, typename OT>
+__global__ void __launch_bounds__(256, 1)
+tc_conv_resw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                    const ConvParams p) {
+  using Cfg = ConvRwCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + STAGES * Cfg::A_BYTES;
+  uint8_t* sStg = sW + Cfg::W_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + Cfg::STG_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint64_t* wfull = bars + 2 * STAGES + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int taps = p.ks * p.ks;
+  const int tiles_img = p.tiles_x * p.tiles_y;
+  const int per_key = p.B * tiles_img;
+  const int keys = p.groups * p.tiles_n;                      // <= gridDim.x (checked by the launcher)
+  const int nct = (int)gridDim.x / keys;                      // CTAs sharing a key
+  const int key = (int)blockIdx.x % keys, ci = (int)blockIdx.x / keys;
+  const int g = key / p.tiles_n, nb = key - g * p.tiles_n;
+  const bool active = ci < nct;
+  const uint32_t a_bytes = (uint32_t)(p.TW * p.TH) * Cfg::CP * 2;
+
+  if (warp == 0 && lane == 0) {
+    bw::prefetch_tmap(&tmX);
+    bw::prefetch_tmap(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      bw::mbar_init(&full[i], 1);
+      bw::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      bw::mbar_init(&tfull[i], 1);
+      bw::mbar_init(&tempty[i], 128);
+    }
+    bw::mbar_init(wfull, 1);
+    bw::fence_mbar_init();
+  }
+  if (warp == 2) bw::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  bw::tc_fence_before();
+  __syncthreads();
+  bw::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && active) {
+      bw::mbar_arrive_expect_tx(wfull, (uint32_t)taps * BN * 64);
+#pragma unroll 1
+      for (int t = 0; t < taps; ++t)
+        bw::tma_load_2d(&tmW, wfull, sW + t * BN * 64, t * Cfg::CP, g * p.w_group_rows + nb * BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pos = ci; pos < per_key; pos += nct) {
+        const int b = pos / tiles_img, r = pos - b * tiles_img;
+        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        const int ix0 = tx * p.TW * p.stride + p.off, iy0 = ty * p.TH * p.stride + p.off;
+        for (int t = 0; t < taps; ++t) {
+          const int dy = t / p.ks, dx = t - dy * p.ks;
+          bw::mbar_wait(&empty[stage], phase ^ 1);
+          bw::mbar_arrive_expect_tx(&full[stage], a_bytes);
+          if (p.x5d) bw::tma_load_5d(&tmX, &full[stage], sA + stage * Cfg::A_BYTES, 0, ix0 + dx, iy0 + dy, b, g);
+          else bw::tma_load_4d(&tmX, &full[stage], sA + stage * Cfg::A_BYTES, g * Cfg::CP, ix0 + dx, iy0 + dy, b);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && active) {
+      constexpr uint32_t idesc = bw::umma_idesc_bf16(128, BN);
+      int stage = 0, iter = 0;
+      uint32_t phase = 0;
+      bw::mbar_wait(wfull, 0);
+      bw::tc_fence_after();
+      const uint64_t db_base = bw::umma_smem_desc_kmajor(bw::smem_u32(sW), 64);
+      for (int pos = ci; pos < per_key; pos += nct, ++iter) {
+        const int as = iter & 1;
+        const uint32_t aphase = (iter >> 1) & 1;
+        bw::mbar_wait(&tempty[as], aphase ^ 1);
+        bw::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int t = 0; t < taps; ++t) {
+          bw::mbar_wait(&full[stage], phase);
+          bw::tc_fence_after();
+          const uint64_t da = bw::umma_smem_desc_kmajor(bw::smem_u32(sA + stage * Cfg::A_BYTES), 64);
+          const uint64_t db = db_base + (uint64_t)((t * BN * 64) >> 4);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) bw::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (t | k) != 0);
+          bw::umma_commit(&empty[stage]);
+          if (t == taps - 1) bw::umma_commit(&tfull[as]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4 && active) {
+    const int ew = warp - 4;
+    int iter = 0;
+    const float* bias = p.bias ? p.bias + g * p.w_group_rows : nullptr;
+    for (int pos = ci; pos < per_key; pos += nct, ++iter) {
+      const int b = pos / tiles_img, rr = pos - b * tiles_img;
+      const int ty = rr / p.tiles_x, tx = rr - ty * p.tiles_x;
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1;
+      bw::mbar_wait(&tfull[as], aphase);
+      bw::tc_fence_after();
+      const int r = ew * 32 + lane;                 // row of the tile = (j, i) pixel
+      const int j = r / p.TW, i = r - j * p.TW;
+      const int oy = ty * p.TH + j, ox = tx * p.TW + i;
+      const bool row_ok = (j < p.TH) && oy < p.oh && ox < p.ow;
+      OT* orow = reinterpret_cast<OT*>(p.out) + (int64_t)g * p.out_group_stride +
+                 (((int64_t)b * p.oh + oy) * p.ow + ox) * p.ldo;
+      if (sizeof(OT) == 2) {
+        // bf16 results: 32 rows x 32 channels are transposed through a swizzled staging tile so that four lanes write
+        // the 64 contiguous bytes of a pixel with 16-byte stores (the direct form issued 8-byte stores at a pitch of
+        // a whole token row: 32 partially written sectors per instruction, 6x the output bytes in L2 transactions)
+        uint8_t* stg = sStg + ew * 2048;
+        OT* rowp[4];
+        bool rowok[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int r2 = ew * 32 + k * 8 + (lane >> 2);
+          const int j2 = r2 / p.TW, i2 = r2 - j2 * p.TW;
+          const int oy2 = ty * p.TH + j2, ox2 = tx * p.TW + i2;
+          rowok[k] = (j2 < p.TH) && oy2 < p.oh && ox2 < p.ow;
+          rowp[k] = reinterpret_cast<OT*>(p.out) + (int64_t)g * p.out_group_stride +
+                    (((int64_t)b * p.oh + oy2) * p.ow + ox2) * p.ldo;
+        }
+        const int piece = lane & 3;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          bw::tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN + c0, v);
+          bw::tmem_ld_wait();
+          const int col0 = nb * BN + c0;
+          if (col0 >= p.Cout) break;                   // warp-uniform
+#pragma unroll
+          for (int q = 0; q < 32; q += 8) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q + e]);
+            if (bias && col0 + q < p.Cout) {
+              float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + q));
+              float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + q + 4));
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            if (ACT == DGTD_ACT_RELU) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+            }
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+            u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((((q >> 3) ^ (lane >> 1)) & 3) << 4)) = u;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int row = k * 8 + (lane >> 2);
+            const uint4 u = *reinterpret_cast<const uint4*>(stg + row * 64 + (((piece ^ (row >> 1)) & 3) << 4));
+            if (rowok[k] && col0 + piece * 8 < p.Cout) *reinterpret_cast<uint4*>(rowp[k] + col0 + piece * 8) = u;
+          }
+          __syncwarp();                                // the staging tile is rewritten by the next chunk
+        }
+      } else {
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        bw::tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN + c0, v);
+        bw::tmem_ld_wait();
+        const int col0 = nb * BN + c0;
+        if (row_ok && col0 < p.Cout) {
+#pragma unroll
+          for (int q = 0; q < 32; q += 8) {
+            if (col0 + q >= p.Cout) break;
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q + e]);
+            if (bias) {
+              float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + q));
+              float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + q + 4));
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            if (ACT == DGTD_ACT_RELU) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+            }
+            store4(orow + col0 + q, f[0], f[1], f[2], f[3]);
+            store4(orow + col0 + q + 4, f[4], f[5], f[6], f[7]);
+          }
+        }
+      }
+      }
+      bw::tc_fence_before();
+      bw::mbar_arrive(&tempty[as]);
+    }
+  }
+
+  bw::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    bw::tc_fence_after();
+    bw::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // 3x3 / stride 1 / pad 1 variant (decoder conv1, conv2 and the identity-grid conv3): ONE halo tile per
 // output tile.  The per-tap kernel above re-reads the input nine times from L2 (9 x 8 KB of A per 128
 // output pixels); with only 32 output channels per group that makes the grouped decoder convs L2-feed
@@ -208,7 +440,11 @@ struct HaloCfg {
   static constexpr int W_BYTES = 9 * BN * 64;               // all taps of one (group, n-block)
   static constexpr int STAGES = BN >= 128 ? 4 : 8;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int STG_BYTES = 4 * 2 * 2048;            // per epilogue warp: two 32-row x 64-byte staging tiles
+  // epilogue warps: 4 (one per TMEM lane quadrant) for the 32-column tiles, whose single chunk is not worth splitting;
+  // 8 (two per quadrant, half of the columns each) from 64 columns up -- with 4 warps the N = 128 conv1 of the decoder
+  // bank ran the tensor-core pipe at 38 %: one warp per scheduler, every TMEM load / bias load / store latency exposed
+  static constexpr int NEPI = BN >= 64 ? 8 : 4;
+  static constexpr int STG_BYTES = NEPI * 2 * 2048;         // per epilogue warp: two 32-row x 64-byte staging tiles
   static constexpr int SMEM_BYTES = STAGES * HALO_STAGE + 2 * W_BYTES + STG_BYTES + 256 + 1024;
 };
 
@@ -221,7 +457,7 @@ __device__ __forceinline__ uint64_t halo_desc(uint32_t addr, uint32_t sbo_bytes)
 }
 
 template <int BN, int ACT, typename OT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(128 + 32 * HaloCfg<BN>::NEPI, 1)
 tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmO, const ConvParams p) {
   using Cfg = HaloCfg<BN>;
@@ -279,7 +515,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       bw::mbar_init(&tfull[i], 1);
-      bw::mbar_init(&tempty[i], 128);
+      bw::mbar_init(&tempty[i], 32 * Cfg::NEPI);
       bw::mbar_init(&wfull[i], 1);
       bw::mbar_init(&wempty[i], 1);
     }
@@ -358,7 +594,8 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    const int ew = warp - 4;
+    const int ew = (warp - 4) & 3, part = (warp - 4) >> 2;   // TMEM lane quadrant (= warp % 4), column half
+    constexpr int CPW = BN / (Cfg::NEPI / 4);                // columns per epilogue warp
     int iter = 0;
     uint32_t sbuf = 0;
     Walk wk;
@@ -378,9 +615,9 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         // bf16 results leave through a 64B-swizzled staging tile (32 rows = 4 image rows x 8 pixels, 64 B each)
         // and ONE 5-D TMA store per 32 channels: full lines instead of 32 scattered 8-byte stores per lane;
         // the tensor map clips tile rows / channels beyond the image.
-        uint8_t* stg = sStg + ew * 4096;
+        uint8_t* stg = sStg + (warp - 4) * 4096;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = part * CPW; c0 < (part + 1) * CPW; c0 += 32) {
           uint32_t v[32];
           bw::tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN + c0, v);
           bw::tmem_ld_wait();
@@ -425,7 +662,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         OT* orow = reinterpret_cast<OT*>(p.out) + (int64_t)g * p.out_group_stride +
                    (((int64_t)b * p.oh + oy) * p.ow + ox) * p.ldo;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = part * CPW; c0 < (part + 1) * CPW; c0 += 32) {
           uint32_t v[32];
           bw::tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN + c0, v);
           bw::tmem_ld_wait();
@@ -534,7 +771,7 @@ static int conv_halo_launch(const void* x, int B, int h, int wd, int ldx, int64_
   int nct = keys < sm_count() ? sm_count() / keys : 1;
   if (nct > per_key) nct = (int)per_key;
   const int grid = keys < sm_count() ? keys * nct : sm_count();
-  kern<<<grid, 256, Cfg::SMEM_BYTES, s>>>(tmX, tmW, tmO, p);
+  kern<<<grid, 128 + 32 * Cfg::NEPI, Cfg::SMEM_BYTES, s>>>(tmX, tmW, tmO, p);
   return 0;
 }
 
@@ -577,6 +814,33 @@ static int conv_launch(const CUtensorMap& tmX, const __nv_bfloat16* w, int Ktot,
   int rc = make_tmap(&tmW, w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
   p.tiles_n = cdiv(p.Cout, BN);
+  {   // resident weights: one (group, n-block) key per CTA, when every key gets at least one CTA and all taps fit
+    using Rw = ConvRwCfg<BN>;
+    const int keys = p.groups * p.tiles_n;
+    const int64_t per_key = (int64_t)p.B * p.tiles_x * p.tiles_y;
+    static int use_rw = -1;
+    if (use_rw < 0) {
+      const char* e = getenv("DGTD_CONV_RESW");
+      use_rw = e ? atoi(e) : 1;
+    }
+    if (use_rw && BN >= 64 && keys <= sm_count() && p.ks * p.ks <= Rw::MAX_TAPS && per_key < (1ll << 31)) {
+      auto kern_rw = tc_conv_resw_kernel<BN, ACT, OT>;
+      static bool configured_rw = false;
+      if (!configured_rw) {
+        cudaError_t e = cudaFuncSetAttribute(kern_rw, cudaFuncAttributeMaxDynamicSharedMemorySize, Rw::SMEM_BYTES);
+        if (e != cudaSuccess) {
+          set_error("tc_conv(resident weights): cannot opt in to %d B of shared memory: %s", Rw::SMEM_BYTES,
+                    cudaGetErrorString(e));
+          return -2;
+        }
+        configured_rw = true;
+      }
+      int nct = sm_count() / keys;
+      if (nct > per_key) nct = (int)per_key;
+      kern_rw<<<keys * nct, 256, Rw::SMEM_BYTES, s>>>(tmX, tmW, p);
+      return 0;
+    }
+  }
   int64_t tiles = (int64_t)p.groups * p.B * p.tiles_x * p.tiles_y * p.tiles_n;
   int grid = tiles < sm_count() ? (int)tiles : sm_count();
   kern<<<grid, 256, Cfg::SMEM_BYTES, s>>>(tmX, tmW, p);

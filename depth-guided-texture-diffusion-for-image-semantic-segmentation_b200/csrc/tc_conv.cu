@@ -202,12 +202,13 @@ struct ConvRwCfg {
   static constexpr int W_BYTES = MAX_TAPS * BN * CP * 2;
   static constexpr int STAGES = 8;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int STG_BYTES = 4 * 2048;   // per epilogue warp: one 32-row x 64-byte staging tile
+  static constexpr int NEPI = 8;               // two epilogue warps per TMEM lane quadrant, half of the columns each
+  static constexpr int STG_BYTES = NEPI * 2048;   // per epilogue warp: one 32-row x 64-byte staging tile
   static constexpr int SMEM_BYTES = STAGES * A_BYTES + W_BYTES + STG_BYTES + 256 + 1024;
 };
 
 template <int BN, int ACT, typename OT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(128 + 32 * ConvRwCfg<BN>::NEPI, 1)
 tc_conv_resw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                     const ConvParams p) {
   using Cfg = ConvRwCfg<BN>;
@@ -246,7 +247,7 @@ tc_conv_resw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       bw::mbar_init(&tfull[i], 1);
-      bw::mbar_init(&tempty[i], 128);
+      bw::mbar_init(&tempty[i], 32 * Cfg::NEPI);
     }
     bw::mbar_init(wfull, 1);
     bw::fence_mbar_init();
@@ -307,7 +308,8 @@ tc_conv_resw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       }
     }
   } else if (warp >= 4 && active) {
-    const int ew = warp - 4;
+    const int ew = (warp - 4) & 3, part = (warp - 4) >> 2;   // TMEM lane quadrant (= warp % 4), column half
+    constexpr int CPW = BN / (Cfg::NEPI / 4);
     int iter = 0;
     const float* bias = p.bias ? p.bias + g * p.w_group_rows : nullptr;
     for (int pos = ci; pos < per_key; pos += nct, ++iter) {
@@ -327,7 +329,7 @@ tc_conv_resw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         // bf16 results: 32 rows x 32 channels are transposed through a swizzled staging tile so that four lanes write
         // the 64 contiguous bytes of a pixel with 16-byte stores (the direct form issued 8-byte stores at a pitch of
         // a whole token row: 32 partially written sectors per instruction, 6x the output bytes in L2 transactions)
-        uint8_t* stg = sStg + ew * 2048;
+        uint8_t* stg = sStg + (warp - 4) * 2048;
         OT* rowp[4];
         bool rowok[4];
 #pragma unroll
@@ -341,7 +343,7 @@ tc_conv_resw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
         const int piece = lane & 3;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = part * CPW; c0 < (part + 1) * CPW; c0 += 32) {
           uint32_t v[32];
           bw::tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN + c0, v);
           bw::tmem_ld_wait();
@@ -380,7 +382,7 @@ tc_conv_resw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
       } else {
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = part * CPW; c0 < (part + 1) * CPW; c0 += 32) {
         uint32_t v[32];
         bw::tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN + c0, v);
         bw::tmem_ld_wait();
@@ -837,7 +839,7 @@ static int conv_launch(const CUtensorMap& tmX, const __nv_bfloat16* w, int Ktot,
       }
       int nct = sm_count() / keys;
       if (nct > per_key) nct = (int)per_key;
-      kern_rw<<<keys * nct, 256, Rw::SMEM_BYTES, s>>>(tmX, tmW, p);
+      kern_rw<<<keys * nct, 128 + 32 * Rw::NEPI, Rw::SMEM_BYTES, s>>>(tmX, tmW, p);
       return 0;
     }
   }

@@ -23,7 +23,7 @@ int dgtd_conv_nhwc_grouped_fwd(const void* x, const void* w, const float* bias, 
   DGTD_CHECK_ARG(B > 0 && h > 0 && wd > 0 && oh > 0 && ow > 0 && Cin > 0 && Cout > 0 && ks > 0 && stride > 0 &&
                      groups > 0,
                  "conv_nhwc: bad shape");
-  const bool out_split = groups == 1 && out_group_stride > 0;   // 32-channel output chunks scattered group-major
+  const bool out_split = groups == 1 && out_group_stride > 0 && ldo < Cout;   // 32-channel output chunks scattered group-major
   DGTD_CHECK_ARG(ldx >= Cin && (ldo >= Cout || (out_split && ldo >= 32)), "conv_nhwc: leading dims too small");
   DGTD_CHECK_ARG(!out_split || dtype_in == DGTD_BF16, "conv_nhwc: the chunk-scattered output is a bf16 (tcgen05) mode");
   DGTD_CHECK_ARG(act == DGTD_ACT_NONE || act == DGTD_ACT_RELU, "conv_nhwc: activation must be none or relu");

@@ -879,9 +879,9 @@ int tc_conv_nhwc(const void* x, const void* w, const float* bias, void* out, int
   p.groups = groups; p.w_group_rows = w_group_rows; p.out_group_stride = out_group_stride;
   p.bias = bias; p.out = out;
   // group-major operands (round 2): x_group_stride != 32 = every group a dense (B, h, w, ldx) tensor; groups == 1 with
-  // an out_group_stride = the 32-channel chunks of the output scattered to dense (B, oh, ow, ldo) tensors
+  // an out_group_stride and a pixel pitch ldo < Cout = the 32-channel chunks of the output scattered to dense (B, oh, ow, ldo) tensors
   p.x5d = groups > 1 && x_group_stride != 32;
-  p.out_split = groups == 1 && out_group_stride > 0;
+  p.out_split = groups == 1 && out_group_stride > 0 && ldo < Cout;
   if (p.x5d && (x_group_stride % 8 || ldx < 32)) {
     set_error("conv_nhwc(bf16): x_group_stride must be a multiple of 8 elements");
     return -1;

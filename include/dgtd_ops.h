@@ -225,8 +225,8 @@ int dgtd_conv_nhwc_fwd(const void* x, const void* w, const float* bias, void* ou
  * latent channels) and tap-major weights (Cout rows, ks*ks*32).
  * Group-major operands (bf16): x_group_stride == 32 means the groups' 32-channel slices interleave in
  * every pixel row of x (pitch ldx); any larger multiple of 8 means group g is its own dense tensor
- * (B,h,w,ldx) at x + g*x_group_stride.  With groups == 1 and out_group_stride > 0 (3x3 stride-1 conv,
- * bf16 output, Cout % 32 == 0) the 32-channel chunk c of the output is written to the dense tensor
+ * (B,h,w,ldx) at x + g*x_group_stride.  With groups == 1, out_group_stride > 0 and a pixel pitch ldo < Cout
+ * (3x3 stride-1 conv, bf16 output, Cout % 32 == 0) the 32-channel chunk c of the output is written to the dense tensor
  * (B,oh,ow,ldo) at out + c*out_group_stride -- the layout the next grouped conv reads as group-major. */
 int dgtd_conv_nhwc_grouped_fwd(const void* x, const void* w, const float* bias, void* out, int B,
                                int h, int wd, int Cin, int ldx, int oh, int ow, int Cout, int ldo,

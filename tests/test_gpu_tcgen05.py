@@ -126,6 +126,43 @@ def test_conv_nhwc_grouped_bf16(OP, B, h, w, G, Cout, ks, stride, off, relu):
     assert rel(outb.float().cpu().double(), out.cpu().double()) <= 5e-3
 
 
+def test_conv_nhwc_group_major_operands_match_interleaved(OP):
+    """Round 2: the decoder bank keeps its hidden maps group-major (every group a dense (B,h,w,32) tensor).  conv1 with
+    the chunk-scattered output, conv2 / the folded strided conv3 reading group-major input: bit-identical to the
+    interleaved-slice form (same MMAs on the same values, only the addresses differ)."""
+    from dgtd_b200.twig.ops.capi import ACT_NONE, ACT_RELU
+    g = torch.Generator().manual_seed(11)
+    B, h, w, D = 2, 24, 40, 5
+    gs = B * h * w * 32
+    emb = torch.randn(B, h, w, 32, generator=g).to(torch.bfloat16).cuda()
+    w1 = (torch.randn(32 * D, 9 * 32, generator=g) / 18.0).to(torch.bfloat16).cuda()
+    b1 = torch.randn(32 * D, generator=g).cuda()
+    w2 = (torch.randn(32 * D, 9 * 32, generator=g) / 18.0).to(torch.bfloat16).cuda()
+    b2 = torch.randn(32 * D, generator=g).cuda()
+    E = 64
+    w3 = (torch.randn(D * E, 16 * 32, generator=g) / 24.0).to(torch.bfloat16).cuda()
+    b3 = torch.randn(D * E, generator=g).cuda()
+    # interleaved slices
+    h1 = torch.full((B, h, w, 32 * D), float("nan"), dtype=torch.bfloat16).cuda()
+    OP.conv_nhwc_grouped(emb, w1, b1, 32, (h, w), 3, 1, -1, ACT_RELU, h1, 32 * D, 32 * D, 1, 0, 32 * D, 0)
+    h2 = torch.full_like(h1, float("nan"))
+    OP.conv_nhwc_grouped(h1, w2, b2, 32, (h, w), 3, 1, -1, ACT_RELU, h2, 32, 32 * D, D, 32, 32, 32)
+    o = torch.full((D, B, (h // 2) * (w // 2), E), float("nan"), dtype=torch.bfloat16).cuda()
+    OP.conv_nhwc_grouped(h2, w3, b3, 32, (h // 2, w // 2), 4, 2, -1, ACT_NONE, o, E, E, D, 32, E, B * (h // 2) * (w // 2) * E)
+    # group-major
+    g1 = torch.full((D, B, h, w, 32), float("nan"), dtype=torch.bfloat16).cuda()
+    OP.conv_nhwc_grouped(emb, w1, b1, 32, (h, w), 3, 1, -1, ACT_RELU, g1, 32 * D, 32, 1, 0, 32 * D, gs)
+    g2 = torch.full_like(g1, float("nan"))
+    OP.conv_nhwc_grouped(g1[0], w2, b2, 32, (h, w), 3, 1, -1, ACT_RELU, g2, 32, 32, D, gs, 32, gs)
+    og = torch.full_like(o, float("nan"))
+    OP.conv_nhwc_grouped(g2[0], w3, b3, 32, (h // 2, w // 2), 4, 2, -1, ACT_NONE, og, E, E, D, gs, E,
+                         B * (h // 2) * (w // 2) * E)
+    torch.cuda.synchronize()
+    assert torch.equal(g1.permute(1, 2, 3, 0, 4).reshape(B, h, w, 32 * D), h1)
+    assert torch.equal(g2.permute(1, 2, 3, 0, 4).reshape(B, h, w, 32 * D), h2)
+    assert torch.isfinite(og.float()).all() and torch.equal(og, o)
+
+
 @pytest.mark.parametrize("Mo,No,Kr,lda,ldb,tr", [
     (512, 128, 4096, 512, 128, False),     # trunk shape (stage 0 pwconv)
     (256, 1024, 2304, 256, 1024, True),

@@ -165,6 +165,50 @@ transpose_split_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ 
     }
   }
 }
+// K-concatenated form of the split product (one GEMM, one fp32 accumulation in TMEM, no accumulator round trips):
+//   [x_hi | x_lo | x_hi] . [A_hi | A_hi | A_lo]^T = x_hi A_hi + x_lo A_hi + x_hi A_lo
+// rows of 3 * W bf16; x_hi is stored twice (57 MB more written at batch 64) against two fp32 read-modify-write
+// passes over the 113 MB accumulator per product in the three-GEMM form.
+__global__ void split3_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a3, int64_t rows, int W4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // float4 index
+  if (i >= rows * W4) return;
+  const int64_t r = i / W4;
+  const int c = (int)(i - r * W4) * 4, W = W4 * 4;
+  const float4 v = *reinterpret_cast<const float4*>(x + i * 4);
+  const float f[4] = {v.x, v.y, v.z, v.w};
+  float h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    h[e] = __bfloat162float(__float2bfloat16_rn(f[e]));
+    l[e] = f[e] - h[e];
+  }
+  __nv_bfloat16* o = a3 + r * 3 * W + c;
+  store4(o, h[0], h[1], h[2], h[3]);
+  store4(o + W, l[0], l[1], l[2], l[3]);
+  store4(o + 2 * W, h[0], h[1], h[2], h[3]);
+}
+// per plane (R x C fp32) -> (C rows) x [hi(R) | lo(R) | hi(R)] bf16
+__global__ void __launch_bounds__(256)
+transpose_split3_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ a3, int R, int C) {
+  __shared__ float tile[32][33];
+  const int64_t pb = (int64_t)blockIdx.z * R * C;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8)
+    tile[i][tx] = (r0 + i < R && c0 + tx < C) ? t[pb + (int64_t)(r0 + i) * C + c0 + tx] : 0.f;
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (c < C && r < R) {
+      const float v = tile[tx][i];
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      __nv_bfloat16* o = a3 + ((int64_t)blockIdx.z * C + c) * 3 * R + r;
+      o[0] = h;
+      o[R] = __float2bfloat16_rn(v - __bfloat162float(h));
+      o[2 * R] = h;
+    }
+  }
+}
 // out[p][i][j] = | x[p][i][j] - yt[p][j][i] + (u_i * sin_w[j] + t_i * cos_w[j]) |   (EpiHighpass, transposed input)
 __global__ void __launch_bounds__(256)
 highpass_finish_kernel(const float* __restrict__ x, const float* __restrict__ yt, const float* __restrict__ sc_h,
@@ -273,6 +317,37 @@ int dgtd_fft_highpass_tc_fwd(const float* x, const void* Ph_hi, const void* Ph_l
   if ((rc = dgtd_linear_residual_fwd(lo, Ph_hi, zeros, nullptr, nullptr, 1, ws_f32, ws_f32, R2, H, H, DGTD_BF16, stream))) return rc;
   highpass_finish_kernel<<<dim3(cdiv(W, 32), cdiv(H, 32), planes), 256, 0, s>>>(x, ws_f32, sc_h, sc_w, coef, out, H, W);
   DGTD_LAUNCH_CHECK("fft_highpass_tc.finish");
+  return 0;
+}
+
+// The same operator with each split product as ONE K-concatenated GEMM (see split3_bf16_kernel).
+// Ph_cat / Pw_cat: [P_hi | P_hi | P_lo] per row (H x 3H, W x 3W bf16); ws_a: planes*H*W*3 bf16; ws_f32: planes*H*W fp32.
+int dgtd_fft_highpass_tc3_fwd(const float* x, const void* Ph_cat, const void* Pw_cat, const float* sc_h, const float* sc_w,
+                              void* ws_a, float* ws_f32, float* coef, float* out, int planes, int H, int W,
+                              dgtd_stream_t stream) {
+  DGTD_CHECK_ARG(x && Ph_cat && Pw_cat && sc_h && sc_w && ws_a && ws_f32 && coef && out, "fft_highpass_tc3: null pointer");
+  DGTD_CHECK_ARG(planes > 0 && planes <= 65535 && H > 0 && W > 0 && (W % 8) == 0 && (H % 8) == 0,
+                 "fft_highpass_tc3: H and W must be multiples of 8 (got %dx%d)", H, W);
+  cudaStream_t s = (cudaStream_t)stream;
+  __nv_bfloat16* a3 = (__nv_bfloat16*)ws_a;
+  {  // partial sums live in ws_f32 until the first GEMM overwrites it
+    int rc0 = launch_imag_coef(x, sc_h, sc_w, ws_f32, coef, planes, H, W, s);
+    if (rc0) return rc0;
+  }
+  const int64_t R = (int64_t)planes * H, R2 = (int64_t)planes * W;
+  DGTD_CHECK_ARG(R < (1ll << 31) && R2 < (1ll << 31), "fft_highpass_tc3: too many rows");
+  split3_bf16_kernel<<<(unsigned)cdiv(R * (W / 4), (int64_t)256), 256, 0, s>>>(x, a3, R, W / 4);
+  DGTD_LAUNCH_CHECK("fft_highpass_tc3.split");
+  int rc;
+  // T[(p,i), j] = sum_k x[(p,i), k] A_w[j, k]
+  if ((rc = dgtd_linear_fwd(a3, Pw_cat, nullptr, ws_f32, (int)R, W, 3 * W, W, DGTD_BF16, DGTD_F32, DGTD_ACT_NONE, stream))) return rc;
+  // per plane transpose (+ split): Tt[(p,j), i] = T[(p,i), j]
+  transpose_split3_kernel<<<dim3(cdiv(W, 32), cdiv(H, 32), planes), 256, 0, s>>>(ws_f32, a3, H, W);
+  DGTD_LAUNCH_CHECK("fft_highpass_tc3.transpose");
+  // Yt[(p,j), i'] = sum_i Tt[(p,j), i] A_h[i', i]
+  if ((rc = dgtd_linear_fwd(a3, Ph_cat, nullptr, ws_f32, (int)R2, H, 3 * H, H, DGTD_BF16, DGTD_F32, DGTD_ACT_NONE, stream))) return rc;
+  highpass_finish_kernel<<<dim3(cdiv(W, 32), cdiv(H, 32), planes), 256, 0, s>>>(x, ws_f32, sc_h, sc_w, coef, out, H, W);
+  DGTD_LAUNCH_CHECK("fft_highpass_tc3.finish");
   return 0;
 }
 

@@ -30,6 +30,7 @@ SIGNATURES = {
     "dgtd_lowpass_projector": [_P, _P, _I, _I, _P],
     "dgtd_fft_highpass_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "dgtd_fft_highpass_tc_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "dgtd_fft_highpass_tc3_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "dgtd_diffusion_front_fwd": [_P] * 11 + [_I] * 6 + [_P],
     "dgtd_message_passing_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     "dgtd_message_passing_tiled_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P],

@@ -68,6 +68,13 @@ int dgtd_fft_highpass_tc_fwd(const float* x, const void* Ph_hi, const void* Ph_l
                              const float* sc_h, const float* sc_w, const float* zeros, void* ws_hi, void* ws_lo,
                              float* ws_f32, float* coef, float* out, int planes, int H, int W, dgtd_stream_t stream);
 
+/* Same operator, each split product as ONE K-concatenated tcgen05 GEMM: [x_hi | x_lo | x_hi] . [A_hi | A_hi | A_lo]^T
+ * (one fp32 accumulation in TMEM, no accumulator round trips through HBM).  Ph_cat / Pw_cat: [P_hi | P_hi | P_lo]
+ * per row (H x 3H, W x 3W bf16); ws_a: planes*H*W*3 bf16; ws_f32: planes*H*W fp32.  H, W multiples of 8. */
+int dgtd_fft_highpass_tc3_fwd(const float* x, const void* Ph_cat, const void* Pw_cat, const float* sc_h, const float* sc_w,
+                              void* ws_a, float* ws_f32, float* coef, float* out, int planes, int H, int W,
+                              dgtd_stream_t stream);
+
 /* ---- a3..a6 fused: cod.py:1295-1298 + MessagePassing.forward :1189-1206 ------------------- */
 /* nearest GxG sample of emb1 -> regressor 1x1 conv (3 -> C*49) + sigmoid -> random-walk
  * normalisation; depth -> (encoder1 1x1 conv o bilinear down) -> C x G x G state; T stencil

@@ -29,50 +29,87 @@ __device__ __forceinline__ float seg_sum(float v) {
   for (int off = LPR / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
   return v;
 }
-template <typename AT, typename OT, int VPL, int LPR>
+// U row groups per warp: all loads of the U rows a lane touches are issued before the first reduction (with one row per
+// lane group the C <= 128 stages had a single 16-byte load per operand in flight per lane and ran at half the HBM rate).
+template <typename AT, typename OT, int VPL, int LPR, int U>
 __global__ void __launch_bounds__(256)
 ln_tokens_kernel(const float* __restrict__ x, const AT* __restrict__ add, float* __restrict__ sum_out,
                  const float* __restrict__ ln_w, const float* __restrict__ ln_b, OT* __restrict__ out, int64_t rows,
                  int C, float eps) {
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & (LPR - 1);
-  int64_t row = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW + ((threadIdx.x & 31) / LPR);
-  const bool live = row < rows;
-  if (!live) row = rows - 1;            // keep the whole warp in the shuffles; stores are predicated
+  const int64_t row0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * (RPW * U) + ((threadIdx.x & 31) / LPR);
   const int nq = C >> 2;
-  float4 v[VPL];
-  float s = 0.f;
+  float4 v[U][VPL];
+  int64_t rowu[U];
+  bool liveu[U];
 #pragma unroll
-  for (int j = 0; j < VPL; ++j) {
-    const int q = j * LPR + lane;
-    if (q < nq) {
-      v[j] = *reinterpret_cast<const float4*>(x + row * C + q * 4);
-      if (add) {
-        const float4 a = ld4<AT>(add + row * C + q * 4);
-        v[j].x += a.x; v[j].y += a.y; v[j].z += a.z; v[j].w += a.w;
+  for (int u = 0; u < U; ++u) {
+    int64_t row = row0 + u * RPW;
+    liveu[u] = row < rows;
+    if (!liveu[u]) row = rows - 1;      // keep the whole warp in the shuffles; stores are predicated
+    rowu[u] = row;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int q = j * LPR + lane;
+      if (q < nq) v[u][j] = *reinterpret_cast<const float4*>(x + row * C + q * 4);
+    }
+  }
+  if (add) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float4 a[VPL];
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const int q = j * LPR + lane;
+        if (q < nq) a[j] = ld4<AT>(add + rowu[u] * C + q * 4);
       }
-      if (sum_out && live) *reinterpret_cast<float4*>(sum_out + row * C + q * 4) = v[j];
-      s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
-    }
-  }
-  const float mean = seg_sum<LPR>(s) / C;
-  float qq = 0.f;
 #pragma unroll
-  for (int j = 0; j < VPL; ++j) {
-    if (j * LPR + lane < nq) {
-      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
-      qq += (a * a + b * b) + (c * c + d * d);
+      for (int j = 0; j < VPL; ++j) {
+        const int q = j * LPR + lane;
+        if (q < nq) { v[u][j].x += a[j].x; v[u][j].y += a[j].y; v[u][j].z += a[j].z; v[u][j].w += a[j].w; }
+      }
     }
   }
-  const float rstd = 1.0f / sqrtf(seg_sum<LPR>(qq) / C + eps);
-  if (!live) return;
+  float4 g[VPL], be[VPL];
 #pragma unroll
   for (int j = 0; j < VPL; ++j) {
     const int q = j * LPR + lane;
     if (q < nq) {
-      const float4 g = *reinterpret_cast<const float4*>(ln_w + q * 4), be = *reinterpret_cast<const float4*>(ln_b + q * 4);
-      store4(out + row * C + q * 4, (v[j].x - mean) * rstd * g.x + be.x, (v[j].y - mean) * rstd * g.y + be.y,
-             (v[j].z - mean) * rstd * g.z + be.z, (v[j].w - mean) * rstd * g.w + be.w);
+      g[j] = *reinterpret_cast<const float4*>(ln_w + q * 4);
+      be[j] = *reinterpret_cast<const float4*>(ln_b + q * 4);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int64_t row = rowu[u];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int q = j * LPR + lane;
+      if (q < nq) {
+        if (sum_out && liveu[u]) *reinterpret_cast<float4*>(sum_out + row * C + q * 4) = v[u][j];
+        s += (v[u][j].x + v[u][j].y) + (v[u][j].z + v[u][j].w);
+      }
+    }
+    const float mean = seg_sum<LPR>(s) / C;
+    float qq = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      if (j * LPR + lane < nq) {
+        const float a = v[u][j].x - mean, b = v[u][j].y - mean, c = v[u][j].z - mean, d = v[u][j].w - mean;
+        qq += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    const float rstd = 1.0f / sqrtf(seg_sum<LPR>(qq) / C + eps);
+    if (liveu[u]) {
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const int q = j * LPR + lane;
+        if (q < nq)
+          store4(out + row * C + q * 4, (v[u][j].x - mean) * rstd * g[j].x + be[j].x, (v[u][j].y - mean) * rstd * g[j].y + be[j].y,
+                 (v[u][j].z - mean) * rstd * g[j].z + be[j].z, (v[u][j].w - mean) * rstd * g[j].w + be[j].w);
+      }
     }
   }
 }
@@ -517,15 +554,15 @@ int dgtd_ln_tokens_fwd(const float* x, const void* add, int add_dtype, float* su
   DGTD_CHECK_ARG(!add || add_dtype == DGTD_F32 || add_dtype == DGTD_BF16, "ln_tokens: bad add dtype");
   DGTD_CHECK_ARG(out_dtype == DGTD_F32 || out_dtype == DGTD_BF16, "ln_tokens: bad out dtype");
   cudaStream_t s = (cudaStream_t)stream;
-#define DGTD_LNT(AT, OT, V, L)                                                                                    \
-  ln_tokens_kernel<AT, OT, V, L><<<(unsigned)cdiv(rows, (int64_t)(8 * (32 / L))), 256, 0, s>>>(                     \
+#define DGTD_LNT(AT, OT, V, L, U)                                                                                 \
+  ln_tokens_kernel<AT, OT, V, L, U><<<(unsigned)cdiv(rows, (int64_t)(8 * (32 / L) * U)), 256, 0, s>>>(             \
       x, (const AT*)add, sum_out, ln_w, ln_b, (OT*)out, rows, C, eps)
 #define DGTD_LNT_V(AT, OT)                         \
   do {                                             \
-    if (C <= 64) DGTD_LNT(AT, OT, 1, 16);          \
-    else if (C <= 128) DGTD_LNT(AT, OT, 1, 32);    \
-    else if (C <= 512) DGTD_LNT(AT, OT, 4, 32);    \
-    else DGTD_LNT(AT, OT, 16, 32);                 \
+    if (C <= 64) DGTD_LNT(AT, OT, 1, 16, 4);       \
+    else if (C <= 128) DGTD_LNT(AT, OT, 1, 32, 4); \
+    else if (C <= 512) DGTD_LNT(AT, OT, 4, 32, 1); \
+    else DGTD_LNT(AT, OT, 16, 32, 1);              \
   } while (0)
   const bool abf = add && add_dtype == DGTD_BF16;
   if (out_dtype == DGTD_BF16) {

@@ -204,25 +204,35 @@ __global__ void split3_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* _
   store4(o + W, l[0], l[1], l[2], l[3]);
   store4(o + 2 * W, h[0], h[1], h[2], h[3]);
 }
-// per plane (R x C fp32) -> (C rows) x [hi(R) | lo(R) | hi(R)] bf16
+// per plane (R x C fp32) -> (C rows) x [hi(R) | lo(R) | hi(R)] bf16.  64 x 32 tiles: eight loads in flight per thread,
+// two adjacent r per lane on the way out (4-byte bf16x2 stores, 128 B per warp instruction).  R even.
 __global__ void __launch_bounds__(256)
 transpose_split3_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ a3, int R, int C) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[64][33];
   const int64_t pb = (int64_t)blockIdx.z * R * C;
-  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int i = ty; i < 32; i += 8)
-    tile[i][tx] = (r0 + i < R && c0 + tx < C) ? t[pb + (int64_t)(r0 + i) * C + c0 + tx] : 0.f;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int rr = r0 + ty + 8 * e;
+    v[e] = (rr < R && c0 + tx < C) ? __ldg(t + pb + (int64_t)rr * C + c0 + tx) : 0.f;
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) tile[ty + 8 * e][tx] = v[e];
   __syncthreads();
-  for (int i = ty; i < 32; i += 8) {
-    const int c = c0 + i, r = r0 + tx;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int cl = ty + 8 * e, c = c0 + cl, r = r0 + 2 * tx;
     if (c < C && r < R) {
-      const float v = tile[tx][i];
-      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const float v0 = tile[2 * tx][cl], v1 = tile[2 * tx + 1][cl];
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+      const float2 hf = __bfloat1622float2(h);
+      const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
       __nv_bfloat16* o = a3 + ((int64_t)blockIdx.z * C + c) * 3 * R + r;
-      o[0] = h;
-      o[R] = __float2bfloat16_rn(v - __bfloat162float(h));
-      o[2 * R] = h;
+      *reinterpret_cast<__nv_bfloat162*>(o) = h;
+      *reinterpret_cast<__nv_bfloat162*>(o + R) = l;
+      *reinterpret_cast<__nv_bfloat162*>(o + 2 * R) = h;
     }
   }
 }
@@ -369,7 +379,7 @@ int dgtd_fft_highpass_tc3_fwd(const float* x, const void* Ph_cat, const void* Pw
   // T[(p,i), j] = sum_k x[(p,i), k] A_w[j, k]
   if ((rc = dgtd_linear_fwd(a3, Pw_cat, nullptr, ws_f32, (int)R, W, 3 * W, W, DGTD_BF16, DGTD_F32, DGTD_ACT_NONE, stream))) return rc;
   // per plane transpose (+ split): Tt[(p,j), i] = T[(p,i), j]
-  transpose_split3_kernel<<<dim3(cdiv(W, 32), cdiv(H, 32), planes), 256, 0, s>>>(ws_f32, a3, H, W);
+  transpose_split3_kernel<<<dim3(cdiv(W, 32), cdiv(H, 64), planes), 256, 0, s>>>(ws_f32, a3, H, W);
   DGTD_LAUNCH_CHECK("fft_highpass_tc3.transpose");
   // Yt[(p,j), i'] = sum_i Tt[(p,j), i] A_h[i', i]
   if ((rc = dgtd_linear_fwd(a3, Ph_cat, nullptr, ws_f32, (int)R2, H, 3 * H, H, DGTD_BF16, DGTD_F32, DGTD_ACT_NONE, stream))) return rc;

@@ -86,12 +86,14 @@ struct TcCfg {
   static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + 1024;  // +align slack
 };
 
-template <int BN, int ACT, typename OT, bool RESIDUAL, bool CONV3 = false>
+// TF32: fp32 operands read as they are (kind::tf32, 10-bit mantissas): a k-block is still 128 bytes per row = 32 elements,
+// one instruction covers K = 8.  Used where an fp32 activation would otherwise be cast to bf16 by a separate pass.
+template <int BN, int ACT, typename OT, bool RESIDUAL, bool CONV3 = false, bool TF32 = false>
 __global__ void __launch_bounds__(384, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcParams p) {
   using Cfg = TcCfg<BN>;
-  constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
+  constexpr int BM = Cfg::BM, BK = TF32 ? Cfg::BK / 2 : Cfg::BK, STAGES = Cfg::STAGES;   // elements per 128-byte k-block row
   extern __shared__ __align__(1024) uint8_t smem[];   // 128B-swizzle atoms need 1024-byte alignment
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
@@ -158,7 +160,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     if (lane == 0) {
       // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = bw::umma_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = TF32 ? bw::umma_idesc_tf32(BM, BN) : bw::umma_idesc_bf16(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
@@ -174,8 +176,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t da = bw::umma_smem_desc_kmajor(bw::smem_u32(sA + stage * Cfg::A_BYTES), 128);
           const uint64_t db = bw::umma_smem_desc_kmajor(bw::smem_u32(sB + stage * Cfg::B_BYTES), 128);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)  // +32 B per K=16 step inside the 128B swizzle atom
-            bw::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) {  // +32 B per K step (16 bf16 / 8 tf32) inside the 128B swizzle atom
+            if (TF32) bw::umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            else bw::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
           bw::umma_commit(&empty[stage]);            // smem slot free once these MMAs retire
           if (kb == num_kb - 1) bw::umma_commit(&tfull[as]);  // accumulator complete
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -245,6 +249,41 @@ static int tc_launch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B
   p.tiles_n = cdiv(p.N, BN);
   int tiles = p.tiles_m * p.tiles_n;
   int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, 384, Cfg::SMEM_BYTES, s>>>(tmA, tmB, p);
+  return 0;
+}
+
+// fp32 operands on kind::tf32 (N <= 64): out fp32 = A[M,K] . B[N,K]^T + bias
+template <int BN>
+static int tc_launch_tf32(const float* A, const float* B, TcParams p, cudaStream_t s) {
+  using Cfg = TcCfg<BN>;
+  auto kern = tc_gemm_kernel<BN, DGTD_ACT_NONE, float, false, false, true>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("tc_gemm(tf32): cannot opt in to %d B of shared memory: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return -2;
+    }
+    configured = true;
+  }
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.M}, str[1] = {(uint64_t)p.K * 4};
+    uint32_t box[2] = {32, 128};
+    int rc = make_tmap(&tmA, A, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N}, str[1] = {(uint64_t)p.K * 4};
+    uint32_t box[2] = {32, (uint32_t)BN};
+    int rc = make_tmap(&tmB, B, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  p.tiles_m = cdiv(p.M, 128);
+  p.tiles_n = cdiv(p.N, BN);
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
   kern<<<grid, 384, Cfg::SMEM_BYTES, s>>>(tmA, tmB, p);
   return 0;
 }
@@ -381,6 +420,23 @@ int dgtd_linear_fwd(const void* a, const void* w, const float* bias, void* out, 
   }
 #undef DGTD_SIMT_LIN
   DGTD_LAUNCH_CHECK("linear(fp32)");
+  return 0;
+}
+
+int dgtd_linear_tf32_fwd(const float* a, const float* w, const float* bias, float* out, int M, int N, int K, int ldo,
+                         dgtd_stream_t stream) {
+  DGTD_CHECK_ARG(a && w && out, "linear_tf32: null pointer");
+  DGTD_CHECK_ARG(M > 0 && N > 0 && N <= 64 && K > 0 && ldo >= N, "linear_tf32: bad shape M=%d N=%d K=%d ldo=%d (N <= 64)", M, N, K,
+                 ldo);
+  DGTD_CHECK_ARG(K % 4 == 0 && N % 8 == 0 && ldo % 4 == 0, "linear_tf32: K, ldo must be multiples of 4, N of 8");
+  DGTD_CHECK_ARG((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                 "linear_tf32: operands must be 16-byte aligned");
+  TcParams p{};
+  p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.ldo = ldo; p.rows_per_sample = 1;
+  const int rc = N <= 32 ? tc_launch_tf32<32>(a, w, p, (cudaStream_t)stream) : tc_launch_tf32<64>(a, w, p, (cudaStream_t)stream);
+  if (rc) return rc;
+  DGTD_LAUNCH_CHECK("linear_tf32(tcgen05)");
   return 0;
 }
 

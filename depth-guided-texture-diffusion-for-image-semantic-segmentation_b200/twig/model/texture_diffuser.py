@@ -361,6 +361,14 @@ class ShapePropEncoder(nn.Module):
                         lambda conv=conv, i=i: (fw.detach().reshape(L, 4 * L)[:, i * L:(i + 1) * L].float()
                                                 @ conv.bias.detach().float()).contiguous())
             a = o.view(-1, o.shape[-1])
+            if mode == BF16 and _HEAD_TF32 and L % 8 == 0 and L <= 64:
+                # tcgen05 projection (N = 24) straight from the fp32 stage output: TF32 products, no bf16 copy
+                w32 = pk.get(f"headf{i}.tf32", [conv.weight, fw],
+                             lambda conv=conv, i=i: (fw.detach().reshape(L, 4 * L)[:, i * L:(i + 1) * L].float()
+                                                     @ conv.weight.detach().reshape(L, -1).float()).contiguous())
+                levels.append(OP.linear_tf32(a, w32, bl))
+                hw.append((o.shape[1], o.shape[2]))
+                continue
             if mode == BF16:       # tcgen05 projection (N=24): cast the fp32 stage output once
                 a = OP.cast(a, torch.bfloat16)
             levels.append(OP.linear(a, wl, bl, out_dtype=F32))
@@ -476,6 +484,8 @@ def _decoder_front(decoders: Sequence[ShapePropDecoder], emb: torch.Tensor) -> t
     return h2
 
 
+# head projections of the bf16 mode on kind::tf32 from the fp32 stage outputs (default) or on bf16 copies (DGTD_HEAD_TF32=0)
+_HEAD_TF32 = os.environ.get("DGTD_HEAD_TF32", "1") != "0"
 # hidden maps of the bf16 decoder bank: group-major (default) or interleaved channel slices (DGTD_DEC_GROUP_MAJOR=0, A/B)
 _GROUP_MAJOR = os.environ.get("DGTD_DEC_GROUP_MAJOR", "1") != "0"
 

@@ -176,6 +176,11 @@ int dgtd_dwconv7_ln_tma_fwd(const float* x, const float* dw_wT, const float* dw_
  * the stored values (eps inside the sqrt).  C multiple of 128. */
 int dgtd_dwconv7_stats_tma_fwd(const float* x, const float* dw_wT, const float* dw_b, void* y, float* stats, int B,
                                int h, int w, int C, float eps, dgtd_stream_t stream);
+/* Thin projection of an fp32 activation on the tensor pipe without a bf16 copy (the head projections of cod.py:1174,
+ * N = 24): out (M,ldo) fp32 = a (M,K) fp32 . w (N,K)^T fp32 + bias, products in TF32 (tcgen05 kind::tf32), fp32
+ * accumulation.  N <= 64, N % 8 == 0, K % 4 == 0. */
+int dgtd_linear_tf32_fwd(const float* a, const float* w, const float* bias, float* out, int M, int N, int K, int ldo,
+                         dgtd_stream_t stream);
 /* out[M,N] = act(rstd_m * (a[M,K] . w[N,K]^T - mean_m * col_s[N]) + bias[N]) on tcgen05, a / w bf16:
  * == act(LN(a) . W1^T + b1) when w = W1 * ln_weight (rounded to bf16), col_s[n] = sum_k w[n,k] (of the rounded values),
  * bias = W1 . ln_bias + b1, row_stats[m] = (mean, rstd) of row m of a (float2).  pwconv1 with its LayerNorm folded

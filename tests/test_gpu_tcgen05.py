@@ -126,6 +126,23 @@ def test_conv_nhwc_grouped_bf16(OP, B, h, w, G, Cout, ks, stride, off, relu):
     assert rel(outb.float().cpu().double(), out.cpu().double()) <= 5e-3
 
 
+@pytest.mark.parametrize("M,N,K", [(4096, 24, 128), (1000, 24, 256), (36864, 24, 512), (300, 64, 1024), (129, 8, 36)])
+def test_linear_tf32_reads_fp32_operands(OP, M, N, K):
+    """Thin projections on kind::tf32 (the head of cod.py:1174 in bf16 mode): fp32 operands, TF32 products (10-bit
+    mantissas, truncated by the tensor core), fp32 accumulation: within 2e-3 of the float64 product relative to max|ref|
+    -- and exact when the operands are representable in TF32."""
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    ref = a.double() @ w.double().t() + b.double()
+    got = OP.linear_tf32(a.cuda(), w.cuda(), b.cuda())
+    assert rel(got, ref) <= 2e-3
+    a16, w16 = a.to(torch.bfloat16).float(), w.to(torch.bfloat16).float()   # 8-bit mantissas: exact products in TF32
+    ref16 = a16.double() @ w16.double().t() + b.double()
+    assert rel(OP.linear_tf32(a16.cuda(), w16.cuda(), b.cuda()), ref16) <= 2e-6
+
+
 def test_conv_nhwc_group_major_operands_match_interleaved(OP):
     """Round 2: the decoder bank keeps its hidden maps group-major (every group a dense (B,h,w,32) tensor).  conv1 with
     the chunk-scattered output, conv2 / the folded strided conv3 reading group-major input: bit-identical to the

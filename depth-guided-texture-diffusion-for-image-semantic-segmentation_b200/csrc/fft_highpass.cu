@@ -44,14 +44,14 @@ __global__ void projector_fill_kernel(float* __restrict__ P, int n) {
 constexpr int COEF_CHUNKS = 16;
 __global__ void __launch_bounds__(256)
 imag_coef_partial_kernel(const float* __restrict__ x, const float* __restrict__ sc_h, const float* __restrict__ sc_w,
-                         float* __restrict__ partial, int H, int W) {
+                         float* __restrict__ partial, int H, int W, int vec) {
   __shared__ float red[4][8];
   const int plane = blockIdx.y, chunk = blockIdx.x;
   const int total = H * W, len = (total + COEF_CHUNKS - 1) / COEF_CHUNKS;
   const int i0 = chunk * len, i1 = min(total, i0 + len);
   const float* p = x + (int64_t)plane * total;
   float q[4] = {0.f, 0.f, 0.f, 0.f};
-  if ((W & 3) == 0 && (len & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+  if (vec && (W & 3) == 0 && (len & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
     // four columns of one row per step (W % 4 == 0): one division and one 16-byte load per four elements
 #pragma unroll 3
     for (int i = i0 + threadIdx.x * 4; i < i1; i += 1024) {
@@ -101,9 +101,13 @@ __global__ void imag_coef_final_kernel(const float* __restrict__ partial, float*
 }
 
 // `scratch`: >= planes * COEF_CHUNKS * 4 floats that nothing reads before the next kernel of the caller overwrites it
+// vec = 1: four columns per step (the tensor-core variants).  The exact fp32 entry keeps the element-wise summation
+// order its golden vectors and the 1e-4 gradient tests were validated with: the two orders agree to 2e-7, but the
+// decoders behind this operator are ReLU networks and a pre-activation within that distance of zero flips its mask
+// against the float64 oracle (seen once: one conv1 weight gradient of the 128^2 backbone test off by 1e-2).
 static int launch_imag_coef(const float* x, const float* sc_h, const float* sc_w, float* scratch, float* coef, int planes,
-                            int H, int W, cudaStream_t s) {
-  imag_coef_partial_kernel<<<dim3(COEF_CHUNKS, planes), 256, 0, s>>>(x, sc_h, sc_w, scratch, H, W);
+                            int H, int W, cudaStream_t s, int vec) {
+  imag_coef_partial_kernel<<<dim3(COEF_CHUNKS, planes), 256, 0, s>>>(x, sc_h, sc_w, scratch, H, W, vec);
   DGTD_LAUNCH_CHECK("fft_highpass.coef(partial)");
   imag_coef_final_kernel<<<cdiv(planes * 4, 256), 256, 0, s>>>(scratch, coef, planes * 4, (float)H * (float)W);
   DGTD_LAUNCH_CHECK("fft_highpass.coef");
@@ -298,7 +302,7 @@ int dgtd_fft_highpass_fwd(const float* x, const float* Ph, const float* Pw, cons
   DGTD_CHECK_ARG(planes <= 65535, "fft_highpass: too many planes");
   cudaStream_t s = (cudaStream_t)stream;
   {  // partial sums live in `tmp` until the first GEMM overwrites it (H*W >= 64 floats per plane)
-    int rc0 = launch_imag_coef(x, sc_h, sc_w, tmp, coef, planes, H, W, s);
+    int rc0 = launch_imag_coef(x, sc_h, sc_w, tmp, coef, planes, H, W, s, 0);
     if (rc0) return rc0;
   }
   {  // tmp = x . A_w^T over all (plane,row) rows at once
@@ -333,7 +337,7 @@ int dgtd_fft_highpass_tc_fwd(const float* x, const void* Ph_hi, const void* Ph_l
   __nv_bfloat16* hi = (__nv_bfloat16*)ws_hi;
   __nv_bfloat16* lo = (__nv_bfloat16*)ws_lo;
   {  // partial sums live in ws_f32 until the first GEMM overwrites it
-    int rc0 = launch_imag_coef(x, sc_h, sc_w, ws_f32, coef, planes, H, W, s);
+    int rc0 = launch_imag_coef(x, sc_h, sc_w, ws_f32, coef, planes, H, W, s, 1);
     if (rc0) return rc0;
   }
   split_bf16_kernel<<<(unsigned)cdiv(n / 4, (int64_t)256), 256, 0, s>>>(x, hi, lo, n / 4);
@@ -368,7 +372,7 @@ int dgtd_fft_highpass_tc3_fwd(const float* x, const void* Ph_cat, const void* Pw
   cudaStream_t s = (cudaStream_t)stream;
   __nv_bfloat16* a3 = (__nv_bfloat16*)ws_a;
   {  // partial sums live in ws_f32 until the first GEMM overwrites it
-    int rc0 = launch_imag_coef(x, sc_h, sc_w, ws_f32, coef, planes, H, W, s);
+    int rc0 = launch_imag_coef(x, sc_h, sc_w, ws_f32, coef, planes, H, W, s, 1);
     if (rc0) return rc0;
   }
   const int64_t R = (int64_t)planes * H, R2 = (int64_t)planes * W;

@@ -905,8 +905,9 @@ def run_ours(args):
             peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
             ach = flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
             roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "traffic": 271.1e6, "traffic_note": "DRAM bytes of one stage-2 pwconv2 launch (M=36864,N=512,K=2048) "
-                    "from profiles/r1_ncu_full_stage2.md; algorithmic bytes of that launch 302 MB",
+                    "traffic": 270.0e6, "traffic_note": "DRAM bytes of one stage-2 pwconv2 launch (M=36864,N=512,K=2048) "
+                    "from profiles/r2_ncu_stage2_gemms.md (229.2 MB read + 40.8 MB written; 271.1 MB in "
+                    "profiles/r1_ncu_full_stage2.md); algorithmic bytes of that launch 302 MB",
                     "kernel": "tc_gemm2_kernel (tcgen05 cta_group::2) on the stage-2/3 pointwise GEMMs (N, K >= 512)",
                     "launches_timed": n, "avg_launch_ms": ms / max(n, 1),
                     "all_trunk_gemms": {"achieved": fa / (msa * 1e-3) / 1e12 if msa > 0 else 0.0, "launches": na,

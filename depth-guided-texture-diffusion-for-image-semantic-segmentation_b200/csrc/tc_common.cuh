@@ -107,6 +107,11 @@ struct TcParams {
   // col_s[n] = sum_k W'[n,k] (of the bf16-rounded W') and bias = W1 . ln_bias + b1.
   const float2* row_stats = nullptr;   // [M] (mean, rstd) of each row of A
   const float* col_s = nullptr;        // [N]
+  // LayerNorm over the N = 128 columns of every output row fused on the accumulator read-back (the stem of cod.py:1127-1128,
+  // tc_gemm2_kernel<128, ..., LNROW = true>): out = LN(acc + bias) * ln_w + ln_b
+  const float* ln_w = nullptr;
+  const float* ln_b = nullptr;
+  float ln_eps = 0.f;
   // implicit 3x3 / stride 1 / pad 1 convolution (tc_gemm_kernel<..., CONV3 = true>): the A operand of k-block
   // (tap, 64-channel chunk) is one 4-D TMA box {64 ch, 16 px, 8 rows, 1 image} of the NHWC input shifted by the
   // tap (zero fill outside the image = padding); M tiles are 8 x 16 pixel patches.
@@ -331,9 +336,73 @@ __device__ __forceinline__ void tc_epilogue_tile_tma(const TcParams& p, const CU
   }
 }
 
+// Epilogue with a LayerNorm over the 128 columns of the tile (BN = N = 128, fp32 output, 8 epilogue warps).  The two warps
+// of a TMEM lane quadrant hold 64 columns each of the same 32 rows: every lane sums its 64 values (and their squares) in
+// registers, the pair exchanges the partial sums through `xch` (double buffered by tile parity) across a 64-thread named
+// barrier, and each warp normalises and stores its own half through its two staging tiles.  One pass over the registers:
+// var = E[x^2] - mean^2 in fp32 (the stem's outputs have |mean| ~ sigma; the bf16 mode's tolerance is 2e-2).
+template <class Release>
+__device__ __forceinline__ void tc_epilogue_tile_tma_ln128(const TcParams& p, const CUtensorMap* tmOut, uint32_t tmem_tile,
+                                                           int quad, int half, int lane, int row0, uint8_t* stg,
+                                                           float2* xch, int parity, uint32_t& sbuf, Release release) {
+  const uint32_t t0 = tmem_tile + ((uint32_t)(quad * 32) << 16) + half * 64;
+  const int colbase = half * 64;
+  const uint32_t swz = (uint32_t)(lane & 7);
+  uint32_t v[2][32];
+  bw::tmem_ld_32x32(t0, v[0]);
+  bw::tmem_ld_32x32(t0 + 32, v[1]);
+  bw::tmem_ld_wait();
+  bw::tc_fence_before();
+  release();
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + colbase + c * 32 + j));
+      const float x0 = __uint_as_float(v[c][j]) + b.x, x1 = __uint_as_float(v[c][j + 1]) + b.y;
+      const float x2 = __uint_as_float(v[c][j + 2]) + b.z, x3 = __uint_as_float(v[c][j + 3]) + b.w;
+      v[c][j] = __float_as_uint(x0); v[c][j + 1] = __float_as_uint(x1);
+      v[c][j + 2] = __float_as_uint(x2); v[c][j + 3] = __float_as_uint(x3);
+      s += (x0 + x1) + (x2 + x3);
+      q += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3);
+    }
+  float2* mine = xch + ((parity * 2 + half) * 4 + quad) * 32;
+  const float2* theirs = xch + ((parity * 2 + (half ^ 1)) * 4 + quad) * 32;
+  mine[lane] = make_float2(s, q);
+  asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");   // the two warps of this quadrant
+  const float2 o = theirs[lane];
+  const float mean = (s + o.x) * (1.0f / 128.0f);
+  const float var = fmaxf((q + o.y) * (1.0f / 128.0f) - mean * mean, 0.f);
+  const float rstd = 1.0f / sqrtf(var + p.ln_eps);
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint8_t* tile = stg + (sbuf & 1) * 4096;
+    if (lane == 0) bw::tma_store_wait_read<1>();
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_w + colbase + c * 32 + j));
+      const float4 be = __ldg(reinterpret_cast<const float4*>(p.ln_b + colbase + c * 32 + j));
+      *reinterpret_cast<float4*>(tile + lane * 128 + ((((uint32_t)(j >> 2)) ^ swz) << 4)) =
+          make_float4((__uint_as_float(v[c][j]) - mean) * rstd * g.x + be.x, (__uint_as_float(v[c][j + 1]) - mean) * rstd * g.y + be.y,
+                      (__uint_as_float(v[c][j + 2]) - mean) * rstd * g.z + be.z, (__uint_as_float(v[c][j + 3]) - mean) * rstd * g.w + be.w);
+    }
+    bw::fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      bw::tma_store_2d(tmOut, tile, colbase + c * 32, row0);
+      bw::tma_store_commit();
+    }
+    ++sbuf;
+  }
+}
+
 int sm_count();
 // 2-CTA (cta_group::2) variant, tc_gemm2.cu; returns 1 when the shape is not handled there.
 int tc_gemm2_launch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B, int64_t ldb, TcParams p,
                     int act, int dtype_out, bool residual, cudaStream_t s);
+int tc_gemm2_ln_launch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B, int64_t ldb, TcParams p, cudaStream_t s);
 
 }  // namespace dgtd

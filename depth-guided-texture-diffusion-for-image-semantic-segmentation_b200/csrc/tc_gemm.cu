@@ -423,6 +423,26 @@ int dgtd_linear_fwd(const void* a, const void* w, const float* bias, void* out, 
   return 0;
 }
 
+int dgtd_linear_ln_fwd(const void* a, const void* w, const float* bias, const float* ln_w, const float* ln_b, float eps,
+                       float* out, int M, int N, int K, dgtd_stream_t stream) {
+  DGTD_CHECK_ARG(a && w && ln_w && ln_b && out, "linear_ln: null pointer");
+  DGTD_CHECK_ARG(M >= 256 && N == 128 && K > 0 && K % 8 == 0, "linear_ln: needs N == 128, M >= 256, K %% 8 == 0 (M=%d N=%d K=%d)", M, N, K);
+  DGTD_CHECK_ARG((reinterpret_cast<uintptr_t>(ln_w) & 15) == 0 && (reinterpret_cast<uintptr_t>(ln_b) & 15) == 0 &&
+                     (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                 "linear_ln: bias / ln_w / ln_b / out must be 16-byte aligned");
+  TcParams p{};
+  p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.ldo = N; p.rows_per_sample = 1;
+  p.ln_w = ln_w; p.ln_b = ln_b; p.ln_eps = eps;
+  const int rc = tc_gemm2_ln_launch((const __nv_bfloat16*)a, K, (const __nv_bfloat16*)w, K, p, (cudaStream_t)stream);
+  if (rc > 0) {
+    set_error("linear_ln: shape not handled by the 2-CTA kernel");
+    return -1;
+  }
+  if (rc) return rc;
+  DGTD_LAUNCH_CHECK("linear_ln(tcgen05)");
+  return 0;
+}
+
 int dgtd_linear_tf32_fwd(const float* a, const float* w, const float* bias, float* out, int M, int N, int K, int ldo,
                          dgtd_stream_t stream) {
   DGTD_CHECK_ARG(a && w && out, "linear_tf32: null pointer");

@@ -77,10 +77,11 @@ struct Tc2Cfg {
   static constexpr int STAGES = BN >= 256 ? 5 : 6;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int STG_BYTES = 8 * 2 * 4096;   // 8 epilogue warps x 2 staging tiles of 4 KB
-  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + STG_BYTES + 512 + 1024;
+  static constexpr int XCH_BYTES = BN == 128 ? 2 * 8 * 32 * 8 : 0;   // LNROW: (sum, sum of squares) of 2 tile parities x 8 warps
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + STG_BYTES + 512 + XCH_BYTES + 1024;
 };
 
-template <int BN, int ACT, typename OT, bool RESIDUAL, int NEPI = 8>
+template <int BN, int ACT, typename OT, bool RESIDUAL, int NEPI = 8, bool LNROW = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEPI, 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
@@ -209,9 +210,16 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       bw::mbar_wait(&tfull[as], aphase);
       bw::tc_fence_after();
       const uint32_t rel = bw2::map_to_rank(&tempty[as], 0);
-      tc_epilogue_tile_tma<BN, ACT, OT, RESIDUAL, NEPI / 4>(p, &tmOut, &tmRes, tmem_base + as * BN, quad, half, lane,
-                                                  z * p.split_rows + m_blk * 256 + (int)rank * BM + quad * 32, n_blk, stg, rbar,
-                                                  sbuf, [rel] { bw2::mbar_arrive_cluster(rel); });
+      if constexpr (LNROW) {
+        static_assert(!LNROW || (BN == 128 && NEPI == 8 && !RESIDUAL && sizeof(OT) == 4), "row LayerNorm: one 128-column fp32 tile");
+        tc_epilogue_tile_tma_ln128(p, &tmOut, tmem_base + as * BN, quad, half, lane, m_blk * 256 + (int)rank * BM + quad * 32, stg,
+                                   reinterpret_cast<float2*>(sStg + Cfg::STG_BYTES + 512), iter & 1, sbuf,
+                                   [rel] { bw2::mbar_arrive_cluster(rel); });
+      } else {
+        tc_epilogue_tile_tma<BN, ACT, OT, RESIDUAL, NEPI / 4>(p, &tmOut, &tmRes, tmem_base + as * BN, quad, half, lane,
+                                                    z * p.split_rows + m_blk * 256 + (int)rank * BM + quad * 32, n_blk, stg, rbar,
+                                                    sbuf, [rel] { bw2::mbar_arrive_cluster(rel); });
+      }
     }
     if (lane == 0) bw::tma_store_wait_all<0>();   // all results are in global memory before exit
   }
@@ -225,11 +233,11 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-template <int BN, int ACT, typename OT, bool RESIDUAL, int NEPI = 8>
+template <int BN, int ACT, typename OT, bool RESIDUAL, int NEPI = 8, bool LNROW = false>
 static int tc2_launch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B, int64_t ldb, TcParams p,
                       cudaStream_t s) {
   using Cfg = Tc2Cfg<BN>;
-  auto kern = tc_gemm2_kernel<BN, ACT, OT, RESIDUAL, NEPI>;
+  auto kern = tc_gemm2_kernel<BN, ACT, OT, RESIDUAL, NEPI, LNROW>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -317,6 +325,13 @@ int tc_gemm2_launch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B,
   if (p.N % 256 == 0 && pair_tiles_256 >= sm_count() / 2)
     return tc2_dispatch<256>(A, lda, B, ldb, p, act, dtype_out, residual, s);
   return tc2_dispatch<128>(A, lda, B, ldb, p, act, dtype_out, residual, s);
+}
+
+// out (M x 128 fp32) = LayerNorm_rows(A . B^T + bias) * ln_w + ln_b, the LayerNorm fused in the epilogue (p.ln_w / p.ln_b / p.ln_eps set).
+// Returns 1 when the shape is not handled here.
+int tc_gemm2_ln_launch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B, int64_t ldb, TcParams p, cudaStream_t s) {
+  if (p.N != 128 || p.M < 256 || p.ldo != 128 || (reinterpret_cast<uintptr_t>(p.out) & 15)) return 1;
+  return tc2_launch<128, DGTD_ACT_NONE, float, false, 8, true>(A, lda, B, ldb, p, s);
 }
 
 // Split-K partial products for weight gradients: partial[z] (M x N fp32) = A[:, Kz] . B[:, Kz]^T

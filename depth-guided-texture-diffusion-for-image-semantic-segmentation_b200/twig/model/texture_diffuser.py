@@ -325,8 +325,14 @@ class ShapePropEncoder(nn.Module):
             # tcgen05 stem: bf16 patches (K = 48) x weights -> fp32, LayerNorm rows in place
             w0b = pk.get("stem.bf16", [st_conv.weight], lambda: w0.to(torch.bfloat16))
             B, _, H, W = image.shape
-            x = OP.linear(OP.stem_patches(image, grid, BF16), w0b, st_conv.bias.detach(), out_dtype=F32)
-            x = OP.ln_rows_(x, st_ln.weight.detach(), st_ln.bias.detach(), st_ln.eps).view(B, H // 4, W // 4, self.dims[0])
+            patches = OP.stem_patches(image, grid, BF16)
+            if _STEM_LN_FUSED and self.dims[0] == 128 and patches.shape[0] >= 256:
+                # the row LayerNorm in the GEMM's epilogue: the fp32 map is written once instead of written, read and rewritten
+                x = OP.linear_ln(patches, w0b, st_conv.bias.detach().float(), st_ln.weight.detach().float(),
+                                 st_ln.bias.detach().float(), st_ln.eps).view(B, H // 4, W // 4, self.dims[0])
+            else:
+                x = OP.linear(patches, w0b, st_conv.bias.detach(), out_dtype=F32)
+                x = OP.ln_rows_(x, st_ln.weight.detach(), st_ln.bias.detach(), st_ln.eps).view(B, H // 4, W // 4, self.dims[0])
         else:
             x = OP.stem(image, grid, w0, st_conv.bias.detach(), st_ln.weight.detach(), st_ln.bias.detach(), st_ln.eps)
         outs = []
@@ -484,6 +490,8 @@ def _decoder_front(decoders: Sequence[ShapePropDecoder], emb: torch.Tensor) -> t
     return h2
 
 
+# stem of the bf16 mode: LayerNorm fused in the K = 48 GEMM's epilogue (default) or as a separate in-place pass (DGTD_STEM_LN=0)
+_STEM_LN_FUSED = os.environ.get("DGTD_STEM_LN", "1") != "0"
 # head projections of the bf16 mode on kind::tf32 from the fp32 stage outputs (default) or on bf16 copies (DGTD_HEAD_TF32=0)
 _HEAD_TF32 = os.environ.get("DGTD_HEAD_TF32", "1") != "0"
 # hidden maps of the bf16 decoder bank: group-major (default) or interleaved channel slices (DGTD_DEC_GROUP_MAJOR=0, A/B)

@@ -50,6 +50,7 @@ SIGNATURES = {
     "dgtd_dwconv7_ln_tma_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "dgtd_linear_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "dgtd_dwconv7_stats_tma_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "dgtd_linear_ln_fwd": [_P, _P, _P, _P, _P, _F, _P, _I, _I, _I, _P],
     "dgtd_linear_tf32_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "dgtd_linear_lnfold_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "dgtd_linear_residual_fwd": [_P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P],

@@ -21,7 +21,7 @@ from ..capi import ACT_GELU, ACT_NONE, ACT_RELU, BF16, F32, call, check_cuda, pt
 __all__ = [
     "surface_normals", "HighpassPlan", "fft_highpass", "diffusion_front", "MessagePassingFunction",
     "message_passing_core", "message_passing_tiled", "conv1x1_nchw_autograd", "resize_bilinear_nchw_autograd", "conv1x1_nchw", "resize_nchw", "layer_norm",
-    "stem", "stem_patches", "ln_rows_", "fusion_sum", "ln_patchify", "dwconv7_ln", "dwconv7_ln_tma", "linear", "linear_tf32", "linear_residual_", "fusion_head", "conv_nhwc", "conv_nhwc_grouped",
+    "stem", "stem_patches", "ln_rows_", "fusion_sum", "ln_patchify", "dwconv7_ln", "dwconv7_ln_tma", "linear", "linear_ln", "linear_tf32", "linear_residual_", "fusion_head", "conv_nhwc", "conv_nhwc_grouped",
     "resize_nhwc", "cast", "nhwc_to_nchw", "nchw_to_nhwc", "enable_gemm_profile", "collect_gemm_profile",
 ]
 
@@ -427,6 +427,19 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: 
     ldo = out.shape[-1]
     with _timed(2.0 * M * N * K, din == BF16, (M, N, K)):
         call("dgtd_linear_fwd", ptr(a), ptr(w), ptr(bias), ptr(out), M, N, K, ldo, din, dout, act, stream())
+    return out
+
+
+def linear_ln(a: torch.Tensor, w: torch.Tensor, bias, ln_w: torch.Tensor, ln_b: torch.Tensor, eps: float) -> torch.Tensor:
+    """out[M,128] fp32 = LayerNorm_rows(a[M,K] bf16 @ w[128,K]^T bf16 + bias) * ln_w + ln_b, the LayerNorm fused in the GEMM's
+    epilogue (M >= 256)."""
+    check_cuda(a, w, bias, ln_w, ln_b)
+    K = a.shape[-1]
+    M = a.numel() // K
+    N = w.shape[0]
+    assert w.shape[1] == K and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.is_contiguous()
+    out = torch.empty(tuple(a.shape[:-1]) + (N,), device=a.device, dtype=torch.float32)
+    call("dgtd_linear_ln_fwd", ptr(a), ptr(w), ptr(bias), ptr(ln_w), ptr(ln_b), float(eps), ptr(out), M, N, K, stream())
     return out
 
 

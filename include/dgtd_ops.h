@@ -176,6 +176,11 @@ int dgtd_dwconv7_ln_tma_fwd(const float* x, const float* dw_wT, const float* dw_
  * the stored values (eps inside the sqrt).  C multiple of 128. */
 int dgtd_dwconv7_stats_tma_fwd(const float* x, const float* dw_wT, const float* dw_b, void* y, float* stats, int B,
                                int h, int w, int C, float eps, dgtd_stream_t stream);
+/* GEMM with the row LayerNorm fused in its epilogue (the stem of cod.py:1127-1128 in bf16 mode: conv 4x4/4 as a K = 48
+ * GEMM + LayerNorm(channels_first) over the 128 output channels): out (M,128) fp32 = LN(a (M,K) bf16 . w (128,K)^T bf16
+ * + bias) * ln_w + ln_b.  N == 128, M >= 256, K % 8 == 0. */
+int dgtd_linear_ln_fwd(const void* a, const void* w, const float* bias, const float* ln_w, const float* ln_b, float eps,
+                       float* out, int M, int N, int K, dgtd_stream_t stream);
 /* Thin projection of an fp32 activation on the tensor pipe without a bf16 copy (the head projections of cod.py:1174,
  * N = 24): out (M,ldo) fp32 = a (M,K) fp32 . w (N,K)^T fp32 + bias, products in TF32 (tcgen05 kind::tf32), fp32
  * accumulation.  N <= 64, N % 8 == 0, K % 4 == 0. */

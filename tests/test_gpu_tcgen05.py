@@ -126,6 +126,22 @@ def test_conv_nhwc_grouped_bf16(OP, B, h, w, G, Cout, ks, stride, off, relu):
     assert rel(outb.float().cpu().double(), out.cpu().double()) <= 5e-3
 
 
+@pytest.mark.parametrize("M,K", [(9216, 48), (300, 48), (5000, 128), (256, 64)])
+def test_linear_with_row_layernorm_epilogue(OP, M, K):
+    """The stem GEMM with its LayerNorm fused on the accumulator read-back (two epilogue warps per TMEM lane quadrant
+    exchange their partial sums): equal to GEMM + two-pass LayerNorm of the same bf16 operands to 2e-5 of max|ref|,
+    rows with a large common offset included (one-pass variance in fp32)."""
+    g = torch.Generator().manual_seed(M + K)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    w = (torch.randn(128, K, generator=g) / K ** 0.5).to(torch.bfloat16)
+    b = torch.randn(128, generator=g) + 3.0          # a common offset of ~3 sigma in every row
+    lw, lb = torch.rand(128, generator=g) + 0.5, torch.randn(128, generator=g)
+    y = a.double() @ w.double().t() + b.double()
+    ref = torch.nn.functional.layer_norm(y, (128,), lw.double(), lb.double(), 1e-6)
+    got = OP.linear_ln(a.cuda(), w.cuda(), b.cuda(), lw.cuda(), lb.cuda(), 1e-6)
+    assert rel(got, ref) <= 2e-5
+
+
 @pytest.mark.parametrize("M,N,K", [(4096, 24, 128), (1000, 24, 256), (36864, 24, 512), (300, 64, 1024), (129, 8, 36)])
 def test_linear_tf32_reads_fp32_operands(OP, M, N, K):
     """Thin projections on kind::tf32 (the head of cod.py:1174 in bf16 mode): fp32 operands, TF32 products (10-bit
